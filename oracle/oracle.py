@@ -1,0 +1,174 @@
+"""ctypes front-end of the CPU oracle (oracle_kin.c) -- TEST INFRASTRUCTURE ONLY.
+
+Only tests/, ``__graft_entry__.smoke()`` and bench.py's CPU legs import this
+module.  The product package never does (tests/test_boundary_cpu.py greps for it).
+
+A kinematic chain is passed as a neutral *description* dict so the oracle does
+not depend on the product's classes::
+
+    {"isjoint": int32[m], "axis": int32[m], "flip": int32[m], "jindex": int32[m],
+     "T": float64[m,4,4] (row-major constant of each ET; identity for joints),
+     "qlim": float64[m,2], "n": number_of_joints}
+
+which is exactly the per-ET payload the reference hands ``fknm.ET_init``
+(reference ET.py:100-125).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def build(force: bool = False) -> str:
+    """Compile oracle_kin.c -> liboracle_kin.so (gcc, a second or two)."""
+    so = os.path.join(_HERE, "liboracle_kin.so")
+    src = os.path.join(_HERE, "oracle_kin.c")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(
+            ["gcc", "-O2", "-fopenmp", "-ffp-contract=off", "-shared", "-fPIC", src, "-o", so, "-lm"]
+        )
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = C.CDLL(build())
+        _LIB.orc_rand_u01.restype = C.c_double
+        _LIB.orc_rand_u01.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32]
+        _LIB.orc_num_threads.restype = C.c_int
+    return _LIB
+
+
+def _p(a, t):
+    return None if a is None else a.ctypes.data_as(C.POINTER(t))
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _f64(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+
+
+class Chain:
+    """Holds a chain description in the C layout the oracle functions take."""
+
+    def __init__(self, desc):
+        self.isjoint = _i32(desc["isjoint"])
+        self.axis = _i32(desc["axis"])
+        self.flip = _i32(desc["flip"])
+        self.jindex = _i32(desc["jindex"])
+        self.T = _f64(desc["T"]).reshape(-1, 16)
+        self.m = int(self.isjoint.shape[0])
+        self.n = int(self.isjoint.sum())
+        ql = _f64(desc["qlim"]).reshape(-1, 2)
+        sel = self.isjoint.astype(bool)
+        # joint limits in chain order, as ETS_init caches them (fknm.cpp:1096-1108)
+        self.qlim_l = np.ascontiguousarray(ql[sel, 0])
+        self.qlim_h = np.ascontiguousarray(ql[sel, 1])
+
+    def _head(self):
+        return (
+            C.c_int(self.m),
+            _p(self.isjoint, C.c_int),
+            _p(self.axis, C.c_int),
+            _p(self.flip, C.c_int),
+            _p(self.jindex, C.c_int),
+            _p(self.T, C.c_double),
+        )
+
+    def _head_n(self):
+        h = self._head()
+        return (h[0], C.c_int(self.n)) + h[1:]
+
+    # ------------------------------------------------------------------ FK
+    def fkine(self, q, base=None, tool=None):
+        q = np.atleast_2d(_f64(q))
+        N, ld = q.shape
+        out = np.empty((N, 4, 4))
+        base, tool = _f64(base), _f64(tool)
+        lib().orc_fkine(*self._head(), _p(q, C.c_double), C.c_long(N), C.c_long(ld),
+                        _p(base, C.c_double), _p(tool, C.c_double), _p(out, C.c_double))
+        return out
+
+    def _jac(self, fn, q, tool):
+        q = np.atleast_2d(_f64(q))
+        N, ld = q.shape
+        out = np.empty((N, 6, self.n))
+        tool = _f64(tool)
+        fn(*self._head_n(), _p(q, C.c_double), C.c_long(N), C.c_long(ld), _p(tool, C.c_double),
+           _p(out, C.c_double))
+        return out
+
+    def jacob0(self, q, tool=None):
+        return self._jac(lib().orc_jacob0, q, tool)
+
+    def jacobe(self, q, tool=None):
+        return self._jac(lib().orc_jacobe, q, tool)
+
+    def fkine_jacob0(self, q, base=None, tool=None):
+        return self.fkine(q, base, tool), self.jacob0(q, tool)
+
+    # ------------------------------------------------------------------ IK
+    def ik_lm(self, Tep, q0=None, ilimit=30, slimit=100, tol=1e-6, joint_limits=True, mask=None,
+              k=1.0, method="chan", seed=0, semantics=0, rng_per_row=True):
+        Tep = _f64(Tep).reshape(-1, 4, 4)
+        N = Tep.shape[0]
+        n = self.n
+        if q0 is not None:
+            q0 = np.ascontiguousarray(np.broadcast_to(_f64(q0).reshape(-1, n), (N, n)))
+        we = None if mask is None else _f64(mask)
+        meth = {"c": 0, "w": 1, "s": 2}[method[0].lower()]
+        q = np.empty((N, n))
+        succ = np.empty(N, dtype=np.int32)
+        its = np.empty(N, dtype=np.int32)
+        srch = np.empty(N, dtype=np.int32)
+        E = np.empty(N)
+        lib().orc_ik_lm(*self._head_n(), _p(self.qlim_l, C.c_double), _p(self.qlim_h, C.c_double),
+                        _p(Tep, C.c_double), C.c_long(N), _p(q0, C.c_double), C.c_int(ilimit),
+                        C.c_int(slimit), C.c_double(tol), C.c_int(int(bool(joint_limits))),
+                        _p(we, C.c_double), C.c_double(k), C.c_int(meth), C.c_uint64(seed),
+                        C.c_int(semantics), C.c_int(int(bool(rng_per_row))), _p(q, C.c_double),
+                        _p(succ, C.c_int), _p(its, C.c_int), _p(srch, C.c_int), _p(E, C.c_double))
+        return q, succ, its, srch, E
+
+
+def angle_axis(Te, Tep):
+    Te, Tep = _f64(Te), _f64(Tep)
+    e = np.empty(6)
+    lib().orc_angle_axis(_p(Te, C.c_double), _p(Tep, C.c_double), _p(e, C.c_double))
+    return e
+
+
+def rand_u01(seed, row, search, joint):
+    return lib().orc_rand_u01(seed, row, search, joint)
+
+
+def rne(n, mdh, L, grav, q, qd, qdd, fext=None):
+    """L: 24 doubles per link (reference DHRobot.py:1340-1358); grav: the vector handed to
+    frne, i.e. MINUS the robot's gravity (reference DHRobot.py:1449)."""
+    L, grav = _f64(L), _f64(grav)
+    q = np.atleast_2d(_f64(q)); qd = np.atleast_2d(_f64(qd)); qdd = np.atleast_2d(_f64(qdd))
+    N = q.shape[0]
+    fext = _f64(fext)
+    tau = np.empty((N, n))
+    lib().orc_rne(C.c_int(n), C.c_int(mdh), _p(L, C.c_double), _p(grav, C.c_double),
+                  _p(q, C.c_double), _p(qd, C.c_double), _p(qdd, C.c_double), C.c_long(N),
+                  _p(fext, C.c_double), _p(tau, C.c_double))
+    return tau
+
+
+def set_threads(t: int):
+    lib().orc_set_threads(C.c_int(t))
+
+
+def num_threads() -> int:
+    return lib().orc_num_threads()
