@@ -1,0 +1,193 @@
+/*
+ * b2kin.h -- C ABI of libb2kin.so: batched serial-chain kinematics / dynamics on B200 (sm_100a).
+ *
+ * This is the drop-in boundary for the reference's native fast path
+ * (petercorke/robotics-toolbox-python, src/roboticstoolbox/core/).  Each entry point names
+ * the reference interface it replaces (file:line relative to the reference repo).  The
+ * reference boundary is two CPython extension modules taking PyObject tuples and PyCapsule
+ * handles (fknm.cpp:23-93, frne.c:42-62); this one is plain C: POD arguments, opaque handles,
+ * no Python.h, no torch types.  INTEGRATION.md shows the ctypes binding a reference maintainer
+ * would add.
+ *
+ * Conventions
+ *   - every batched array is a DEVICE pointer, contiguous, row-major:
+ *       q (N, ldq)   T (N,4,4)   J (N,6,n)   tau (N,n)   Tep (N,4,4)
+ *     i.e. the values of numpy.asarray(reference_result) for row i of the batch
+ *     (reference batch FK layout: fknm.cpp:1005,1048-1051; single-q results are F-ordered
+ *     there, fknm.cpp:993,813 -- same values, different strides).
+ *   - small per-call constants (base, tool, gravity, fext, mask) are HOST pointers, fp64,
+ *     4x4 matrices row-major; NULL means "not given" exactly like None in the reference.
+ *   - dtype selects the arithmetic type of the device arrays: B2K_F32 or B2K_F64.
+ *   - stream is a cudaStream_t passed as void* (NULL = legacy default stream).  All compute
+ *     entry points are asynchronous on that stream.
+ *   - every function returns 0 on success, a negative b2k_status otherwise; the message for
+ *     the calling thread is available from b2k_last_error().
+ *   - handles are immutable after creation: safe to use from many host threads / streams
+ *     (the reference's frne capsule is mutated per call, frne.c:142-153,193-207).
+ */
+#ifndef B2KIN_H
+#define B2KIN_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2K_VERSION 100 /* 0.1.0 */
+
+#define B2K_F32 0
+#define B2K_F64 1
+
+/* largest number of joints a chain / DH robot may have (kernels are unrolled per n) */
+#define B2K_MAX_JOINTS 10
+/* largest q row width (max jindex + 1); reference: q may be wider than n, methods.cpp:338 */
+#define B2K_MAX_QWIDTH 16
+
+/* elementary-transform axis codes, as reference ET.py:244-266 */
+#define B2K_RX 0
+#define B2K_RY 1
+#define B2K_RZ 2
+#define B2K_TX 3
+#define B2K_TY 4
+#define B2K_TZ 5
+
+/* LM damping rule, reference ik.cpp:157-209 / IK.py:997-1005 */
+#define B2K_LM_CHAN 0     /* Wn = lambda * E * I   */
+#define B2K_LM_WAMPLER 1  /* Wn = lambda * I       */
+#define B2K_LM_SUGIHARA 2 /* Wn = (E + lambda) * I */
+
+/* which of the reference's two LM loops to reproduce */
+#define B2K_IK_SEM_CPP 0    /* fknm.IK_LM_c -> _IK_loop, ik.cpp:19-75 (ETS.ik_LM)       */
+#define B2K_IK_SEM_PYTHON 1 /* IKSolver._solve + IK_LM.step, IK.py:297-367,994-1017 (ETS.ikine_LM) */
+
+typedef enum {
+    B2K_OK = 0,
+    B2K_ERR_INVALID = -1, /* bad argument (shape, dtype, NULL, n too large, ...) */
+    B2K_ERR_CUDA = -2,    /* a CUDA runtime call failed; message carries cudaGetErrorString */
+    B2K_ERR_ALLOC = -3
+} b2k_status;
+
+typedef struct b2k_chain_s *b2k_chain_t; /* replaces the "ETS" PyCapsule, structs.h:25-56 */
+typedef struct b2k_rne_s *b2k_rne_t;     /* replaces the "Robot" PyCapsule, frne.h            */
+
+const char *b2k_last_error(void);
+int b2k_version(void);
+
+/* ---------------------------------------------------------------- chain description
+ * Replaces fknm.ET_init + fknm.ETS_init (fknm.cpp:1182-1239, 1066-1114; Python side
+ * ET.py:100-125, ETS.py:62-69).  m elementary transforms, in chain order:
+ *   isjoint[i]  1 = variable joint, 0 = constant
+ *   axis[i]     B2K_RX..B2K_TZ (joints only)
+ *   flip[i]     1 = joint moves in the opposite direction (eta = -q)
+ *   jindex[i]   column of q this joint reads (joints only)
+ *   T[i*16..]   constant 4x4, row-major (constants only; ignored for joints)
+ *   qlim[i*2..] joint limits low/high (joints only; the caller applies the reference defaults
+ *               [-pi,pi] / [0,1], ET.py:109-115)
+ * All constants are copied (the reference keeps a borrowed pointer, fknm.cpp:1207).
+ * Runs of constants are folded into one SE(3) constant per joint on the host -- the
+ * reference's own ETS.compile() rule, ETS.py:857-906.
+ */
+int b2k_chain_create(int m, const int32_t *isjoint, const int32_t *axis, const int32_t *flip,
+                     const int32_t *jindex, const double *T, const double *qlim,
+                     b2k_chain_t *out);
+int b2k_chain_destroy(b2k_chain_t chain);
+/* n = joints, m = elementary transforms, q_width = max jindex + 1 */
+int b2k_chain_info(b2k_chain_t chain, int *n, int *m, int *q_width);
+
+/* ---------------------------------------------------------------- forward kinematics
+ * Replaces fknm.ETS_fkine (fknm.cpp:923-1064 -> _ETS_fkine methods.cpp:318-352):
+ *   T[i] = base * prod_k ET_k(q[i, jindex_k]) * tool
+ * ldq = row stride of q in elements (>= q_width).
+ */
+int b2k_fkine(b2k_chain_t chain, int dtype, const void *q, int64_t N, int64_t ldq,
+              const double *base, const double *tool, void *T, void *stream);
+
+/* Replaces fknm.ETS_jacob0 (fknm.cpp:785-850 -> _ETS_jacob0 methods.cpp:112-216), batched:
+ * J[i] = geometric Jacobian in the chain's start frame, (6,n) row-major per row; no base
+ * (reference RobotKinematics.py:158), tool included. */
+int b2k_jacob0(b2k_chain_t chain, int dtype, const void *q, int64_t N, int64_t ldq,
+               const double *tool, void *J, void *stream);
+
+/* Replaces fknm.ETS_jacobe (fknm.cpp:852-921 -> _ETS_jacobe methods.cpp:219-316), batched:
+ * Jacobian in the end-effector frame. */
+int b2k_jacobe(b2k_chain_t chain, int dtype, const void *q, int64_t N, int64_t ldq,
+               const double *tool, void *J, void *stream);
+
+/* Fused pose + base-frame Jacobian in one pass over q (the BASELINE headline op):
+ * T as b2k_fkine (base and tool applied), J as b2k_jacob0 (tool applied, no base). */
+int b2k_fkine_jacob0(b2k_chain_t chain, int dtype, const void *q, int64_t N, int64_t ldq,
+                     const double *base, const double *tool, void *T, void *J, void *stream);
+
+/* Fused pose + end-effector-frame Jacobian. */
+int b2k_fkine_jacobe(b2k_chain_t chain, int dtype, const void *q, int64_t N, int64_t ldq,
+                     const double *base, const double *tool, void *T, void *J, void *stream);
+
+/* ---------------------------------------------------------------- inverse kinematics
+ * Replaces fknm.IK_LM_c (fknm.cpp:394-525 -> _IK_LM_Chan/_Wampler/_Sugihara ik.cpp:157-209
+ * -> _IK_loop ik.cpp:19-75) for N targets at once, and -- with semantics =
+ * B2K_IK_SEM_PYTHON -- the Python solver behind ETS.ikine_LM (IK.py:297-367, 994-1017).
+ *   Tep      (N,4,4) device, row-major
+ *   q0       (N,n) device initial guesses or NULL (then drawn inside the joint limits)
+ *   we       host 6-vector of Cartesian weights or NULL (= ones); We = diag(we)
+ *   reject_jl  reject converged solutions outside the joint limits and restart
+ *   seed     seed of the counter-based restart generator (the reference uses unseeded libc
+ *            rand(), ik.cpp:293, or numpy default_rng, IK.py:166)
+ *   rng_per_row  1: restart draws keyed by (seed,row,search); 0: shared by all rows
+ *            (IKSolver.solve reuses one set of restarts for a whole trajectory, IK.py:222-272)
+ * Outputs (device): q_out (N,n), success/iterations/searches int32 (N), residual (N) in dtype
+ * -- the tuple IK_LM_c returns (fknm.cpp:516), one entry per target.
+ * Requires jindex == 0..n-1 in chain order (the reference C++ loop assumes it, ik.cpp:34-35).
+ */
+int b2k_ik_lm(b2k_chain_t chain, int dtype, const void *Tep, int64_t N, const void *q0,
+              int ilimit, int slimit, double tol, int reject_jl, const double *we, double lambda,
+              int method, uint64_t seed, int semantics, int rng_per_row, void *q_out,
+              int32_t *success, int32_t *iterations, int32_t *searches, void *residual,
+              void *stream);
+
+/* ---------------------------------------------------------------- inverse dynamics (DH RNE)
+ * b2k_rne_create replaces frne.init (frne.c:233-299): n links, mdh = 0 standard / 1 modified
+ * DH, L = 24 doubles per link packed as reference DHRobot.py:1340-1358
+ *   [alpha, a, theta, d, sigma, offset, m, r(3), I(9 row-major), Jm, G, B, Tc+, Tc-].
+ * b2k_rne replaces the per-row frne.frne loop (frne.c:106-230 -> newton_euler ne.c:62-492):
+ *   tau[i] = RNE(q[i], qd[i], qdd[i]) for i < N, arrays (N,n).
+ *   grav : host 3-vector handed to the recursion as the base acceleration, i.e. MINUS the
+ *          robot's gravity exactly as DHRobot.rne passes it (DHRobot.py:1449); must not be NULL
+ *   fext : host 6-vector wrench at the tip or NULL (= zeros)
+ */
+int b2k_rne_create(int n, int mdh, const double *L, b2k_rne_t *out);
+int b2k_rne_destroy(b2k_rne_t rne);
+int b2k_rne(b2k_rne_t rne, int dtype, const void *q, const void *qd, const void *qdd, int64_t N,
+            const double *grav, const double *fext, void *tau, void *stream);
+
+/* ---------------------------------------------------------------- host-buffer front ends
+ * The same operations for callers that hold HOST arrays (what the reference's API takes):
+ * the library streams row chunks host->device, runs the kernel and streams results back on
+ * several CUDA streams so copies overlap compute.  Pinned host memory (b2k_host_alloc, or
+ * memory the caller registered) gets full PCIe/C2C bandwidth; pageable memory works too.
+ * Synchronous: results are complete in the host arrays on return.  device = CUDA ordinal.
+ */
+int b2k_host_alloc(void **ptr, int64_t bytes);
+int b2k_host_free(void *ptr);
+int b2k_fkine_jacob0_host(b2k_chain_t chain, int dtype, const void *q_host, int64_t N,
+                          int64_t ldq, const double *base, const double *tool, void *T_host,
+                          void *J_host, int device);
+int b2k_fkine_host(b2k_chain_t chain, int dtype, const void *q_host, int64_t N, int64_t ldq,
+                   const double *base, const double *tool, void *T_host, int device);
+int b2k_rne_host(b2k_rne_t rne, int dtype, const void *q_host, const void *qd_host,
+                 const void *qdd_host, int64_t N, const double *grav, const double *fext,
+                 void *tau_host, int device);
+
+/* number of kernel launches this library has issued in the calling process (all threads);
+ * bench.py reports the delta over its timed region as "gpu_launches". */
+int64_t b2k_launch_count(void);
+
+/* kernel variant switch for measurements: 0 = default (lane-per-configuration, warp-tiled
+ * I/O), 1 = literal warp-per-configuration walk (one joint configuration per warp).
+ * Affects b2k_fkine / b2k_fkine_jacob0 only. */
+int b2k_set_variant(int variant);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2KIN_H */

@@ -59,7 +59,7 @@ class Builder:
         return self
 
     def se3(self, T):
-        self.rows.append((0, 0, 0, 0, np.array(T, dtype=float), (-math.pi, math.pi)))
+        self.rows.append((0, 0, 0, 0, np.array(T, dtype=float), (0.0, 1.0)))  # axis "SE3" is not "R..": ET.py:109-115
         return self
 
     def joint(self, axis, flip=False, jindex=None, qlim=None):
@@ -99,7 +99,7 @@ def panda_ets():
     b.const(TX, -0.0825).const(RX, -90 * deg).const(TZ, 0.384).joint(RZ)
     b.const(RX, 90 * deg).joint(RZ)
     b.const(TX, 0.088).const(RX, 90 * deg).const(TZ, 0.107).joint(RZ)
-    b.const(TZ, 0.103).const(RZ, -math.pi / 4)
+    b.const(TZ, 103 * 1e-3).const(RZ, -math.pi / 4)  # tool_offset = (103) * mm, Panda.py:32
     return b.desc()
 
 
@@ -225,13 +225,13 @@ def panda_mdh_links():
         (0.0825, 0.0, pi / 2, [-3.0718, -0.0698], 3.587895, [2.58530e-02, 1.95520e-02, 2.83230e-02, 7.79600e-03, 8.64100e-03, -1.33200e-03]),
         (-0.0825, 0.384, -pi / 2, [-2.8973, 2.8973], 1.225946, [3.55490e-02, 2.94740e-02, 8.62700e-03, -2.11700e-03, 2.29000e-04, -4.03700e-03]),
         (0.0, 0.0, pi / 2, [-0.0175, 3.7525], 1.666555, [1.96400e-03, 4.35400e-03, 5.43300e-03, 1.09000e-04, 3.41000e-04, -1.15800e-03]),
-        (0.088, 0.107, pi / 2, [-2.8973, 2.8973], 7.35522e-01, [1.25160e-02, 1.00270e-02, 4.81500e-03, -4.28000e-04, -7.41000e-04, -1.19600e-03]),
+        (0.088, 107 * 1e-3, pi / 2, [-2.8973, 2.8973], 7.35522e-01, [1.25160e-02, 1.00270e-02, 4.81500e-03, -4.28000e-04, -7.41000e-04, -1.19600e-03]),
     ]
     return [dict(a=a, d=d, alpha=al, qlim=ql, m=m, I=I, G=1.0) for a, d, al, ql, m, I in P]
 
 
 def panda_mdh_tool():
-    return transl(0, 0, 0.103) @ trotz(-math.pi / 4)
+    return transl(0, 0, 103 * 1e-3) @ trotz(-math.pi / 4)
 
 
 def inertia3(I):

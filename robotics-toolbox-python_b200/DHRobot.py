@@ -1,0 +1,225 @@
+"""DH / MDH serial-link robots: kinematics through the compiled ETS chain, inverse dynamics
+through the batched RNE kernel.
+
+Mirrors the hot-path part of the reference's ``DHRobot`` (reference
+src/roboticstoolbox/robot/DHRobot.py): ``ets()`` 878-918, ``fkine`` 920-979, ``jacobe`` 1066-1140,
+``jacob0`` 1142-1198, ``rne`` 1373-1456 with its parameter packing ``_init_rne`` 1340-1361 and
+dirty tracking (DHLink.py:24-51), ``ikine_LM`` 2454-2474.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional
+
+import numpy as np
+
+from . import _buffers as B
+from . import _lib
+from ._se3 import SE3
+from .DHLink import DHLink
+from .ET import ET
+from .ETS import ETS, _mat44
+
+
+class DHRobot:
+    def __init__(self, links: List[DHLink], name: str = "", manufacturer: str = "", base=None, tool=None,
+                 gravity=None, **kwargs):
+        self._rne_ob = None
+        if not links or not all(isinstance(l, DHLink) for l in links):
+            raise TypeError("links must be a non-empty list of DHLink")
+        mdh = {l.mdh for l in links}
+        if len(mdh) != 1:
+            raise ValueError("Robot has mixed D&H links conventions")
+        self.links = list(links)
+        for l in self.links:
+            l._robot = self
+        self.name, self.manufacturer = name, manufacturer
+        self._base = np.eye(4) if base is None else _mat44(base, "base")
+        self._tool = np.eye(4) if tool is None else _mat44(tool, "tool")
+        # reference BaseRobot.py:83 default
+        self._gravity = np.array([0.0, 0.0, -9.81]) if gravity is None else np.asarray(gravity, dtype=np.float64).reshape(3)
+        self._rne_ob = None
+        self._dynchanged = False
+        self._ets_cache = None
+        self._configs = {}
+
+    # ---- structure
+    @property
+    def n(self) -> int:
+        return len(self.links)
+
+    @property
+    def mdh(self) -> int:
+        return int(self.links[0].mdh)
+
+    @property
+    def base(self) -> SE3:
+        return SE3(self._base)
+
+    @base.setter
+    def base(self, T):
+        self._base = np.eye(4) if T is None else _mat44(T, "base")
+        self._ets_cache = None
+
+    @property
+    def tool(self) -> SE3:
+        return SE3(self._tool)
+
+    @tool.setter
+    def tool(self, T):
+        self._tool = np.eye(4) if T is None else _mat44(T, "tool")
+        self._ets_cache = None
+
+    @property
+    def gravity(self) -> np.ndarray:
+        return self._gravity
+
+    @gravity.setter
+    def gravity(self, g):
+        self._gravity = np.asarray(g, dtype=np.float64).reshape(3)
+        self.dynchanged()
+
+    @property
+    def qlim(self) -> np.ndarray:
+        out = np.zeros((2, self.n))
+        for j, l in enumerate(self.links):
+            if l.qlim is None:
+                out[:, j] = (-np.pi, np.pi) if l.isrevolute else (0.0, 1.0)
+            else:
+                out[:, j] = l.qlim
+        return out
+
+    def addconfiguration(self, name, q):
+        self._configs[name] = np.asarray(q, dtype=np.float64)
+        setattr(self, name, self._configs[name])
+
+    def __len__(self):
+        return self.n
+
+    def __iter__(self):
+        return iter(self.links)
+
+    # ---- kinematics: reference DHRobot.ets (878-918) then the ETS hot path
+    def ets(self) -> ETS:
+        if self._ets_cache is None:
+            parts = []
+            if not np.array_equal(self._base, np.eye(4)):
+                parts.append(ETS(ET.SE3(self._base)))
+            parts.extend(l.ets for l in self.links)
+            if not np.array_equal(self._tool, np.eye(4)):
+                parts.append(ETS(ET.SE3(self._tool)))
+            self._ets_cache = ETS.from_links(parts)
+        return self._ets_cache
+
+    def fkine(self, q, **kwargs) -> SE3:
+        """Base and tool incorporated, joint offsets applied (reference DHRobot.fkine 920-979)."""
+        return self.ets().fkine(q, **kwargs)
+
+    def eval(self, q, **kwargs):
+        return self.ets().eval(q, **kwargs)
+
+    def jacobe(self, q, **kwargs):
+        """Jacobian in the end-effector frame (reference DHRobot.jacobe 1066-1140)."""
+        return self.ets().jacobe(q, **kwargs)
+
+    def jacob0(self, q, **kwargs):
+        """Jacobian in the world frame = tr2jac(T) @ jacobe, base rotation included
+        (reference DHRobot.jacob0 1142-1198)."""
+        return self.ets().jacob0(q, **kwargs)
+
+    def fkine_jacob0(self, q, **kwargs):
+        return self.ets().fkine_jacob0(q, **kwargs)
+
+    def ikine_LM(self, Tep, q0=None, ilimit=30, slimit=100, tol=1e-6, joint_limits=False, mask=None, seed=None,
+                 **kwargs):
+        """reference DHRobot.ikine_LM 2454-2474 (note joint_limits defaults to False here)."""
+        return self.ets().ikine_LM(Tep=Tep, q0=q0, ilimit=ilimit, slimit=slimit, tol=tol,
+                                   joint_limits=joint_limits, mask=mask, seed=seed, **kwargs)
+
+    def ik_LM(self, Tep, **kwargs):
+        return self.ets().ik_LM(Tep, **kwargs)
+
+    # ---- inverse dynamics
+    def dynchanged(self, what=None):
+        """Mark the packed dynamic parameters stale (reference BaseRobot.py:383-398)."""
+        self._dynchanged = True
+
+    def _pack_rne(self) -> np.ndarray:
+        """24 doubles per link (reference DHRobot._init_rne 1340-1358)."""
+        L = np.zeros(24 * self.n)
+        for i, l in enumerate(self.links):
+            j = 24 * i
+            L[j:j + 6] = (l.alpha, l.a, l.theta, l.d, l.sigma, l.offset)
+            L[j + 6] = l.m
+            L[j + 7:j + 10] = l.r
+            L[j + 10:j + 19] = l.I.flatten()
+            L[j + 19:j + 22] = (l.Jm, l.G, l.B)
+            L[j + 22:j + 24] = l.Tc
+        return L
+
+    def _init_rne(self):
+        h = _lib.vp()
+        L = self._pack_rne()
+        _lib.check(_lib.lib().b2k_rne_create(self.n, self.mdh, _lib.dptr(L), C.byref(h)))
+        self._rne_ob = h
+        self._dynchanged = False
+
+    def delete_rne(self):
+        """reference DHRobot.delete_rne 1363-1371"""
+        if self._rne_ob is not None:
+            try:
+                _lib.lib().b2k_rne_destroy(self._rne_ob)
+            except Exception:
+                pass
+            self._dynchanged = False
+            self._rne_ob = None
+
+    def __del__(self):
+        self.delete_rne()
+
+    def rne(self, q, qd=None, qdd=None, gravity=None, fext=None, base_wrench=False, dtype=None):
+        """Inverse dynamics tau = RNE(q, qd, qdd): (n,) for one state, (N,n) for a trajectory
+        (reference DHRobot.rne 1373-1456 -> frne.frne per row)."""
+        if base_wrench:
+            raise NotImplementedError("base_wrench uses the reference's pure-Python rne_python; outside the accelerated path")
+        if self._rne_ob is None or self._dynchanged:  # @_check_rne, DHLink.py:24-51
+            self.delete_rne()
+            self._init_rne()
+        n = self.n
+        for x, nm in ((q, "q"), (qd, "qd"), (qdd, "qdd")):
+            if x is None:
+                raise ValueError(f"{nm} must be given")
+            B.check_numeric(x, nm)
+        dt = B.pick_dtype(q, dtype)
+        host = not B.is_tensor(q)
+
+        def norm(x):
+            if B.is_tensor(x):
+                return x.reshape(1, -1) if x.dim() == 1 else x
+            a = np.asarray(x, dtype=dt if np.asarray(x).dtype in (np.float32, np.float64) else np.float64)
+            return a.reshape(1, -1) if a.ndim == 1 else a
+
+        single = (q.dim() if B.is_tensor(q) else np.ndim(q)) == 1
+        q2, qd2, qdd2 = norm(q), norm(qd), norm(qdd)
+        N = q2.shape[0]
+        for x, nm in ((q2, "q"), (qd2, "qd"), (qdd2, "qdd")):
+            if x.ndim != 2 or tuple(x.shape) != (N, n):
+                raise ValueError(f"{nm} must have shape ({n},) or (N,{n}); got {tuple(x.shape)}")
+        g = self._gravity if gravity is None else np.asarray(gravity, dtype=np.float64).reshape(3)
+        # the recursion has no base: rotate gravity instead (reference 1431-1433), and hand it over negated (1449)
+        g = self._base[:3, :3].T @ g
+        ng = np.ascontiguousarray(-g)
+        fx = None if fext is None else np.ascontiguousarray(np.asarray(fext, dtype=np.float64).reshape(6))
+        L = _lib.lib()
+        if host:
+            t = B.require_cuda()
+            qh, qdh, qddh = (np.ascontiguousarray(x, dtype=dt) for x in (q2, qd2, qdd2))
+            tau = np.empty((N, n), dtype=dt)
+            _lib.check(L.b2k_rne_host(self._rne_ob, B.code(dt), qh.ctypes.data, qdh.ctypes.data, qddh.ctypes.data, N,
+                                      _lib.dptr(ng), _lib.dptr(fx), tau.ctypes.data, t.cuda.current_device()))
+        else:
+            qt, qdt, qddt = (B.to_device(x, dt) for x in (q2, qd2, qdd2))
+            tau = B.empty((N, n), dt, like=qt)
+            _lib.check(L.b2k_rne(self._rne_ob, B.code(dt), B.ptr(qt), B.ptr(qdt), B.ptr(qddt), N, _lib.dptr(ng),
+                                 _lib.dptr(fx), B.ptr(tau), B.stream_ptr(qt)))
+        return tau[0] if single else tau

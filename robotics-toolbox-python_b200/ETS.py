@@ -1,0 +1,428 @@
+"""Elementary transform sequences -- the operator API of the hot path.
+
+Keeps the reference's ``ETS`` method names, argument meaning and error behaviour for the path
+this package accelerates (reference src/roboticstoolbox/robot/ETS.py):
+
+    eval / fkine   ETS.py:951-1141   -> b2k_fkine          (reference: fknm.ETS_fkine)
+    jacob0         ETS.py:1143-1266  -> b2k_jacob0         (reference: fknm.ETS_jacob0, one q per call)
+    jacobe         ETS.py:1268-1332  -> b2k_jacobe         (reference: fknm.ETS_jacobe, one q per call)
+    ik_LM          ETS.py:2014-2170  -> b2k_ik_lm, C++ loop semantics   (reference: fknm.IK_LM_c)
+    ikine_LM       ETS.py:2443-2637  -> b2k_ik_lm, Python solver semantics (reference: IK.IK_LM.solve)
+    fkine_jacob0   (extension)       -> b2k_fkine_jacob0   one pass giving pose and Jacobian
+
+All of them accept an (N, n) batch of joint coordinates (the reference only batches fkine) as a
+numpy array / list (host: results come back as numpy) or a CUDA torch tensor (results stay on
+the device).  There is no Python / sympy fallback: a non-numeric q raises TypeError exactly like
+the reference's C layer does (fknm.cpp:1304-1318), and the reference's silent fall-through to
+slow Python (ETS.py:1075-1078) is deliberately not reproduced.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Union
+
+import numpy as np
+
+from . import _buffers as B
+from . import _lib
+from ._se3 import SE3
+from .ET import AXES, ET
+from .IK import IKSolution
+
+
+def _mat44(T, name):
+    """None / SE3-like / array -> fp64 (4,4) or None."""
+    if T is None:
+        return None
+    T = getattr(T, "A", T)
+    T = np.ascontiguousarray(np.asarray(T, dtype=np.float64))
+    if T.shape != (4, 4):
+        raise ValueError(f"{name} must be a 4x4 matrix")
+    return T
+
+
+class ETS:
+    """A sequence of :class:`ET` (reference ETS.py:57-69, 760-840)."""
+
+    def __init__(self, arg: Union[None, ET, "ETS", List] = None):
+        ets: List[ET] = []
+        if arg is None:
+            pass
+        elif isinstance(arg, ET):
+            ets = [arg.copy()]
+        elif isinstance(arg, ETS):
+            ets = [e.copy() for e in arg._ets]
+        elif isinstance(arg, (list, tuple)):
+            for a in arg:
+                if isinstance(a, ET):
+                    ets.append(a.copy())
+                elif isinstance(a, ETS):
+                    ets.extend(e.copy() for e in a._ets)
+                else:
+                    raise TypeError("bad arg")
+        else:
+            raise TypeError("Invalid arg")
+        self._ets = ets
+        self._assign_jindices()
+        self._handle = None
+
+    # jindex auto-numbering, reference ETS.py:803-840
+    def _assign_jindices(self):
+        joints = [e for e in self._ets if e.isjoint]
+        n = len(joints)
+        have = sum(1 for j in joints if j.jindex is not None)
+        seq = sum(1 for k, j in enumerate(joints) if j.jindex is not None and j.jindex == k)
+        self._auto_jindex = False
+        if n and have == n - 1 and seq == n - 1 and joints[-1].jindex is None:
+            joints[-1].jindex = n - 1
+            self._auto_jindex = True
+        elif have > 0 and have != n:
+            raise ValueError("You can not have some jindices set for the ET's in arg. It must be all or none")
+        elif have == 0 and n > 0:
+            for k, j in enumerate(joints):
+                j.jindex = k
+            self._auto_jindex = True
+
+    @staticmethod
+    def from_links(link_ets: List["ETS"]) -> "ETS":
+        """Concatenate per-link ETSs into a robot chain.  When every link's joint index was only
+        auto-assigned (each link numbered its own joint 0), the joints are renumbered 0..n-1 in
+        chain order -- what the reference's robot constructor does (BaseRobot.py:336-352)."""
+        renumber = all(e._auto_jindex or e.n == 0 for e in link_ets)
+        parts: List[ET] = []
+        for e in link_ets:
+            for et in e._ets:
+                c = et.copy()
+                if renumber and c.isjoint:
+                    c._jindex = None
+                parts.append(c)
+        return ETS(parts)
+
+    # ---- composition
+    def __mul__(self, other):
+        if isinstance(other, ET):
+            return ETS([*self._ets, other])
+        if isinstance(other, ETS):
+            return ETS([*self._ets, *other._ets])
+        return NotImplemented
+
+    __add__ = __mul__
+
+    def __len__(self):
+        return len(self._ets)
+
+    def __iter__(self):
+        return iter(self._ets)
+
+    def __getitem__(self, i):
+        r = self._ets[i]
+        return ETS(r) if isinstance(i, slice) else r
+
+    def __repr__(self):
+        return " ⊕ ".join(repr(e) for e in self._ets)
+
+    # ---- structure, reference ETS.py:400-760
+    @property
+    def n(self) -> int:
+        return sum(1 for e in self._ets if e.isjoint)
+
+    @property
+    def m(self) -> int:
+        return len(self._ets)
+
+    def joints(self) -> List[ET]:
+        return [e for e in self._ets if e.isjoint]
+
+    def joint_idx(self) -> List[int]:
+        return [i for i, e in enumerate(self._ets) if e.isjoint]
+
+    @property
+    def jindices(self) -> np.ndarray:
+        return np.array([e.jindex for e in self.joints()], dtype=int)
+
+    @property
+    def qlim(self) -> np.ndarray:
+        """(2, n) joint limits with the reference's defaults for unset limits (ET.py:109-115)."""
+        ql = np.array([e._qlim_default() for e in self.joints()], dtype=np.float64).reshape(-1, 2)
+        return ql.T.copy()
+
+    @property
+    def structure(self) -> str:
+        return "".join("R" if e.isrotation else "P" for e in self.joints())
+
+    def compile(self) -> "ETS":
+        """Fold runs of constants into single SE(3) constants (reference ETS.py:857-906).  The
+        native chain compiler applies the same rule internally; this is for inspection."""
+        out: List[ET] = []
+        acc = None
+        for e in self._ets:
+            if e.isjoint:
+                if acc is not None:
+                    out.append(ET.SE3(acc))
+                    acc = None
+                out.append(e.copy())
+            else:
+                acc = e.A() if acc is None else acc @ e.A()
+        if acc is not None:
+            out.append(ET.SE3(acc))
+        return ETS(out)
+
+    def describe(self) -> dict:
+        """Neutral per-ET description: exactly what the reference marshals into fknm.ET_init
+        (ET.py:100-125).  Consumed by b2k_chain_create and by the test oracle."""
+        m = self.m
+        d = {
+            "isjoint": np.zeros(m, np.int32), "axis": np.zeros(m, np.int32), "flip": np.zeros(m, np.int32),
+            "jindex": np.zeros(m, np.int32), "T": np.tile(np.eye(4), (m, 1, 1)), "qlim": np.zeros((m, 2)),
+            "n": self.n,
+        }
+        for i, e in enumerate(self._ets):
+            d["isjoint"][i] = int(e.isjoint)
+            d["axis"][i] = AXES.get(e.axis, 0)
+            d["flip"][i] = int(e.isflip)
+            d["jindex"][i] = e.jindex if (e.isjoint and e.jindex is not None) else 0
+            d["T"][i] = e.A() if not e.isjoint else np.eye(4)
+            d["qlim"][i] = e._qlim_default()
+        return d
+
+    # ---- native handle
+    def _update_internals(self):
+        """Drop the compiled chain (call after mutating an ET's jindex / qlim); reference ETS.py:62-69."""
+        self._release()
+
+    def _release(self):
+        if getattr(self, "_handle", None):
+            try:
+                _lib.lib().b2k_chain_destroy(self._handle)
+            except Exception:
+                pass
+        self._handle = None
+
+    def __del__(self):
+        self._release()
+
+    @property
+    def _chain(self):
+        if self._handle is None:
+            if self.n < 1:
+                raise ValueError("the ETS has no joints; nothing to evaluate on the GPU")
+            d = self.describe()
+            h = _lib.vp()
+            ip = _lib.ip
+            T = np.ascontiguousarray(d["T"], dtype=np.float64)
+            ql = np.ascontiguousarray(d["qlim"], dtype=np.float64)
+            _lib.check(_lib.lib().b2k_chain_create(
+                self.m, d["isjoint"].ctypes.data_as(ip), d["axis"].ctypes.data_as(ip),
+                d["flip"].ctypes.data_as(ip), d["jindex"].ctypes.data_as(ip), _lib.dptr(T), _lib.dptr(ql),
+                C.byref(h)))
+            self._handle = h
+            self._qwidth = int(max(self.jindices)) + 1
+        return self._handle
+
+    # ---- argument normalisation
+    def _qbatch(self, q):
+        """-> (q2d, single).  Shape rules of the reference's C layer (fknm.cpp:963-988): 1-D, (1,w)
+        and (w,1) are ONE configuration, anything else is a trajectory of rows.  Deviation: for a
+        1-joint chain an (N,1) array is N rows (the reference misreads it)."""
+        B.check_numeric(q)
+        nd = q.dim() if B.is_tensor(q) else np.ndim(q)
+        if not B.is_tensor(q):
+            q = np.asarray(q)
+            if q.dtype not in (np.float32, np.float64):
+                q = q.astype(np.float64)
+        if nd == 0:
+            q = q.reshape(1, 1)
+            single = True
+        elif nd == 1:
+            q = q.reshape(1, -1)
+            single = True
+        elif nd == 2:
+            r, c = q.shape
+            if r == 1:
+                single = True
+            elif c == 1 and self.n > 1:
+                q = q.reshape(1, -1)
+                single = True
+            else:
+                single = False
+        else:
+            raise ValueError("q must be 1-D or 2-D")
+        _ = self._chain
+        if q.shape[1] < self._qwidth:
+            raise ValueError(f"q has {q.shape[1]} columns but the ETS reads joint index {self._qwidth - 1}")
+        if q.shape[1] > _lib.MAX_QWIDTH:
+            raise ValueError(f"q rows wider than {_lib.MAX_QWIDTH} are not supported")
+        return q, single
+
+    # ------------------------------------------------------------------ forward kinematics
+    def eval(self, q, base=None, tool=None, include_base: bool = True, dtype=None):
+        """Forward kinematics as arrays: (4,4) for one q, (N,4,4) for an (N,n) batch
+        (reference ETS.eval, ETS.py:1021-1078 -> fknm.ETS_fkine)."""
+        q2, single = self._qbatch(q)
+        dt = B.pick_dtype(q2, dtype)
+        base = _mat44(base, "base") if include_base else None
+        tool = _mat44(tool, "tool")
+        L = _lib.lib()
+        N = q2.shape[0]
+        if not B.is_tensor(q2):
+            t = B.require_cuda()
+            qh = np.ascontiguousarray(q2, dtype=dt)
+            T = np.empty((N, 4, 4), dtype=dt)
+            _lib.check(L.b2k_fkine_host(self._chain, B.code(dt), qh.ctypes.data, N, qh.shape[1], _lib.dptr(base),
+                                        _lib.dptr(tool), T.ctypes.data, t.cuda.current_device()))
+            return T[0] if single else T
+        qd = B.to_device(q2, dt)
+        T = B.empty((N, 4, 4), dt, like=qd)
+        _lib.check(L.b2k_fkine(self._chain, B.code(dt), B.ptr(qd), N, qd.shape[1], _lib.dptr(base), _lib.dptr(tool),
+                               B.ptr(T), B.stream_ptr(qd)))
+        return T[0] if single else T
+
+    def fkine(self, q, base=None, tool=None, include_base: bool = True, dtype=None) -> SE3:
+        """Forward kinematics as an SE3 container (reference ETS.fkine, ETS.py:951-1019); one
+        batched container instead of N Python objects."""
+        T = self.eval(q, base, tool, include_base, dtype)
+        return SE3(B.to_host(T) if B.is_tensor(T) else T)
+
+    # ------------------------------------------------------------------ Jacobians
+    def _jac(self, fn_name, q, tool, dtype):
+        q2, single = self._qbatch(q)
+        dt = B.pick_dtype(q2, dtype)
+        tool = _mat44(tool, "tool")
+        host = not B.is_tensor(q2)
+        qd = B.to_device(q2, dt)
+        N = qd.shape[0]
+        J = B.empty((N, 6, self.n), dt, like=qd)
+        fn = getattr(_lib.lib(), fn_name)
+        _lib.check(fn(self._chain, B.code(dt), B.ptr(qd), N, qd.shape[1], _lib.dptr(tool), B.ptr(J), B.stream_ptr(qd)))
+        if host:
+            J = B.to_host(J)
+        return J[0] if single else J
+
+    def jacob0(self, q, tool=None, dtype=None):
+        """Geometric Jacobian in the start frame of the chain: (6,n) or (N,6,n)
+        (reference ETS.jacob0, ETS.py:1143-1199 -> fknm.ETS_jacob0)."""
+        return self._jac("b2k_jacob0", q, tool, dtype)
+
+    def jacobe(self, q, tool=None, dtype=None):
+        """Geometric Jacobian in the end-effector frame (reference ETS.jacobe, ETS.py:1268-1332)."""
+        return self._jac("b2k_jacobe", q, tool, dtype)
+
+    def fkine_jacob0(self, q, base=None, tool=None, include_base: bool = True, dtype=None):
+        """Pose and base-frame Jacobian from ONE pass over q (extension; the reference needs
+        ETS.eval + a Python loop of ETS.jacob0).  Returns (T, J)."""
+        q2, single = self._qbatch(q)
+        dt = B.pick_dtype(q2, dtype)
+        base = _mat44(base, "base") if include_base else None
+        tool = _mat44(tool, "tool")
+        L = _lib.lib()
+        N = q2.shape[0]
+        n = self.n
+        if not B.is_tensor(q2):
+            t = B.require_cuda()
+            qh = np.ascontiguousarray(q2, dtype=dt)
+            T = np.empty((N, 4, 4), dtype=dt)
+            J = np.empty((N, 6, n), dtype=dt)
+            _lib.check(L.b2k_fkine_jacob0_host(self._chain, B.code(dt), qh.ctypes.data, N, qh.shape[1],
+                                               _lib.dptr(base), _lib.dptr(tool), T.ctypes.data, J.ctypes.data,
+                                               t.cuda.current_device()))
+        else:
+            qd = B.to_device(q2, dt)
+            T = B.empty((N, 4, 4), dt, like=qd)
+            J = B.empty((N, 6, n), dt, like=qd)
+            _lib.check(L.b2k_fkine_jacob0(self._chain, B.code(dt), B.ptr(qd), N, qd.shape[1], _lib.dptr(base),
+                                          _lib.dptr(tool), B.ptr(T), B.ptr(J), B.stream_ptr(qd)))
+        return (T[0], J[0]) if single else (T, J)
+
+    def fkine_jacob0_into(self, q, T, J, base=None, tool=None):
+        """Zero-allocation host form of :meth:`fkine_jacob0`: q, T, J are caller-owned C-contiguous
+        numpy arrays (ideally from ``pinned_empty``) of one dtype; results are written in place."""
+        t = B.require_cuda()
+        dt = q.dtype
+        if T.dtype != dt or J.dtype != dt or dt not in (np.float32, np.float64):
+            raise TypeError("q, T, J must share dtype float32 or float64")
+        if not (q.flags.c_contiguous and T.flags.c_contiguous and J.flags.c_contiguous):
+            raise ValueError("q, T, J must be C-contiguous")
+        N = q.shape[0]
+        if T.shape != (N, 4, 4) or J.shape != (N, 6, self.n):
+            raise ValueError("T must be (N,4,4) and J (N,6,n)")
+        _lib.check(_lib.lib().b2k_fkine_jacob0_host(
+            self._chain, B.code(np.dtype(dt)), q.ctypes.data, N, q.shape[1], _lib.dptr(_mat44(base, "base")),
+            _lib.dptr(_mat44(tool, "tool")), T.ctypes.data, J.ctypes.data, t.cuda.current_device()))
+
+    # ------------------------------------------------------------------ inverse kinematics
+    def _ik(self, Tep, q0, ilimit, slimit, tol, mask, joint_limits, k, method, seed, semantics, rng_per_row, dtype):
+        Tep = getattr(Tep, "A", Tep)
+        B.check_numeric(Tep, "Tep")
+        host = not B.is_tensor(Tep)
+        dt = B.pick_dtype(Tep, dtype)
+        Td = B.to_device(Tep, dt)
+        if Td.dim() == 2:
+            if tuple(Td.shape) != (4, 4):
+                raise ValueError("Tep must be a 4x4 SE3 matrix")
+            Td = Td.reshape(1, 4, 4)
+            single = True
+        elif Td.dim() == 3 and tuple(Td.shape[1:]) == (4, 4):
+            single = False
+        else:
+            raise ValueError("Tep must be (4,4) or (N,4,4)")
+        N = Td.shape[0]
+        n = self.n
+        q0d = None
+        if q0 is not None:
+            B.check_numeric(q0, "q0")
+            q0d = B.to_device(q0, dt)
+            if q0d.numel() == n:
+                q0d = q0d.reshape(1, n).expand(N, n).contiguous()
+            elif tuple(q0d.shape) != (N, n):
+                raise ValueError(f"q0 must have {n} elements or shape ({N},{n})")
+        we = None if mask is None else np.ascontiguousarray(np.asarray(mask, dtype=np.float64).reshape(6))
+        m = str(method).lower()
+        meth = 2 if m.startswith("s") else (1 if m.startswith("w") else 0)  # fknm.cpp:481-495: 's', 'w', else chan
+        q = B.empty((N, n), dt, like=Td)
+        succ = B.empty_i32((N,), like=Td)
+        its = B.empty_i32((N,), like=Td)
+        srch = B.empty_i32((N,), like=Td)
+        E = B.empty((N,), dt, like=Td)
+        if seed is None:
+            seed = int(np.random.default_rng().integers(0, 2**63 - 1))
+        _lib.check(_lib.lib().b2k_ik_lm(
+            self._chain, B.code(dt), B.ptr(Td), N, B.ptr(q0d), int(ilimit), int(slimit), float(tol),
+            int(bool(joint_limits)), _lib.dptr(we), float(k), meth, int(seed) & (2**64 - 1), semantics,
+            int(bool(rng_per_row)), B.ptr(q), B.ptr(succ), B.ptr(its), B.ptr(srch), B.ptr(E), B.stream_ptr(Td)))
+        if host:
+            q, succ, its, srch, E = (B.to_host(x) for x in (q, succ, its, srch, E))
+        return q, succ, its, srch, E, single
+
+    def ik_LM(self, Tep, q0=None, ilimit: int = 30, slimit: int = 100, tol: float = 1e-6, mask=None,
+              joint_limits: bool = True, k: float = 1.0, method: str = "chan", seed: Optional[int] = 0, dtype=None):
+        """Levenberg-Marquardt IK with the semantics of the reference's C++ solver
+        (ETS.ik_LM, ETS.py:2014-2170 -> fknm.IK_LM_c).  One target (4,4) returns the reference's tuple
+        ``(q, success, iterations, searches, residual)``; an (N,4,4) batch returns the same tuple of
+        arrays, row i being the reference called on target i."""
+        q, s, it, sr, E, single = self._ik(Tep, q0, ilimit, slimit, tol, mask, joint_limits, k, method, seed,
+                                           _lib.SEM_CPP, True, dtype)
+        if single:
+            return q[0], int(s[0]), int(it[0]), int(sr[0]), float(E[0])
+        return q, s, it, sr, E
+
+    def ikine_LM(self, Tep, q0=None, ilimit: int = 30, slimit: int = 100, tol: float = 1e-6, mask=None,
+                 joint_limits: bool = True, seed: Optional[int] = None, k: float = 1.0, method: str = "chan",
+                 kq: float = 0.0, km: float = 0.0, ps: float = 0.0, pi=0.3, dtype=None, **kwargs) -> IKSolution:
+        """Levenberg-Marquardt IK with the semantics of the reference's Python solver class
+        (ETS.ikine_LM, ETS.py:2443-2637 -> IK_LM.solve, IK.py:174-367, 912-1017): returns an
+        :class:`IKSolution`; for an (N,4,4) trajectory q is (N,n), success is the conjunction,
+        iterations / searches are summed and residual is the minimum (IK.py:263-290)."""
+        if kq != 0.0 or km != 0.0:
+            raise NotImplementedError("null-space terms (kq, km) are outside the accelerated path (SURVEY 2.1 row 5)")
+        q, s, it, sr, E, single = self._ik(Tep, q0, ilimit, slimit, tol, mask, joint_limits, k, method, seed,
+                                           _lib.SEM_PYTHON, False, dtype)
+        if B.is_tensor(q):
+            q, s, it, sr, E = (B.to_host(x) for x in (q, s, it, sr, E))
+        fail = "iteration and search limit reached"
+        if single:
+            ok = bool(s[0])
+            return IKSolution(q=q[0], success=ok, iterations=int(it[0]), searches=int(sr[0]),
+                              residual=float(E[0]), reason="Success" if ok else fail)
+        ok = bool(s.all())
+        return IKSolution(q=q, success=ok, iterations=int(it.sum()), searches=int(sr.sum()),
+                          residual=float(E.min()), reason="" if ok else fail)

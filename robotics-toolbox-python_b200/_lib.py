@@ -1,0 +1,137 @@
+"""ctypes binding of libb2kin.so (the C ABI declared in include/b2kin.h).
+
+There is no CPU fallback: if the CUDA library has not been built, or no CUDA device is
+present when a compute entry point is called, this raises -- loudly -- instead of silently
+computing on the host.  PyTorch is used only for device buffers and streams.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libb2kin.so")
+
+F32, F64 = 0, 1
+MAX_JOINTS = 10
+MAX_QWIDTH = 16
+LM_METHODS = {"chan": 0, "wampler": 1, "sugihara": 2}
+SEM_CPP, SEM_PYTHON = 0, 1
+
+_lib = None
+
+vp = C.c_void_p
+i64 = C.c_int64
+dp = C.POINTER(C.c_double)
+ip = C.POINTER(C.c_int32)
+
+_PROTOS = {
+    "b2k_last_error": (C.c_char_p, []),
+    "b2k_version": (C.c_int, []),
+    "b2k_chain_create": (C.c_int, [C.c_int, ip, ip, ip, ip, dp, dp, C.POINTER(vp)]),
+    "b2k_chain_destroy": (C.c_int, [vp]),
+    "b2k_chain_info": (C.c_int, [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "b2k_fkine": (C.c_int, [vp, C.c_int, vp, i64, i64, dp, dp, vp, vp]),
+    "b2k_jacob0": (C.c_int, [vp, C.c_int, vp, i64, i64, dp, vp, vp]),
+    "b2k_jacobe": (C.c_int, [vp, C.c_int, vp, i64, i64, dp, vp, vp]),
+    "b2k_fkine_jacob0": (C.c_int, [vp, C.c_int, vp, i64, i64, dp, dp, vp, vp, vp]),
+    "b2k_fkine_jacobe": (C.c_int, [vp, C.c_int, vp, i64, i64, dp, dp, vp, vp, vp]),
+    "b2k_ik_lm": (C.c_int, [vp, C.c_int, vp, i64, vp, C.c_int, C.c_int, C.c_double, C.c_int, dp, C.c_double,
+                            C.c_int, C.c_uint64, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp]),
+    "b2k_rne_create": (C.c_int, [C.c_int, C.c_int, dp, C.POINTER(vp)]),
+    "b2k_rne_destroy": (C.c_int, [vp]),
+    "b2k_rne": (C.c_int, [vp, C.c_int, vp, vp, vp, i64, dp, dp, vp, vp]),
+    "b2k_host_alloc": (C.c_int, [C.POINTER(vp), i64]),
+    "b2k_host_free": (C.c_int, [vp]),
+    "b2k_fkine_jacob0_host": (C.c_int, [vp, C.c_int, vp, i64, i64, dp, dp, vp, vp, C.c_int]),
+    "b2k_fkine_host": (C.c_int, [vp, C.c_int, vp, i64, i64, dp, dp, vp, C.c_int]),
+    "b2k_rne_host": (C.c_int, [vp, C.c_int, vp, vp, vp, i64, dp, dp, vp, C.c_int]),
+    "b2k_launch_count": (C.c_int64, []),
+    "b2k_set_variant": (C.c_int, [C.c_int]),
+}
+
+EXPORTED_SYMBOLS = tuple(_PROTOS)
+
+
+class B2KError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load libb2kin.so (once).  Raises ImportError with build instructions if it is absent."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} not found: the CUDA library is not built. Run "
+                "`python -c 'import __graft_entry__ as g; g.build()'` (or `make -C robotics-toolbox-python_b200/csrc`). "
+                "There is no CPU fallback."
+            )
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in _PROTOS.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(rc: int):
+    """Translate a b2k_status into the exception class the reference would raise."""
+    if rc == 0:
+        return
+    msg = lib().b2k_last_error().decode("utf-8", "replace")
+    if rc == -1:
+        raise ValueError(msg)
+    raise B2KError(msg)
+
+
+def dptr(a):
+    """Optional host fp64 array -> double* (None -> NULL)."""
+    if a is None:
+        return None
+    return a.ctypes.data_as(dp)
+
+
+def f64_or_none(a, shape):
+    if a is None:
+        return None
+    a = np.ascontiguousarray(np.asarray(a, dtype=np.float64))
+    if a.shape != shape:
+        a = a.reshape(shape)
+    return a
+
+
+def launch_count() -> int:
+    return int(lib().b2k_launch_count())
+
+
+def set_variant(v: int):
+    check(lib().b2k_set_variant(int(v)))
+
+
+def pinned_empty(shape, dtype=np.float64):
+    """A numpy array backed by page-locked host memory (cudaHostAlloc), so the host-buffer
+    front ends move it at full PCIe / C2C bandwidth.  The memory is released when the array
+    (and all views of it) are garbage collected."""
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape)) * dtype.itemsize
+    p = vp()
+    check(lib().b2k_host_alloc(C.byref(p), max(n, 1)))
+
+    class _Owner:
+        def __init__(self, ptr):
+            self.ptr = ptr
+
+        def __del__(self):
+            try:
+                lib().b2k_host_free(self.ptr)
+            except Exception:
+                pass
+
+    buf = (C.c_char * max(n, 1)).from_address(p.value)
+    buf._owner = _Owner(p)  # keep-alive chain: ndarray -> buf -> owner
+    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+    return arr

@@ -1,0 +1,373 @@
+// b2k_api.cu -- extern "C" entry points of libb2kin.so (see include/b2kin.h), argument
+// validation, error strings, launch accounting and the pipelined host-buffer front ends.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <atomic>
+#include <map>
+#include <mutex>
+#include <tuple>
+#include <vector>
+
+#include "b2k_common.cuh"
+
+// per-dtype launchers (b2k_fkj_f32.cu / b2k_fkj_f64.cu / b2k_rne.cu / b2k_ik_*.cu)
+int b2k_fkj_launch_f32(const b2k_chain_s *, int, const void *, long long, long long, const double *, const double *,
+                       void *, void *, cudaStream_t);
+int b2k_fkj_launch_f64(const b2k_chain_s *, int, const void *, long long, long long, const double *, const double *,
+                       void *, void *, cudaStream_t);
+int b2k_fkw_launch(const b2k_chain_s *, int dtype, int mode, const void *, long long, long long, const double *,
+                   const double *, void *, void *, cudaStream_t);
+int b2k_rne_launch(const b2k_rne_s *, int dtype, const void *, const void *, const void *, long long, const double *,
+                   const double *, void *, cudaStream_t);
+
+enum { FKJ_T = 1, FKJ_J0 = 2, FKJ_JE = 4 };
+
+// ------------------------------------------------------------------ error / accounting plumbing
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+static std::atomic<int> g_variant{0};
+
+void b2k_set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int b2k_cuda_fail(cudaError_t e, const char *what)
+{
+    b2k_set_error("CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
+    return B2K_ERR_CUDA;
+}
+
+void b2k_count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+int b2k_get_variant() { return g_variant.load(std::memory_order_relaxed); }
+
+int b2k_num_sms(int *device_out)
+{
+    static std::mutex mu;
+    static std::map<int, int> cache;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (device_out) *device_out = dev;
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find(dev);
+    if (it != cache.end()) return it->second;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cache[dev] = sms;
+    return sms;
+}
+
+int b2k_blocks_per_sm(const void *func, int threads, size_t smem)
+{
+    static std::mutex mu;
+    static std::map<std::tuple<int, const void *, int, size_t>, int> cache;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+    auto key = std::make_tuple(dev, func, threads, smem);
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        auto it = cache.find(key);
+        if (it != cache.end()) return it->second;
+    }
+    cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return b2k_cuda_fail(e, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)");
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, func, threads, smem);
+    if (e != cudaSuccess) return b2k_cuda_fail(e, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
+    std::lock_guard<std::mutex> lk(mu);
+    cache[key] = per_sm;
+    return per_sm;
+}
+
+extern "C" const char *b2k_last_error(void) { return g_err; }
+extern "C" int b2k_version(void) { return B2K_VERSION; }
+extern "C" int64_t b2k_launch_count(void) { return (int64_t)g_launches.load(); }
+extern "C" int b2k_set_variant(int v)
+{
+    if (v != 0 && v != 1) { b2k_set_error("b2k_set_variant: variant must be 0 or 1"); return B2K_ERR_INVALID; }
+    g_variant.store(v);
+    return B2K_OK;
+}
+
+// ------------------------------------------------------------------ validation helpers
+static int check_common(const char *fn, const b2k_chain_s *c, int dtype, const void *q, int64_t N, int64_t ldq)
+{
+    if (!c) { b2k_set_error("%s: chain handle is NULL", fn); return B2K_ERR_INVALID; }
+    if (dtype != B2K_F32 && dtype != B2K_F64) { b2k_set_error("%s: dtype must be B2K_F32 or B2K_F64", fn); return B2K_ERR_INVALID; }
+    if (N < 0) { b2k_set_error("%s: N = %lld is negative", fn, (long long)N); return B2K_ERR_INVALID; }
+    if (N > 0 && !q) { b2k_set_error("%s: q is NULL", fn); return B2K_ERR_INVALID; }
+    if (ldq < c->q_width || ldq > B2K_MAX_QWIDTH) {
+        b2k_set_error("%s: q row width %lld outside [%d, %d] (chain reads columns up to %d)", fn, (long long)ldq,
+                      c->q_width, B2K_MAX_QWIDTH, c->q_width - 1);
+        return B2K_ERR_INVALID;
+    }
+    if (((uintptr_t)q) & 7) { b2k_set_error("%s: q must be 8-byte aligned", fn); return B2K_ERR_INVALID; }
+    return B2K_OK;
+}
+
+static int check_out(const char *fn, const char *name, const void *p, int64_t N)
+{
+    if (N > 0 && !p) { b2k_set_error("%s: %s is NULL", fn, name); return B2K_ERR_INVALID; }
+    if (((uintptr_t)p) & 7) { b2k_set_error("%s: %s must be 8-byte aligned", fn, name); return B2K_ERR_INVALID; }
+    return B2K_OK;
+}
+
+static int check_affine(const char *fn, const char *name, const double *M)
+{
+    if (M && (M[12] != 0.0 || M[13] != 0.0 || M[14] != 0.0 || M[15] != 1.0)) {
+        b2k_set_error("%s: %s is not an SE(3)/affine matrix (bottom row must be 0 0 0 1)", fn, name);
+        return B2K_ERR_INVALID;
+    }
+    return B2K_OK;
+}
+
+static int fkj_dispatch(const char *fn, b2k_chain_t c, int dtype, int mode, const void *q, int64_t N, int64_t ldq,
+                        const double *base, const double *tool, void *T, void *J, void *stream)
+{
+    int rc = check_common(fn, c, dtype, q, N, ldq);
+    if (rc) return rc;
+    if ((mode & FKJ_T) && (rc = check_out(fn, "T", T, N))) return rc;
+    if ((mode & (FKJ_J0 | FKJ_JE)) && (rc = check_out(fn, "J", J, N))) return rc;
+    if ((rc = check_affine(fn, "base", base)) || (rc = check_affine(fn, "tool", tool))) return rc;
+    if (N == 0) return B2K_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (b2k_get_variant() == 1 && !(mode & FKJ_JE))
+        return b2k_fkw_launch(c, dtype, mode, q, N, ldq, base, tool, T, J, st);
+    if (dtype == B2K_F64) return b2k_fkj_launch_f64(c, mode, q, N, ldq, base, tool, T, J, st);
+    return b2k_fkj_launch_f32(c, mode, q, N, ldq, base, tool, T, J, st);
+}
+
+extern "C" int b2k_fkine(b2k_chain_t c, int dtype, const void *q, int64_t N, int64_t ldq, const double *base,
+                         const double *tool, void *T, void *stream)
+{
+    return fkj_dispatch("b2k_fkine", c, dtype, FKJ_T, q, N, ldq, base, tool, T, nullptr, stream);
+}
+
+extern "C" int b2k_jacob0(b2k_chain_t c, int dtype, const void *q, int64_t N, int64_t ldq, const double *tool, void *J,
+                          void *stream)
+{
+    return fkj_dispatch("b2k_jacob0", c, dtype, FKJ_J0, q, N, ldq, nullptr, tool, nullptr, J, stream);
+}
+
+extern "C" int b2k_jacobe(b2k_chain_t c, int dtype, const void *q, int64_t N, int64_t ldq, const double *tool, void *J,
+                          void *stream)
+{
+    return fkj_dispatch("b2k_jacobe", c, dtype, FKJ_JE, q, N, ldq, nullptr, tool, nullptr, J, stream);
+}
+
+extern "C" int b2k_fkine_jacob0(b2k_chain_t c, int dtype, const void *q, int64_t N, int64_t ldq, const double *base,
+                                const double *tool, void *T, void *J, void *stream)
+{
+    return fkj_dispatch("b2k_fkine_jacob0", c, dtype, FKJ_T | FKJ_J0, q, N, ldq, base, tool, T, J, stream);
+}
+
+extern "C" int b2k_fkine_jacobe(b2k_chain_t c, int dtype, const void *q, int64_t N, int64_t ldq, const double *base,
+                                const double *tool, void *T, void *J, void *stream)
+{
+    return fkj_dispatch("b2k_fkine_jacobe", c, dtype, FKJ_T | FKJ_JE, q, N, ldq, base, tool, T, J, stream);
+}
+
+extern "C" int b2k_rne(b2k_rne_t r, int dtype, const void *q, const void *qd, const void *qdd, int64_t N,
+                       const double *grav, const double *fext, void *tau, void *stream)
+{
+    const char *fn = "b2k_rne";
+    if (!r) { b2k_set_error("%s: rne handle is NULL", fn); return B2K_ERR_INVALID; }
+    if (dtype != B2K_F32 && dtype != B2K_F64) { b2k_set_error("%s: dtype must be B2K_F32 or B2K_F64", fn); return B2K_ERR_INVALID; }
+    if (N < 0) { b2k_set_error("%s: N is negative", fn); return B2K_ERR_INVALID; }
+    if (!grav) { b2k_set_error("%s: grav is NULL (pass -robot.gravity like DHRobot.rne)", fn); return B2K_ERR_INVALID; }
+    int rc;
+    if ((rc = check_out(fn, "q", q, N)) || (rc = check_out(fn, "qd", qd, N)) || (rc = check_out(fn, "qdd", qdd, N)) ||
+        (rc = check_out(fn, "tau", tau, N)))
+        return rc;
+    if (N == 0) return B2K_OK;
+    return b2k_rne_launch(r, dtype, q, qd, qdd, N, grav, fext, tau, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------ host-buffer front ends
+extern "C" int b2k_host_alloc(void **ptr, int64_t bytes)
+{
+    if (!ptr || bytes < 0) { b2k_set_error("b2k_host_alloc: bad arguments"); return B2K_ERR_INVALID; }
+    *ptr = nullptr;
+    if (bytes == 0) return B2K_OK;
+    B2K_CUDA(cudaHostAlloc(ptr, (size_t)bytes, cudaHostAllocPortable));
+    return B2K_OK;
+}
+
+extern "C" int b2k_host_free(void *ptr)
+{
+    if (ptr) B2K_CUDA(cudaFreeHost(ptr));
+    return B2K_OK;
+}
+
+namespace {
+// A small pool of per-device pipeline slots (device staging buffers + stream), reused across calls.
+struct Slot {
+    cudaStream_t st = nullptr;
+    void *d_in[3] = {nullptr, nullptr, nullptr};
+    void *d_out[2] = {nullptr, nullptr};
+    size_t in_cap[3] = {0, 0, 0}, out_cap[2] = {0, 0};
+};
+struct Pipe {
+    int device = -1;
+    std::vector<Slot> slots;
+};
+std::mutex g_pipe_mu;
+std::map<int, Pipe> g_pipes;
+
+int ensure(void **p, size_t *cap, size_t need)
+{
+    if (*cap >= need) return B2K_OK;
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+    *cap = 0;
+    B2K_CUDA(cudaMalloc(p, need));
+    *cap = need;
+    return B2K_OK;
+}
+
+constexpr int kSlots = 3;
+constexpr long long kChunkRows = 1 << 17; // 128k rows per chunk: ~60 MB of Panda fp64 output
+
+// Generic chunked pipeline: for each chunk, H2D the inputs, run `kernel`, D2H the outputs, round-robin
+// over kSlots streams so the copy engines and the SMs overlap.
+template <typename F>
+int run_pipeline(int device, long long N, int n_in, const void *const *h_in, const size_t *in_row_bytes, int n_out,
+                 void *const *h_out, const size_t *out_row_bytes, F kernel)
+{
+    int prev = 0;
+    B2K_CUDA(cudaGetDevice(&prev));
+    B2K_CUDA(cudaSetDevice(device));
+    std::lock_guard<std::mutex> lk(g_pipe_mu);
+    Pipe &P = g_pipes[device];
+    if (P.slots.empty()) {
+        P.device = device;
+        P.slots.resize(kSlots);
+        for (auto &s : P.slots) B2K_CUDA(cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking));
+    }
+    const long long chunk = N < kChunkRows ? N : kChunkRows;
+    int rc = B2K_OK;
+    long long done = 0;
+    int k = 0;
+    while (done < N && rc == B2K_OK) {
+        Slot &s = P.slots[k % kSlots];
+        const long long rows = (N - done) < chunk ? (N - done) : chunk;
+        for (int i = 0; i < n_in && rc == B2K_OK; i++) {
+            rc = ensure(&s.d_in[i], &s.in_cap[i], (size_t)chunk * in_row_bytes[i]);
+            if (rc) break;
+            cudaError_t e = cudaMemcpyAsync(s.d_in[i], (const char *)h_in[i] + (size_t)done * in_row_bytes[i],
+                                            (size_t)rows * in_row_bytes[i], cudaMemcpyHostToDevice, s.st);
+            if (e != cudaSuccess) rc = b2k_cuda_fail(e, "cudaMemcpyAsync H2D");
+        }
+        for (int i = 0; i < n_out && rc == B2K_OK; i++) rc = ensure(&s.d_out[i], &s.out_cap[i], (size_t)chunk * out_row_bytes[i]);
+        if (rc == B2K_OK) rc = kernel(s, rows);
+        for (int i = 0; i < n_out && rc == B2K_OK; i++) {
+            cudaError_t e = cudaMemcpyAsync((char *)h_out[i] + (size_t)done * out_row_bytes[i], s.d_out[i],
+                                            (size_t)rows * out_row_bytes[i], cudaMemcpyDeviceToHost, s.st);
+            if (e != cudaSuccess) rc = b2k_cuda_fail(e, "cudaMemcpyAsync D2H");
+        }
+        done += rows;
+        k++;
+    }
+    for (auto &s : P.slots) {
+        cudaError_t e = cudaStreamSynchronize(s.st);
+        if (e != cudaSuccess && rc == B2K_OK) rc = b2k_cuda_fail(e, "cudaStreamSynchronize");
+    }
+    cudaSetDevice(prev);
+    return rc;
+}
+} // namespace
+
+extern "C" int b2k_fkine_jacob0_host(b2k_chain_t c, int dtype, const void *q, int64_t N, int64_t ldq, const double *base,
+                                     const double *tool, void *T, void *J, int device)
+{
+    const char *fn = "b2k_fkine_jacob0_host";
+    int rc = check_common(fn, c, dtype, q, N, ldq);
+    if (rc) return rc;
+    if ((rc = check_out(fn, "T", T, N)) || (rc = check_out(fn, "J", J, N))) return rc;
+    if (N == 0) return B2K_OK;
+    const size_t es = dtype == B2K_F64 ? 8 : 4;
+    const void *h_in[1] = {q};
+    size_t in_b[1] = {(size_t)ldq * es};
+    void *h_out[2] = {T, J};
+    size_t out_b[2] = {16 * es, (size_t)6 * c->n * es};
+    return run_pipeline(device, N, 1, h_in, in_b, 2, h_out, out_b, [&](Slot &s, long long rows) {
+        return b2k_fkine_jacob0(c, dtype, s.d_in[0], rows, ldq, base, tool, s.d_out[0], s.d_out[1], s.st);
+    });
+}
+
+extern "C" int b2k_fkine_host(b2k_chain_t c, int dtype, const void *q, int64_t N, int64_t ldq, const double *base,
+                              const double *tool, void *T, int device)
+{
+    const char *fn = "b2k_fkine_host";
+    int rc = check_common(fn, c, dtype, q, N, ldq);
+    if (rc) return rc;
+    if ((rc = check_out(fn, "T", T, N))) return rc;
+    if (N == 0) return B2K_OK;
+    const size_t es = dtype == B2K_F64 ? 8 : 4;
+    const void *h_in[1] = {q};
+    size_t in_b[1] = {(size_t)ldq * es};
+    void *h_out[1] = {T};
+    size_t out_b[1] = {16 * es};
+    return run_pipeline(device, N, 1, h_in, in_b, 1, h_out, out_b, [&](Slot &s, long long rows) {
+        return b2k_fkine(c, dtype, s.d_in[0], rows, ldq, base, tool, s.d_out[0], s.st);
+    });
+}
+
+extern "C" int b2k_rne_host(b2k_rne_t r, int dtype, const void *q, const void *qd, const void *qdd, int64_t N,
+                            const double *grav, const double *fext, void *tau, int device)
+{
+    const char *fn = "b2k_rne_host";
+    if (!r) { b2k_set_error("%s: rne handle is NULL", fn); return B2K_ERR_INVALID; }
+    if (dtype != B2K_F32 && dtype != B2K_F64) { b2k_set_error("%s: bad dtype", fn); return B2K_ERR_INVALID; }
+    if (N < 0 || (N > 0 && (!q || !qd || !qdd || !tau || !grav))) { b2k_set_error("%s: NULL argument", fn); return B2K_ERR_INVALID; }
+    if (N == 0) return B2K_OK;
+    const size_t es = dtype == B2K_F64 ? 8 : 4;
+    const void *h_in[3] = {q, qd, qdd};
+    size_t in_b[3] = {r->n * es, r->n * es, r->n * es};
+    void *h_out[1] = {tau};
+    size_t out_b[1] = {r->n * es};
+    return run_pipeline(device, N, 3, h_in, in_b, 1, h_out, out_b, [&](Slot &s, long long rows) {
+        return b2k_rne(r, dtype, s.d_in[0], s.d_in[1], s.d_in[2], rows, grav, fext, s.d_out[0], s.st);
+    });
+}
+
+// ------------------------------------------------------------------ inverse kinematics
+int b2k_ik_launch_f32(const b2k_chain_s *, const void *, long long, const void *, int, int, double, int, const double *,
+                      double, int, unsigned long long, int, int, void *, int *, int *, int *, void *, cudaStream_t);
+int b2k_ik_launch_f64(const b2k_chain_s *, const void *, long long, const void *, int, int, double, int, const double *,
+                      double, int, unsigned long long, int, int, void *, int *, int *, int *, void *, cudaStream_t);
+
+extern "C" int b2k_ik_lm(b2k_chain_t c, int dtype, const void *Tep, int64_t N, const void *q0, int ilimit, int slimit,
+                         double tol, int reject_jl, const double *we, double lambda, int method, uint64_t seed,
+                         int semantics, int rng_per_row, void *q_out, int32_t *success, int32_t *iterations,
+                         int32_t *searches, void *residual, void *stream)
+{
+    const char *fn = "b2k_ik_lm";
+    if (!c) { b2k_set_error("%s: chain handle is NULL", fn); return B2K_ERR_INVALID; }
+    if (dtype != B2K_F32 && dtype != B2K_F64) { b2k_set_error("%s: dtype must be B2K_F32 or B2K_F64", fn); return B2K_ERR_INVALID; }
+    if (N < 0) { b2k_set_error("%s: N is negative", fn); return B2K_ERR_INVALID; }
+    if (!c->dense_jindex) {
+        b2k_set_error("%s: the chain's jindices must be 0..n-1 in chain order (the reference C++ solver assumes it, ik.cpp:34-35)", fn);
+        return B2K_ERR_INVALID;
+    }
+    if (ilimit < 1 || slimit < 1) { b2k_set_error("%s: ilimit and slimit must be >= 1", fn); return B2K_ERR_INVALID; }
+    if (method != B2K_LM_CHAN && method != B2K_LM_WAMPLER && method != B2K_LM_SUGIHARA) { b2k_set_error("%s: bad method %d", fn, method); return B2K_ERR_INVALID; }
+    if (semantics != B2K_IK_SEM_CPP && semantics != B2K_IK_SEM_PYTHON) { b2k_set_error("%s: bad semantics %d", fn, semantics); return B2K_ERR_INVALID; }
+    int rc;
+    if ((rc = check_out(fn, "Tep", Tep, N)) || (rc = check_out(fn, "q_out", q_out, N)) ||
+        (rc = check_out(fn, "success", success, N)) || (rc = check_out(fn, "iterations", iterations, N)) ||
+        (rc = check_out(fn, "searches", searches, N)) || (rc = check_out(fn, "residual", residual, N)))
+        return rc;
+    if (N == 0) return B2K_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == B2K_F64)
+        return b2k_ik_launch_f64(c, Tep, N, q0, ilimit, slimit, tol, reject_jl, we, lambda, method, seed, semantics,
+                                 rng_per_row, q_out, success, iterations, searches, residual, st);
+    return b2k_ik_launch_f32(c, Tep, N, q0, ilimit, slimit, tol, reject_jl, we, lambda, method, seed, semantics,
+                             rng_per_row, q_out, success, iterations, searches, residual, st);
+}

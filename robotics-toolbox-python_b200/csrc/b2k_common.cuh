@@ -1,0 +1,122 @@
+// b2k_common.cuh -- shared types between the host-side chain compiler and the sm_100a kernels.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/b2kin.h"
+
+#define B2K_WARPS_PER_BLOCK 4
+#define B2K_THREADS (32 * B2K_WARPS_PER_BLOCK)
+
+// Structure classes of a folded SE(3) constant A = [Ra | ta] (exact 0/1 pattern tests on the
+// host, so the specialised device paths are bit-identical to the general product).
+enum : int {
+    AK_IDENT = 0, // Ra = I
+    AK_RX = 1,    // Ra = [[1,0,0],[0,a,b],[0,c,d]]
+    AK_RY = 2,    // Ra = [[a,0,b],[0,1,0],[c,0,d]]
+    AK_RZ = 3,    // Ra = [[a,b,0],[c,d,0],[0,0,1]]
+    AK_GEN = 4,   // anything else
+    AK_ROTMASK = 7,
+    AK_TX = 8, // ta.x != 0
+    AK_TY = 16,
+    AK_TZ = 32
+};
+
+// Device-side chain: n steps of (constant A_j, joint j) followed by a tail constant A_n.
+// Passed BY VALUE as a __grid_constant__ kernel parameter so every entry is a constant-bank
+// operand (no loads in the unrolled chain walk).
+template <typename real, int N>
+struct ChainP {
+    real A[N + 1][12]; // row-major 3x4: r00 r01 r02 tx | r10 r11 r12 ty | r20 r21 r22 tz
+    real B[12];        // base, applied to the pose only (reference RobotKinematics.py:94 vs :158)
+    int akind[N + 1];
+    int axis[N];  // B2K_RX..B2K_TZ
+    int flip[N];  // 0 / 1
+    int jidx[N];  // column of q
+    int has_base; // 0: B is identity
+    int all_rz;   // every joint is an unflipped Rz (DH robots, Panda): switch-free fast path
+};
+
+// Host-side compiled chain (fp64 master copy); see b2k_chain.cu.
+struct b2k_chain_s {
+    int n, m, q_width;
+    double A[B2K_MAX_JOINTS + 1][12];
+    int axis[B2K_MAX_JOINTS];
+    int flip[B2K_MAX_JOINTS];
+    int jidx[B2K_MAX_JOINTS];
+    double qlim_l[B2K_MAX_JOINTS];
+    double qlim_h[B2K_MAX_JOINTS];
+    int all_rz;
+    int dense_jindex; // jidx[j] == j for all j
+};
+
+struct b2k_rne_s {
+    int n, mdh;
+    double L[B2K_MAX_JOINTS][24];
+};
+
+// ---- error plumbing (b2k_api.cu)
+void b2k_set_error(const char *fmt, ...);
+int b2k_cuda_fail(cudaError_t e, const char *what);
+void b2k_count_launch(int n = 1);
+int b2k_get_variant();
+int b2k_num_sms(int *device_out = nullptr);
+// resident blocks per SM for (kernel, threads, dynamic smem), cached; also raises the kernel's
+// dynamic shared-memory limit.  <0 on CUDA error.
+int b2k_blocks_per_sm(const void *func, int threads, size_t smem);
+
+#define B2K_CUDA(call)                                   \
+    do {                                                 \
+        cudaError_t _e = (call);                         \
+        if (_e != cudaSuccess) return b2k_cuda_fail(_e, #call); \
+    } while (0)
+
+// ---- small host helpers shared by launchers
+void b2k_mat_to34(const double *T16, double *A12);          // row-major 4x4 -> 3x4
+void b2k_mul34(const double *A, const double *B, double *C); // C = A*B on 3x4 affine
+int b2k_classify34(const double *A);
+void b2k_ident34(double *A);
+
+template <typename real, int N>
+void b2k_fill_chain(const b2k_chain_s *c, const double *base, const double *tool, bool base_into_chain,
+                    ChainP<real, N> &P)
+{
+    double A0[12], An[12], tmp[12];
+    for (int j = 0; j <= N; j++)
+        for (int k = 0; k < 12; k++) P.A[j][k] = (real)c->A[j][k];
+    for (int k = 0; k < 12; k++) { A0[k] = c->A[0][k]; An[k] = c->A[N][k]; }
+    double B[12];
+    b2k_ident34(B);
+    P.has_base = 0;
+    if (base) {
+        b2k_mat_to34(base, tmp);
+        if (base_into_chain) { // pose-only kernels: fold base into the first constant
+            b2k_mul34(tmp, A0, B);
+            for (int k = 0; k < 12; k++) A0[k] = B[k];
+            b2k_ident34(B);
+        } else {
+            for (int k = 0; k < 12; k++) B[k] = tmp[k];
+            P.has_base = (b2k_classify34(B) != AK_IDENT);
+        }
+    }
+    if (tool) {
+        b2k_mat_to34(tool, tmp);
+        double t2[12];
+        if (N == 0) {
+            b2k_mul34(A0, tmp, t2);
+            for (int k = 0; k < 12; k++) A0[k] = t2[k];
+        } else {
+            b2k_mul34(An, tmp, t2);
+            for (int k = 0; k < 12; k++) An[k] = t2[k];
+        }
+    }
+    for (int k = 0; k < 12; k++) { P.A[0][k] = (real)A0[k]; P.A[N][k] = (real)(N == 0 ? A0[k] : An[k]); P.B[k] = (real)B[k]; }
+    for (int j = 0; j <= N; j++) {
+        double Aj[12];
+        for (int k = 0; k < 12; k++) Aj[k] = (j == 0) ? A0[k] : (j == N ? An[k] : c->A[j][k]);
+        P.akind[j] = b2k_classify34(Aj);
+    }
+    for (int j = 0; j < N; j++) { P.axis[j] = c->axis[j]; P.flip[j] = c->flip[j]; P.jidx[j] = c->jidx[j]; }
+    P.all_rz = c->all_rz;
+}

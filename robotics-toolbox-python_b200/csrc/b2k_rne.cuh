@@ -1,0 +1,357 @@
+// b2k_rne.cuh -- batched recursive Newton-Euler inverse dynamics for DH / MDH arms (sm_100a).
+//
+// Replaces the per-row frne.frne loop of DHRobot.rne (reference DHRobot.py:1442-1451 ->
+// frne.c:106-230 -> newton_euler ne.c:62-492, rot_mat frne.c:310-351).
+//
+// Mapping (DESIGN.md "Kernel K3"): like the FK kernel, a warp owns a tile of 32 rows.  The
+// (q, qd, qdd) tiles are loaded with coalesced 8-byte-granule loads into a per-warp smem stage
+// and stay there for both recursions; lane l runs the Luh-Walker-Paul recursion for row l in
+// registers with all link constants (sin/cos(alpha), a, d, m, r, I, G^2 Jm, ...) coming from
+// the constant bank (kernel parameter struct).  The forward recursion keeps only what the
+// backward one needs per link: F_j = m a_c, N_j = I wd + w x (I w), sin/cos(theta_j).  tau is
+// staged and written back coalesced.  HBM-bound: 4n reals per row (192 B for Puma560 fp64).
+//
+// The arithmetic mirrors ne.c operation by operation (including its quirks for a prismatic
+// first joint under modified DH, ne.c:187-204) so results track the reference to rounding.
+#pragma once
+
+#include "b2k_fkj.cuh"
+
+template <typename real, int N>
+struct RneP {
+    // per link
+    real sa[N], ca[N]; // sin/cos(alpha) evaluated on the host with libm, as frne.c:325-326 does per call
+    real A[N], D[N], st0[N], ct0[N], offset[N];
+    real m[N], r[N][3], I[N][9];
+    real c_jm[N];  // G*G*Jm
+    real c_b[N];   // G*G*B
+    real c_tcp[N]; // |G|*Tc+
+    real c_tcm[N]; // |G|*Tc-
+    int prismatic[N];
+    real grav[3];
+    real fext[6];
+};
+
+template <typename real>
+struct V3 {
+    real x, y, z;
+};
+template <typename real> __device__ __forceinline__ V3<real> vadd(V3<real> a, V3<real> b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+template <typename real> __device__ __forceinline__ V3<real> vcross(V3<real> a, V3<real> b)
+{
+    return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
+}
+template <typename real> __device__ __forceinline__ V3<real> vscale(V3<real> a, real s) { return {s * a.x, s * a.y, s * a.z}; }
+template <typename real> __device__ __forceinline__ real vdot(V3<real> a, V3<real> b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+
+// link rotation R (columns n, o, a) from sin/cos(theta), sin/cos(alpha); frne.c:329-347
+template <typename real, bool MDH>
+struct LinkRot {
+    real nx, ny, nz, ox, oy, oz, ax, ay, az;
+    __device__ __forceinline__ LinkRot(real st, real ct, real sa, real ca)
+    {
+        if (!MDH) {
+            nx = ct; ox = -ca * st; ax = sa * st;
+            ny = st; oy = ca * ct;  ay = -sa * ct;
+            nz = 0;  oz = sa;       az = ca;
+        } else {
+            nx = ct;      ox = -st;     ax = 0;
+            ny = st * ca; oy = ca * ct; ay = -sa;
+            nz = st * sa; oz = ct * sa; az = ca;
+        }
+    }
+    __device__ __forceinline__ V3<real> mul(V3<real> v) const
+    {
+        return {nx * v.x + ox * v.y + ax * v.z, ny * v.x + oy * v.y + ay * v.z, nz * v.x + oz * v.y + az * v.z};
+    }
+    __device__ __forceinline__ V3<real> tmul(V3<real> v) const
+    {
+        return {nx * v.x + ny * v.y + nz * v.z, ox * v.x + oy * v.y + oz * v.z, ax * v.x + ay * v.y + az * v.z};
+    }
+};
+
+template <typename real, int N, bool MDH>
+__global__ void __launch_bounds__(B2K_THREADS)
+k_rne(const __grid_constant__ RneP<real, N> P, const real *__restrict__ q, const real *__restrict__ qd,
+      const real *__restrict__ qdd, long long nrows, real *__restrict__ tau, int warp_smem_bytes)
+{
+    typedef typename Granule<real>::type gran_t;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    constexpr int LDP = N | 1; // odd row stride in elements
+    real *sq = reinterpret_cast<real *>(smem_raw + (size_t)warp * warp_smem_bytes);
+    real *sqd = sq + 32 * LDP;
+    real *sqdd = sqd + 32 * LDP;
+    real *sout = sqdd + 32 * LDP;
+    const long long ntiles = (nrows + 31) >> 5;
+    const float inv_n = 1.0f / (float)N;
+
+    for (long long tile = (long long)blockIdx.x * B2K_WARPS_PER_BLOCK + warp; tile < ntiles;
+         tile += (long long)gridDim.x * B2K_WARPS_PER_BLOCK) {
+        const long long row0 = tile << 5;
+        const int rows_here = (int)((nrows - row0) < 32 ? (nrows - row0) : 32);
+        stage_q_tile<real>(sq, q + row0 * N, rows_here, N, inv_n, lane);
+        stage_q_tile<real>(sqd, qd + row0 * N, rows_here, N, inv_n, lane);
+        stage_q_tile<real>(sqdd, qdd + row0 * N, rows_here, N, inv_n, lane);
+        __syncwarp();
+        const int myrow = (lane < rows_here ? lane : 0) * LDP;
+        const real *mq = sq + myrow, *mqd = sqd + myrow, *mqdd = sqdd + myrow;
+
+        // stash for the backward recursion
+        V3<real> Fm[N], Nm[N];
+        real sth[N], cth[N];
+        const V3<real> gravity = {P.grav[0], P.grav[1], P.grav[2]};
+        V3<real> w = {0, 0, 0}, wd = {0, 0, 0}, acc = {0, 0, 0}; // of link j-1 on entry
+
+        // ---------------- forward recursion (ne.c:137-240 MDH, 245-347 DH)
+#pragma unroll
+        for (int j = 0; j < N; j++) {
+            const bool pris = P.prismatic[j] != 0;
+            real st, ct, d;
+            if (!pris) {
+                b2k_sincos<real>(mq[j] + P.offset[j], &st, &ct);
+                d = P.D[j];
+            } else {
+                st = P.st0[j]; ct = P.ct0[j];
+                d = mq[j] + P.offset[j];
+            }
+            sth[j] = st; cth[j] = ct;
+            const LinkRot<real, MDH> R(st, ct, P.sa[j], P.ca[j]);
+            const V3<real> pstar = MDH ? V3<real>{P.A[j], -d * P.sa[j], d * P.ca[j]} : V3<real>{P.A[j], d * P.sa[j], d * P.ca[j]};
+            const V3<real> qdv = {0, 0, mqd[j]}, qddv = {0, 0, mqdd[j]};
+            V3<real> wn, wdn, accn, t1, t2, t3;
+            if (MDH) {
+                if (!pris) {
+                    if (j == 0) {
+                        wn = qdv; wdn = qddv; t1 = gravity;
+                    } else {
+                        t1 = R.tmul(w);
+                        wn = vadd(t1, qdv);
+                        t3 = R.tmul(wd);
+                        t2 = vcross(t1, qdv);
+                        t1 = vadd(t2, t3);
+                        wdn = vadd(t1, qddv);
+                        t1 = vcross(w, pstar);
+                        t2 = vcross(w, t1);
+                        t1 = vcross(wd, pstar);
+                        t1 = vadd(t1, t2);
+                        t1 = vadd(t1, acc);
+                    }
+                    accn = R.tmul(t1);
+                } else {
+                    if (j == 0) {
+                        wn = qdv; wdn = qddv; accn = gravity; // sic, ne.c:187-204
+                    } else {
+                        wn = R.tmul(w);
+                        wdn = R.tmul(wd);
+                        t1 = vcross(wd, pstar);
+                        t3 = vcross(w, pstar);
+                        t2 = vcross(w, t3);
+                        t1 = vadd(t1, t2);
+                        t1 = vadd(t1, acc);
+                        accn = R.tmul(t1);
+                        t2 = R.tmul(w);
+                        t1 = vcross(t2, qdv);
+                        t1 = vscale(t1, (real)2);
+                        accn = vadd(accn, t1);
+                        accn = vadd(accn, qddv);
+                    }
+                }
+            } else {
+                if (!pris) {
+                    t1 = (j == 0) ? qdv : vadd(w, qdv);
+                    wn = R.tmul(t1);
+                    if (j == 0) t3 = qddv;
+                    else {
+                        t1 = vadd(wd, qddv);
+                        t2 = vcross(w, qdv);
+                        t3 = vadd(t1, t2);
+                    }
+                    wdn = R.tmul(t3);
+                    t1 = vcross(wdn, pstar);
+                    t2 = vcross(wn, pstar);
+                    t3 = vcross(wn, t2);
+                    accn = vadd(t1, t3);
+                    t1 = R.tmul(j == 0 ? gravity : acc);
+                    accn = vadd(accn, t1);
+                } else {
+                    if (j == 0) {
+                        wn = {0, 0, 0}; wdn = {0, 0, 0};
+                        t1 = vadd(qddv, gravity);
+                        accn = R.tmul(t1);
+                    } else {
+                        wn = R.tmul(w);
+                        wdn = R.tmul(wd);
+                        t1 = vadd(qddv, acc);
+                        accn = R.tmul(t1);
+                    }
+                    t1 = vcross(wdn, pstar);
+                    accn = vadd(accn, t1);
+                    t1 = R.tmul(qdv);
+                    t2 = vcross(wn, t1);
+                    t2 = vscale(t2, (real)2);
+                    accn = vadd(accn, t2);
+                    t2 = vcross(wn, pstar);
+                    t3 = vcross(wn, t2);
+                    accn = vadd(accn, t3);
+                }
+            }
+            w = wn; wd = wdn; acc = accn;
+            // centre-of-mass acceleration, ne.c:228-232 / 335-339, then the link wrench terms
+            const V3<real> rc = {P.r[j][0], P.r[j][1], P.r[j][2]};
+            t1 = vcross(wd, rc);
+            t2 = vcross(w, rc);
+            t3 = vcross(w, t2);
+            V3<real> abar = vadd(t1, t3);
+            abar = vadd(abar, acc);
+            Fm[j] = vscale(abar, P.m[j]);
+            const real *I = P.I[j]; // read column-major like vmath.c mat_vect_mult
+            t2 = {I[0] * wd.x + I[3] * wd.y + I[6] * wd.z, I[1] * wd.x + I[4] * wd.y + I[7] * wd.z,
+                  I[2] * wd.x + I[5] * wd.y + I[8] * wd.z};
+            t3 = {I[0] * w.x + I[3] * w.y + I[6] * w.z, I[1] * w.x + I[4] * w.y + I[7] * w.z,
+                  I[2] * w.x + I[5] * w.y + I[8] * w.z};
+            Nm[j] = vadd(t2, vcross(w, t3));
+        }
+
+        // ---------------- backward recursion (ne.c:358-403 MDH, 409-457 DH) + joint torque (ne.c:464-491)
+        real tq[N];
+        V3<real> f = {0, 0, 0}, nn = {0, 0, 0}; // of link j+1 on entry
+        const V3<real> f_tip = {P.fext[0], P.fext[1], P.fext[2]}, n_tip = {P.fext[3], P.fext[4], P.fext[5]};
+#pragma unroll
+        for (int j = N - 1; j >= 0; j--) {
+            const bool pris = P.prismatic[j] != 0;
+            const V3<real> rc = {P.r[j][0], P.r[j][1], P.r[j][2]};
+            V3<real> fj, nj, t1, t2, t3, t4;
+            if (MDH) {
+                const V3<real> F = Fm[j];
+                if (j == N - 1) {
+                    fj = vadd(f_tip, F);
+                    t1 = n_tip;
+                } else {
+                    const LinkRot<real, MDH> Rn(sth[j + 1], cth[j + 1], P.sa[j + 1], P.ca[j + 1]);
+                    const real dn = P.prismatic[j + 1] ? (mq[j + 1] + P.offset[j + 1]) : P.D[j + 1];
+                    const V3<real> pstar_n = {P.A[j + 1], -dn * P.sa[j + 1], dn * P.ca[j + 1]};
+                    t1 = Rn.mul(f);
+                    fj = vadd(t1, F);
+                    t1 = Rn.mul(nn);
+                    t4 = Rn.mul(f);
+                    t3 = vcross(pstar_n, t4);
+                    t1 = vadd(t1, t3);
+                }
+                t2 = vcross(rc, F);
+                t1 = vadd(t1, t2);
+                nj = vadd(t1, Nm[j]);
+            } else {
+                const real dj = pris ? (mq[j] + P.offset[j]) : P.D[j];
+                const V3<real> pstar = {P.A[j], dj * P.sa[j], dj * P.ca[j]};
+                t4 = Fm[j];
+                t2 = vadd(pstar, rc);
+                t1 = vcross(t2, t4);
+                if (j != N - 1) {
+                    const LinkRot<real, MDH> Rn(sth[j + 1], cth[j + 1], P.sa[j + 1], P.ca[j + 1]);
+                    fj = vadd(t4, Rn.mul(f));
+                    t2 = Rn.tmul(pstar);
+                    t3 = vcross(t2, f);
+                    t3 = vadd(t3, nn);
+                    t2 = Rn.mul(t3);
+                    t1 = vadd(t1, t2);
+                } else {
+                    fj = vadd(t4, f_tip);
+                    t2 = vcross(pstar, f_tip);
+                    t1 = vadd(t1, t2);
+                    t1 = vadd(t1, n_tip);
+                }
+                nj = vadd(t1, Nm[j]);
+            }
+            f = fj; nn = nj;
+            // torque about / force along the joint axis
+            V3<real> zax;
+            if (MDH) zax = {0, 0, 1};
+            else zax = {0, P.sa[j], P.ca[j]}; // R_j^T z0 = (n.z, o.z, a.z)
+            real t = pris ? vdot(fj, zax) : vdot(nj, zax);
+            const real qdj = mqd[j];
+            t += P.c_jm[j] * mqdd[j];
+            t += P.c_b[j] * qdj;
+            t += (qdj > 0 ? P.c_tcp[j] : (real)0) + (qdj < 0 ? P.c_tcm[j] : (real)0);
+            tq[j] = t;
+        }
+        // ---------------- stage tau and write it back coalesced
+        real *orow = sout + (size_t)lane * LDP;
+#pragma unroll
+        for (int j = 0; j < N; j++) orow[j] = tq[j];
+        __syncwarp();
+        {
+            const int cnt = rows_here * N;
+            real *gt = tau + row0 * N;
+            for (int i = lane; i < cnt; i += 32) {
+                int r = __float2int_rz(((float)i + 0.5f) * inv_n);
+                int c = i - r * N;
+                gt[i] = sout[r * LDP + c];
+            }
+        }
+        __syncwarp();
+    }
+}
+
+template <typename real, int N>
+int rne_launch_n(const b2k_rne_s *r, const real *q, const real *qd, const real *qdd, long long nrows,
+                 const double *grav, const double *fext, real *tau, cudaStream_t st)
+{
+    RneP<real, N> P;
+    for (int j = 0; j < N; j++) {
+        const double *l = r->L[j];
+        const double alpha = l[0], A = l[1], theta = l[2], D = l[3], offset = l[5];
+        const double G = l[20];
+        P.sa[j] = (real)sin(alpha);
+        P.ca[j] = (real)cos(alpha);
+        P.A[j] = (real)A;
+        P.D[j] = (real)D;
+        P.st0[j] = (real)sin(theta);
+        P.ct0[j] = (real)cos(theta);
+        P.offset[j] = (real)offset;
+        P.prismatic[j] = ((int)l[4]) != 0;
+        P.m[j] = (real)l[6];
+        for (int k = 0; k < 3; k++) P.r[j][k] = (real)l[7 + k];
+        for (int k = 0; k < 9; k++) P.I[j][k] = (real)l[10 + k];
+        P.c_jm[j] = (real)(G * G * l[19]);
+        P.c_b[j] = (real)(G * G * l[21]);
+        P.c_tcp[j] = (real)(fabs(G) * l[22]);
+        P.c_tcm[j] = (real)(fabs(G) * l[23]);
+    }
+    for (int k = 0; k < 3; k++) P.grav[k] = (real)grav[k];
+    for (int k = 0; k < 6; k++) P.fext[k] = fext ? (real)fext[k] : (real)0;
+    const size_t wsm = ((size_t)4 * 32 * (N | 1) * sizeof(real) + 15) & ~(size_t)15;
+    const size_t smem = wsm * B2K_WARPS_PER_BLOCK;
+    const long long ntiles = (nrows + 31) / 32;
+    const long long nblk_needed = (ntiles + B2K_WARPS_PER_BLOCK - 1) / B2K_WARPS_PER_BLOCK;
+    auto launch = [&](auto kern) -> int {
+        int per_sm = b2k_blocks_per_sm((const void *)kern, B2K_THREADS, smem);
+        if (per_sm < 1) return per_sm < 0 ? per_sm : (b2k_set_error("rne kernel does not fit on an SM"), B2K_ERR_INVALID);
+        long long grid = (long long)b2k_num_sms() * per_sm;
+        if (grid > nblk_needed) grid = nblk_needed;
+        if (grid < 1) grid = 1;
+        kern<<<(unsigned)grid, B2K_THREADS, smem, st>>>(P, q, qd, qdd, nrows, tau, (int)wsm);
+        b2k_count_launch();
+        B2K_CUDA(cudaGetLastError());
+        return B2K_OK;
+    };
+    if (r->mdh) return launch(k_rne<real, N, true>);
+    return launch(k_rne<real, N, false>);
+}
+
+template <typename real>
+int rne_launch(const b2k_rne_s *r, const void *q, const void *qd, const void *qdd, long long nrows, const double *grav,
+               const double *fext, void *tau, cudaStream_t st)
+{
+#define B2K_CASE(NN) \
+    case NN: return rne_launch_n<real, NN>(r, (const real *)q, (const real *)qd, (const real *)qdd, nrows, grav, fext, (real *)tau, st);
+    switch (r->n) {
+        B2K_CASE(1) B2K_CASE(2) B2K_CASE(3) B2K_CASE(4) B2K_CASE(5)
+        B2K_CASE(6) B2K_CASE(7) B2K_CASE(8) B2K_CASE(9) B2K_CASE(10)
+    default:
+        b2k_set_error("rne: unsupported joint count %d", r->n);
+        return B2K_ERR_INVALID;
+    }
+#undef B2K_CASE
+}

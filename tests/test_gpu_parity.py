@@ -1,0 +1,435 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against
+  (1) the committed golden fixtures produced by the compiled reference (tests/golden/*.npz),
+  (2) the literal KATs of the reference's own tests (tests/golden/reference_kats.json),
+  (3) the CPU oracle on fresh seeded inputs, including ragged / edge sizes,
+  (4) size-independent properties at BASELINE.json's full sizes (1M rows).
+Tolerances (BASELINE.json north_star): fp64 rtol 1e-10 (+ atol 1e-12: analytically-zero entries
+come out as +-1e-17, see the golden 1.29e-16 at reference tests/test_ETS.py:330); fp32 rtol 1e-4,
+atol 1e-5.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+import b2kin as rtb  # noqa: E402
+from oracle import chains as ch  # noqa: E402
+from oracle import oracle as orc  # noqa: E402
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+KAT = json.load(open(os.path.join(G, "reference_kats.json")))
+TOL = {np.float64: dict(rtol=1e-10, atol=1e-12), np.float32: dict(rtol=1e-4, atol=1e-5)}
+AX = ["Rx", "Ry", "Rz", "tx", "ty", "tz"]
+
+
+def ets_from_desc(z, p=""):
+    """Rebuild a product ETS from a fixture's neutral chain description."""
+    ets = []
+    m = len(z[p + "isjoint"])
+    for i in range(m):
+        if z[p + "isjoint"][i]:
+            ets.append(rtb.ET(AX[int(z[p + "axis"][i])], flip=bool(z[p + "flip"][i]), jindex=int(z[p + "jindex"][i]),
+                              qlim=z[p + "qlim"][i]))
+        else:
+            ets.append(rtb.ET.SE3(z[p + "T"][i]))
+    return rtb.ETS(ets)
+
+
+def dev(a, dt=np.float64):
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).cuda()
+
+
+def host(t):
+    return t.cpu().numpy()
+
+
+def opt(a):
+    return None if a.size == 0 else a
+
+
+def ref_inputs(Q, dt):
+    """fp32 runs are compared on the fp32-rounded inputs (the rounding of q is not the kernel's error)."""
+    return Q.astype(dt).astype(np.float64)
+
+
+# ------------------------------------------------------------------ KATs of the reference's own tests
+def test_kat_panda_pose_and_jacobian():
+    panda = rtb.models.Panda()
+    q = np.array(KAT["panda_fkine"]["q"])
+    np.testing.assert_array_almost_equal(panda.fkine(q).A, np.array(KAT["panda_fkine"]["T"]), decimal=6)
+    ans = np.array(KAT["panda_jacob0"]["J"])
+    # the reference accepts q as list, 1-D, (1,n) and (n,1) (tests/test_ETS.py:295-359)
+    for qq in (q, list(q), q[None, :], q[:, None]):
+        J = panda.jacob0(qq)
+        assert J.shape == (6, 7)
+        np.testing.assert_array_almost_equal(J, ans, decimal=6)
+    with pytest.raises(TypeError):
+        panda.ets().jacob0("Wfgsrth")
+    # jacobe == tr2jac(T^T) @ jacob0 (tests/test_ETS.py:365-398)
+    T = panda.ets().eval(q)
+    blk = np.zeros((6, 6)); blk[:3, :3] = T[:3, :3].T; blk[3:, 3:] = T[:3, :3].T
+    np.testing.assert_array_almost_equal(panda.jacobe(q), blk @ panda.jacob0(q))
+
+
+def test_kat_puma_rne():
+    puma = rtb.models.Puma560()
+    for c in KAT["puma560_rne"]["cases"]:
+        tau = puma.rne(puma.qn, np.full(6, float(c["qd"])), np.full(6, float(c["qdd"])), gravity=c.get("gravity"),
+                       fext=c.get("fext"))
+        assert tau.shape == (6,)
+        np.testing.assert_array_almost_equal(tau, np.array(c["tau"], dtype=float), decimal=4)
+    # trajectory form (tests/test_DHRobot.py:1065-1076) and delete / re-init (1078-1090)
+    z, o = np.zeros(6), np.ones(6)
+    t = puma.rne(np.c_[puma.qn, puma.qn].T, np.c_[z, o].T, np.c_[z, o].T)
+    np.testing.assert_array_almost_equal(t[0], KAT["puma560_rne"]["cases"][0]["tau"], decimal=4)
+    np.testing.assert_array_almost_equal(t[1], KAT["puma560_rne"]["cases"][2]["tau"], decimal=4)
+    puma.delete_rne()
+    np.testing.assert_array_almost_equal(puma.rne(puma.qn, z, z), KAT["puma560_rne"]["cases"][0]["tau"], decimal=4)
+
+
+def test_kat_ik_converges():
+    """tests/test_IK.py:186-251, 451-492, 632-708: success + small residual for all three methods."""
+    panda = rtb.models.Panda()
+    Tep = panda.fkine(panda.qr).A
+    for method, k in (("chan", 1.0), ("sugihara", 0.1), ("wampler", 0.01)):
+        q, ok, it, sr, E = panda.ik_LM(Tep, method=method, k=k)
+        assert ok == 1 and E < 1e-5 and q.shape == (7,)
+        assert np.abs(panda.fkine(q).A - Tep).max() < 5e-3
+        sol = panda.ikine_LM(Tep, method=method, k=k, seed=0)
+        assert sol.success and sol.residual < 1e-5
+        assert np.abs(panda.fkine(sol.q).A - Tep).max() < 5e-3
+    puma = rtb.models.Puma560()
+    T = puma.fkine(puma.qn).A
+    sol = puma.ikine_LM(T, seed=0)  # tests/test_DHRobot.py:965-972
+    assert sol.success
+    np.testing.assert_array_almost_equal(puma.fkine(sol.q).A, T, decimal=4)
+
+
+# ------------------------------------------------------------------ fixtures from the compiled reference
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+@pytest.mark.parametrize("name", ["panda_fkj.npz", "ur10_fkj.npz"])
+def test_fixture_fkj(name, dt):
+    z = np.load(os.path.join(G, name))
+    e = ets_from_desc(z)
+    Q = z["Q"]
+    if dt == np.float32:
+        keep = np.abs(Q).max(axis=1) < 100  # fp32 cannot even represent the 1e6-rad row's angles
+        Q = Q[keep]
+        C = orc.Chain({k: z[k] for k in ("isjoint", "axis", "flip", "jindex", "T", "qlim")})
+        Qr = ref_inputs(Q, dt)
+        Tr, J0r, Jer = C.fkine(Qr), C.jacob0(Qr), C.jacobe(Qr)
+    else:
+        Tr, J0r, Jer = z["Tfk"], z["J0"], z["Je"]
+    q = dev(Q, dt)
+    np.testing.assert_allclose(host(e.eval(q)), Tr, **TOL[dt])
+    np.testing.assert_allclose(host(e.jacob0(q)), J0r, **TOL[dt])
+    np.testing.assert_allclose(host(e.jacobe(q)), Jer, **TOL[dt])
+    T, J = e.fkine_jacob0(q)
+    np.testing.assert_allclose(host(T), Tr, **TOL[dt])
+    np.testing.assert_allclose(host(J), J0r, **TOL[dt])
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+def test_fixture_random_chains(dt):
+    """All six ET kinds, flips, SE3 constants, n = 1..10, base and tool."""
+    z = np.load(os.path.join(G, "random_fkj.npz"))
+    for c in range(int(z["nchains"])):
+        p = f"c{c}_"
+        e = ets_from_desc(z, p)
+        base, tool = opt(z[p + "base"]), opt(z[p + "tool"])
+        Q = z[p + "Q"]
+        if dt == np.float32:
+            C = orc.Chain({k: z[p + k] for k in ("isjoint", "axis", "flip", "jindex", "T", "qlim")})
+            Qr = ref_inputs(Q, dt)
+            Tr, J0r, Jer = C.fkine(Qr, base, tool), C.jacob0(Qr, tool), C.jacobe(Qr, tool)
+        else:
+            Tr, J0r, Jer = z[p + "Tfk"], z[p + "J0"], z[p + "Je"]
+        q = dev(Q, dt)
+        tol = dict(TOL[dt])
+        if dt == np.float64:
+            tol["atol"] = 1e-11  # chains with |t| up to ~5: scale the absolute floor with the reach
+        np.testing.assert_allclose(host(e.eval(q, base=base, tool=tool)), Tr, err_msg=f"chain {c}", **tol)
+        np.testing.assert_allclose(host(e.jacob0(q, tool=tool)), J0r, err_msg=f"chain {c}", **tol)
+        np.testing.assert_allclose(host(e.jacobe(q, tool=tool)), Jer, err_msg=f"chain {c}", **tol)
+        T, J = e.fkine_jacob0(q, base=base, tool=tool)
+        np.testing.assert_allclose(host(T), Tr, err_msg=f"chain {c}", **tol)
+        np.testing.assert_allclose(host(J), J0r, err_msg=f"chain {c}", **tol)
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+def test_fixture_rne(dt):
+    tol = dict(rtol=1e-10, atol=1e-10) if dt == np.float64 else dict(rtol=2e-4, atol=2e-3)
+    z = np.load(os.path.join(G, "puma_rne.npz"))
+    puma = rtb.models.Puma560()
+    a = [dev(z[k], dt) for k in ("q", "qd", "qdd")]
+    if dt == np.float32:  # compare on the rounded inputs
+        L = puma._pack_rne()
+        qq = [ref_inputs(z[k], dt) for k in ("q", "qd", "qdd")]
+        want = [orc.rne(6, 0, L, -z["gravity"], *qq), orc.rne(6, 0, L, -z["gravity"], *qq, z["fext"]),
+                orc.rne(6, 0, L, np.zeros(3), *qq), orc.rne(6, 0, L, -z["g2"], *qq, z["fext"])]
+    else:
+        want = [z["tau"], z["tau_fext"], z["tau_zerog"], z["tau_g2"]]
+    np.testing.assert_allclose(host(puma.rne(*a)), want[0], **tol)
+    np.testing.assert_allclose(host(puma.rne(*a, fext=z["fext"])), want[1], **tol)
+    np.testing.assert_allclose(host(puma.rne(*a, gravity=[0, 0, 0])), want[2], **tol)
+    np.testing.assert_allclose(host(puma.rne(*a, gravity=z["g2"], fext=z["fext"])), want[3], **tol)
+    if dt == np.float64:
+        z = np.load(os.path.join(G, "panda_mdh_rne.npz"))
+        pm = rtb.models.PandaMDH()
+        a = [dev(z[k]) for k in ("q", "qd", "qdd")]
+        np.testing.assert_allclose(host(pm.rne(*a)), z["tau"], **tol)
+        np.testing.assert_allclose(host(pm.rne(*a, fext=z["fext"])), z["tau_fext"], **tol)
+
+
+def test_fixture_rne_random_links():
+    """Random DH / MDH robots with prismatic joints, offsets, friction -- reference frne outputs."""
+    z = np.load(os.path.join(G, "random_rne.npz"))
+    for c in range(int(z["ncases"])):
+        p = f"c{c}_"
+        L = z[p + "L"].reshape(-1, 24)
+        mdh = bool(int(z[p + "mdh"]))
+        links = []
+        for l in L:
+            links.append(rtb.DHLink(alpha=l[0], a=l[1], theta=l[2], d=l[3], sigma=int(l[4]), offset=l[5], mdh=mdh,
+                                    m=l[6], r=l[7:10], I=l[10:19].reshape(3, 3), Jm=l[19], G=l[20], B=l[21], Tc=l[22:24]))
+        rob = rtb.DHRobot(links, gravity=z[p + "gravity"])
+        tau = rob.rne(dev(z[p + "q"]), dev(z[p + "qd"]), dev(z[p + "qdd"]), fext=z[p + "fext"])
+        np.testing.assert_allclose(host(tau), z[p + "tau"], rtol=1e-9, atol=1e-9, err_msg=f"case {c}")
+
+
+def test_fixture_ik_fp64_explicit_q0():
+    """Row i of the batch == the reference called on target i: explicit q0, slimit=1, fp64."""
+    z = np.load(os.path.join(G, "panda_ik.npz"))
+    e = rtb.models.Panda().ets()
+    Tep, q0 = dev(z["Tep"]), dev(z["q0"])
+    for tag, method, k in (("chan1", "chan", 1.0), ("chan01", "chan", 0.1), ("sugi", "sugihara", 1e-4)):
+        q, s, it, sr, E = (host(x) for x in e.ik_LM(Tep, q0=q0, slimit=1, joint_limits=False, k=k, method=method))
+        same = (s == z[tag + "_success"]) & (it == z[tag + "_it"]) & (sr == z[tag + "_search"])
+        assert same.mean() >= 0.98, f"{tag}: {same.mean():.3f} of rows reproduce the reference's counters"
+        ok = same & (s == 1)
+        np.testing.assert_allclose(q[ok], z[tag + "_q"][ok], atol=1e-7)
+        np.testing.assert_allclose(E[ok], z[tag + "_E"][ok], atol=1e-11)
+    # fmod wrap + joint-limit rejection (ik.cpp:50-52)
+    q, s, it, sr, E = (host(x) for x in e.ik_LM(Tep, q0=q0, slimit=1, joint_limits=True, k=1.0))
+    assert ((s == z["jl_success"]) & (it == z["jl_it"])).mean() >= 0.98
+    # masked (position-only) solve
+    q, s, it, sr, E = (host(x) for x in e.ik_LM(Tep, q0=q0, slimit=1, joint_limits=False, mask=z["mask"], k=1.0))
+    assert (s == z["mask_success"]).mean() >= 0.95
+    pos_err = np.abs(orc.Chain(e.describe()).fkine(q)[:, :3, 3] - z["Tep"][:, :3, 3]).max(axis=1)
+    assert (pos_err[s == 1] < 5e-3).all()
+
+
+def test_ik_restarts_match_oracle_stream():
+    """With the documented counter-based restart generator the whole multi-start run is
+    reproducible: same (seed,row,search,joint) draws as oracle_kin.c, so counters agree."""
+    z = np.load(os.path.join(G, "panda_ik.npz"))
+    e = rtb.models.Panda().ets()
+    C = orc.Chain(e.describe())
+    for sem, fn in ((0, "ik"), (1, "ikine")):
+        for jl in (True, False):
+            want = C.ik_lm(z["Tep"], q0=None, joint_limits=jl, k=1.0, seed=7, semantics=sem, rng_per_row=True)
+            got = e._ik(dev(z["Tep"]), None, 30, 100, 1e-6, None, jl, 1.0, "chan", 7, sem, True, None)[:5]
+            q, s, it, sr, E = (host(x) for x in got)
+            assert s.mean() == want[1].mean() == 1.0
+            same = (it == want[2]) & (sr == want[3])
+            assert same.mean() >= 0.97, f"sem {sem} jl {jl}: {same.mean():.3f}"
+            np.testing.assert_allclose(q[same], want[0][same], atol=1e-6)
+    # reference statistics with its own (unseeded) restarts: same success rate, similar search count
+    q, s, it, sr, E = (host(x) for x in e.ik_LM(dev(z["Tep"]), joint_limits=True, k=1.0, seed=3))
+    assert s.mean() == z["rs_success"].mean() == 1.0
+    assert abs(sr.mean() - z["rs_search"].mean()) < 0.5
+
+
+def test_ik_fp32_outcomes():
+    """Config 4 protocol at reduced size: fp32, reachable targets, chan k=0.1 and k=1.0."""
+    e = rtb.models.Panda().ets()
+    C = orc.Chain(e.describe())
+    rng = np.random.default_rng(2)
+    qs = rng.uniform(-np.pi, np.pi, (20000, 7))
+    Tep = C.fkine(qs)
+    for k, jl in ((0.1, False), (1.0, True)):
+        q, s, it, sr, E = (host(x) for x in e.ik_LM(dev(Tep, np.float32), joint_limits=jl, k=k, seed=5))
+        assert s.mean() > 0.999
+        ok = s == 1
+        assert (E[ok] < 1e-6).all()
+        err = np.abs(C.fkine(q.astype(np.float64)) - Tep).max(axis=(1, 2))
+        assert np.percentile(err[ok], 99.9) < 5e-3  # E < 1e-6 <=> ||e|| < 1.4e-3
+        if jl:
+            assert (np.abs(q[ok]) <= np.pi + 1e-6).all()
+    sol = e.ikine_LM(Tep[:500].astype(np.float32), seed=1)
+    assert sol.success and sol.q.shape == (500, 7) and sol.searches >= 500
+
+
+# ------------------------------------------------------------------ oracle on fresh inputs, edge sizes
+@pytest.mark.parametrize("N", [1, 2, 31, 32, 33, 1000, 100001])
+def test_sizes_and_ragged_tiles(N):
+    e = rtb.models.Panda().ets()
+    C = orc.Chain(e.describe())
+    Q = np.random.default_rng(N).uniform(-np.pi, np.pi, (N, 7))
+    T, J = e.fkine_jacob0(dev(Q))
+    np.testing.assert_allclose(host(T), C.fkine(Q), rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(host(J), C.jacob0(Q), rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(host(e.jacobe(dev(Q))), C.jacobe(Q), rtol=1e-10, atol=1e-12)
+    puma = rtb.models.Puma560()
+    q, qd, qdd = Q[:, :6], np.cos(Q[:, :6]), np.sin(Q[:, :6])
+    np.testing.assert_allclose(host(puma.rne(dev(q), dev(qd), dev(qdd))),
+                               orc.rne(6, 0, puma._pack_rne(), -puma.gravity, q, qd, qdd), rtol=1e-10, atol=1e-10)
+
+
+def test_empty_batch():
+    e = rtb.models.Panda().ets()
+    q = torch.empty((0, 7), dtype=torch.float64, device="cuda")
+    assert tuple(e.eval(q).shape) == (0, 4, 4)
+    assert tuple(e.jacob0(q).shape) == (0, 6, 7)
+
+
+def test_wide_q_and_permuted_jindex():
+    """q may be wider than n and jindices need not be 0..n-1 (reference methods.cpp:338, appendix C.13)."""
+    ET = rtb.ET
+    e = ET.Rz(jindex=4) * ET.tx(0.3) * ET.Ry(jindex=0, flip=True) * ET.tz(jindex=2) * ET.Rx(0.4) * ET.Rx(jindex=5)
+    C = orc.Chain(e.describe())
+    Q = np.random.default_rng(1).uniform(-2, 2, (777, 9))
+    np.testing.assert_allclose(host(e.eval(dev(Q))), C.fkine(Q), rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(host(e.jacob0(dev(Q))), C.jacob0(Q), rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(host(e.jacobe(dev(Q))), C.jacobe(Q), rtol=1e-10, atol=1e-12)
+    with pytest.raises(ValueError):
+        e.eval(dev(Q[:, :5]))  # too narrow for jindex 5
+    with pytest.raises(ValueError):
+        e.ik_LM(np.eye(4))  # the IK loop needs dense jindices (ik.cpp:34-35)
+
+
+def test_api_shapes_and_types():
+    panda = rtb.models.Panda()
+    e = panda.ets()
+    q = np.array([0.1, 0.2, 0.3, 0.4, 0.5, 0.6, 0.7])
+    assert e.eval(q).shape == (4, 4) and isinstance(e.eval(q), np.ndarray)
+    assert e.eval(q[None, :]).shape == (4, 4)  # (1,n) is ONE configuration (fknm.cpp:970-975)
+    assert e.eval(q[:, None]).shape == (4, 4)  # (n,1) too (fknm.cpp:976-981)
+    assert e.eval(np.tile(q, (5, 1))).shape == (5, 4, 4)
+    assert len(e.fkine(np.tile(q, (5, 1)))) == 5
+    t = e.eval(torch.from_numpy(q).cuda())
+    assert isinstance(t, torch.Tensor) and t.is_cuda and tuple(t.shape) == (4, 4)
+    f = e.eval(np.tile(q, (3, 1)).astype(np.float32))
+    assert f.dtype == np.float32
+    with pytest.raises(TypeError):
+        e.eval("abc")
+    with pytest.raises(TypeError):
+        e.eval(np.array(["a"] * 7, dtype=object))
+    with pytest.raises(ValueError):
+        e.eval(q, base=np.eye(3))
+    # base on the pose but not on the Jacobian (RobotKinematics.py:94 vs :158)
+    panda.base = ch.trotz(0.5) @ ch.transl(1, 2, 3)
+    T0 = e.eval(q)
+    np.testing.assert_allclose(panda.fkine(q).A, panda.base.A @ T0, atol=1e-13)
+    np.testing.assert_allclose(panda.jacob0(q), e.jacob0(q), atol=0)
+    np.testing.assert_allclose(panda.fkine(q, include_base=False).A, T0, atol=0)
+    # DHRobot: base rotation IS in jacob0 (DHRobot.py:1186)
+    ur = rtb.models.UR10()
+    q6 = q[:6]
+    J_nobase = ur.jacob0(q6)
+    ur.base = ch.trotx(0.7)
+    R = ur.base.A[:3, :3]
+    blk = np.zeros((6, 6)); blk[:3, :3] = R; blk[3:, 3:] = R
+    np.testing.assert_allclose(ur.jacob0(q6), blk @ J_nobase, atol=1e-13)
+
+
+def test_host_pipeline_matches_device_path():
+    """The pipelined host-buffer front end (chunks over several streams) returns the same bits."""
+    e = rtb.models.Panda().ets()
+    N = 300_001  # more than two 128k-row chunks, ragged tail
+    Q = np.random.default_rng(4).uniform(-np.pi, np.pi, (N, 7))
+    Th, Jh = e.fkine_jacob0(Q)
+    Td, Jd = e.fkine_jacob0(dev(Q))
+    assert np.array_equal(Th, host(Td)) and np.array_equal(Jh, host(Jd))
+    qp = rtb.pinned_empty((N, 7)); qp[:] = Q
+    Tp = rtb.pinned_empty((N, 4, 4)); Jp = rtb.pinned_empty((N, 6, 7))
+    e.fkine_jacob0_into(qp, Tp, Jp)
+    assert np.array_equal(Tp, Th) and np.array_equal(Jp, Jh)
+    puma = rtb.models.Puma560()
+    q, qd, qdd = Q[:, :6], np.cos(Q[:, :6]), np.sin(Q[:, :6])
+    assert np.array_equal(puma.rne(q, qd, qdd), host(puma.rne(dev(q), dev(qd), dev(qdd))))
+
+
+# ------------------------------------------------------------------ properties at full BASELINE sizes
+def test_full_size_properties_panda_1M():
+    """Config 2 at full size: 1M rows, seed 0, fp64.  Size-independent checks + an oracle subset."""
+    e = rtb.models.Panda().ets()
+    N = 1_000_000
+    Q = np.random.default_rng(0).uniform(-np.pi, np.pi, (N, 7))
+    q = dev(Q)
+    T, J = e.fkine_jacob0(q)
+    # (i) fused == separate kernels, bit for bit
+    assert torch.equal(T, e.eval(q)) and torch.equal(J, e.jacob0(q))
+    # (ii) rotation blocks orthonormal, bottom row exact
+    R = T[:, :3, :3]
+    assert (R @ R.transpose(1, 2) - torch.eye(3, dtype=T.dtype, device="cuda")).abs().max().item() < 1e-13
+    assert torch.equal(T[:, 3, :], torch.tensor([0.0, 0, 0, 1], dtype=T.dtype, device="cuda").expand(N, 4))
+    # (iii) jacobe == blkdiag(R^T, R^T) jacob0 (tests/test_ETS.py:396-398)
+    Je = e.jacobe(q)
+    Rt = R.transpose(1, 2)
+    JeX = torch.cat([Rt @ J[:, :3, :], Rt @ J[:, 3:, :]], dim=1)
+    assert (Je - JeX).abs().max().item() < 1e-13
+    # (iv) periodicity: q + 2 pi gives the same pose to rounding
+    T2 = e.eval(q + 2 * np.pi)
+    assert (T2 - T).abs().max().item() < 1e-12
+    # (v) a 64k random subset + the first/last rows against the oracle
+    idx = np.unique(np.r_[0, N - 1, np.random.default_rng(9).integers(0, N, 65536)])
+    C = orc.Chain(e.describe())
+    np.testing.assert_allclose(host(T[idx]), C.fkine(Q[idx]), rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(host(J[idx]), C.jacob0(Q[idx]), rtol=1e-10, atol=1e-12)
+    # (vi) linear rows of J0 vs central differences of the pose (tests/test_jacob.py:27-39)
+    h = 1e-6
+    sub = q[:4096]
+    for j in (0, 3, 6):
+        dq = torch.zeros(7, dtype=q.dtype, device="cuda"); dq[j] = h
+        dp = (e.eval(sub + dq)[:, :3, 3] - e.eval(sub - dq)[:, :3, 3]) / (2 * h)
+        assert (dp - J[:4096, :3, j]).abs().max().item() < 1e-7
+
+
+def test_full_size_properties_puma_rne_1M():
+    """Config 3 at full size: linearity of tau in qdd (tau = M(q) qdd + h(q,qd)) and in gravity."""
+    puma = rtb.models.Puma560()
+    N = 1_000_000
+    rng = np.random.default_rng(1)
+    ql = puma.qlim
+    q = dev(rng.uniform(ql[0], ql[1], (N, 6)))
+    qd = dev(rng.normal(size=(N, 6)))
+    a, b = dev(rng.normal(size=(N, 6))), dev(rng.normal(size=(N, 6)))
+    qd[-1000:] = 0.0  # Coulomb qd == 0 branch (ne.c:487-490)
+    z = torch.zeros_like(a)
+    t_ab, t_a, t_b, t_0 = (puma.rne(q, qd, x) for x in (a + b, a, b, z))
+    scale = t_ab.abs().max().item()
+    assert (t_ab - t_a - t_b + t_0).abs().max().item() < 1e-11 * scale
+    # gravity enters linearly: tau(g) - tau(0) doubles when g doubles
+    g = np.array([0, 0, -9.81])
+    d1 = puma.rne(q, qd, a, gravity=g) - puma.rne(q, qd, a, gravity=[0, 0, 0])
+    d2 = puma.rne(q, qd, a, gravity=2 * g) - puma.rne(q, qd, a, gravity=[0, 0, 0])
+    assert (d2 - 2 * d1).abs().max().item() < 1e-10 * scale
+    idx = np.r_[0, N - 1, np.random.default_rng(3).integers(0, N, 20000)]
+    ref = orc.rne(6, 0, puma._pack_rne(), -puma.gravity, host(q[idx]), host(qd[idx]), host(a[idx]))
+    np.testing.assert_allclose(host(t_a[idx]), ref, rtol=1e-10, atol=1e-10)
+
+
+def test_full_size_ur10_fp32():
+    """Config 5's per-GPU shard: UR10 DH chain, 1M rows, fp32."""
+    e = rtb.models.UR10().ets()
+    N = 1 << 20
+    Q = np.random.default_rng(3).uniform(-np.pi, np.pi, (N, 6)).astype(np.float32)
+    T, J = e.fkine_jacob0(dev(Q, np.float32))
+    idx = np.r_[0, N - 1, np.random.default_rng(5).integers(0, N, 30000)]
+    C = orc.Chain(e.describe())
+    Qr = Q[idx].astype(np.float64)
+    np.testing.assert_allclose(host(T[idx]), C.fkine(Qr), rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(host(J[idx]), C.jacob0(Qr), rtol=1e-4, atol=1e-5)
+
+
+def test_launch_counter_moves():
+    e = rtb.models.Panda().ets()
+    n0 = rtb.launch_count()
+    e.eval(dev(np.zeros((10, 7))))
+    assert rtb.launch_count() == n0 + 1
