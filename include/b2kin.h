@@ -182,6 +182,10 @@ int b2k_rne_host(b2k_rne_t rne, int dtype, const void *q_host, const void *qd_ho
  * bench.py reports the delta over its timed region as "gpu_launches". */
 int64_t b2k_launch_count(void);
 
+/* Test hook: evaluates the kernels' in-house sincos (csrc/b2k_trig.cuh) on n device values so
+ * its accuracy can be checked in isolation: s[i], c[i] = sin(x[i]), cos(x[i]). */
+int b2k_selftest_sincos(int dtype, const void *x, int64_t n, void *s, void *c, void *stream);
+
 /* kernel variant switch for measurements: 0 = default (lane-per-configuration, warp-tiled
  * I/O), 1 = literal warp-per-configuration walk (one joint configuration per warp).
  * Affects b2k_fkine / b2k_fkine_jacob0 only. */

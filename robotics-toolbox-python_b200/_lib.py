@@ -50,6 +50,7 @@ _PROTOS = {
     "b2k_rne_host": (C.c_int, [vp, C.c_int, vp, vp, vp, i64, dp, dp, vp, C.c_int]),
     "b2k_launch_count": (C.c_int64, []),
     "b2k_set_variant": (C.c_int, [C.c_int]),
+    "b2k_selftest_sincos": (C.c_int, [C.c_int, vp, i64, vp, vp, vp]),
 }
 
 EXPORTED_SYMBOLS = tuple(_PROTOS)

@@ -23,6 +23,47 @@ enum : int {
     AK_TZ = 32
 };
 
+// Constants of the in-house sincos (b2k_trig.cuh).  They live in the kernel-parameter constant
+// bank so every polynomial coefficient is an immediate c[0x0][..] operand of an FMA; literal
+// doubles would each cost two MOV-immediate instructions on the uniform datapath.
+template <typename real>
+struct TrigC {
+    real two_over_pi, magic, pio2_hi, pio2_mid, pio2_lo, fast_limit;
+    real s[6]; // sin(r) = r + r^3 (s0 + z s1 + ... ), z = r^2
+    real c[6]; // cos(r) = 1 - z/2 + z^2 (c0 + z c1 + ...)
+};
+
+template <typename real>
+inline void b2k_fill_trig(TrigC<real> &t);
+template <>
+inline void b2k_fill_trig<double>(TrigC<double> &t)
+{
+    t.two_over_pi = 0.6366197723675814;
+    t.magic = 6755399441055744.0; // 1.5 * 2^52: adds k = rint(x 2/pi) into the low mantissa bits
+    t.pio2_hi = 1.5707963267948966;
+    t.pio2_mid = 6.123233995736766e-17;
+    t.pio2_lo = -1.4973849048591698e-33;
+    t.fast_limit = 105615.0; // same validity bound CUDA's own three-FMA reduction uses
+    const double s[6] = {-1.66666666666666324348e-01, 8.33333333332248946124e-03, -1.98412698298579493134e-04,
+                         2.75573137070700676789e-06, -2.50507602534068634195e-08, 1.58969099521155010221e-10};
+    const double c[6] = {4.16666666666666019037e-02, -1.38888888888741095749e-03, 2.48015872894767294178e-05,
+                         -2.75573143513906633035e-07, 2.08757232129817482790e-09, -1.13596475577881948265e-11};
+    for (int i = 0; i < 6; i++) { t.s[i] = s[i]; t.c[i] = c[i]; }
+}
+template <>
+inline void b2k_fill_trig<float>(TrigC<float> &t)
+{
+    t.two_over_pi = 0.6366197723675814f;
+    t.magic = 12582912.0f; // 1.5 * 2^23
+    t.pio2_hi = 1.5707963705062866f;
+    t.pio2_mid = -4.371138828673793e-08f;
+    t.pio2_lo = -1.7151245100058819e-15f;
+    t.fast_limit = 105615.0f;
+    const float s[6] = {-1.6666654611e-1f, 8.3321608736e-3f, -1.9515295891e-4f, 0.f, 0.f, 0.f};
+    const float c[6] = {4.166664568298827e-2f, -1.388731625493765e-3f, 2.443315711809948e-5f, 0.f, 0.f, 0.f};
+    for (int i = 0; i < 6; i++) { t.s[i] = s[i]; t.c[i] = c[i]; }
+}
+
 // Device-side chain: n steps of (constant A_j, joint j) followed by a tail constant A_n.
 // Passed BY VALUE as a __grid_constant__ kernel parameter so every entry is a constant-bank
 // operand (no loads in the unrolled chain walk).
@@ -36,6 +77,7 @@ struct ChainP {
     int jidx[N];  // column of q
     int has_base; // 0: B is identity
     int all_rz;   // every joint is an unflipped Rz (DH robots, Panda): switch-free fast path
+    TrigC<real> trig;
 };
 
 // Host-side compiled chain (fp64 master copy); see b2k_chain.cu.
@@ -119,4 +161,5 @@ void b2k_fill_chain(const b2k_chain_s *c, const double *base, const double *tool
     }
     for (int j = 0; j < N; j++) { P.axis[j] = c->axis[j]; P.flip[j] = c->flip[j]; P.jidx[j] = c->jidx[j]; }
     P.all_rz = c->all_rz;
+    b2k_fill_trig<real>(P.trig);
 }

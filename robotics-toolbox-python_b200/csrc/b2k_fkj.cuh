@@ -2,14 +2,16 @@
 //
 // Mapping (DESIGN.md "Kernel K12"): a warp owns a TILE of 32 joint configurations.  Lane l
 // walks the serial chain of row (tile*32 + l) entirely in registers -- pose as four 3-vectors
-// (bottom row 0 0 0 1 implied), chain constants read straight from the constant bank (the
-// chain is a __grid_constant__ kernel parameter, so every folded constant is an immediate
-// c[0x0][..] operand of the FMA).  The warp as a whole moves the tile's q block and its T / J
-// blocks between HBM and registers through a per-warp shared-memory stage so that every
-// global access is a fully coalesced 256-byte warp transaction:
-//     q tile  (32 x ldq)   : coalesced loads -> smem (odd row stride) -> one row per lane
-//     T tile  (32 x 16)    : registers -> smem (odd granule stride) -> coalesced 8-byte stores
-//     J tile  (32 x 6n)    : same
+// (bottom row 0 0 0 1 implied), chain constants and sincos coefficients read straight from the
+// constant bank (the chain is a __grid_constant__ kernel parameter, so every folded constant is
+// an immediate c[0x0][..] operand of the FMA).  The warp as a whole moves the tile's q block and
+// its T / J blocks between HBM and registers through a per-warp shared-memory stage so that
+// every global access is a fully coalesced warp transaction:
+//     q tile  (32 x ldq)  : 16-byte cp.async (LDGSTS) straight into smem, issued for tile t+1
+//                           while tile t's results drain; one row per lane read back
+//     T tile  (32 x 16)   : registers -> 16-byte vector STS (odd row stride in 16-byte units,
+//                           conflict free) -> LDS.128 + STG.128 (512 B per warp instruction)
+//     J tile  (32 x 6n)   : same; for Panda fp64 the stage is the exact image of the output block
 // No tensor cores: the products are 3x3 / 6xn (far below an MMA tile) -- this is HBM-bound
 // streaming work (520 B per evaluation for Panda fp64).
 //
@@ -19,19 +21,10 @@
 // reference's end-effector-frame walk + blkdiag(R,R) rotation.  Same values to rounding.
 #pragma once
 
+#include <type_traits>
+
 #include "b2k_common.cuh"
-
-template <typename real>
-__device__ __forceinline__ void b2k_sincos(real x, real *s, real *c);
-template <>
-__device__ __forceinline__ void b2k_sincos<double>(double x, double *s, double *c) { sincos(x, s, c); }
-template <>
-__device__ __forceinline__ void b2k_sincos<float>(float x, float *s, float *c) { sincosf(x, s, c); }
-
-// 8-byte staging granule: one double or two floats
-template <typename real> struct Granule;
-template <> struct Granule<double> { typedef double type; static constexpr int PER = 1; };
-template <> struct Granule<float> { typedef float2 type; static constexpr int PER = 2; };
+#include "b2k_trig.cuh"
 
 // pose T = [c0 c1 c2 p] (columns), all in registers
 template <typename real>
@@ -110,9 +103,9 @@ template <typename real>
 __device__ __forceinline__ void pose_mul_const_left(Pose<real> &T, const real *A, int kind)
 {
     const int rk = kind & AK_ROTMASK;
+    real *cols[4] = {T.c0, T.c1, T.c2, T.p};
     if (rk == AK_IDENT) {
     } else if (rk == AK_RX) { // rows 1,2 mix
-        real *cols[4] = {T.c0, T.c1, T.c2, T.p};
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             real a = cols[j][1], b = cols[j][2];
@@ -120,7 +113,6 @@ __device__ __forceinline__ void pose_mul_const_left(Pose<real> &T, const real *A
             cols[j][2] = fma(A[9], a, A[10] * b);
         }
     } else if (rk == AK_RY) { // rows 0,2 mix
-        real *cols[4] = {T.c0, T.c1, T.c2, T.p};
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             real a = cols[j][0], b = cols[j][2];
@@ -128,7 +120,6 @@ __device__ __forceinline__ void pose_mul_const_left(Pose<real> &T, const real *A
             cols[j][2] = fma(A[8], a, A[10] * b);
         }
     } else if (rk == AK_RZ) { // rows 0,1 mix
-        real *cols[4] = {T.c0, T.c1, T.c2, T.p};
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             real a = cols[j][0], b = cols[j][1];
@@ -136,7 +127,6 @@ __device__ __forceinline__ void pose_mul_const_left(Pose<real> &T, const real *A
             cols[j][1] = fma(A[4], a, A[5] * b);
         }
     } else {
-        real *cols[4] = {T.c0, T.c1, T.c2, T.p};
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             real a = cols[j][0], b = cols[j][1], c = cols[j][2];
@@ -165,11 +155,11 @@ __device__ __forceinline__ void rot_cols(real *a, real *b, real s, real c)
 
 // T <- T * ET(eta) for a joint of the given axis (eta already sign-flipped)
 template <typename real>
-__device__ __forceinline__ void pose_joint_right(Pose<real> &T, int axis, real eta)
+__device__ __forceinline__ void pose_joint_right(Pose<real> &T, int axis, real eta, const TrigC<real> &tc)
 {
     if (axis < 3) {
         real s, c;
-        b2k_sincos<real>(eta, &s, &c);
+        b2k_sincos(eta, tc, &s, &c);
         if (axis == B2K_RZ) rot_cols(T.c0, T.c1, s, c);
         else if (axis == B2K_RX) rot_cols(T.c1, T.c2, s, c);
         else rot_cols(T.c2, T.c0, s, c);
@@ -203,11 +193,11 @@ __device__ __forceinline__ void rot_rows(Pose<real> &T, real s, real c)
 
 // T <- ET(eta) * T
 template <typename real>
-__device__ __forceinline__ void pose_joint_left(Pose<real> &T, int axis, real eta)
+__device__ __forceinline__ void pose_joint_left(Pose<real> &T, int axis, real eta, const TrigC<real> &tc)
 {
     if (axis < 3) {
         real s, c;
-        b2k_sincos<real>(eta, &s, &c);
+        b2k_sincos(eta, tc, &s, &c);
         if (axis == B2K_RZ) rot_rows<real, 0, 1>(T, s, c);
         else if (axis == B2K_RX) rot_rows<real, 1, 2>(T, s, c);
         else rot_rows<real, 2, 0>(T, s, c);
@@ -266,7 +256,7 @@ __device__ __forceinline__ void chain_forward(const ChainP<real, N> &P, GetQ get
                 for (int i = 0; i < 3; i++) { zj[j][i] = T.c2[i]; pj[j][i] = T.p[i]; }
             }
             real s, c;
-            b2k_sincos<real>(eta, &s, &c);
+            b2k_sincos(eta, P.trig, &s, &c);
             rot_cols(T.c0, T.c1, s, c);
         } else {
             const int ax = P.axis[j];
@@ -282,221 +272,339 @@ __device__ __forceinline__ void chain_forward(const ChainP<real, N> &P, GetQ get
                     pj[j][i] = T.p[i];
                 }
             }
-            pose_joint_right(T, ax, eta);
+            pose_joint_right(T, ax, eta, P.trig);
         }
     }
     pose_mul_const_right(T, P.A[N], P.akind[N]);
 }
 
-// ------------------------------------------------------------------ per-warp staging helpers
-// stage row stride in 8-byte granules: odd, so that one-row-per-lane accesses are conflict free
-__host__ __device__ constexpr int stage_stride(int granules_per_row) { return granules_per_row | 1; }
-
-template <typename real>
-__host__ __device__ constexpr int granules(int elems) { return elems * (int)sizeof(real) / 8; }
-
-// bytes of per-warp shared memory needed by the FK/J kernels
-template <typename real>
-inline size_t fkj_warp_smem(int n, int ldq, bool wt, bool wj)
+// base-frame Jacobian row (6 x N, row-major) of one configuration from the walk's stash
+template <typename real, int N, bool ALLRZ>
+__device__ __forceinline__ void jacob0_row(const ChainP<real, N> &P, const Pose<real> &T, real (*zj)[3],
+                                           real (*pj)[3], real *row)
 {
-    size_t q = (size_t)32 * (ldq | 1) * sizeof(real);
-    size_t t = wt ? (size_t)32 * stage_stride(granules<real>(16)) * 8 : 0;
-    size_t j = wj ? (size_t)32 * stage_stride(granules<real>(6 * n)) * 8 : 0;
-    size_t m = q > t ? q : t;
-    return m > j ? m : j;
-}
-
-// coalesced copy of the warp's q tile into shared memory (row stride ldq -> ldq|1)
-template <typename real>
-__device__ __forceinline__ void stage_q_tile(real *sq, const real *__restrict__ gq, int rows_here, int ldq,
-                                             float inv_ldq, int lane)
-{
-    const int cnt = rows_here * ldq;
-    const int ldqp = ldq | 1;
-    for (int i = lane; i < cnt; i += 32) {
-        int r = __float2int_rz(((float)i + 0.5f) * inv_ldq);
-        int c = i - r * ldq;
-        sq[r * ldqp + c] = gq[i];
-    }
-}
-
-// coalesced write-out of a staged tile: ROWG granules per row, staged with stride S
-template <typename real, int ROWG>
-__device__ __forceinline__ void drain_tile(const typename Granule<real>::type *stage,
-                                           typename Granule<real>::type *__restrict__ gout, int rows_here, int lane)
-{
-    constexpr int S = stage_stride(ROWG);
-    const int lim = rows_here * ROWG;
-#pragma unroll 4
-    for (int it = 0; it < ROWG; ++it) {
-        int i = it * 32 + lane;
-        if (i < lim) {
-            int r = i / ROWG;
-            int c = i - r * ROWG;
-            gout[i] = stage[r * S + c];
+#pragma unroll
+    for (int j = 0; j < N; j++) {
+        const bool rev = ALLRZ ? true : (P.axis[j] < 3);
+        if (rev) {
+            real dx = T.p[0] - pj[j][0], dy = T.p[1] - pj[j][1], dz = T.p[2] - pj[j][2];
+            row[0 * N + j] = fma(zj[j][1], dz, -(zj[j][2] * dy));
+            row[1 * N + j] = fma(zj[j][2], dx, -(zj[j][0] * dz));
+            row[2 * N + j] = fma(zj[j][0], dy, -(zj[j][1] * dx));
+            row[3 * N + j] = zj[j][0];
+            row[4 * N + j] = zj[j][1];
+            row[5 * N + j] = zj[j][2];
+        } else {
+            row[0 * N + j] = zj[j][0];
+            row[1 * N + j] = zj[j][1];
+            row[2 * N + j] = zj[j][2];
+            row[3 * N + j] = (real)0;
+            row[4 * N + j] = (real)0;
+            row[5 * N + j] = (real)0;
         }
     }
 }
 
+// ------------------------------------------------------------------ per-warp staging of output tiles
+// A tile of 32 rows x ROW_ELEMS reals is staged in units of UB bytes (16 when a row is a whole
+// number of 16-byte units, else 8) with a row stride of S units, S odd and >= units per row, so
+// that the one-row-per-lane vector stores are bank-conflict free.  The warp then copies the tile
+// to global memory unit by unit: consecutive lanes -> consecutive units -> full-width coalesced
+// stores.  When S equals the units per row the stage is the exact image of the output block.
+template <typename real, int ROW_ELEMS>
+struct TileStage {
+    static constexpr int ROW_BYTES = ROW_ELEMS * (int)sizeof(real);
+    static constexpr int UB = (ROW_BYTES % 16 == 0) ? 16 : (ROW_BYTES % 8 == 0 ? 8 : 4);
+    static constexpr int RU = ROW_BYTES / UB;          // units per row
+    static constexpr int S = RU | 1;                   // stage row stride in units (odd)
+    static constexpr int BYTES = 32 * S * UB;
+    typedef typename std::conditional<UB == 16, uint4, typename std::conditional<UB == 8, uint2, unsigned>::type>::type unit_t;
+
+    // lane writes its row (ROW_ELEMS values in registers) with vector stores
+    static __device__ __forceinline__ void put_row(unsigned char *stage, int lane, const real *row)
+    {
+        unit_t *dst = reinterpret_cast<unit_t *>(stage) + lane * S;
+#pragma unroll
+        for (int u = 0; u < RU; u++) {
+            unit_t v;
+            if constexpr (sizeof(real) == 8) {
+                if constexpr (UB == 16) {
+                    v.x = __double2loint(row[2 * u]); v.y = __double2hiint(row[2 * u]);
+                    v.z = __double2loint(row[2 * u + 1]); v.w = __double2hiint(row[2 * u + 1]);
+                } else {
+                    v.x = __double2loint(row[u]); v.y = __double2hiint(row[u]);
+                }
+            } else {
+                if constexpr (UB == 16) {
+                    v.x = __float_as_int(row[4 * u]); v.y = __float_as_int(row[4 * u + 1]);
+                    v.z = __float_as_int(row[4 * u + 2]); v.w = __float_as_int(row[4 * u + 3]);
+                } else if constexpr (UB == 8) {
+                    v.x = __float_as_int(row[2 * u]); v.y = __float_as_int(row[2 * u + 1]);
+                } else {
+                    v = (unsigned)__float_as_int(row[u]);
+                }
+            }
+            dst[u] = v;
+        }
+    }
+
+    // warp copies the staged tile to gout (the tile's block of the output array)
+    static __device__ __forceinline__ void drain(const unsigned char *stage, real *gout, int rows_here, int lane)
+    {
+        const unit_t *src = reinterpret_cast<const unit_t *>(stage);
+        unit_t *dst = reinterpret_cast<unit_t *>(gout);
+        constexpr int ITERS = RU; // 32 rows * RU units / 32 lanes
+        if (rows_here == 32) {
+            if constexpr (S == RU) { // exact image: flat copy, immediate offsets
+#pragma unroll
+                for (int it = 0; it < ITERS; it++) dst[it * 32 + lane] = src[it * 32 + lane];
+            } else if constexpr (32 % RU == 0) { // whole rows per warp pass: immediate offsets again
+                constexpr int RPP = 32 / RU; // rows per pass
+                const int base = (lane / RU) * S + (lane % RU);
+#pragma unroll
+                for (int it = 0; it < ITERS; it++) dst[it * 32 + lane] = src[base + it * RPP * S];
+            } else { // incremental (row, col) walk: no division in the loop
+                int c = lane % RU;
+                int off = (lane / RU) * S + c;
+#pragma unroll
+                for (int it = 0; it < ITERS; it++) {
+                    dst[it * 32 + lane] = src[off];
+                    c += 32 % RU;
+                    off += (32 / RU) * S + (32 % RU);
+                    if (c >= RU) { c -= RU; off += S - RU; }
+                }
+            }
+        } else { // ragged last tile
+            const int lim = rows_here * RU;
+            for (int u = lane; u < lim; u += 32) {
+                int r = u / RU, c = u - r * RU;
+                dst[u] = src[r * S + c];
+            }
+        }
+    }
+};
+
+// pose row: 16 reals, bottom row 0 0 0 1
+template <typename real>
+__device__ __forceinline__ void pose_to_row(const Pose<real> &T, real *row)
+{
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        row[i * 4 + 0] = T.c0[i];
+        row[i * 4 + 1] = T.c1[i];
+        row[i * 4 + 2] = T.c2[i];
+        row[i * 4 + 3] = T.p[i];
+    }
+    row[12] = (real)0; row[13] = (real)0; row[14] = (real)0; row[15] = (real)1;
+}
+
+// ------------------------------------------------------------------ q tile loading
+// qmode 1: the smem tile is the exact image of the 32 x ldq global block, filled with 16-byte
+//          cp.async (no registers, asynchronous: used to prefetch the next tile);
+// qmode 0: padded rows (stride ldq|1), element-wise copy -- used when the exact image would make
+//          the one-row-per-lane reads collide (gcd(ldq, banks) > 2) or q is not 16-byte aligned.
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
+{
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+
+template <typename real>
+__device__ __forceinline__ void load_q_tile(real *sq, const real *__restrict__ gq, int rows_here, int ldq,
+                                            float inv_ldq, int qmode, int lane)
+{
+    const int cnt = rows_here * ldq;
+    if (qmode == 1) {
+        if (rows_here == 32) {
+            const int units = (32 * ldq * (int)sizeof(real)) >> 4;
+            const uint4 *g = reinterpret_cast<const uint4 *>(gq);
+            uint4 *s = reinterpret_cast<uint4 *>(sq);
+            for (int u = lane; u < units; u += 32) cp_async16(s + u, g + u);
+        } else {
+            for (int i = lane; i < cnt; i += 32) sq[i] = gq[i];
+        }
+    } else {
+        const int ldqp = ldq | 1;
+        for (int i = lane; i < cnt; i += 32) {
+            int r = __float2int_rz(((float)i + 0.5f) * inv_ldq);
+            int c = i - r * ldq;
+            sq[r * ldqp + c] = gq[i];
+        }
+    }
+}
+
+// bytes of per-warp shared memory: [q tile][output stage]
+template <typename real>
+inline size_t fkj_q_bytes(int ldq) { return ((size_t)32 * (ldq | 1) * sizeof(real) + 15) & ~(size_t)15; }
+
+template <typename real, int N>
+inline size_t fkj_warp_smem(int ldq, bool wt, bool wj)
+{
+    size_t t = wt ? (size_t)TileStage<real, 16>::BYTES : 0;
+    size_t j = wj ? (size_t)TileStage<real, 6 * N>::BYTES : 0;
+    return fkj_q_bytes<real>(ldq) + (t > j ? t : j);
+}
+
+// registers: cap at 128/thread (4 resident blocks of 128 threads per SM) where the stash allows it
+template <typename real, int N, bool WJ>
+struct FkjBounds {
+    static constexpr int MINB = (!WJ) ? 5 : (sizeof(real) == 4 ? 4 : (N <= 7 ? 4 : 3));
+};
+
 // ------------------------------------------------------------------ forward walk: pose and/or base-frame Jacobian
 template <typename real, int N, bool WT, bool WJ, bool ALLRZ>
-__global__ void __launch_bounds__(B2K_THREADS)
+__global__ void __launch_bounds__(B2K_THREADS, FkjBounds<real, N, WJ>::MINB)
 k_fkj_forward(const __grid_constant__ ChainP<real, N> P, const real *__restrict__ q, long long nrows, int ldq,
-              float inv_ldq, real *__restrict__ Tout, real *__restrict__ Jout, int warp_smem_bytes)
+              float inv_ldq, int qmode, real *__restrict__ Tout, real *__restrict__ Jout, int warp_smem_bytes,
+              int q_bytes)
 {
-    typedef typename Granule<real>::type gran_t;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     unsigned char *wbase = smem_raw + (size_t)warp * warp_smem_bytes;
     real *sq = reinterpret_cast<real *>(wbase);
-    real *so = reinterpret_cast<real *>(wbase);
-    const int ldqp = ldq | 1;
+    unsigned char *so = wbase + q_bytes;
+    const int ldqs = qmode ? ldq : (ldq | 1);
     const long long ntiles = (nrows + 31) >> 5;
+    const long long tstride = (long long)gridDim.x * B2K_WARPS_PER_BLOCK;
 
-    for (long long tile = (long long)blockIdx.x * B2K_WARPS_PER_BLOCK + warp; tile < ntiles;
-         tile += (long long)gridDim.x * B2K_WARPS_PER_BLOCK) {
+    long long tile = (long long)blockIdx.x * B2K_WARPS_PER_BLOCK + warp;
+    if (tile < ntiles) {
+        const long long row0 = tile << 5;
+        load_q_tile<real>(sq, q + row0 * ldq, (int)((nrows - row0) < 32 ? (nrows - row0) : 32), ldq, inv_ldq, qmode, lane);
+    }
+    for (; tile < ntiles; tile += tstride) {
         const long long row0 = tile << 5;
         const int rows_here = (int)((nrows - row0) < 32 ? (nrows - row0) : 32);
-        stage_q_tile<real>(sq, q + row0 * ldq, rows_here, ldq, inv_ldq, lane);
+        cp_async_wait_all();
         __syncwarp();
-        const real *myq = sq + (lane < rows_here ? lane : 0) * ldqp;
+        const real *myq = sq + (lane < rows_here ? lane : 0) * ldqs;
 
         Pose<real> T;
         real zj[WJ ? N : 1][3], pj[WJ ? N : 1][3];
         chain_forward<real, N, WJ, ALLRZ>(P, [&](int, int col) { return myq[col]; }, T, zj, pj);
-        __syncwarp(); // all lanes are done reading q: the stage may be overwritten
-
+        __syncwarp(); // every lane has read its q row: prefetch the next tile's q behind the drain
+        {
+            const long long nt = tile + tstride;
+            if (nt < ntiles) {
+                const long long r0 = nt << 5;
+                load_q_tile<real>(sq, q + r0 * ldq, (int)((nrows - r0) < 32 ? (nrows - r0) : 32), ldq, inv_ldq, qmode, lane);
+            }
+        }
         if (WT) {
             Pose<real> Tb = T;
             if (P.has_base) pose_mul_const_left(Tb, P.B, AK_GEN | AK_TX | AK_TY | AK_TZ);
-            constexpr int S = stage_stride(granules<real>(16)) * Granule<real>::PER; // stride in elements
-            real *row = so + lane * S;
-#pragma unroll
-            for (int i = 0; i < 3; i++) {
-                row[i * 4 + 0] = Tb.c0[i];
-                row[i * 4 + 1] = Tb.c1[i];
-                row[i * 4 + 2] = Tb.c2[i];
-                row[i * 4 + 3] = Tb.p[i];
-            }
-            row[12] = (real)0; row[13] = (real)0; row[14] = (real)0; row[15] = (real)1;
+            real row[16];
+            pose_to_row(Tb, row);
+            TileStage<real, 16>::put_row(so, lane, row);
             __syncwarp();
-            drain_tile<real, granules<real>(16)>(reinterpret_cast<const gran_t *>(so),
-                                                 reinterpret_cast<gran_t *>(Tout + row0 * 16), rows_here, lane);
+            TileStage<real, 16>::drain(so, Tout + row0 * 16, rows_here, lane);
             __syncwarp();
         }
         if (WJ) {
-            constexpr int S = stage_stride(granules<real>(6 * N)) * Granule<real>::PER;
-            real *row = so + lane * S;
-#pragma unroll
-            for (int j = 0; j < N; j++) {
-                const bool rev = ALLRZ ? true : (P.axis[j] < 3);
-                if (rev) {
-                    real dx = T.p[0] - pj[j][0], dy = T.p[1] - pj[j][1], dz = T.p[2] - pj[j][2];
-                    row[0 * N + j] = fma(zj[j][1], dz, -(zj[j][2] * dy));
-                    row[1 * N + j] = fma(zj[j][2], dx, -(zj[j][0] * dz));
-                    row[2 * N + j] = fma(zj[j][0], dy, -(zj[j][1] * dx));
-                    row[3 * N + j] = zj[j][0];
-                    row[4 * N + j] = zj[j][1];
-                    row[5 * N + j] = zj[j][2];
-                } else {
-                    row[0 * N + j] = zj[j][0];
-                    row[1 * N + j] = zj[j][1];
-                    row[2 * N + j] = zj[j][2];
-                    row[3 * N + j] = (real)0;
-                    row[4 * N + j] = (real)0;
-                    row[5 * N + j] = (real)0;
-                }
-            }
+            real row[6 * N];
+            jacob0_row<real, N, ALLRZ>(P, T, zj, pj, row);
+            TileStage<real, 6 * N>::put_row(so, lane, row);
             __syncwarp();
-            drain_tile<real, granules<real>(6 * N)>(reinterpret_cast<const gran_t *>(so),
-                                                    reinterpret_cast<gran_t *>(Jout + row0 * (6 * N)), rows_here, lane);
+            TileStage<real, 6 * N>::drain(so, Jout + row0 * (6 * N), rows_here, lane);
             __syncwarp();
         }
     }
+    cp_async_wait_all();
 }
 
 // ------------------------------------------------------------------ backward walk: end-effector-frame Jacobian (+ pose)
 // Reference _ETS_jacobe, methods.cpp:219-316: U starts at the tool and is left-multiplied by
 // each ET walking from the tip to the base; column j is read off U before joint j is applied.
 template <typename real, int N, bool WT>
-__global__ void __launch_bounds__(B2K_THREADS)
+__global__ void __launch_bounds__(B2K_THREADS, FkjBounds<real, N, true>::MINB)
 k_fkj_backward(const __grid_constant__ ChainP<real, N> P, const real *__restrict__ q, long long nrows, int ldq,
-               float inv_ldq, real *__restrict__ Tout, real *__restrict__ Jout, int warp_smem_bytes)
+               float inv_ldq, int qmode, real *__restrict__ Tout, real *__restrict__ Jout, int warp_smem_bytes,
+               int q_bytes)
 {
-    typedef typename Granule<real>::type gran_t;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     unsigned char *wbase = smem_raw + (size_t)warp * warp_smem_bytes;
     real *sq = reinterpret_cast<real *>(wbase);
-    real *so = reinterpret_cast<real *>(wbase);
-    const int ldqp = ldq | 1;
+    unsigned char *so = wbase + q_bytes;
+    const int ldqs = qmode ? ldq : (ldq | 1);
     const long long ntiles = (nrows + 31) >> 5;
+    const long long tstride = (long long)gridDim.x * B2K_WARPS_PER_BLOCK;
 
-    for (long long tile = (long long)blockIdx.x * B2K_WARPS_PER_BLOCK + warp; tile < ntiles;
-         tile += (long long)gridDim.x * B2K_WARPS_PER_BLOCK) {
+    long long tile = (long long)blockIdx.x * B2K_WARPS_PER_BLOCK + warp;
+    if (tile < ntiles) {
+        const long long row0 = tile << 5;
+        load_q_tile<real>(sq, q + row0 * ldq, (int)((nrows - row0) < 32 ? (nrows - row0) : 32), ldq, inv_ldq, qmode, lane);
+    }
+    for (; tile < ntiles; tile += tstride) {
         const long long row0 = tile << 5;
         const int rows_here = (int)((nrows - row0) < 32 ? (nrows - row0) : 32);
-        stage_q_tile<real>(sq, q + row0 * ldq, rows_here, ldq, inv_ldq, lane);
+        cp_async_wait_all();
         __syncwarp();
-        const real *myq = sq + (lane < rows_here ? lane : 0) * ldqp;
+        const real *myq = sq + (lane < rows_here ? lane : 0) * ldqs;
 
         Pose<real> U;
-        real Je[N][6];
+        real row[6 * N]; // Je, row-major 6 x N
         pose_from_const(U, P.A[N]);
 #pragma unroll
         for (int j = N - 1; j >= 0; j--) {
             const int ax = P.axis[j];
             const real sg = P.flip[j] ? (real)-1 : (real)1;
+            real col[6];
             switch (ax) {
-            case B2K_RX: je_col_rev<real, 0>(U, sg, Je[j]); break;
-            case B2K_RY: je_col_rev<real, 1>(U, sg, Je[j]); break;
-            case B2K_RZ: je_col_rev<real, 2>(U, sg, Je[j]); break;
-            case B2K_TX: je_col_pri<real, 0>(U, sg, Je[j]); break;
-            case B2K_TY: je_col_pri<real, 1>(U, sg, Je[j]); break;
-            default: je_col_pri<real, 2>(U, sg, Je[j]); break;
+            case B2K_RX: je_col_rev<real, 0>(U, sg, col); break;
+            case B2K_RY: je_col_rev<real, 1>(U, sg, col); break;
+            case B2K_RZ: je_col_rev<real, 2>(U, sg, col); break;
+            case B2K_TX: je_col_pri<real, 0>(U, sg, col); break;
+            case B2K_TY: je_col_pri<real, 1>(U, sg, col); break;
+            default: je_col_pri<real, 2>(U, sg, col); break;
             }
-            pose_joint_left(U, ax, sg * myq[P.jidx[j]]);
+#pragma unroll
+            for (int k = 0; k < 6; k++) row[k * N + j] = col[k];
+            pose_joint_left(U, ax, sg * myq[P.jidx[j]], P.trig);
             pose_mul_const_left(U, P.A[j], P.akind[j]);
         }
         __syncwarp();
-
+        {
+            const long long nt = tile + tstride;
+            if (nt < ntiles) {
+                const long long r0 = nt << 5;
+                load_q_tile<real>(sq, q + r0 * ldq, (int)((nrows - r0) < 32 ? (nrows - r0) : 32), ldq, inv_ldq, qmode, lane);
+            }
+        }
         if (WT) {
             Pose<real> Tb = U;
             if (P.has_base) pose_mul_const_left(Tb, P.B, AK_GEN | AK_TX | AK_TY | AK_TZ);
-            constexpr int S = stage_stride(granules<real>(16)) * Granule<real>::PER;
-            real *row = so + lane * S;
-#pragma unroll
-            for (int i = 0; i < 3; i++) {
-                row[i * 4 + 0] = Tb.c0[i];
-                row[i * 4 + 1] = Tb.c1[i];
-                row[i * 4 + 2] = Tb.c2[i];
-                row[i * 4 + 3] = Tb.p[i];
-            }
-            row[12] = (real)0; row[13] = (real)0; row[14] = (real)0; row[15] = (real)1;
+            real trow[16];
+            pose_to_row(Tb, trow);
+            TileStage<real, 16>::put_row(so, lane, trow);
             __syncwarp();
-            drain_tile<real, granules<real>(16)>(reinterpret_cast<const gran_t *>(so),
-                                                 reinterpret_cast<gran_t *>(Tout + row0 * 16), rows_here, lane);
+            TileStage<real, 16>::drain(so, Tout + row0 * 16, rows_here, lane);
             __syncwarp();
         }
-        {
-            constexpr int S = stage_stride(granules<real>(6 * N)) * Granule<real>::PER;
-            real *row = so + lane * S;
-#pragma unroll
-            for (int j = 0; j < N; j++)
-#pragma unroll
-                for (int k = 0; k < 6; k++) row[k * N + j] = Je[j][k];
-            __syncwarp();
-            drain_tile<real, granules<real>(6 * N)>(reinterpret_cast<const gran_t *>(so),
-                                                    reinterpret_cast<gran_t *>(Jout + row0 * (6 * N)), rows_here, lane);
-            __syncwarp();
-        }
+        TileStage<real, 6 * N>::put_row(so, lane, row);
+        __syncwarp();
+        TileStage<real, 6 * N>::drain(so, Jout + row0 * (6 * N), rows_here, lane);
+        __syncwarp();
     }
+    cp_async_wait_all();
 }
 
 // ------------------------------------------------------------------ launcher
 enum { FKJ_T = 1, FKJ_J0 = 2, FKJ_JE = 4 };
+
+inline int b2k_gcd(int a, int b) { return b ? b2k_gcd(b, a % b) : a; }
+
+// can the q tile be kept as an exact image in shared memory (16-byte cp.async path)?
+template <typename real>
+inline int fkj_qmode(const void *q, int ldq)
+{
+    if (((uintptr_t)q) & 15) return 0;
+    const int slots = sizeof(real) == 8 ? 16 : 32; // distinct banks-worth of elements per wavefront
+    return b2k_gcd(ldq, slots) <= 2 ? 1 : 0;
+}
 
 template <typename real, int N>
 int fkj_launch_n(const b2k_chain_s *c, int mode, const real *q, long long nrows, int ldq, const double *base,
@@ -506,11 +614,18 @@ int fkj_launch_n(const b2k_chain_s *c, int mode, const real *q, long long nrows,
     const bool wt = mode & FKJ_T, wj0 = mode & FKJ_J0, wje = mode & FKJ_JE;
     // pose-only: base folded into the first constant; fused: base applied to the pose at the end
     b2k_fill_chain<real, N>(c, base, tool, /*base_into_chain=*/(wt && !wj0 && !wje), P);
-    const size_t wsm = (fkj_warp_smem<real>(N, ldq, wt, wj0 || wje) + 15) & ~(size_t)15;
+    const size_t qb = fkj_q_bytes<real>(ldq);
+    const size_t wsm = (fkj_warp_smem<real, N>(ldq, wt, wj0 || wje) + 15) & ~(size_t)15;
     const size_t smem = wsm * B2K_WARPS_PER_BLOCK;
     const long long ntiles = (nrows + 31) / 32;
     const long long nblk_needed = (ntiles + B2K_WARPS_PER_BLOCK - 1) / B2K_WARPS_PER_BLOCK;
     const float inv_ldq = 1.0f / (float)ldq;
+    const int qmode = fkj_qmode<real>(q, ldq);
+    if (wt && (((uintptr_t)T) & 15)) { b2k_set_error("fkj: T must be 16-byte aligned"); return B2K_ERR_INVALID; }
+    if ((wj0 || wje) && (((uintptr_t)J) % TileStage<real, 6 * N>::UB)) {
+        b2k_set_error("fkj: J must be %d-byte aligned", TileStage<real, 6 * N>::UB);
+        return B2K_ERR_INVALID;
+    }
 
     auto launch = [&](auto kern) -> int {
         int per_sm = b2k_blocks_per_sm((const void *)kern, B2K_THREADS, smem);
@@ -518,7 +633,7 @@ int fkj_launch_n(const b2k_chain_s *c, int mode, const real *q, long long nrows,
         long long grid = (long long)b2k_num_sms() * per_sm;
         if (grid > nblk_needed) grid = nblk_needed;
         if (grid < 1) grid = 1;
-        kern<<<(unsigned)grid, B2K_THREADS, smem, st>>>(P, q, nrows, ldq, inv_ldq, T, J, (int)wsm);
+        kern<<<(unsigned)grid, B2K_THREADS, smem, st>>>(P, q, nrows, ldq, inv_ldq, qmode, T, J, (int)wsm, (int)qb);
         b2k_count_launch();
         B2K_CUDA(cudaGetLastError());
         return B2K_OK;

@@ -30,6 +30,7 @@ struct RneP {
     int prismatic[N];
     real grav[3];
     real fext[6];
+    TrigC<real> trig;
 };
 
 template <typename real>
@@ -71,31 +72,39 @@ struct LinkRot {
 };
 
 template <typename real, int N, bool MDH>
-__global__ void __launch_bounds__(B2K_THREADS)
+__global__ void __launch_bounds__(B2K_THREADS, (sizeof(real) == 4 || N <= 6) ? 4 : 3)
 k_rne(const __grid_constant__ RneP<real, N> P, const real *__restrict__ q, const real *__restrict__ qd,
-      const real *__restrict__ qdd, long long nrows, real *__restrict__ tau, int warp_smem_bytes)
+      const real *__restrict__ qdd, long long nrows, real *__restrict__ tau, int warp_smem_bytes, int in_bytes,
+      int qmode)
 {
-    typedef typename Granule<real>::type gran_t;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    constexpr int LDP = N | 1; // odd row stride in elements
-    real *sq = reinterpret_cast<real *>(smem_raw + (size_t)warp * warp_smem_bytes);
-    real *sqd = sq + 32 * LDP;
-    real *sqdd = sqd + 32 * LDP;
-    real *sout = sqdd + 32 * LDP;
+    unsigned char *wbase = smem_raw + (size_t)warp * warp_smem_bytes;
+    real *sq = reinterpret_cast<real *>(wbase);
+    real *sqd = reinterpret_cast<real *>(wbase + in_bytes);
+    real *sqdd = reinterpret_cast<real *>(wbase + 2 * in_bytes);
+    unsigned char *sout = wbase + 3 * in_bytes;
+    const int lds = qmode ? N : (N | 1); // smem row stride of the input tiles
     const long long ntiles = (nrows + 31) >> 5;
+    const long long tstride = (long long)gridDim.x * B2K_WARPS_PER_BLOCK;
     const float inv_n = 1.0f / (float)N;
 
-    for (long long tile = (long long)blockIdx.x * B2K_WARPS_PER_BLOCK + warp; tile < ntiles;
-         tile += (long long)gridDim.x * B2K_WARPS_PER_BLOCK) {
+    auto load_inputs = [&](long long t) {
+        const long long r0 = t << 5;
+        const int rh = (int)((nrows - r0) < 32 ? (nrows - r0) : 32);
+        load_q_tile<real>(sq, q + r0 * N, rh, N, inv_n, qmode, lane);
+        load_q_tile<real>(sqd, qd + r0 * N, rh, N, inv_n, qmode, lane);
+        load_q_tile<real>(sqdd, qdd + r0 * N, rh, N, inv_n, qmode, lane);
+    };
+    long long tile = (long long)blockIdx.x * B2K_WARPS_PER_BLOCK + warp;
+    if (tile < ntiles) load_inputs(tile);
+    for (; tile < ntiles; tile += tstride) {
         const long long row0 = tile << 5;
         const int rows_here = (int)((nrows - row0) < 32 ? (nrows - row0) : 32);
-        stage_q_tile<real>(sq, q + row0 * N, rows_here, N, inv_n, lane);
-        stage_q_tile<real>(sqd, qd + row0 * N, rows_here, N, inv_n, lane);
-        stage_q_tile<real>(sqdd, qdd + row0 * N, rows_here, N, inv_n, lane);
+        cp_async_wait_all();
         __syncwarp();
-        const int myrow = (lane < rows_here ? lane : 0) * LDP;
+        const int myrow = (lane < rows_here ? lane : 0) * lds;
         const real *mq = sq + myrow, *mqd = sqd + myrow, *mqdd = sqdd + myrow;
 
         // stash for the backward recursion
@@ -110,7 +119,7 @@ k_rne(const __grid_constant__ RneP<real, N> P, const real *__restrict__ q, const
             const bool pris = P.prismatic[j] != 0;
             real st, ct, d;
             if (!pris) {
-                b2k_sincos<real>(mq[j] + P.offset[j], &st, &ct);
+                b2k_sincos(mq[j] + P.offset[j], P.trig, &st, &ct);
                 d = P.D[j];
             } else {
                 st = P.st0[j]; ct = P.ct0[j];
@@ -277,21 +286,15 @@ k_rne(const __grid_constant__ RneP<real, N> P, const real *__restrict__ q, const
             tq[j] = t;
         }
         // ---------------- stage tau and write it back coalesced
-        real *orow = sout + (size_t)lane * LDP;
-#pragma unroll
-        for (int j = 0; j < N; j++) orow[j] = tq[j];
+        // the inputs of this tile are dead (tq holds the results): prefetch the next tile behind the drain
         __syncwarp();
-        {
-            const int cnt = rows_here * N;
-            real *gt = tau + row0 * N;
-            for (int i = lane; i < cnt; i += 32) {
-                int r = __float2int_rz(((float)i + 0.5f) * inv_n);
-                int c = i - r * N;
-                gt[i] = sout[r * LDP + c];
-            }
-        }
+        if (tile + tstride < ntiles) load_inputs(tile + tstride);
+        TileStage<real, N>::put_row(sout, lane, tq);
+        __syncwarp();
+        TileStage<real, N>::drain(sout, tau + row0 * N, rows_here, lane);
         __syncwarp();
     }
+    cp_async_wait_all();
 }
 
 template <typename real, int N>
@@ -321,8 +324,12 @@ int rne_launch_n(const b2k_rne_s *r, const real *q, const real *qd, const real *
     }
     for (int k = 0; k < 3; k++) P.grav[k] = (real)grav[k];
     for (int k = 0; k < 6; k++) P.fext[k] = fext ? (real)fext[k] : (real)0;
-    const size_t wsm = ((size_t)4 * 32 * (N | 1) * sizeof(real) + 15) & ~(size_t)15;
+    b2k_fill_trig<real>(P.trig);
+    const size_t inb = fkj_q_bytes<real>(N);
+    const size_t wsm = (3 * inb + (size_t)TileStage<real, N>::BYTES + 15) & ~(size_t)15;
     const size_t smem = wsm * B2K_WARPS_PER_BLOCK;
+    const int qmode = (fkj_qmode<real>(q, N) && fkj_qmode<real>(qd, N) && fkj_qmode<real>(qdd, N)) ? 1 : 0;
+    if (((uintptr_t)tau) % TileStage<real, N>::UB) { b2k_set_error("rne: tau must be %d-byte aligned", TileStage<real, N>::UB); return B2K_ERR_INVALID; }
     const long long ntiles = (nrows + 31) / 32;
     const long long nblk_needed = (ntiles + B2K_WARPS_PER_BLOCK - 1) / B2K_WARPS_PER_BLOCK;
     auto launch = [&](auto kern) -> int {
@@ -331,7 +338,7 @@ int rne_launch_n(const b2k_rne_s *r, const real *q, const real *qd, const real *
         long long grid = (long long)b2k_num_sms() * per_sm;
         if (grid > nblk_needed) grid = nblk_needed;
         if (grid < 1) grid = 1;
-        kern<<<(unsigned)grid, B2K_THREADS, smem, st>>>(P, q, qd, qdd, nrows, tau, (int)wsm);
+        kern<<<(unsigned)grid, B2K_THREADS, smem, st>>>(P, q, qd, qdd, nrows, tau, (int)wsm, (int)inb, qmode);
         b2k_count_launch();
         B2K_CUDA(cudaGetLastError());
         return B2K_OK;

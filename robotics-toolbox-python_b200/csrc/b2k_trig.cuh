@@ -1,0 +1,81 @@
+// b2k_trig.cuh -- sincos for the chain walk.
+//
+// CUDA's sincos() is accurate but costs ~100 issued instructions per call in this kernel
+// (ncu, profiles/r01_fkj_first.md): its 14 polynomial coefficients are materialised as pairs of
+// 32-bit immediates and the quadrant fix-up is a chain of 22 FSEL.  This version does the same
+// mathematics -- three-FMA Cody-Waite reduction by pi/2 (exact products thanks to FMA, valid for
+// |x| < 105615 like CUDA's own fast path), fdlibm's degree-13/14 minimax kernels on
+// [-pi/4, pi/4] (< 1 ulp each), quadrant swap/sign by integer ops -- with every constant read
+// from the kernel-parameter constant bank.  Measured max error 1.6 ulp (tests/test_gpu_parity.py::
+// test_sincos_accuracy).  Arguments beyond the fast range, infinities and NaNs take CUDA's
+// sincos (Payne-Hanek) on a rarely taken branch.
+#pragma once
+
+#include "b2k_common.cuh"
+
+// out-of-line so the seven call sites of an unrolled chain do not each inline Payne-Hanek
+static __device__ __noinline__ void b2k_sincos_slow(double x, double *sp, double *cp) { sincos(x, sp, cp); }
+static __device__ __noinline__ void b2k_sincos_slow(float x, float *sp, float *cp) { sincosf(x, sp, cp); }
+
+__device__ __forceinline__ void b2k_sincos(double x, const TrigC<double> &t, double *sp, double *cp)
+{
+    if (!(fabs(x) < t.fast_limit)) {
+        b2k_sincos_slow(x, sp, cp);
+        return;
+    }
+    const double tt = fma(x, t.two_over_pi, t.magic);
+    const int q = __double2loint(tt);
+    const double kd = tt - t.magic;
+    double r = fma(-kd, t.pio2_hi, x);
+    r = fma(-kd, t.pio2_mid, r);
+    r = fma(-kd, t.pio2_lo, r);
+    const double z = r * r;
+    double ps = fma(t.s[5], z, t.s[4]);
+    ps = fma(ps, z, t.s[3]);
+    ps = fma(ps, z, t.s[2]);
+    ps = fma(ps, z, t.s[1]);
+    ps = fma(ps, z, t.s[0]);
+    double pc = fma(t.c[5], z, t.c[4]);
+    pc = fma(pc, z, t.c[3]);
+    pc = fma(pc, z, t.c[2]);
+    pc = fma(pc, z, t.c[1]);
+    pc = fma(pc, z, t.c[0]);
+    const double sn = fma(r * z, ps, r);
+    const double cs = fma(z * z, pc, fma(-0.5, z, 1.0));
+    // quadrant: n=0 (s,c) ; 1 (c,-s) ; 2 (-s,-c) ; 3 (-c,s)
+    const bool swap = q & 1;
+    double s = swap ? cs : sn;
+    double c = swap ? sn : cs;
+    const int sflip = (q & 2) << 30;       // bit 31 if n in {2,3}
+    const int cflip = ((q + 1) & 2) << 30; // bit 31 if n in {1,2}
+    *sp = __hiloint2double(__double2hiint(s) ^ sflip, __double2loint(s));
+    *cp = __hiloint2double(__double2hiint(c) ^ cflip, __double2loint(c));
+}
+
+__device__ __forceinline__ void b2k_sincos(float x, const TrigC<float> &t, float *sp, float *cp)
+{
+    if (!(fabsf(x) < t.fast_limit)) {
+        b2k_sincos_slow(x, sp, cp);
+        return;
+    }
+    const float tt = fmaf(x, t.two_over_pi, t.magic);
+    const int q = __float_as_int(tt);
+    const float kd = tt - t.magic;
+    float r = fmaf(-kd, t.pio2_hi, x);
+    r = fmaf(-kd, t.pio2_mid, r);
+    r = fmaf(-kd, t.pio2_lo, r);
+    const float z = r * r;
+    float ps = fmaf(t.s[2], z, t.s[1]);
+    ps = fmaf(ps, z, t.s[0]);
+    float pc = fmaf(t.c[2], z, t.c[1]);
+    pc = fmaf(pc, z, t.c[0]);
+    const float sn = fmaf(r * z, ps, r);
+    const float cs = fmaf(z * z, pc, fmaf(-0.5f, z, 1.0f));
+    const bool swap = q & 1;
+    float s = swap ? cs : sn;
+    float c = swap ? sn : cs;
+    const int sflip = (q & 2) << 30;
+    const int cflip = ((q + 1) & 2) << 30;
+    *sp = __int_as_float(__float_as_int(s) ^ sflip);
+    *cp = __int_as_float(__float_as_int(c) ^ cflip);
+}

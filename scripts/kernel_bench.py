@@ -1,0 +1,138 @@
+#!/usr/bin/env python3
+"""Device-timed micro-benchmarks of every hot-path kernel (one JSON line per case).
+
+Each case: W warm-up launches, then K launches bracketed by CUDA events on the launching stream;
+inputs rotate over enough distinct batches to exceed the 126 MB L2.  `frac` is algorithmic bytes
+ / time / MEASURED_PEAKS hbm_gbs.  Usage:  python scripts/kernel_bench.py [--rows 1000000] [--only substr]
+"""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+sys.path.insert(0, ROOT)
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+import b2kin as rtb  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--rows", type=int, default=1_000_000)
+ap.add_argument("--ik-rows", type=int, default=100_000)
+ap.add_argument("--steps", type=int, default=50)
+ap.add_argument("--warmup", type=int, default=10)
+ap.add_argument("--only", default="")
+ap.add_argument("--variant", type=int, default=0)
+args = ap.parse_args()
+try:
+    PEAK = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+except Exception:
+    PEAK = 6650.0
+dev = torch.device("cuda", 0)
+torch.cuda.set_device(0)
+if args.variant:
+    rtb.set_variant(args.variant)
+
+
+def timeit(fn, nbuf):
+    for i in range(args.warmup):
+        fn(i % nbuf)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        fn(i % nbuf)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / args.steps
+
+
+def report(name, ms, rows, bytes_per_row, extra=None):
+    gbs = bytes_per_row * rows / (ms * 1e-3) / 1e9
+    d = {"case": name, "rows": rows, "ms": round(ms, 5), "rows_per_s": rows / (ms * 1e-3), "GBps": round(gbs, 1),
+         "frac_of_hbm": round(gbs / PEAK, 4), "bytes_per_row": bytes_per_row}
+    if extra:
+        d.update(extra)
+    print(json.dumps(d), flush=True)
+
+
+def want(name):
+    return args.only in name
+
+
+N = args.rows
+rng = np.random.default_rng(0)
+tdt = {np.float32: torch.float32, np.float64: torch.float64}
+
+for robot_name, robot in (("panda", rtb.models.Panda()), ("ur10", rtb.models.UR10())):
+    ets = robot.ets()
+    n = ets.n
+    for dt in (np.float64, np.float32):
+        es = np.dtype(dt).itemsize
+        tag = f"{robot_name}_{'f64' if dt == np.float64 else 'f32'}"
+        nbuf = max(2, int(np.ceil(300e6 / (N * n * es))))
+        nbuf = min(nbuf, 8)
+        qs = [torch.from_numpy(rng.uniform(-np.pi, np.pi, (N, n)).astype(dt)).to(dev) for _ in range(nbuf)]
+        T = torch.empty((N, 4, 4), dtype=tdt[dt], device=dev)
+        J = torch.empty((N, 6, n), dtype=tdt[dt], device=dev)
+        L = rtb._lib.lib()
+        ch = ets._chain
+        st = torch.cuda.current_stream().cuda_stream
+        code = rtb._lib.F64 if dt == np.float64 else rtb._lib.F32
+        if want(f"fkine_{tag}"):
+            report(f"fkine_{tag}", timeit(lambda i: L.b2k_fkine(ch, code, qs[i].data_ptr(), N, n, None, None, T.data_ptr(), st), nbuf), N, (n + 16) * es)
+        if want(f"fkine_jacob0_{tag}"):
+            report(f"fkine_jacob0_{tag}", timeit(lambda i: L.b2k_fkine_jacob0(ch, code, qs[i].data_ptr(), N, n, None, None, T.data_ptr(), J.data_ptr(), st), nbuf), N, (n + 16 + 6 * n) * es)
+        if want(f"jacob0_{tag}") and robot_name == "panda":
+            report(f"jacob0_{tag}", timeit(lambda i: L.b2k_jacob0(ch, code, qs[i].data_ptr(), N, n, None, J.data_ptr(), st), nbuf), N, (n + 6 * n) * es)
+        if want(f"jacobe_{tag}") and robot_name == "panda":
+            report(f"jacobe_{tag}", timeit(lambda i: L.b2k_jacobe(ch, code, qs[i].data_ptr(), N, n, None, J.data_ptr(), st), nbuf), N, (n + 6 * n) * es)
+        del qs, T, J
+
+puma = rtb.models.Puma560()
+for dt in (np.float64, np.float32):
+    tag = "f64" if dt == np.float64 else "f32"
+    if not want(f"rne_puma_{tag}"):
+        continue
+    es = np.dtype(dt).itemsize
+    nbuf = 3
+    ql = puma.qlim
+    bufs = [tuple(torch.from_numpy(a.astype(dt)).to(dev) for a in (rng.uniform(ql[0], ql[1], (N, 6)), rng.normal(size=(N, 6)), rng.normal(size=(N, 6)))) for _ in range(nbuf)]
+    tau = torch.empty((N, 6), dtype=tdt[dt], device=dev)
+    puma.rne(*bufs[0])  # builds the handle
+    L = rtb._lib.lib()
+    st = torch.cuda.current_stream().cuda_stream
+    code = rtb._lib.F64 if dt == np.float64 else rtb._lib.F32
+    g = np.ascontiguousarray(-puma.gravity)
+    report(f"rne_puma_{tag}", timeit(lambda i: L.b2k_rne(puma._rne_ob, code, bufs[i][0].data_ptr(), bufs[i][1].data_ptr(), bufs[i][2].data_ptr(), N, rtb._lib.dptr(g), None, tau.data_ptr(), st), nbuf), N, 24 * es)
+    del bufs, tau
+
+# IK (config 4): reachable targets, chan
+if want("ik_"):
+    from oracle import oracle as orc
+
+    panda = rtb.models.Panda().ets()
+    M = args.ik_rows
+    qs = np.random.default_rng(2).uniform(-np.pi, np.pi, (M, 7))
+    Tep = orc.Chain(panda.describe()).fkine(qs)
+    for dt in (np.float32, np.float64):
+        tag = "f64" if dt == np.float64 else "f32"
+        Td = torch.from_numpy(Tep.astype(dt)).to(dev)
+        for k, jl in ((0.1, False), (1.0, True)):
+            name = f"ik_lm_panda_{tag}_chan{k}_jl{int(jl)}"
+            if not want(name):
+                continue
+            out = {}
+
+            def run(i):
+                out["r"] = panda.ik_LM(Td, joint_limits=jl, k=k, seed=5 + i)
+
+            steps, args.steps = args.steps, 5
+            wu, args.warmup = args.warmup, 1
+            ms = timeit(run, 1 << 30)
+            args.steps, args.warmup = steps, wu
+            q, s, it, sr, E = out["r"]
+            report(name, ms, M, (16 + 7 + 4) * np.dtype(dt).itemsize,
+                   {"solves_per_s": M / (ms * 1e-3), "success": float(s.float().mean()), "mean_it": float(it.float().mean()),
+                    "max_it": int(it.max()), "mean_searches": float(sr.float().mean()), "max_searches": int(sr.max())})

@@ -271,14 +271,47 @@ def test_sizes_and_ragged_tiles(N):
     e = rtb.models.Panda().ets()
     C = orc.Chain(e.describe())
     Q = np.random.default_rng(N).uniform(-np.pi, np.pi, (N, 7))
+    sq = (lambda a: a[0]) if N == 1 else (lambda a: a)  # a (1,n) q is ONE configuration (fknm.cpp:970-975)
     T, J = e.fkine_jacob0(dev(Q))
-    np.testing.assert_allclose(host(T), C.fkine(Q), rtol=1e-10, atol=1e-12)
-    np.testing.assert_allclose(host(J), C.jacob0(Q), rtol=1e-10, atol=1e-12)
-    np.testing.assert_allclose(host(e.jacobe(dev(Q))), C.jacobe(Q), rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(host(T), sq(C.fkine(Q)), rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(host(J), sq(C.jacob0(Q)), rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(host(e.jacobe(dev(Q))), sq(C.jacobe(Q)), rtol=1e-10, atol=1e-12)
+    for dt in (np.float32,):
+        Qr = ref_inputs(Q, dt)
+        T32, J32 = e.fkine_jacob0(dev(Q, dt))
+        np.testing.assert_allclose(host(T32), sq(C.fkine(Qr)), **TOL[dt])
+        np.testing.assert_allclose(host(J32), sq(C.jacob0(Qr)), **TOL[dt])
     puma = rtb.models.Puma560()
     q, qd, qdd = Q[:, :6], np.cos(Q[:, :6]), np.sin(Q[:, :6])
-    np.testing.assert_allclose(host(puma.rne(dev(q), dev(qd), dev(qdd))),
-                               orc.rne(6, 0, puma._pack_rne(), -puma.gravity, q, qd, qdd), rtol=1e-10, atol=1e-10)
+    want = orc.rne(6, 0, puma._pack_rne(), -puma.gravity, q, qd, qdd)
+    if N == 1:  # rne keeps (N, n) for 2-D input (DHRobot.py:1416-1424)
+        np.testing.assert_allclose(host(puma.rne(dev(q), dev(qd), dev(qdd))), want, rtol=1e-10, atol=1e-10)
+    else:
+        np.testing.assert_allclose(host(puma.rne(dev(q), dev(qd), dev(qdd))), want, rtol=1e-10, atol=1e-10)
+
+
+def test_sincos_accuracy():
+    """The in-house sincos (csrc/b2k_trig.cuh) against extended-precision libm."""
+    L = rtb._lib.lib()
+    rng = np.random.default_rng(0)
+    x = np.concatenate([rng.uniform(-np.pi, np.pi, 400000), rng.uniform(-100, 100, 200000),
+                        rng.uniform(-1e5, 1e5, 200000), rng.uniform(-1e9, 1e9, 1000),
+                        np.array([0.0, -0.0, np.pi / 2, np.pi, -np.pi, 1e-300, 105614.9, 105615.1, 1e22])])
+    ld = np.longdouble
+    for dt, lim in ((np.float64, 2.0), (np.float32, 2.5)):
+        xd = dev(x, dt)
+        s, c = torch.empty_like(xd), torch.empty_like(xd)
+        rtb._lib.check(L.b2k_selftest_sincos(0 if dt == np.float32 else 1, xd.data_ptr(), xd.numel(), s.data_ptr(),
+                                             c.data_ptr(), torch.cuda.current_stream().cuda_stream))
+        xr = host(xd).astype(ld)
+        rs, rc = np.sin(xr), np.cos(xr)
+        eps = np.finfo(dt).eps
+        # error in ulps of the result, with an absolute floor of one ulp(1) near the zeros of sin / cos
+        us = np.abs(host(s).astype(ld) - rs) / np.maximum(np.abs(rs) * eps, ld(eps) * eps)
+        uc = np.abs(host(c).astype(ld) - rc) / np.maximum(np.abs(rc) * eps, ld(eps) * eps)
+        small = np.abs(xr) < 100
+        assert float(us[small].max()) < lim and float(uc[small].max()) < lim, (dt, float(us[small].max()), float(uc[small].max()))
+        assert float(np.abs(host(s).astype(ld) - rs).max()) < 4 * eps and float(np.abs(host(c).astype(ld) - rc).max()) < 4 * eps
 
 
 def test_empty_batch():
