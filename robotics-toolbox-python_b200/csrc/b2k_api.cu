@@ -89,7 +89,7 @@ extern "C" int b2k_version(void) { return B2K_VERSION; }
 extern "C" int64_t b2k_launch_count(void) { return (int64_t)g_launches.load(); }
 extern "C" int b2k_set_variant(int v)
 {
-    if (v != 0 && v != 1) { b2k_set_error("b2k_set_variant: variant must be 0 or 1"); return B2K_ERR_INVALID; }
+    if (v < 0 || v > 4) { b2k_set_error("b2k_set_variant: variant must be 0..4"); return B2K_ERR_INVALID; }
     g_variant.store(v);
     return B2K_OK;
 }

@@ -113,6 +113,11 @@ extern "C" int b2k_chain_create(int m, const int32_t *isjoint, const int32_t *ax
         }
     }
     memcpy(c->A[n], acc, sizeof(acc)); // tail constant
+    c->dh_like = c->all_rz;
+    for (int k = 1; k < n && c->dh_like; k++) {
+        const int rk = b2k_classify34(c->A[k]) & AK_ROTMASK;
+        if (rk != AK_IDENT && rk != AK_RX) c->dh_like = 0;
+    }
     c->q_width = qw;
     *out = c;
     return B2K_OK;

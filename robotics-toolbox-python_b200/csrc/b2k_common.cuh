@@ -8,6 +8,9 @@
 
 #define B2K_WARPS_PER_BLOCK 4
 #define B2K_THREADS (32 * B2K_WARPS_PER_BLOCK)
+#ifndef B2K_L2_PREFETCH_TILES
+#define B2K_L2_PREFETCH_TILES 4 // how many of a warp's tiles ahead its q block is prefetched into L2
+#endif
 
 // Structure classes of a folded SE(3) constant A = [Ra | ta] (exact 0/1 pattern tests on the
 // host, so the specialised device paths are bit-identical to the general product).
@@ -76,7 +79,7 @@ struct ChainP {
     int flip[N];  // 0 / 1
     int jidx[N];  // column of q
     int has_base; // 0: B is identity
-    int all_rz;   // every joint is an unflipped Rz (DH robots, Panda): switch-free fast path
+    int all_rz;   // every joint is an unflipped Rz
     TrigC<real> trig;
 };
 
@@ -90,6 +93,7 @@ struct b2k_chain_s {
     double qlim_l[B2K_MAX_JOINTS];
     double qlim_h[B2K_MAX_JOINTS];
     int all_rz;
+    int dh_like;      // all_rz and every inter-joint constant A_1..A_{n-1} has the Rx form (or is a pure translation)
     int dense_jindex; // jidx[j] == j for all j
 };
 

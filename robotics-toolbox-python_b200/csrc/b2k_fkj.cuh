@@ -241,24 +241,56 @@ __device__ __forceinline__ void je_col_pri(const Pose<real> &U, real sg, real *c
 // Jacobian column is z_j x (p_e - p_j) | z_j (revolute) or z_j | 0 (prismatic).
 // getq(j, col) returns this row's coordinate of joint j, stored in column col of q (shared
 // memory in the FK kernels; registers, indexed by the compile-time j, in the IK kernel).
-template <typename real, int N, bool WJ, bool ALLRZ, typename GetQ>
+// PROF selects the code shape (uniform for the whole grid, decided on the host):
+//   1 "DH-like": every joint is an unflipped Rz and every inter-joint constant has the Rx form
+//     [[1,0,0],[0,a,b],[0,c,d]] (+ translation) -- standard / modified DH robots and the Panda ETS.
+//     Straight-line code: no switches (the compiler if-converts small uniform switches into
+//     select chains, ncu profiles/r01_fkj_v2.md), all n sincos evaluated as one interleaved batch.
+//   0 generic: any axis / flip / constant, runtime (uniform) switches.
+template <typename real, int N, bool WJ, int PROF, typename GetQ>
 __device__ __forceinline__ void chain_forward(const ChainP<real, N> &P, GetQ getq, Pose<real> &T,
                                               real (*zj)[3], real (*pj)[3])
 {
-    pose_from_const(T, P.A[0]);
+    if constexpr (PROF == 1) {
+        real eta[N], sn[N], cs[N];
 #pragma unroll
-    for (int j = 0; j < N; j++) {
-        if (j > 0) pose_mul_const_right(T, P.A[j], P.akind[j]);
-        if (ALLRZ) {
-            real eta = getq(j, P.jidx[j]);
+        for (int j = 0; j < N; j++) eta[j] = getq(j, P.jidx[j]);
+        b2k_sincos_batch<real, N>(eta, P.trig, sn, cs);
+        pose_from_const(T, P.A[0]);
+#pragma unroll
+        for (int j = 0; j < N; j++) {
+            if (j > 0) {
+                const real *A = P.A[j];
+#pragma unroll
+                for (int i = 0; i < 3; i++) {
+                    T.p[i] = fma(T.c0[i], A[3], fma(T.c1[i], A[7], fma(T.c2[i], A[11], T.p[i])));
+                    real a = T.c1[i], b = T.c2[i];
+                    T.c1[i] = fma(a, A[5], b * A[9]);
+                    T.c2[i] = fma(a, A[6], b * A[10]);
+                }
+            }
             if (WJ) {
 #pragma unroll
                 for (int i = 0; i < 3; i++) { zj[j][i] = T.c2[i]; pj[j][i] = T.p[i]; }
             }
-            real s, c;
-            b2k_sincos(eta, P.trig, &s, &c);
-            rot_cols(T.c0, T.c1, s, c);
-        } else {
+            rot_cols(T.c0, T.c1, sn[j], cs[j]);
+        }
+        if (P.akind[N] != AK_IDENT) { // tail constant (tool folded in): any SE(3)
+            const real *A = P.A[N];
+#pragma unroll
+            for (int i = 0; i < 3; i++) {
+                real a = T.c0[i], b = T.c1[i], c = T.c2[i];
+                T.p[i] = fma(a, A[3], fma(b, A[7], fma(c, A[11], T.p[i])));
+                T.c0[i] = fma(a, A[0], fma(b, A[4], c * A[8]));
+                T.c1[i] = fma(a, A[1], fma(b, A[5], c * A[9]));
+                T.c2[i] = fma(a, A[2], fma(b, A[6], c * A[10]));
+            }
+        }
+    } else {
+        pose_from_const(T, P.A[0]);
+#pragma unroll
+        for (int j = 0; j < N; j++) {
+            if (j > 0) pose_mul_const_right(T, P.A[j], P.akind[j]);
             const int ax = P.axis[j];
             real eta = getq(j, P.jidx[j]);
             const real sg = P.flip[j] ? (real)-1 : (real)1;
@@ -274,18 +306,18 @@ __device__ __forceinline__ void chain_forward(const ChainP<real, N> &P, GetQ get
             }
             pose_joint_right(T, ax, eta, P.trig);
         }
+        pose_mul_const_right(T, P.A[N], P.akind[N]);
     }
-    pose_mul_const_right(T, P.A[N], P.akind[N]);
 }
 
 // base-frame Jacobian row (6 x N, row-major) of one configuration from the walk's stash
-template <typename real, int N, bool ALLRZ>
+template <typename real, int N, int PROF>
 __device__ __forceinline__ void jacob0_row(const ChainP<real, N> &P, const Pose<real> &T, real (*zj)[3],
                                            real (*pj)[3], real *row)
 {
 #pragma unroll
     for (int j = 0; j < N; j++) {
-        const bool rev = ALLRZ ? true : (P.axis[j] < 3);
+        const bool rev = PROF == 1 ? true : (P.axis[j] < 3);
         if (rev) {
             real dx = T.p[0] - pj[j][0], dy = T.p[1] - pj[j][1], dz = T.p[2] - pj[j][2];
             row[0 * N + j] = fma(zj[j][1], dz, -(zj[j][2] * dy));
@@ -316,7 +348,12 @@ struct TileStage {
     static constexpr int ROW_BYTES = ROW_ELEMS * (int)sizeof(real);
     static constexpr int UB = (ROW_BYTES % 16 == 0) ? 16 : (ROW_BYTES % 8 == 0 ? 8 : 4);
     static constexpr int RU = ROW_BYTES / UB;          // units per row
-    static constexpr int S = RU | 1;                   // stage row stride in units (odd)
+    // bank-conflict degree of one-row-per-lane vector stores at row stride RU units
+    static constexpr int cgcd(int a, int b) { return b ? cgcd(b, a % b) : a; }
+    static constexpr int WAVE = UB == 16 ? 8 : (UB == 8 ? 16 : 32); // lanes served per shared-memory wavefront
+    // exact image of the output block when that costs at most 2-way conflicts, else pad to an odd stride
+    static constexpr int S = (cgcd(RU, WAVE) <= 2) ? RU : (RU | 1);
+    static constexpr bool EXACT = (S == RU);
     static constexpr int BYTES = 32 * S * UB;
     typedef typename std::conditional<UB == 16, uint4, typename std::conditional<UB == 8, uint2, unsigned>::type>::type unit_t;
 
@@ -346,6 +383,50 @@ struct TileStage {
             }
             dst[u] = v;
         }
+    }
+
+    // Asynchronous drain through the TMA engine (cp.async.bulk shared -> global): no LDS/STG
+    // instructions, no registers, and the warp moves on to its next tile while the copy is in
+    // flight.  Exact-image stages go out as ONE bulk copy issued by lane 0; padded stages as one
+    // bulk copy per row issued by the lane that owns the row.  Returns false when this tile cannot
+    // use bulk copies (size / alignment not a multiple of 16 bytes): caller falls back to drain().
+    // Call wait_reads() before the stage is written again.
+    static __device__ __forceinline__ bool drain_async(unsigned char *stage, real *gout, int rows_here, int lane)
+    {
+        if constexpr (EXACT) {
+            const unsigned bytes = (unsigned)rows_here * ROW_BYTES;
+            if (bytes & 15u) return false;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) {
+                const unsigned s = (unsigned)__cvta_generic_to_shared(stage);
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gout), "r"(s), "r"(bytes) : "memory");
+            }
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            return true;
+        } else if constexpr (UB == 16) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane < rows_here) {
+                const unsigned s = (unsigned)__cvta_generic_to_shared(stage + (size_t)lane * S * UB);
+                const unsigned bytes = ROW_BYTES;
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gout + (size_t)lane * ROW_ELEMS), "r"(s), "r"(bytes) : "memory");
+            }
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            return true;
+        } else {
+            return false;
+        }
+    }
+    // every lane's outstanding bulk copies have finished READING shared memory
+    static __device__ __forceinline__ void wait_reads()
+    {
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        __syncwarp();
+    }
+    static __device__ __forceinline__ void wait_all()
+    {
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
 
     // warp copies the staged tile to gout (the tile's block of the output array)
@@ -398,6 +479,32 @@ __device__ __forceinline__ void pose_to_row(const Pose<real> &T, real *row)
     row[12] = (real)0; row[13] = (real)0; row[14] = (real)0; row[15] = (real)1;
 }
 
+// The pose block needs no transposition through shared memory: a row is 16 contiguous reals
+// (128 B in fp64, 64 B in fp32), so each lane stores its own row with full-sector vector stores
+// straight from registers.
+template <typename real>
+__device__ __forceinline__ void store_pose_row(const Pose<real> &T, real *grow)
+{
+    real row[16];
+    pose_to_row(T, row);
+    if constexpr (sizeof(real) == 8) {
+        double4 *g = reinterpret_cast<double4 *>(grow);
+#pragma unroll
+        for (int u = 0; u < 4; u++) { // 256-bit stores (sm_100): one full 32-byte sector per instruction per lane
+            asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(g + u), "d"(row[4 * u]), "d"(row[4 * u + 1]),
+                         "d"(row[4 * u + 2]), "d"(row[4 * u + 3]) : "memory");
+        }
+    } else {
+        float4 *g = reinterpret_cast<float4 *>(grow);
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(g + 2 * u), "f"(row[8 * u]),
+                         "f"(row[8 * u + 1]), "f"(row[8 * u + 2]), "f"(row[8 * u + 3]), "f"(row[8 * u + 4]),
+                         "f"(row[8 * u + 5]), "f"(row[8 * u + 6]), "f"(row[8 * u + 7]) : "memory");
+        }
+    }
+}
+
 // ------------------------------------------------------------------ q tile loading
 // qmode 1: the smem tile is the exact image of the 32 x ldq global block, filled with 16-byte
 //          cp.async (no registers, asynchronous: used to prefetch the next tile);
@@ -434,6 +541,20 @@ __device__ __forceinline__ void load_q_tile(real *sq, const real *__restrict__ g
     }
 }
 
+// Under a saturated write stream a DRAM read waits far longer than one tile's worth of work
+// (ncu: the warps' top stall was the cp.async wait, profiles/r01_fkj_v4.md), so the q block of a
+// tile further ahead is pulled into L2 with fire-and-forget prefetches; the cp.async that later
+// stages it into shared memory is then an L2 hit.  Costs one instruction, no registers, no smem.
+template <typename real>
+__device__ __forceinline__ void prefetch_q_tile_l2(const real *gq, int rows_here, int ldq, int lane)
+{
+    const char *p = reinterpret_cast<const char *>(gq);
+    const char *first = reinterpret_cast<const char *>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)127);
+    const char *end = p + (size_t)rows_here * ldq * sizeof(real);
+    for (const char *a = first + (size_t)lane * 128; a < end; a += 32 * 128)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+}
+
 // bytes of per-warp shared memory: [q tile][output stage]
 template <typename real>
 inline size_t fkj_q_bytes(int ldq) { return ((size_t)32 * (ldq | 1) * sizeof(real) + 15) & ~(size_t)15; }
@@ -441,9 +562,9 @@ inline size_t fkj_q_bytes(int ldq) { return ((size_t)32 * (ldq | 1) * sizeof(rea
 template <typename real, int N>
 inline size_t fkj_warp_smem(int ldq, bool wt, bool wj)
 {
-    size_t t = wt ? (size_t)TileStage<real, 16>::BYTES : 0;
+    (void)wt; // the pose block is stored straight from registers
     size_t j = wj ? (size_t)TileStage<real, 6 * N>::BYTES : 0;
-    return fkj_q_bytes<real>(ldq) + (t > j ? t : j);
+    return fkj_q_bytes<real>(ldq) + j;
 }
 
 // registers: cap at 128/thread (4 resident blocks of 128 threads per SM) where the stash allows it
@@ -453,12 +574,14 @@ struct FkjBounds {
 };
 
 // ------------------------------------------------------------------ forward walk: pose and/or base-frame Jacobian
-template <typename real, int N, bool WT, bool WJ, bool ALLRZ>
+template <typename real, int N, bool WT, bool WJ, int PROF>
 __global__ void __launch_bounds__(B2K_THREADS, FkjBounds<real, N, WJ>::MINB)
 k_fkj_forward(const __grid_constant__ ChainP<real, N> P, const real *__restrict__ q, long long nrows, int ldq,
               float inv_ldq, int qmode, real *__restrict__ Tout, real *__restrict__ Jout, int warp_smem_bytes,
-              int q_bytes)
+              int q_bytes, int dbg)
 {
+    // dbg (measurement skeletons, b2k_set_variant 2 / 3): bit 0 = skip the chain walk (memory
+    // traffic only), bit 1 = skip the output stores (arithmetic only).  0 in normal operation.
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -473,6 +596,14 @@ k_fkj_forward(const __grid_constant__ ChainP<real, N> P, const real *__restrict_
     if (tile < ntiles) {
         const long long row0 = tile << 5;
         load_q_tile<real>(sq, q + row0 * ldq, (int)((nrows - row0) < 32 ? (nrows - row0) : 32), ldq, inv_ldq, qmode, lane);
+#pragma unroll
+        for (int k = 1; k < B2K_L2_PREFETCH_TILES; k++) {
+            const long long ft = tile + k * tstride;
+            if (ft < ntiles) {
+                const long long r0 = ft << 5;
+                prefetch_q_tile_l2<real>(q + r0 * ldq, (int)((nrows - r0) < 32 ? (nrows - r0) : 32), ldq, lane);
+            }
+        }
     }
     for (; tile < ntiles; tile += tstride) {
         const long long row0 = tile << 5;
@@ -483,41 +614,69 @@ k_fkj_forward(const __grid_constant__ ChainP<real, N> P, const real *__restrict_
 
         Pose<real> T;
         real zj[WJ ? N : 1][3], pj[WJ ? N : 1][3];
-        chain_forward<real, N, WJ, ALLRZ>(P, [&](int, int col) { return myq[col]; }, T, zj, pj);
-        __syncwarp(); // every lane has read its q row: prefetch the next tile's q behind the drain
+        real qrow[N];
+#pragma unroll
+        for (int j = 0; j < N; j++) qrow[j] = myq[P.jidx[j]];
+        __syncwarp(); // every lane holds its q row in registers: prefetch the next tile's q now
         {
             const long long nt = tile + tstride;
             if (nt < ntiles) {
                 const long long r0 = nt << 5;
                 load_q_tile<real>(sq, q + r0 * ldq, (int)((nrows - r0) < 32 ? (nrows - r0) : 32), ldq, inv_ldq, qmode, lane);
             }
+            const long long ft = tile + B2K_L2_PREFETCH_TILES * tstride;
+            if (ft < ntiles) {
+                const long long r0 = ft << 5;
+                prefetch_q_tile_l2<real>(q + r0 * ldq, (int)((nrows - r0) < 32 ? (nrows - r0) : 32), ldq, lane);
+            }
+        }
+        if (dbg & 1) { // memory skeleton: fabricate outputs from q without walking the chain
+            pose_from_const(T, P.A[0]);
+            T.p[0] = qrow[0];
+            if (WJ) {
+#pragma unroll
+                for (int j = 0; j < N; j++)
+#pragma unroll
+                    for (int i = 0; i < 3; i++) { zj[j][i] = qrow[j]; pj[j][i] = qrow[(j + i) % N]; }
+            }
+        } else {
+            chain_forward<real, N, WJ, PROF>(P, [&](int j, int) { return qrow[j]; }, T, zj, pj);
+        }
+        if (dbg & 2) { // arithmetic skeleton: keep the results alive without writing them
+            real acc = T.p[0] + T.c0[0] + T.c1[1] + T.c2[2] + T.p[1] + T.p[2];
+            if (WJ) {
+#pragma unroll
+                for (int j = 0; j < N; j++) acc += zj[j][0] * pj[j][1] + zj[j][1] * pj[j][2] + zj[j][2] * pj[j][0];
+            }
+            if (acc == (real)123456.789) Tout[row0] = acc;
+            continue;
         }
         if (WT) {
             Pose<real> Tb = T;
             if (P.has_base) pose_mul_const_left(Tb, P.B, AK_GEN | AK_TX | AK_TY | AK_TZ);
-            real row[16];
-            pose_to_row(Tb, row);
-            TileStage<real, 16>::put_row(so, lane, row);
-            __syncwarp();
-            TileStage<real, 16>::drain(so, Tout + row0 * 16, rows_here, lane);
-            __syncwarp();
+            if (lane < rows_here) store_pose_row<real>(Tb, Tout + (row0 + lane) * 16);
         }
         if (WJ) {
+            typedef TileStage<real, 6 * N> JS;
             real row[6 * N];
-            jacob0_row<real, N, ALLRZ>(P, T, zj, pj, row);
-            TileStage<real, 6 * N>::put_row(so, lane, row);
-            __syncwarp();
-            TileStage<real, 6 * N>::drain(so, Jout + row0 * (6 * N), rows_here, lane);
-            __syncwarp();
+            jacob0_row<real, N, PROF>(P, T, zj, pj, row);
+            JS::wait_reads(); // the previous tile's bulk copy has finished reading the stage
+            JS::put_row(so, lane, row);
+            if (!JS::drain_async(so, Jout + row0 * (6 * N), rows_here, lane)) {
+                __syncwarp();
+                JS::drain(so, Jout + row0 * (6 * N), rows_here, lane);
+                __syncwarp();
+            }
         }
     }
     cp_async_wait_all();
+    if (WJ) TileStage<real, 6 * N>::wait_all();
 }
 
 // ------------------------------------------------------------------ backward walk: end-effector-frame Jacobian (+ pose)
 // Reference _ETS_jacobe, methods.cpp:219-316: U starts at the tool and is left-multiplied by
 // each ET walking from the tip to the base; column j is read off U before joint j is applied.
-template <typename real, int N, bool WT>
+template <typename real, int N, bool WT, int PROF>
 __global__ void __launch_bounds__(B2K_THREADS, FkjBounds<real, N, true>::MINB)
 k_fkj_backward(const __grid_constant__ ChainP<real, N> P, const real *__restrict__ q, long long nrows, int ldq,
                float inv_ldq, int qmode, real *__restrict__ Tout, real *__restrict__ Jout, int warp_smem_bytes,
@@ -548,23 +707,51 @@ k_fkj_backward(const __grid_constant__ ChainP<real, N> P, const real *__restrict
         Pose<real> U;
         real row[6 * N]; // Je, row-major 6 x N
         pose_from_const(U, P.A[N]);
+        if constexpr (PROF == 1) { // DH-like chain: straight-line walk, batched sincos
+            real eta[N], sn[N], cs[N];
 #pragma unroll
-        for (int j = N - 1; j >= 0; j--) {
-            const int ax = P.axis[j];
-            const real sg = P.flip[j] ? (real)-1 : (real)1;
-            real col[6];
-            switch (ax) {
-            case B2K_RX: je_col_rev<real, 0>(U, sg, col); break;
-            case B2K_RY: je_col_rev<real, 1>(U, sg, col); break;
-            case B2K_RZ: je_col_rev<real, 2>(U, sg, col); break;
-            case B2K_TX: je_col_pri<real, 0>(U, sg, col); break;
-            case B2K_TY: je_col_pri<real, 1>(U, sg, col); break;
-            default: je_col_pri<real, 2>(U, sg, col); break;
+            for (int j = 0; j < N; j++) eta[j] = myq[P.jidx[j]];
+            b2k_sincos_batch<real, N>(eta, P.trig, sn, cs);
+#pragma unroll
+            for (int j = N - 1; j >= 0; j--) {
+                real col[6];
+                je_col_rev<real, 2>(U, (real)1, col);
+#pragma unroll
+                for (int k = 0; k < 6; k++) row[k * N + j] = col[k];
+                rot_rows<real, 0, 1>(U, sn[j], cs[j]);
+                if (j > 0) { // left-multiply by the Rx-form constant A_j
+                    const real *A = P.A[j];
+                    real *cols[4] = {U.c0, U.c1, U.c2, U.p};
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        real a = cols[k][1], b = cols[k][2];
+                        cols[k][1] = fma(A[5], a, A[6] * b);
+                        cols[k][2] = fma(A[9], a, A[10] * b);
+                    }
+                    U.p[0] += A[3]; U.p[1] += A[7]; U.p[2] += A[11];
+                } else {
+                    pose_mul_const_left(U, P.A[0], P.akind[0]);
+                }
             }
+        } else {
 #pragma unroll
-            for (int k = 0; k < 6; k++) row[k * N + j] = col[k];
-            pose_joint_left(U, ax, sg * myq[P.jidx[j]], P.trig);
-            pose_mul_const_left(U, P.A[j], P.akind[j]);
+            for (int j = N - 1; j >= 0; j--) {
+                const int ax = P.axis[j];
+                const real sg = P.flip[j] ? (real)-1 : (real)1;
+                real col[6];
+                switch (ax) {
+                case B2K_RX: je_col_rev<real, 0>(U, sg, col); break;
+                case B2K_RY: je_col_rev<real, 1>(U, sg, col); break;
+                case B2K_RZ: je_col_rev<real, 2>(U, sg, col); break;
+                case B2K_TX: je_col_pri<real, 0>(U, sg, col); break;
+                case B2K_TY: je_col_pri<real, 1>(U, sg, col); break;
+                default: je_col_pri<real, 2>(U, sg, col); break;
+                }
+#pragma unroll
+                for (int k = 0; k < 6; k++) row[k * N + j] = col[k];
+                pose_joint_left(U, ax, sg * myq[P.jidx[j]], P.trig);
+                pose_mul_const_left(U, P.A[j], P.akind[j]);
+            }
         }
         __syncwarp();
         {
@@ -577,19 +764,21 @@ k_fkj_backward(const __grid_constant__ ChainP<real, N> P, const real *__restrict
         if (WT) {
             Pose<real> Tb = U;
             if (P.has_base) pose_mul_const_left(Tb, P.B, AK_GEN | AK_TX | AK_TY | AK_TZ);
-            real trow[16];
-            pose_to_row(Tb, trow);
-            TileStage<real, 16>::put_row(so, lane, trow);
-            __syncwarp();
-            TileStage<real, 16>::drain(so, Tout + row0 * 16, rows_here, lane);
-            __syncwarp();
+            if (lane < rows_here) store_pose_row<real>(Tb, Tout + (row0 + lane) * 16);
         }
-        TileStage<real, 6 * N>::put_row(so, lane, row);
-        __syncwarp();
-        TileStage<real, 6 * N>::drain(so, Jout + row0 * (6 * N), rows_here, lane);
-        __syncwarp();
+        {
+            typedef TileStage<real, 6 * N> JS;
+            JS::wait_reads();
+            JS::put_row(so, lane, row);
+            if (!JS::drain_async(so, Jout + row0 * (6 * N), rows_here, lane)) {
+                __syncwarp();
+                JS::drain(so, Jout + row0 * (6 * N), rows_here, lane);
+                __syncwarp();
+            }
+        }
     }
     cp_async_wait_all();
+    TileStage<real, 6 * N>::wait_all();
 }
 
 // ------------------------------------------------------------------ launcher
@@ -621,36 +810,48 @@ int fkj_launch_n(const b2k_chain_s *c, int mode, const real *q, long long nrows,
     const long long nblk_needed = (ntiles + B2K_WARPS_PER_BLOCK - 1) / B2K_WARPS_PER_BLOCK;
     const float inv_ldq = 1.0f / (float)ldq;
     const int qmode = fkj_qmode<real>(q, ldq);
-    if (wt && (((uintptr_t)T) & 15)) { b2k_set_error("fkj: T must be 16-byte aligned"); return B2K_ERR_INVALID; }
+    if (wt && (((uintptr_t)T) & 31)) { b2k_set_error("fkj: T must be 32-byte aligned"); return B2K_ERR_INVALID; }
     if ((wj0 || wje) && (((uintptr_t)J) % TileStage<real, 6 * N>::UB)) {
         b2k_set_error("fkj: J must be %d-byte aligned", TileStage<real, 6 * N>::UB);
         return B2K_ERR_INVALID;
     }
 
-    auto launch = [&](auto kern) -> int {
+    const int variant = b2k_get_variant();
+    const int dbg = variant == 2 ? 1 : (variant == 3 ? 2 : 0);
+    auto launch_impl = [&](auto kern, auto... extra) -> int {
         int per_sm = b2k_blocks_per_sm((const void *)kern, B2K_THREADS, smem);
         if (per_sm < 1) return per_sm < 0 ? per_sm : (b2k_set_error("fkj kernel does not fit on an SM (smem %zu B)", smem), B2K_ERR_INVALID);
-        long long grid = (long long)b2k_num_sms() * per_sm;
-        if (grid > nblk_needed) grid = nblk_needed;
+        // One tile per warp, one-shot grid: the hardware block scheduler hands out tiles in address
+        // order as SMs free up, which keeps the set of DRAM pages being written compact.  A
+        // persistent grid-stride loop (variant 4) measured 15-20 % lower write bandwidth on B200
+        // (scripts/exp/exp_mem3.cu: 5.96 vs 6.73 TB/s for this exact store pattern).
+        long long grid = nblk_needed;
+        if (variant == 4) {
+            grid = (long long)b2k_num_sms() * per_sm;
+            if (grid > nblk_needed) grid = nblk_needed;
+        }
         if (grid < 1) grid = 1;
-        kern<<<(unsigned)grid, B2K_THREADS, smem, st>>>(P, q, nrows, ldq, inv_ldq, qmode, T, J, (int)wsm, (int)qb);
+        if (grid > 0x7fffffffLL) { b2k_set_error("fkj: batch too large for one launch"); return B2K_ERR_INVALID; }
+        kern<<<(unsigned)grid, B2K_THREADS, smem, st>>>(P, q, nrows, ldq, inv_ldq, qmode, T, J, (int)wsm, (int)qb, extra...);
         b2k_count_launch();
         B2K_CUDA(cudaGetLastError());
         return B2K_OK;
     };
+    auto launch = [&](auto kern) -> int { return launch_impl(kern, dbg); };   // forward kernels take dbg
+    auto launch_b = [&](auto kern) -> int { return launch_impl(kern); };      // backward kernels do not
 
     if (wje) {
-        if (wt) return launch(k_fkj_backward<real, N, true>);
-        return launch(k_fkj_backward<real, N, false>);
+        if (c->dh_like) return wt ? launch_b(k_fkj_backward<real, N, true, 1>) : launch_b(k_fkj_backward<real, N, false, 1>);
+        return wt ? launch_b(k_fkj_backward<real, N, true, 0>) : launch_b(k_fkj_backward<real, N, false, 0>);
     }
-    if (c->all_rz) {
-        if (wt && wj0) return launch(k_fkj_forward<real, N, true, true, true>);
-        if (wt) return launch(k_fkj_forward<real, N, true, false, true>);
-        return launch(k_fkj_forward<real, N, false, true, true>);
+    if (c->dh_like) {
+        if (wt && wj0) return launch(k_fkj_forward<real, N, true, true, 1>);
+        if (wt) return launch(k_fkj_forward<real, N, true, false, 1>);
+        return launch(k_fkj_forward<real, N, false, true, 1>);
     }
-    if (wt && wj0) return launch(k_fkj_forward<real, N, true, true, false>);
-    if (wt) return launch(k_fkj_forward<real, N, true, false, false>);
-    return launch(k_fkj_forward<real, N, false, true, false>);
+    if (wt && wj0) return launch(k_fkj_forward<real, N, true, true, 0>);
+    if (wt) return launch(k_fkj_forward<real, N, true, false, 0>);
+    return launch(k_fkj_forward<real, N, false, true, 0>);
 }
 
 template <typename real>

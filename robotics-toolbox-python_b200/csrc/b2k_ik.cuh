@@ -144,7 +144,7 @@ __device__ __forceinline__ bool ik_chol_solve(real *A, real *b)
     return ok;
 }
 
-template <typename real, int N, bool ALLRZ>
+template <typename real, int N, int PROF>
 __global__ void __launch_bounds__(B2K_THREADS)
 k_ik_lm(const __grid_constant__ ChainP<real, N> P, const __grid_constant__ IkP<real, N> K,
         const real *__restrict__ Tep, const real *__restrict__ q0, long long nprob, real *__restrict__ q_out,
@@ -193,7 +193,7 @@ k_ik_lm(const __grid_constant__ ChainP<real, N> P, const __grid_constant__ IkP<r
         Pose<real> Te;
         real zj[N][3], pj[N][3], e[6];
         // jindex is dense 0..n-1 here (checked on the host, like the reference's C++ loop assumes)
-        chain_forward<real, N, true, ALLRZ>(P, [&](int j, int) { return q[j]; }, Te, zj, pj);
+        chain_forward<real, N, true, PROF>(P, [&](int j, int) { return q[j]; }, Te, zj, pj);
         ik_angle_axis<real>(Te, Tp, e);
         real Ecur = 0;
 #pragma unroll
@@ -222,7 +222,7 @@ k_ik_lm(const __grid_constant__ ChainP<real, N> P, const __grid_constant__ IkP<r
         real J[N][6];
 #pragma unroll
         for (int j = 0; j < N; j++) {
-            const bool rev = ALLRZ ? true : (P.axis[j] < 3);
+            const bool rev = PROF == 1 ? true : (P.axis[j] < 3);
             if (rev) {
                 real dx = Te.p[0] - pj[j][0], dy = Te.p[1] - pj[j][1], dz = Te.p[2] - pj[j][2];
                 J[j][0] = fma(zj[j][1], dz, -(zj[j][2] * dy));
@@ -328,8 +328,8 @@ int ik_launch_n(const b2k_chain_s *c, const real *Tep, long long nprob, const re
         B2K_CUDA(cudaGetLastError());
         return B2K_OK;
     };
-    if (c->all_rz) return launch(k_ik_lm<real, N, true>);
-    return launch(k_ik_lm<real, N, false>);
+    if (c->dh_like) return launch(k_ik_lm<real, N, 1>);
+    return launch(k_ik_lm<real, N, 0>);
 }
 
 template <typename real>

@@ -28,6 +28,7 @@ struct RneP {
     real c_tcp[N]; // |G|*Tc+
     real c_tcm[N]; // |G|*Tc-
     int prismatic[N];
+    real ps[N][3]; // p* of a revolute link: (a, d sin(alpha), d cos(alpha)) for DH, (a, -d sin(alpha), d cos(alpha)) for MDH
     real grav[3];
     real fext[6];
     TrigC<real> trig;
@@ -71,8 +72,144 @@ struct LinkRot {
     }
 };
 
+// ------------------------------------------------------------------ all-revolute fast path
+// The same recursion as ne.c with the link rotation applied in its factored form
+// (R = Rz(theta) Rx(alpha) for DH, Rx(alpha) Rz(theta) for MDH: 8 flops instead of the 9-entry
+// product with its structural zeros), z-only joint-rate vectors expanded by hand (the compiler
+// may not drop IEEE multiplications by a literal 0), p* taken from the constant bank, and
+// R_{j+1} f_{j+1} computed once per link.  Dropping exact-zero terms does not change any value.
+template <typename real, bool MDH>
+struct FRot { // factored link rotation
+    real st, ct, sa, ca;
+    __device__ __forceinline__ V3<real> tmul(V3<real> v) const // R^T v
+    {
+        if (!MDH) {
+            const real u = fma(ct, v.x, st * v.y), w = fma(ct, v.y, -(st * v.x));
+            return {u, fma(ca, w, sa * v.z), fma(ca, v.z, -(sa * w))};
+        } else {
+            const real wy = fma(ca, v.y, sa * v.z), wz = fma(ca, v.z, -(sa * v.y));
+            return {fma(ct, v.x, st * wy), fma(ct, wy, -(st * v.x)), wz};
+        }
+    }
+    __device__ __forceinline__ V3<real> mul(V3<real> v) const // R v
+    {
+        if (!MDH) {
+            const real m = fma(ca, v.y, -(sa * v.z)), z = fma(sa, v.y, ca * v.z);
+            return {fma(ct, v.x, -(st * m)), fma(st, v.x, ct * m), z};
+        } else {
+            const real u = fma(ct, v.x, -(st * v.y)), w = fma(st, v.x, ct * v.y);
+            return {u, fma(ca, w, -(sa * v.z)), fma(sa, w, ca * v.z)};
+        }
+    }
+};
+
+template <typename real>
+__device__ __forceinline__ V3<real> imul(const real *I, V3<real> v) // vmath.c mat_vect_mult (column-major read)
+{
+    return {fma(I[0], v.x, fma(I[3], v.y, I[6] * v.z)), fma(I[1], v.x, fma(I[4], v.y, I[7] * v.z)),
+            fma(I[2], v.x, fma(I[5], v.y, I[8] * v.z))};
+}
+
 template <typename real, int N, bool MDH>
-__global__ void __launch_bounds__(B2K_THREADS, (sizeof(real) == 4 || N <= 6) ? 4 : 3)
+__device__ __forceinline__ void rne_row_allrev(const RneP<real, N> &P, const real *mq, const real *mqd,
+                                               const real *mqdd, real *tq)
+{
+    V3<real> Fm[N], Nm[N];
+    real sth[N], cth[N];
+    {
+        real th[N];
+#pragma unroll
+        for (int j = 0; j < N; j++) th[j] = mq[j] + P.offset[j];
+        b2k_sincos_batch<real, N>(th, P.trig, sth, cth);
+    }
+    const V3<real> gravity = {P.grav[0], P.grav[1], P.grav[2]};
+    V3<real> w = {0, 0, 0}, wd = {0, 0, 0}, acc = {0, 0, 0};
+#pragma unroll
+    for (int j = 0; j < N; j++) {
+        const FRot<real, MDH> R = {sth[j], cth[j], P.sa[j], P.ca[j]};
+        const V3<real> ps = {P.ps[j][0], P.ps[j][1], P.ps[j][2]};
+        const real qd = mqd[j], qdd = mqdd[j];
+        V3<real> wn, wdn, accn;
+        if (MDH) { // ne.c:144-181
+            if (j == 0) {
+                wn = {0, 0, qd};
+                wdn = {0, 0, qdd};
+                accn = R.tmul(gravity);
+            } else {
+                const V3<real> t1 = R.tmul(w);
+                wn = {t1.x, t1.y, t1.z + qd};
+                const V3<real> t3 = R.tmul(wd);
+                wdn = {fma(t1.y, qd, t3.x), fma(-t1.x, qd, t3.y), t3.z + qdd}; // t1 x (0,0,qd) + t3 + (0,0,qdd)
+                V3<real> a = vcross(w, ps);
+                a = vcross(w, a);
+                a = vadd(vadd(vcross(wd, ps), a), acc);
+                accn = R.tmul(a);
+            }
+        } else { // ne.c:252-288
+            if (j == 0) {
+                wn = R.tmul(V3<real>{0, 0, qd});
+                wdn = R.tmul(V3<real>{0, 0, qdd});
+            } else {
+                wn = R.tmul(V3<real>{w.x, w.y, w.z + qd});
+                wdn = R.tmul(V3<real>{fma(w.y, qd, wd.x), fma(-w.x, qd, wd.y), wd.z + qdd});
+            }
+            const V3<real> t2 = vcross(wn, ps);
+            accn = vadd(vcross(wdn, ps), vcross(wn, t2));
+            accn = vadd(accn, R.tmul(j == 0 ? gravity : acc));
+        }
+        w = wn; wd = wdn; acc = accn;
+        const V3<real> rc = {P.r[j][0], P.r[j][1], P.r[j][2]};
+        V3<real> abar = vadd(vcross(wd, rc), vcross(w, vcross(w, rc)));
+        abar = vadd(abar, acc);
+        Fm[j] = vscale(abar, P.m[j]);
+        Nm[j] = vadd(imul(P.I[j], wd), vcross(w, imul(P.I[j], w)));
+    }
+    V3<real> f = {0, 0, 0}, nn = {0, 0, 0};
+    const V3<real> f_tip = {P.fext[0], P.fext[1], P.fext[2]}, n_tip = {P.fext[3], P.fext[4], P.fext[5]};
+#pragma unroll
+    for (int j = N - 1; j >= 0; j--) {
+        const V3<real> rc = {P.r[j][0], P.r[j][1], P.r[j][2]};
+        V3<real> fj, nj;
+        if (MDH) { // ne.c:358-398
+            if (j == N - 1) {
+                fj = vadd(f_tip, Fm[j]);
+                nj = n_tip;
+            } else {
+                const FRot<real, MDH> Rn = {sth[j + 1], cth[j + 1], P.sa[j + 1], P.ca[j + 1]};
+                const V3<real> psn = {P.ps[j + 1][0], P.ps[j + 1][1], P.ps[j + 1][2]};
+                const V3<real> Rf = Rn.mul(f);
+                fj = vadd(Rf, Fm[j]);
+                nj = vadd(Rn.mul(nn), vcross(psn, Rf));
+            }
+            nj = vadd(vadd(nj, vcross(rc, Fm[j])), Nm[j]);
+        } else { // ne.c:409-453
+            const V3<real> ps = {P.ps[j][0], P.ps[j][1], P.ps[j][2]};
+            V3<real> t1 = vcross(vadd(ps, rc), Fm[j]);
+            if (j != N - 1) {
+                const FRot<real, MDH> Rn = {sth[j + 1], cth[j + 1], P.sa[j + 1], P.ca[j + 1]};
+                fj = vadd(Fm[j], Rn.mul(f));
+                const V3<real> t3 = vadd(vcross(Rn.tmul(ps), f), nn);
+                t1 = vadd(t1, Rn.mul(t3));
+            } else {
+                fj = vadd(Fm[j], f_tip);
+                t1 = vadd(vadd(t1, vcross(ps, f_tip)), n_tip);
+            }
+            nj = vadd(t1, Nm[j]);
+        }
+        f = fj; nn = nj;
+        real t = MDH ? nj.z : fma(nj.y, P.sa[j], nj.z * P.ca[j]); // n . (R^T z0)
+        const real qdj = mqd[j];
+        t = fma(P.c_jm[j], mqdd[j], t);
+        t = fma(P.c_b[j], qdj, t);
+        t += (qdj > 0 ? P.c_tcp[j] : (real)0) + (qdj < 0 ? P.c_tcm[j] : (real)0);
+        tq[j] = t;
+    }
+}
+
+// ALLREV: every joint is revolute (the usual case) -- strips the prismatic code, which the compiler
+// would otherwise if-convert into always-executed select chains.
+template <typename real, int N, bool MDH, bool ALLREV>
+__global__ void __launch_bounds__(B2K_THREADS, (sizeof(real) == 4) ? 4 : 3)
 k_rne(const __grid_constant__ RneP<real, N> P, const real *__restrict__ q, const real *__restrict__ qd,
       const real *__restrict__ qdd, long long nrows, real *__restrict__ tau, int warp_smem_bytes, int in_bytes,
       int qmode)
@@ -107,25 +244,33 @@ k_rne(const __grid_constant__ RneP<real, N> P, const real *__restrict__ q, const
         const int myrow = (lane < rows_here ? lane : 0) * lds;
         const real *mq = sq + myrow, *mqd = sqd + myrow, *mqdd = sqdd + myrow;
 
+        real tq[N];
+        if constexpr (ALLREV) {
+            rne_row_allrev<real, N, MDH>(P, mq, mqd, mqdd, tq);
+        } else {
         // stash for the backward recursion
         V3<real> Fm[N], Nm[N];
         real sth[N], cth[N];
+        {   // all joint angles up front: one interleaved batch of sincos (frne.c:193-207 rot_mat)
+            real th[N];
+#pragma unroll
+            for (int j = 0; j < N; j++) th[j] = mq[j] + P.offset[j];
+            b2k_sincos_batch<real, N>(th, P.trig, sth, cth);
+            if (!ALLREV) {
+#pragma unroll
+                for (int j = 0; j < N; j++)
+                    if (P.prismatic[j]) { sth[j] = P.st0[j]; cth[j] = P.ct0[j]; }
+            }
+        }
         const V3<real> gravity = {P.grav[0], P.grav[1], P.grav[2]};
         V3<real> w = {0, 0, 0}, wd = {0, 0, 0}, acc = {0, 0, 0}; // of link j-1 on entry
 
         // ---------------- forward recursion (ne.c:137-240 MDH, 245-347 DH)
 #pragma unroll
         for (int j = 0; j < N; j++) {
-            const bool pris = P.prismatic[j] != 0;
-            real st, ct, d;
-            if (!pris) {
-                b2k_sincos(mq[j] + P.offset[j], P.trig, &st, &ct);
-                d = P.D[j];
-            } else {
-                st = P.st0[j]; ct = P.ct0[j];
-                d = mq[j] + P.offset[j];
-            }
-            sth[j] = st; cth[j] = ct;
+            const bool pris = ALLREV ? false : (P.prismatic[j] != 0);
+            const real st = sth[j], ct = cth[j];
+            const real d = pris ? (mq[j] + P.offset[j]) : P.D[j];
             const LinkRot<real, MDH> R(st, ct, P.sa[j], P.ca[j]);
             const V3<real> pstar = MDH ? V3<real>{P.A[j], -d * P.sa[j], d * P.ca[j]} : V3<real>{P.A[j], d * P.sa[j], d * P.ca[j]};
             const V3<real> qdv = {0, 0, mqd[j]}, qddv = {0, 0, mqdd[j]};
@@ -224,12 +369,11 @@ k_rne(const __grid_constant__ RneP<real, N> P, const real *__restrict__ q, const
         }
 
         // ---------------- backward recursion (ne.c:358-403 MDH, 409-457 DH) + joint torque (ne.c:464-491)
-        real tq[N];
         V3<real> f = {0, 0, 0}, nn = {0, 0, 0}; // of link j+1 on entry
         const V3<real> f_tip = {P.fext[0], P.fext[1], P.fext[2]}, n_tip = {P.fext[3], P.fext[4], P.fext[5]};
 #pragma unroll
         for (int j = N - 1; j >= 0; j--) {
-            const bool pris = P.prismatic[j] != 0;
+            const bool pris = ALLREV ? false : (P.prismatic[j] != 0);
             const V3<real> rc = {P.r[j][0], P.r[j][1], P.r[j][2]};
             V3<real> fj, nj, t1, t2, t3, t4;
             if (MDH) {
@@ -239,7 +383,7 @@ k_rne(const __grid_constant__ RneP<real, N> P, const real *__restrict__ q, const
                     t1 = n_tip;
                 } else {
                     const LinkRot<real, MDH> Rn(sth[j + 1], cth[j + 1], P.sa[j + 1], P.ca[j + 1]);
-                    const real dn = P.prismatic[j + 1] ? (mq[j + 1] + P.offset[j + 1]) : P.D[j + 1];
+                    const real dn = (!ALLREV && P.prismatic[j + 1]) ? (mq[j + 1] + P.offset[j + 1]) : P.D[j + 1];
                     const V3<real> pstar_n = {P.A[j + 1], -dn * P.sa[j + 1], dn * P.ca[j + 1]};
                     t1 = Rn.mul(f);
                     fj = vadd(t1, F);
@@ -286,6 +430,7 @@ k_rne(const __grid_constant__ RneP<real, N> P, const real *__restrict__ q, const
             tq[j] = t;
         }
         // ---------------- stage tau and write it back coalesced
+        }
         // the inputs of this tile are dead (tq holds the results): prefetch the next tile behind the drain
         __syncwarp();
         if (tile + tstride < ntiles) load_inputs(tile + tstride);
@@ -321,6 +466,9 @@ int rne_launch_n(const b2k_rne_s *r, const real *q, const real *qd, const real *
         P.c_b[j] = (real)(G * G * l[21]);
         P.c_tcp[j] = (real)(fabs(G) * l[22]);
         P.c_tcm[j] = (real)(fabs(G) * l[23]);
+        P.ps[j][0] = (real)A;
+        P.ps[j][1] = (real)(r->mdh ? -D * sin(alpha) : D * sin(alpha));
+        P.ps[j][2] = (real)(D * cos(alpha));
     }
     for (int k = 0; k < 3; k++) P.grav[k] = (real)grav[k];
     for (int k = 0; k < 6; k++) P.fext[k] = fext ? (real)fext[k] : (real)0;
@@ -335,16 +483,21 @@ int rne_launch_n(const b2k_rne_s *r, const real *q, const real *qd, const real *
     auto launch = [&](auto kern) -> int {
         int per_sm = b2k_blocks_per_sm((const void *)kern, B2K_THREADS, smem);
         if (per_sm < 1) return per_sm < 0 ? per_sm : (b2k_set_error("rne kernel does not fit on an SM"), B2K_ERR_INVALID);
-        long long grid = (long long)b2k_num_sms() * per_sm;
-        if (grid > nblk_needed) grid = nblk_needed;
+        long long grid = nblk_needed; // one tile per warp, one-shot grid (see b2k_fkj.cuh launcher)
+        if (b2k_get_variant() == 4) {
+            grid = (long long)b2k_num_sms() * per_sm;
+            if (grid > nblk_needed) grid = nblk_needed;
+        }
         if (grid < 1) grid = 1;
         kern<<<(unsigned)grid, B2K_THREADS, smem, st>>>(P, q, qd, qdd, nrows, tau, (int)wsm, (int)inb, qmode);
         b2k_count_launch();
         B2K_CUDA(cudaGetLastError());
         return B2K_OK;
     };
-    if (r->mdh) return launch(k_rne<real, N, true>);
-    return launch(k_rne<real, N, false>);
+    bool allrev = true;
+    for (int j = 0; j < N; j++) allrev = allrev && !P.prismatic[j];
+    if (r->mdh) return allrev ? launch(k_rne<real, N, true, true>) : launch(k_rne<real, N, true, false>);
+    return allrev ? launch(k_rne<real, N, false, true>) : launch(k_rne<real, N, false, false>);
 }
 
 template <typename real>

@@ -14,13 +14,27 @@
 #include "b2k_common.cuh"
 
 // out-of-line so the seven call sites of an unrolled chain do not each inline Payne-Hanek
-static __device__ __noinline__ void b2k_sincos_slow(double x, double *sp, double *cp) { sincos(x, sp, cp); }
-static __device__ __noinline__ void b2k_sincos_slow(float x, float *sp, float *cp) { sincosf(x, sp, cp); }
+// (results are returned BY VALUE: taking the address of the caller's s / c would pin them to
+// local memory on the fast path too)
+static __device__ __noinline__ double2 b2k_sincos_slow(double x)
+{
+    double s, c;
+    sincos(x, &s, &c);
+    return make_double2(s, c);
+}
+static __device__ __noinline__ float2 b2k_sincos_slow(float x)
+{
+    float s, c;
+    sincosf(x, &s, &c);
+    return make_float2(s, c);
+}
 
 __device__ __forceinline__ void b2k_sincos(double x, const TrigC<double> &t, double *sp, double *cp)
 {
     if (!(fabs(x) < t.fast_limit)) {
-        b2k_sincos_slow(x, sp, cp);
+        const double2 r = b2k_sincos_slow(x);
+        *sp = r.x;
+        *cp = r.y;
         return;
     }
     const double tt = fma(x, t.two_over_pi, t.magic);
@@ -55,7 +69,9 @@ __device__ __forceinline__ void b2k_sincos(double x, const TrigC<double> &t, dou
 __device__ __forceinline__ void b2k_sincos(float x, const TrigC<float> &t, float *sp, float *cp)
 {
     if (!(fabsf(x) < t.fast_limit)) {
-        b2k_sincos_slow(x, sp, cp);
+        const float2 r = b2k_sincos_slow(x);
+        *sp = r.x;
+        *cp = r.y;
         return;
     }
     const float tt = fmaf(x, t.two_over_pi, t.magic);
@@ -78,4 +94,58 @@ __device__ __forceinline__ void b2k_sincos(float x, const TrigC<float> &t, float
     const int cflip = ((q + 1) & 2) << 30;
     *sp = __int_as_float(__float_as_int(s) ^ sflip);
     *cp = __int_as_float(__float_as_int(c) ^ cflip);
+}
+
+// N independent sincos evaluated stage by stage: every coefficient is fetched once and used N
+// times, and the N dependency chains interleave (instruction-level parallelism for a kernel that
+// runs only ~4 warps per scheduler).
+template <typename real, int N>
+__device__ __forceinline__ void b2k_sincos_batch(const real *x, const TrigC<real> &t, real *s, real *c)
+{
+    bool all_fast = true;
+#pragma unroll
+    for (int j = 0; j < N; j++) all_fast = all_fast && (fabs(x[j]) < t.fast_limit);
+    if (!all_fast) { // rare: huge / non-finite angles somewhere in this row
+#pragma unroll
+        for (int j = 0; j < N; j++) b2k_sincos(x[j], t, &s[j], &c[j]);
+        return;
+    }
+    real r[N], z[N], ps[N], pc[N];
+    int q[N];
+#pragma unroll
+    for (int j = 0; j < N; j++) {
+        const real tt = fma(x[j], t.two_over_pi, t.magic);
+        if constexpr (sizeof(real) == 8) q[j] = __double2loint(tt);
+        else q[j] = __float_as_int(tt);
+        const real kd = tt - t.magic;
+        real rr = fma(-kd, t.pio2_hi, x[j]);
+        rr = fma(-kd, t.pio2_mid, rr);
+        r[j] = fma(-kd, t.pio2_lo, rr);
+        z[j] = r[j] * r[j];
+    }
+    constexpr int D = sizeof(real) == 8 ? 6 : 3; // polynomial terms
+#pragma unroll
+    for (int j = 0; j < N; j++) { ps[j] = t.s[D - 1]; pc[j] = t.c[D - 1]; }
+#pragma unroll
+    for (int k = D - 2; k >= 0; k--) {
+#pragma unroll
+        for (int j = 0; j < N; j++) { ps[j] = fma(ps[j], z[j], t.s[k]); pc[j] = fma(pc[j], z[j], t.c[k]); }
+    }
+#pragma unroll
+    for (int j = 0; j < N; j++) {
+        const real sn = fma(r[j] * z[j], ps[j], r[j]);
+        const real cs = fma(z[j] * z[j], pc[j], fma((real)-0.5, z[j], (real)1));
+        const bool swap = q[j] & 1;
+        const real ss = swap ? cs : sn;
+        const real cc = swap ? sn : cs;
+        const int sflip = (q[j] & 2) << 30;
+        const int cflip = ((q[j] + 1) & 2) << 30;
+        if constexpr (sizeof(real) == 8) {
+            s[j] = __hiloint2double(__double2hiint(ss) ^ sflip, __double2loint(ss));
+            c[j] = __hiloint2double(__double2hiint(cc) ^ cflip, __double2loint(cc));
+        } else {
+            s[j] = __int_as_float(__float_as_int(ss) ^ sflip);
+            c[j] = __int_as_float(__float_as_int(cc) ^ cflip);
+        }
+    }
 }

@@ -13,3 +13,7 @@ if [ -n "${NCU_K:-}" ]; then
   echo "== ncu full capture ($NCU_K)"
   timeout 1200 ncu --set full --clock-control none --import-source on -k regex:$NCU_K -s ${NCU_S:-3} -c ${NCU_C:-1} -f -o gpurun_out/prof_${NCU_NAME:-k} python scripts/kernel_bench.py --steps 3 --warmup 3 --only "${NCU_ONLY:-fkine_jacob0_panda_f64}" > gpurun_out/ncu_full.log 2>&1 ; echo "rc=$?"
 fi
+if [ -n "${NCU2_K:-}" ]; then
+  echo "== ncu full capture 2 ($NCU2_K)"
+  timeout 1200 ncu --set full --clock-control none --import-source on -k regex:$NCU2_K -s ${NCU2_S:-3} -c 1 -f -o gpurun_out/prof_${NCU2_NAME:-k2} python scripts/kernel_bench.py --steps 3 --warmup 3 --only "${NCU2_ONLY:-rne_puma_f64}" > gpurun_out/ncu_full2.log 2>&1 ; echo "rc=$?"
+fi

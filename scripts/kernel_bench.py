@@ -63,6 +63,14 @@ def want(name):
 
 N = args.rows
 rng = np.random.default_rng(0)
+if want("probe_"):
+    # context only (torch library kernels, not part of the product): what this box's HBM does for a
+    # pure-write stream and for a copy of the same footprint as the headline step
+    buf = torch.empty(520_000_000 // 8, dtype=torch.float64, device=dev)
+    src = torch.empty(260_000_000 // 8, dtype=torch.float64, device=dev)
+    report("probe_fill_520MB", timeit(lambda i: buf.fill_(1.0), 1), 1, 520_000_000)
+    report("probe_copy_260MB_to_260MB", timeit(lambda i: buf[: src.numel()].copy_(src), 1), 1, 520_000_000)
+    del buf, src
 tdt = {np.float32: torch.float32, np.float64: torch.float64}
 
 for robot_name, robot in (("panda", rtb.models.Panda()), ("ur10", rtb.models.UR10())):
