@@ -570,7 +570,7 @@ inline size_t fkj_warp_smem(int ldq, bool wt, bool wj)
 // registers: cap at 128/thread (4 resident blocks of 128 threads per SM) where the stash allows it
 template <typename real, int N, bool WJ>
 struct FkjBounds {
-    static constexpr int MINB = (!WJ) ? 5 : (sizeof(real) == 4 ? 4 : (N <= 7 ? 4 : 3));
+    static constexpr int MINB = (!WJ) ? (sizeof(real) == 4 ? 8 : 6) : (sizeof(real) == 4 ? 4 : (N <= 7 ? 4 : 3));
 };
 
 // ------------------------------------------------------------------ forward walk: pose and/or base-frame Jacobian
