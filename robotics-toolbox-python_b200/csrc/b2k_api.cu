@@ -2,6 +2,7 @@
 // validation, error strings, launch accounting and the pipelined host-buffer front ends.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -82,6 +83,29 @@ int b2k_blocks_per_sm(const void *func, int threads, size_t smem)
     std::lock_guard<std::mutex> lk(mu);
     cache[key] = per_sm;
     return per_sm;
+}
+
+int b2k_tiles_per_warp(bool with_jacobian)
+{
+    static const int pose = [] { const char *e = getenv("B2K_TPW_POSE"); int v = e ? atoi(e) : 1; return v < 1 ? 1 : v; }();
+    static const int jac = [] { const char *e = getenv("B2K_TPW_JAC"); int v = e ? atoi(e) : 1; return v < 1 ? 1 : v; }();
+    return with_jacobian ? jac : pose;
+}
+
+void b2k_keep_mempool()
+{
+    static std::mutex mu;
+    static std::map<int, bool> done;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return;
+    std::lock_guard<std::mutex> lk(mu);
+    if (done[dev]) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        unsigned long long thr = ~0ULL;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    done[dev] = true;
 }
 
 extern "C" const char *b2k_last_error(void) { return g_err; }

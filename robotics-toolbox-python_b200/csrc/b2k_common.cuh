@@ -111,6 +111,10 @@ int b2k_num_sms(int *device_out = nullptr);
 // resident blocks per SM for (kernel, threads, dynamic smem), cached; also raises the kernel's
 // dynamic shared-memory limit.  <0 on CUDA error.
 int b2k_blocks_per_sm(const void *func, int threads, size_t smem);
+// once per device: keep freed stream-ordered allocations cached in the default memory pool
+void b2k_keep_mempool();
+// consecutive 32-row tiles one warp processes (tunable through env B2K_TPW_POSE / B2K_TPW_JAC for experiments)
+int b2k_tiles_per_warp(bool with_jacobian);
 
 #define B2K_CUDA(call)                                   \
     do {                                                 \

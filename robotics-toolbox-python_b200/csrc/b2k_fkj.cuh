@@ -578,7 +578,7 @@ template <typename real, int N, bool WT, bool WJ, int PROF>
 __global__ void __launch_bounds__(B2K_THREADS, FkjBounds<real, N, WJ>::MINB)
 k_fkj_forward(const __grid_constant__ ChainP<real, N> P, const real *__restrict__ q, long long nrows, int ldq,
               float inv_ldq, int qmode, real *__restrict__ Tout, real *__restrict__ Jout, int warp_smem_bytes,
-              int q_bytes, int dbg)
+              int q_bytes, int tpw, int dbg)
 {
     // dbg (measurement skeletons, b2k_set_variant 2 / 3): bit 0 = skip the chain walk (memory
     // traffic only), bit 1 = skip the output stores (arithmetic only).  0 in normal operation.
@@ -590,22 +590,23 @@ k_fkj_forward(const __grid_constant__ ChainP<real, N> P, const real *__restrict_
     unsigned char *so = wbase + q_bytes;
     const int ldqs = qmode ? ldq : (ldq | 1);
     const long long ntiles = (nrows + 31) >> 5;
-    const long long tstride = (long long)gridDim.x * B2K_WARPS_PER_BLOCK;
-
-    long long tile = (long long)blockIdx.x * B2K_WARPS_PER_BLOCK + warp;
-    if (tile < ntiles) {
+    // a warp owns `tpw` CONSECUTIVE tiles (one-shot grid: tpw small; persistent measurement variant: all of its share)
+    const long long tstride = 1;
+    long long tile = ((long long)blockIdx.x * B2K_WARPS_PER_BLOCK + warp) * tpw;
+    const long long tile_end = (tile + tpw < ntiles) ? tile + tpw : ntiles;
+    if (tile < tile_end) {
         const long long row0 = tile << 5;
         load_q_tile<real>(sq, q + row0 * ldq, (int)((nrows - row0) < 32 ? (nrows - row0) : 32), ldq, inv_ldq, qmode, lane);
 #pragma unroll
         for (int k = 1; k < B2K_L2_PREFETCH_TILES; k++) {
             const long long ft = tile + k * tstride;
-            if (ft < ntiles) {
+            if (ft < tile_end) {
                 const long long r0 = ft << 5;
                 prefetch_q_tile_l2<real>(q + r0 * ldq, (int)((nrows - r0) < 32 ? (nrows - r0) : 32), ldq, lane);
             }
         }
     }
-    for (; tile < ntiles; tile += tstride) {
+    for (; tile < tile_end; tile += tstride) {
         const long long row0 = tile << 5;
         const int rows_here = (int)((nrows - row0) < 32 ? (nrows - row0) : 32);
         cp_async_wait_all();
@@ -620,12 +621,12 @@ k_fkj_forward(const __grid_constant__ ChainP<real, N> P, const real *__restrict_
         __syncwarp(); // every lane holds its q row in registers: prefetch the next tile's q now
         {
             const long long nt = tile + tstride;
-            if (nt < ntiles) {
+            if (nt < tile_end) {
                 const long long r0 = nt << 5;
                 load_q_tile<real>(sq, q + r0 * ldq, (int)((nrows - r0) < 32 ? (nrows - r0) : 32), ldq, inv_ldq, qmode, lane);
             }
             const long long ft = tile + B2K_L2_PREFETCH_TILES * tstride;
-            if (ft < ntiles) {
+            if (ft < tile_end) {
                 const long long r0 = ft << 5;
                 prefetch_q_tile_l2<real>(q + r0 * ldq, (int)((nrows - r0) < 32 ? (nrows - r0) : 32), ldq, lane);
             }
@@ -680,7 +681,7 @@ template <typename real, int N, bool WT, int PROF>
 __global__ void __launch_bounds__(B2K_THREADS, FkjBounds<real, N, true>::MINB)
 k_fkj_backward(const __grid_constant__ ChainP<real, N> P, const real *__restrict__ q, long long nrows, int ldq,
                float inv_ldq, int qmode, real *__restrict__ Tout, real *__restrict__ Jout, int warp_smem_bytes,
-               int q_bytes)
+               int q_bytes, int tpw)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
@@ -690,14 +691,15 @@ k_fkj_backward(const __grid_constant__ ChainP<real, N> P, const real *__restrict
     unsigned char *so = wbase + q_bytes;
     const int ldqs = qmode ? ldq : (ldq | 1);
     const long long ntiles = (nrows + 31) >> 5;
-    const long long tstride = (long long)gridDim.x * B2K_WARPS_PER_BLOCK;
-
-    long long tile = (long long)blockIdx.x * B2K_WARPS_PER_BLOCK + warp;
-    if (tile < ntiles) {
+    // a warp owns `tpw` CONSECUTIVE tiles (one-shot grid: tpw small; persistent measurement variant: all of its share)
+    const long long tstride = 1;
+    long long tile = ((long long)blockIdx.x * B2K_WARPS_PER_BLOCK + warp) * tpw;
+    const long long tile_end = (tile + tpw < ntiles) ? tile + tpw : ntiles;
+    if (tile < tile_end) {
         const long long row0 = tile << 5;
         load_q_tile<real>(sq, q + row0 * ldq, (int)((nrows - row0) < 32 ? (nrows - row0) : 32), ldq, inv_ldq, qmode, lane);
     }
-    for (; tile < ntiles; tile += tstride) {
+    for (; tile < tile_end; tile += tstride) {
         const long long row0 = tile << 5;
         const int rows_here = (int)((nrows - row0) < 32 ? (nrows - row0) : 32);
         cp_async_wait_all();
@@ -756,7 +758,7 @@ k_fkj_backward(const __grid_constant__ ChainP<real, N> P, const real *__restrict
         __syncwarp();
         {
             const long long nt = tile + tstride;
-            if (nt < ntiles) {
+            if (nt < tile_end) {
                 const long long r0 = nt << 5;
                 load_q_tile<real>(sq, q + r0 * ldq, (int)((nrows - r0) < 32 ? (nrows - r0) : 32), ldq, inv_ldq, qmode, lane);
             }
@@ -821,18 +823,20 @@ int fkj_launch_n(const b2k_chain_s *c, int mode, const real *q, long long nrows,
     auto launch_impl = [&](auto kern, auto... extra) -> int {
         int per_sm = b2k_blocks_per_sm((const void *)kern, B2K_THREADS, smem);
         if (per_sm < 1) return per_sm < 0 ? per_sm : (b2k_set_error("fkj kernel does not fit on an SM (smem %zu B)", smem), B2K_ERR_INVALID);
-        // One tile per warp, one-shot grid: the hardware block scheduler hands out tiles in address
-        // order as SMs free up, which keeps the set of DRAM pages being written compact.  A
-        // persistent grid-stride loop (variant 4) measured 15-20 % lower write bandwidth on B200
-        // (scripts/exp/exp_mem3.cu: 5.96 vs 6.73 TB/s for this exact store pattern).
-        long long grid = nblk_needed;
-        if (variant == 4) {
-            grid = (long long)b2k_num_sms() * per_sm;
-            if (grid > nblk_needed) grid = nblk_needed;
+        // One-shot grid, a few consecutive tiles per warp: the hardware block scheduler hands out
+        // row ranges in address order as SMs free up, which keeps the set of DRAM pages being
+        // written compact.  A persistent grid (variant 4) measured 15-20 % lower write bandwidth
+        // on B200 (scripts/exp/exp_mem3.cu: 5.96 vs 6.73 TB/s for this exact store pattern).
+        long long tpw = b2k_tiles_per_warp(wj0 || wje);
+        if (variant == 4) { // persistent: as many blocks as fit, each warp a contiguous share of the tiles
+            long long g = (long long)b2k_num_sms() * per_sm;
+            if (g > nblk_needed) g = nblk_needed;
+            tpw = (ntiles + g * B2K_WARPS_PER_BLOCK - 1) / (g * B2K_WARPS_PER_BLOCK);
         }
+        long long grid = (ntiles + B2K_WARPS_PER_BLOCK * tpw - 1) / (B2K_WARPS_PER_BLOCK * tpw);
         if (grid < 1) grid = 1;
-        if (grid > 0x7fffffffLL) { b2k_set_error("fkj: batch too large for one launch"); return B2K_ERR_INVALID; }
-        kern<<<(unsigned)grid, B2K_THREADS, smem, st>>>(P, q, nrows, ldq, inv_ldq, qmode, T, J, (int)wsm, (int)qb, extra...);
+        if (grid > 0x7fffffffLL || tpw > 0x7fffffffLL) { b2k_set_error("fkj: batch too large for one launch"); return B2K_ERR_INVALID; }
+        kern<<<(unsigned)grid, B2K_THREADS, smem, st>>>(P, q, nrows, ldq, inv_ldq, qmode, T, J, (int)wsm, (int)qb, (int)tpw, extra...);
         b2k_count_launch();
         B2K_CUDA(cudaGetLastError());
         return B2K_OK;

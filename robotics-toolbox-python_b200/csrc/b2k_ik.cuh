@@ -24,7 +24,7 @@ struct IkP {
     real qlim_l[N], qlim_h[N];
     real we[6];
     real lambda, tol;
-    int ilimit, slimit, method, reject_jl, semantics, rng_per_row, has_q0;
+    int ilimit, slimit, method, reject_jl, semantics, rng_per_row, has_q0, unit_w;
     unsigned long long seed;
 };
 
@@ -144,99 +144,63 @@ __device__ __forceinline__ bool ik_chol_solve(real *A, real *b)
     return ok;
 }
 
+// ------------------------------------------------------------------ one LM evaluation (+ update) in registers
+// Evaluates the pose error e and cost E at q, then forms the Jacobian, the normal equations and the
+// damped update dq (left in g).  Returns false when A cannot be factorised.
+// (K.unit_w: We = I, the common case -- the weights are then left out of the 35 inner products)
 template <typename real, int N, int PROF>
-__global__ void __launch_bounds__(B2K_THREADS)
-k_ik_lm(const __grid_constant__ ChainP<real, N> P, const __grid_constant__ IkP<real, N> K,
-        const real *__restrict__ Tep, const real *__restrict__ q0, long long nprob, real *__restrict__ q_out,
-        int *__restrict__ success, int *__restrict__ iterations, int *__restrict__ searches,
-        real *__restrict__ residual)
+__device__ __forceinline__ bool ik_eval(const ChainP<real, N> &P, const IkP<real, N> &K, const real *Tp, const real *q,
+                                        real &Ecur, real *g, bool skip_step_if_converged)
 {
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const real PI = (real)3.14159265358979323846264338327950288;
-    const real PI_X2 = (real)6.283185307179586;
-
-    real q[N], Tp[12], E = 0;
-    int it = 0, search = 0, iter = 0; // meaning depends on semantics, see below
-    bool active = idx < nprob;
-
-    auto begin_problem = [&]() {
-        const real *t = Tep + idx * 16;
+    Pose<real> Te;
+    real zj[N][3], pj[N][3], e[6];
+    // jindex is dense 0..n-1 here (checked on the host, like the reference's C++ loop assumes)
+    chain_forward<real, N, true, PROF>(P, [&](int j, int) { return q[j]; }, Te, zj, pj);
+    ik_angle_axis<real>(Te, Tp, e);
+    real E = 0;
+    if (K.unit_w) {
 #pragma unroll
-        for (int k = 0; k < 12; k++) Tp[k] = t[k];
-        const unsigned long long row = K.rng_per_row ? (unsigned long long)idx : 0ULL;
-        if (K.has_q0) {
+        for (int k = 0; k < 6; k++) E = fma(e[k], e[k], E);
+    } else {
 #pragma unroll
-            for (int i = 0; i < N; i++) q[i] = q0[idx * N + i];
+        for (int k = 0; k < 6; k++) E += e[k] * K.we[k] * e[k];
+    }
+    E *= (real)0.5;
+    Ecur = E;
+    if (skip_step_if_converged && E < K.tol) return true; // the C++ loop tests E before stepping (ik.cpp:48)
+    real J[N][6];
+#pragma unroll
+    for (int j = 0; j < N; j++) {
+        const bool rev = PROF == 1 ? true : (P.axis[j] < 3);
+        if (rev) {
+            real dx = Te.p[0] - pj[j][0], dy = Te.p[1] - pj[j][1], dz = Te.p[2] - pj[j][2];
+            J[j][0] = fma(zj[j][1], dz, -(zj[j][2] * dy));
+            J[j][1] = fma(zj[j][2], dx, -(zj[j][0] * dz));
+            J[j][2] = fma(zj[j][0], dy, -(zj[j][1] * dx));
+            J[j][3] = zj[j][0]; J[j][4] = zj[j][1]; J[j][5] = zj[j][2];
         } else {
-            ik_rand_q<real, N>(K, row, 0u, q);
+            J[j][0] = zj[j][0]; J[j][1] = zj[j][1]; J[j][2] = zj[j][2];
+            J[j][3] = 0; J[j][4] = 0; J[j][5] = 0;
         }
-        E = 0;
-        if (K.semantics == B2K_IK_SEM_CPP) { it = 0; search = 1; iter = 1; } // fknm.cpp:406, ik.cpp:39
-        else { it = 0; search = 0; iter = 0; }                                  // IK.py:299-312
-    };
-    auto finish = [&](int ok, int its, int srch) {
+    }
+    const real wn = (K.method == B2K_LM_CHAN) ? K.lambda * E : (K.method == B2K_LM_WAMPLER) ? K.lambda : (E + K.lambda);
+    real A[N * (N + 1) / 2];
+    if (K.unit_w) {
 #pragma unroll
-        for (int i = 0; i < N; i++) q_out[idx * N + i] = q[i];
-        success[idx] = ok;
-        iterations[idx] = its;
-        searches[idx] = srch;
-        residual[idx] = E;
-        idx += stride;
-        active = idx < nprob;
-        if (active) begin_problem();
-    };
-    if (active) begin_problem();
-
-    while (active) {
-        // ---- evaluate pose error at q
-        Pose<real> Te;
-        real zj[N][3], pj[N][3], e[6];
-        // jindex is dense 0..n-1 here (checked on the host, like the reference's C++ loop assumes)
-        chain_forward<real, N, true, PROF>(P, [&](int j, int) { return q[j]; }, Te, zj, pj);
-        ik_angle_axis<real>(Te, Tp, e);
-        real Ecur = 0;
+        for (int i = 0; i < N; i++) {
+            real s = 0;
 #pragma unroll
-        for (int k = 0; k < 6; k++) Ecur += e[k] * K.we[k] * e[k];
-        Ecur *= (real)0.5;
-        E = Ecur;
-        const unsigned long long row = K.rng_per_row ? (unsigned long long)idx : 0ULL;
-
-        if (K.semantics == B2K_IK_SEM_CPP && Ecur < K.tol) {
-            // ik.cpp:48-54: wrap with fmod (sign of the dividend), then the limit test
-            bool inlim = true;
+            for (int k = 0; k < 6; k++) s = fma(J[i][k], e[k], s);
+            g[i] = s;
 #pragma unroll
-            for (int i = 0; i < N; i++) {
-                q[i] = b2k_fmod<real>(q[i] + PI, PI_X2) - PI;
-                inlim = inlim && !(q[i] < K.qlim_l[i] || q[i] > K.qlim_h[i]);
-            }
-            if (!K.reject_jl || inlim) { finish(1, it + iter, search); continue; }
-            // converged outside the limits: this search is abandoned (ik.cpp:61-69)
-            it += iter; iter = 0; search++;
-            if (search > K.slimit) { ik_rand_q<real, N>(K, row, (unsigned)(search - 1), q); finish(0, it, search); continue; }
-            ik_rand_q<real, N>(K, row, (unsigned)(search - 1), q);
-            continue;
-        }
-
-        // ---- LM step: g = J^T We e ; A = J^T We J + Wn (packed lower) ; dq = A^-1 g
-        real J[N][6];
+            for (int j = 0; j <= i; j++) {
+                real a = (i == j) ? wn : (real)0;
 #pragma unroll
-        for (int j = 0; j < N; j++) {
-            const bool rev = PROF == 1 ? true : (P.axis[j] < 3);
-            if (rev) {
-                real dx = Te.p[0] - pj[j][0], dy = Te.p[1] - pj[j][1], dz = Te.p[2] - pj[j][2];
-                J[j][0] = fma(zj[j][1], dz, -(zj[j][2] * dy));
-                J[j][1] = fma(zj[j][2], dx, -(zj[j][0] * dz));
-                J[j][2] = fma(zj[j][0], dy, -(zj[j][1] * dx));
-                J[j][3] = zj[j][0]; J[j][4] = zj[j][1]; J[j][5] = zj[j][2];
-            } else {
-                J[j][0] = zj[j][0]; J[j][1] = zj[j][1]; J[j][2] = zj[j][2];
-                J[j][3] = 0; J[j][4] = 0; J[j][5] = 0;
+                for (int k = 0; k < 6; k++) a = fma(J[i][k], J[j][k], a);
+                A[i * (i + 1) / 2 + j] = a;
             }
         }
-        const real wn = (K.method == B2K_LM_CHAN) ? K.lambda * Ecur
-                        : (K.method == B2K_LM_WAMPLER) ? K.lambda : (Ecur + K.lambda);
-        real A[N * (N + 1) / 2], g[N];
+    } else {
 #pragma unroll
         for (int i = 0; i < N; i++) {
             real s = 0;
@@ -251,52 +215,247 @@ k_ik_lm(const __grid_constant__ ChainP<real, N> P, const __grid_constant__ IkP<r
                 A[i * (i + 1) / 2 + j] = a + (i == j ? wn : (real)0);
             }
         }
-        const bool ok = ik_chol_solve<real, N>(A, g);
+    }
+    return ik_chol_solve<real, N>(A, g);
+}
 
+// wrap to [-pi, pi) the way each reference loop does, and test the joint limits
+template <typename real, int N>
+__device__ __forceinline__ bool ik_wrap_and_check(const IkP<real, N> &K, real *q)
+{
+    const real PI = (real)3.14159265358979323846264338327950288;
+    bool inlim = true;
+#pragma unroll
+    for (int i = 0; i < N; i++) {
         if (K.semantics == B2K_IK_SEM_CPP) {
-            bool restart = false;
+            q[i] = b2k_fmod<real>(q[i] + PI, (real)6.283185307179586) - PI; // ik.cpp:51: fmod keeps the dividend's sign
+        } else {
+            real w = b2k_fmod<real>(q[i] + PI, (real)2 * PI);
+            if (w < 0) w += (real)2 * PI; // Python floor-modulo (IK.py:331)
+            q[i] = w - PI;
+        }
+        inlim = inlim && !(q[i] < K.qlim_l[i] || q[i] > K.qlim_h[i]);
+    }
+    return inlim;
+}
+
+// ------------------------------------------------------------------ phase A: one lane per problem (flattened state machine)
+// Every loop trip is exactly one LM evaluation for every active lane, whatever problem / search /
+// iteration the lane is at, so the lanes of a warp never leave the common code.  With
+// two_phase != 0 a lane does only the FIRST search of a problem; a problem whose first search
+// fails is appended to the hard list (with its iteration contribution) for k_ik_restarts.
+template <typename real, int N, int PROF>
+__global__ void __launch_bounds__(B2K_THREADS)
+k_ik_lm(const __grid_constant__ ChainP<real, N> P, const __grid_constant__ IkP<real, N> K,
+        const real *__restrict__ Tep, const real *__restrict__ q0, long long nprob, real *__restrict__ q_out,
+        int *__restrict__ success, int *__restrict__ iterations, int *__restrict__ searches,
+        real *__restrict__ residual, int two_phase, int *__restrict__ hard_idx, int *__restrict__ hard_count)
+{
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool cpp = K.semantics == B2K_IK_SEM_CPP;
+
+    real q[N], Tp[12], E = 0;
+    int it = 0, search = 0, iter = 0; // search is 0-based here; reported 1-based (cpp: ik.cpp:39-69, python: IK.py:299-348)
+    bool active = idx < nprob;
+
+    auto begin_problem = [&]() {
+        const real *t = Tep + idx * 16;
+#pragma unroll
+        for (int k = 0; k < 12; k++) Tp[k] = t[k];
+        const unsigned long long row = K.rng_per_row ? (unsigned long long)idx : 0ULL;
+        if (K.has_q0) {
+#pragma unroll
+            for (int i = 0; i < N; i++) q[i] = q0[idx * N + i];
+        } else {
+            ik_rand_q<real, N>(K, row, 0u, q);
+        }
+        E = 0; it = 0; search = 0;
+        iter = cpp ? 1 : 0; // the C++ loop's first search starts counting at 1 (ik.cpp:39), later ones at 0 (ik.cpp:67)
+    };
+    auto next_problem = [&]() {
+        idx += stride;
+        active = idx < nprob;
+        if (active) begin_problem();
+    };
+    auto finish = [&](int ok, int its, int srch) {
+#pragma unroll
+        for (int i = 0; i < N; i++) q_out[idx * N + i] = q[i];
+        success[idx] = ok;
+        iterations[idx] = its;
+        searches[idx] = srch;
+        residual[idx] = E;
+        next_problem();
+    };
+    // this search failed with `iter` evaluations counted: restart, hand over to phase B, or give up
+    auto search_failed = [&]() {
+        it += iter; iter = 0; search++;
+        const unsigned long long row = K.rng_per_row ? (unsigned long long)idx : 0ULL;
+        if (search >= K.slimit) {
+            if (cpp) { ik_rand_q<real, N>(K, row, (unsigned)search, q); finish(0, it, K.slimit + 1); } // ik.cpp:66-69 then exit
+            else finish(0, it, K.slimit);                                                               // IK.py:360-367
+            return;
+        }
+        if (two_phase) {
+            iterations[idx] = it;
+            hard_idx[atomicAdd(hard_count, 1)] = (int)idx;
+            next_problem();
+            return;
+        }
+        ik_rand_q<real, N>(K, row, (unsigned)search, q);
+    };
+    if (active) begin_problem();
+
+    while (active) {
+        real g[N], Ecur;
+        if (cpp) {
+            // test before stepping (ik.cpp:44-58)
+            const bool ok = ik_eval<real, N, PROF>(P, K, Tp, q, Ecur, g, true);
+            E = Ecur;
+            if (Ecur < K.tol) {
+                const bool inlim = ik_wrap_and_check<real, N>(K, q);
+                if (!K.reject_jl || inlim) finish(1, it + iter, search + 1);
+                else search_failed(); // converged outside the limits: this search is abandoned
+                continue;
+            }
+            iter++;
             if (ok) {
 #pragma unroll
                 for (int i = 0; i < N; i++) q[i] += g[i];
-                iter++;
-                restart = iter > K.ilimit;
-            } else {
-                iter++;
-                restart = true; // unfactorisable normal matrix: abandon this search
             }
-            if (restart) {
-                it += iter; iter = 0; search++;
-                ik_rand_q<real, N>(K, row, (unsigned)(search - 1), q);
-                if (search > K.slimit) { finish(0, it, search); continue; }
-            }
+            if (!ok || iter > K.ilimit) search_failed();
         } else {
-            // Python semantics: count the step, apply it, then test the PRE-step E (IK.py:314-327)
+            // count the step, apply it, then test the PRE-step E (IK.py:314-348)
+            const bool ok = ik_eval<real, N, PROF>(P, K, Tp, q, Ecur, g, false);
+            E = Ecur;
             iter++;
-            bool next_search = false;
-            if (!ok) {
-                next_search = true; // numpy LinAlgError -> abandon search (IK.py:321-324)
-            } else {
+            if (!ok) { search_failed(); continue; } // numpy LinAlgError: abandon the search (IK.py:321-324)
 #pragma unroll
-                for (int i = 0; i < N; i++) q[i] += g[i];
-                if (Ecur < K.tol) {
-                    bool inlim = true;
+            for (int i = 0; i < N; i++) q[i] += g[i];
+            if (Ecur < K.tol) {
+                const bool inlim = ik_wrap_and_check<real, N>(K, q);
+                if (inlim || !K.reject_jl) finish(1, it + iter, search + 1);
+                else search_failed();
+            } else if (iter >= K.ilimit) {
+                search_failed();
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------ phase B: G lanes per hard problem, searches in parallel
+// The restart draws are counter-based (seed, row, search, joint), so search s of a problem does not
+// depend on searches 0..s-1.  A group of G lanes therefore runs G consecutive searches of one hard
+// problem at the same time; the lowest-numbered successful search wins and the iteration counter
+// is the sum of the contributions of all lower-numbered searches plus its own -- exactly what
+// the sequential loop reports, but the latency of a problem needing k restarts drops from
+// k x ilimit LM iterations to ceil(k / G) x ilimit.
+template <typename real, int N, int PROF, int G>
+__global__ void __launch_bounds__(B2K_THREADS)
+k_ik_restarts(const __grid_constant__ ChainP<real, N> P, const __grid_constant__ IkP<real, N> K,
+              const real *__restrict__ Tep, real *__restrict__ q_out, int *__restrict__ success,
+              int *__restrict__ iterations, int *__restrict__ searches, real *__restrict__ residual,
+              const int *__restrict__ hard_idx, const int *__restrict__ hard_count)
+{
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int sub = lane % G, gbase = lane - sub;
+    const bool cpp = K.semantics == B2K_IK_SEM_CPP;
+    const long long ngroups = (long long)gridDim.x * (blockDim.x / G);
+    const int nhard = *hard_count;
+    for (long long h = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / G; ; h += ngroups) {
+        // all lanes of a warp leave together (the loop below uses warp-wide shuffles)
+        const long long h_first = h - (lane / G); // group 0's h in this warp
+        if (h_first >= nhard) break;
+        const bool have = h < nhard;
+        const long long idx = have ? hard_idx[h] : 0;
+        const unsigned long long row = K.rng_per_row ? (unsigned long long)idx : 0ULL;
+        real Tp[12];
 #pragma unroll
-                    for (int i = 0; i < N; i++) {
-                        real w = b2k_fmod<real>(q[i] + PI, (real)2 * PI);
-                        if (w < 0) w += (real)2 * PI; // Python floor-modulo (IK.py:331)
-                        q[i] = w - PI;
-                        inlim = inlim && !(q[i] < K.qlim_l[i] || q[i] > K.qlim_h[i]);
+        for (int k = 0; k < 12; k++) Tp[k] = Tep[idx * 16 + k];
+        int it_total = have ? iterations[idx] : 0;
+        bool done = !have;
+        for (int s0 = 1; s0 < K.slimit; s0 += G) { // batch of searches s0 .. s0+G-1 (0-based; search 0 was phase A)
+            if (__all_sync(FULL, done)) break;
+            const int s = s0 + sub;
+            const bool run = !done && s < K.slimit;
+            real q[N], E = 0;
+            int iters = 0;
+            bool won = false;
+            if (run) ik_rand_q<real, N>(K, row, (unsigned)s, q);
+            bool going = run;
+            while (__any_sync(FULL, going)) {
+                if (going) {
+                    real g[N], Ecur;
+                    if (cpp) {
+                        const bool ok = ik_eval<real, N, PROF>(P, K, Tp, q, Ecur, g, true);
+                        E = Ecur;
+                        if (Ecur < K.tol) {
+                            const bool inlim = ik_wrap_and_check<real, N>(K, q);
+                            won = !K.reject_jl || inlim;
+                            going = false;
+                        } else {
+                            iters++;
+                            if (ok) {
+#pragma unroll
+                                for (int i = 0; i < N; i++) q[i] += g[i];
+                            }
+                            if (!ok || iters > K.ilimit) going = false;
+                        }
+                    } else {
+                        const bool ok = ik_eval<real, N, PROF>(P, K, Tp, q, Ecur, g, false);
+                        E = Ecur;
+                        iters++;
+                        if (!ok) going = false;
+                        else {
+#pragma unroll
+                            for (int i = 0; i < N; i++) q[i] += g[i];
+                            if (Ecur < K.tol) {
+                                const bool inlim = ik_wrap_and_check<real, N>(K, q);
+                                won = inlim || !K.reject_jl;
+                                going = false;
+                            } else if (iters >= K.ilimit) going = false;
+                        }
                     }
-                    if (inlim || !K.reject_jl) { finish(1, it + iter, search + 1); continue; }
-                    next_search = true;
-                } else if (iter >= K.ilimit) {
-                    next_search = true;
                 }
             }
-            if (next_search) {
-                it += iter; iter = 0; search++;
-                if (search >= K.slimit) { finish(0, it, K.slimit); continue; }
-                ik_rand_q<real, N>(K, row, (unsigned)search, q);
+            // group reduction: lowest successful search wins; iteration contributions of the searches before it add up
+            const unsigned wins = (__ballot_sync(FULL, won) >> gbase) & ((1u << G) - 1u);
+            const int wsub = wins ? (__ffs(wins) - 1) : G;
+            int pre = 0, all = 0; // sum of iters over subs < wsub / over the whole batch
+#pragma unroll
+            for (int k = 0; k < G; k++) {
+                const int v = __shfl_sync(FULL, iters, gbase + k);
+                all += v;
+                if (k < wsub) pre += v;
+            }
+            if (!done) {
+                if (wins) {
+                    if (sub == wsub) {
+#pragma unroll
+                        for (int i = 0; i < N; i++) q_out[idx * N + i] = q[i];
+                        success[idx] = 1;
+                        iterations[idx] = it_total + pre + iters;
+                        searches[idx] = s + 1;
+                        residual[idx] = E;
+                    }
+                    done = true;
+                } else {
+                    it_total += all;
+                    if (s0 + G >= K.slimit) { // every search failed: report like the sequential loops do
+                        const int last = K.slimit - 1 - s0; // sub that ran the last search
+                        if (sub == last) {
+                            if (cpp) ik_rand_q<real, N>(K, row, (unsigned)K.slimit, q); // ik.cpp:69: a fresh draw is what remains in q
+#pragma unroll
+                            for (int i = 0; i < N; i++) q_out[idx * N + i] = q[i];
+                            success[idx] = 0;
+                            iterations[idx] = it_total;
+                            searches[idx] = cpp ? K.slimit + 1 : K.slimit;
+                            residual[idx] = E;
+                        }
+                        done = true;
+                    }
+                }
             }
         }
     }
@@ -312,24 +471,55 @@ int ik_launch_n(const b2k_chain_s *c, const real *Tep, long long nprob, const re
     b2k_fill_chain<real, N>(c, nullptr, nullptr, true, P);
     IkP<real, N> K;
     for (int i = 0; i < N; i++) { K.qlim_l[i] = (real)c->qlim_l[i]; K.qlim_h[i] = (real)c->qlim_h[i]; }
-    for (int k = 0; k < 6; k++) K.we[k] = we ? (real)we[k] : (real)1;
+    K.unit_w = 1;
+    for (int k = 0; k < 6; k++) { K.we[k] = we ? (real)we[k] : (real)1; if (K.we[k] != (real)1) K.unit_w = 0; }
     K.lambda = (real)lambda; K.tol = (real)tol;
     K.ilimit = ilimit; K.slimit = slimit; K.method = method; K.reject_jl = reject_jl ? 1 : 0;
     K.semantics = semantics; K.rng_per_row = rng_per_row ? 1 : 0; K.has_q0 = q0 ? 1 : 0; K.seed = seed;
-    auto launch = [&](auto kern) -> int {
+    // Two phases when restarts are allowed and the batch is large enough to matter: phase A runs the
+    // first search of every problem (one lane each); phase B runs the restarts of the problems that
+    // failed it with B2K_IK_GROUP lanes per problem.  Scratch (hard list + counter) is stream-ordered.
+    constexpr int G = 8;
+    const bool two_phase = slimit > 1 && nprob >= 1024 && b2k_get_variant() != 4;
+    int *scratch = nullptr;
+    if (two_phase) {
+        b2k_keep_mempool(); // do not hand the pool's memory back to the OS at every synchronisation
+        B2K_CUDA(cudaMallocAsync((void **)&scratch, sizeof(int) * (size_t)(nprob + 1), st));
+        B2K_CUDA(cudaMemsetAsync(scratch, 0, sizeof(int), st));
+    }
+    int *hard_count = scratch, *hard_idx = scratch ? scratch + 1 : nullptr;
+    auto launch_a = [&](auto kern) -> int {
         int per_sm = b2k_blocks_per_sm((const void *)kern, B2K_THREADS, 0);
         if (per_sm < 1) return per_sm < 0 ? per_sm : (b2k_set_error("ik kernel does not fit on an SM"), B2K_ERR_INVALID);
         long long grid = (long long)b2k_num_sms() * per_sm;
         long long need = (nprob + B2K_THREADS - 1) / B2K_THREADS;
         if (grid > need) grid = need;
         if (grid < 1) grid = 1;
-        kern<<<(unsigned)grid, B2K_THREADS, 0, st>>>(P, K, Tep, q0, nprob, q_out, success, iterations, searches, residual);
+        kern<<<(unsigned)grid, B2K_THREADS, 0, st>>>(P, K, Tep, q0, nprob, q_out, success, iterations, searches, residual,
+                                                     two_phase ? 1 : 0, hard_idx, hard_count);
         b2k_count_launch();
         B2K_CUDA(cudaGetLastError());
         return B2K_OK;
     };
-    if (c->dh_like) return launch(k_ik_lm<real, N, 1>);
-    return launch(k_ik_lm<real, N, 0>);
+    auto launch_b = [&](auto kern) -> int {
+        int per_sm = b2k_blocks_per_sm((const void *)kern, B2K_THREADS, 0);
+        if (per_sm < 1) return per_sm < 0 ? per_sm : (b2k_set_error("ik restart kernel does not fit on an SM"), B2K_ERR_INVALID);
+        long long grid = (long long)b2k_num_sms() * per_sm;
+        long long need = (nprob * G + B2K_THREADS - 1) / B2K_THREADS; // upper bound: every problem hard
+        if (grid > need) grid = need;
+        if (grid < 1) grid = 1;
+        kern<<<(unsigned)grid, B2K_THREADS, 0, st>>>(P, K, Tep, q_out, success, iterations, searches, residual, hard_idx, hard_count);
+        b2k_count_launch();
+        B2K_CUDA(cudaGetLastError());
+        return B2K_OK;
+    };
+    int rc = c->dh_like ? launch_a(k_ik_lm<real, N, 1>) : launch_a(k_ik_lm<real, N, 0>);
+    if (rc == B2K_OK && two_phase) rc = c->dh_like ? launch_b(k_ik_restarts<real, N, 1, G>) : launch_b(k_ik_restarts<real, N, 0, G>);
+    if (scratch) {
+        cudaError_t e = cudaFreeAsync(scratch, st);
+        if (e != cudaSuccess && rc == B2K_OK) rc = b2k_cuda_fail(e, "cudaFreeAsync");
+    }
+    return rc;
 }
 
 template <typename real>
