@@ -160,6 +160,24 @@ int b2k_rne_destroy(b2k_rne_t rne);
 int b2k_rne(b2k_rne_t rne, int dtype, const void *q, const void *qd, const void *qdd, int64_t N,
             const double *grav, const double *fext, void *tau, void *stream);
 
+/* ---------------------------------------------------------------- dynamics built on the recursion
+ * The reference's DynamicsMixin (robot/Dynamics.py) obtains these by looping frne calls in
+ * Python; here each is ONE kernel in which a lane performs all the recursions of its row
+ * (SURVEY 8f-1).  q, qd, qdd, torque are (N,n) device arrays; gravity conventions as b2k_rne
+ * (grav = MINUS the robot's gravity, host 3-vector).
+ *   b2k_rne_inertia   M (N,n,n): row i of M[k] = rne(q_k, 0, e_i, g=0)          Dynamics.py:704-763
+ *   b2k_rne_gravload  taug (N,n) = rne(q, 0, 0, g)                              Dynamics.py:863-921
+ *   b2k_rne_itorque   taui (N,n) = rne(q, 0, qdd, g=0)                          Dynamics.py:1407-1465
+ *   b2k_rne_coriolis  C (N,n,n), on a friction-free copy of the robot           Dynamics.py:765-861
+ *   b2k_rne_accel     qdd (N,n) = M^-1 (torque - rne(q, qd, 0, g)), friction kept  Dynamics.py:424-510
+ */
+int b2k_rne_inertia(b2k_rne_t rne, int dtype, const void *q, int64_t N, void *M, void *stream);
+int b2k_rne_gravload(b2k_rne_t rne, int dtype, const void *q, int64_t N, const double *grav, void *taug, void *stream);
+int b2k_rne_itorque(b2k_rne_t rne, int dtype, const void *q, const void *qdd, int64_t N, void *taui, void *stream);
+int b2k_rne_coriolis(b2k_rne_t rne, int dtype, const void *q, const void *qd, int64_t N, void *C, void *stream);
+int b2k_rne_accel(b2k_rne_t rne, int dtype, const void *q, const void *qd, const void *torque, int64_t N,
+                  const double *grav, void *qdd, void *stream);
+
 /* ---------------------------------------------------------------- host-buffer front ends
  * The same operations for callers that hold HOST arrays (what the reference's API takes):
  * the library streams row chunks host->device, runs the kernel and streams results back on

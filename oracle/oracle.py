@@ -172,3 +172,69 @@ def set_threads(t: int):
 
 def num_threads() -> int:
     return lib().orc_num_threads()
+
+
+# ------------------------------------------------------------------ dynamics fan-outs (reference Dynamics.py), on top of rne()
+# Restated loop for loop from the reference's DynamicsMixin; `rne_fn(q, qd, qdd, grav)` is either this
+# module's rne (C restatement) or the compiled reference's frne via ref_driver.RefRNE.
+def dyn_inertia(rne_fn, n, q):
+    """Dynamics.py:752-758"""
+    q = np.atleast_2d(q)
+    out = np.zeros((q.shape[0], n, n))
+    for k, qk in enumerate(q):
+        out[k] = rne_fn(np.tile(qk, (n, 1)), np.zeros((n, n)), np.eye(n), np.zeros(3))
+    return out
+
+
+def dyn_gravload(rne_fn, n, q, gravity):
+    """Dynamics.py:912-915"""
+    q = np.atleast_2d(q)
+    return rne_fn(q, np.zeros_like(q), np.zeros_like(q), gravity)
+
+
+def dyn_itorque(rne_fn, n, q, qdd):
+    """Dynamics.py:1456-1459"""
+    q = np.atleast_2d(q)
+    return rne_fn(q, np.zeros_like(q), np.atleast_2d(qdd), np.zeros(3))
+
+
+def dyn_coriolis(rne_nofriction_fn, n, q, qd):
+    """Dynamics.py:818-857 (the caller passes an rne of the friction-free robot, line 818)"""
+    q, qd = np.atleast_2d(q), np.atleast_2d(qd)
+    N = q.shape[0]
+    C = np.zeros((N, n, n))
+    Csq = np.zeros((N, n, n))
+    z = np.zeros(n)
+    g0 = np.zeros(3)
+    for k, qk in enumerate(q):
+        for i in range(n):
+            QD = np.zeros(n); QD[i] = 1
+            Csq[k, :, i] = Csq[k, :, i] + rne_nofriction_fn(qk, QD, z, g0)[0]
+    for k, (qk, qdk) in enumerate(zip(q, qd)):
+        for i in range(n):
+            for j in range(i + 1, n):
+                QD = np.zeros(n); QD[i] = 1; QD[j] = 1
+                tau = rne_nofriction_fn(qk, QD, z, g0)[0]
+                C[k, :, j] = C[k, :, j] + (tau - Csq[k, :, j] - Csq[k, :, i]) * qdk[i] / 2
+                C[k, :, i] = C[k, :, i] + (tau - Csq[k, :, j] - Csq[k, :, i]) * qdk[j] / 2
+        C[k] = C[k] + Csq[k] @ np.diag(qdk)
+    return C
+
+
+def dyn_accel(rne_fn, n, q, qd, torque, gravity):
+    """Dynamics.py:490-503"""
+    q, qd, torque = np.atleast_2d(q), np.atleast_2d(qd), np.atleast_2d(torque)
+    out = np.zeros_like(q)
+    for k, (qk, qdk, tk) in enumerate(zip(q, qd, torque)):
+        M = rne_fn(np.tile(qk, (n, 1)), np.zeros((n, n)), np.eye(n), np.zeros(3))
+        tau = rne_fn(qk, qdk, np.zeros(n), gravity)[0]
+        out[k] = np.linalg.solve(M, tk - tau)
+    return out
+
+
+def nofriction_L(L):
+    """robot.nofriction(coulomb=True, viscous=True): B = 0, Tc = 0 in the packed link table (Link.py:1548-1590)."""
+    L = np.array(L, dtype=np.float64).reshape(-1, 24).copy()
+    L[:, 21] = 0.0
+    L[:, 22:24] = 0.0
+    return L.ravel()

@@ -223,3 +223,57 @@ class DHRobot:
             _lib.check(L.b2k_rne(self._rne_ob, B.code(dt), B.ptr(qt), B.ptr(qdt), B.ptr(qddt), N, _lib.dptr(ng),
                                  _lib.dptr(fx), B.ptr(tau), B.stream_ptr(qt)))
         return tau[0] if single else tau
+
+    # ---- dynamics built on the recursion (reference DynamicsMixin, Dynamics.py)
+    def _dyn(self, fn_name, ins, out_tail, gravity=None, use_gravity=False, dtype=None):
+        """Shared front end of the fan-out kernels: every input (N,n) or (n,), one launch."""
+        if self._rne_ob is None or self._dynchanged:
+            self.delete_rne()
+            self._init_rne()
+        n = self.n
+        for x in ins:
+            B.check_numeric(x)
+        dt = B.pick_dtype(ins[0], dtype)
+        host = not B.is_tensor(ins[0])
+        single = (ins[0].dim() if B.is_tensor(ins[0]) else np.ndim(ins[0])) == 1
+        dev = []
+        for x in ins:
+            t = B.to_device(x, dt)
+            t = t.reshape(1, -1) if t.dim() == 1 else t
+            dev.append(t.contiguous())
+        N = dev[0].shape[0]
+        for t in dev:
+            if t.dim() != 2 or tuple(t.shape) != (N, n):
+                raise ValueError(f"inputs must have shape ({n},) or (N,{n}); got {tuple(t.shape)}")
+        out = B.empty((N,) + out_tail, dt, like=dev[0])
+        args = [self._rne_ob, B.code(dt)] + [B.ptr(t) for t in dev] + [N]
+        if use_gravity:
+            g = self._gravity if gravity is None else np.asarray(gravity, dtype=np.float64).reshape(3)
+            g = np.ascontiguousarray(-(self._base[:3, :3].T @ g))  # as DHRobot.rne: reference 1431-1433, 1449
+            args.append(_lib.dptr(g))
+        args += [B.ptr(out), B.stream_ptr(dev[0])]
+        _lib.check(getattr(_lib.lib(), fn_name)(*args))
+        if host:
+            out = B.to_host(out)
+        return out[0] if single else out
+
+    def inertia(self, q, dtype=None):
+        """Joint-space inertia matrix M(q): (n,n) or (N,n,n) (reference Dynamics.inertia, Dynamics.py:704-763)."""
+        return self._dyn("b2k_rne_inertia", [q], (self.n, self.n), dtype=dtype)
+
+    def gravload(self, q, gravity=None, dtype=None):
+        """Gravity load tau_g(q) (reference Dynamics.gravload, Dynamics.py:863-921)."""
+        return self._dyn("b2k_rne_gravload", [q], (self.n,), gravity=gravity, use_gravity=True, dtype=dtype)
+
+    def itorque(self, q, qdd, dtype=None):
+        """Inertia torque M(q) qdd (reference Dynamics.itorque, Dynamics.py:1407-1465)."""
+        return self._dyn("b2k_rne_itorque", [q, qdd], (self.n,), dtype=dtype)
+
+    def coriolis(self, q, qd, dtype=None):
+        """Coriolis / centripetal matrix C(q, qd), friction ignored (reference Dynamics.coriolis, Dynamics.py:765-861)."""
+        return self._dyn("b2k_rne_coriolis", [q, qd], (self.n, self.n), dtype=dtype)
+
+    def accel(self, q, qd, torque, gravity=None, dtype=None):
+        """Forward dynamics qdd = M(q)^-1 (torque - rne(q, qd, 0)), joint friction included
+        (reference Dynamics.accel, Dynamics.py:424-510)."""
+        return self._dyn("b2k_rne_accel", [q, qd, torque], (self.n,), gravity=gravity, use_gravity=True, dtype=dtype)

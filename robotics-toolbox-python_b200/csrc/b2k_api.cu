@@ -395,3 +395,47 @@ extern "C" int b2k_ik_lm(b2k_chain_t c, int dtype, const void *Tep, int64_t N, c
     return b2k_ik_launch_f32(c, Tep, N, q0, ilimit, slimit, tol, reject_jl, we, lambda, method, seed, semantics,
                              rng_per_row, q_out, success, iterations, searches, residual, st);
 }
+
+// ------------------------------------------------------------------ dynamics fan-outs
+int b2k_rne_fan_launch_f32(const b2k_rne_s *, int, const void *, const void *, const void *, long long, const double *, void *, cudaStream_t);
+int b2k_rne_fan_launch_f64(const b2k_rne_s *, int, const void *, const void *, const void *, long long, const double *, void *, cudaStream_t);
+enum { FAN_INERTIA = 0, FAN_GRAVLOAD = 1, FAN_ITORQUE = 2, FAN_CORIOLIS = 3, FAN_ACCEL = 4 };
+
+static int fan_dispatch(const char *fn, b2k_rne_t r, int dtype, int mode, const void *in0, const void *in1, const void *in2,
+                        int nin, int64_t N, const double *grav, bool need_grav, void *out, void *stream)
+{
+    if (!r) { b2k_set_error("%s: rne handle is NULL", fn); return B2K_ERR_INVALID; }
+    if (dtype != B2K_F32 && dtype != B2K_F64) { b2k_set_error("%s: dtype must be B2K_F32 or B2K_F64", fn); return B2K_ERR_INVALID; }
+    if (N < 0) { b2k_set_error("%s: N is negative", fn); return B2K_ERR_INVALID; }
+    if (need_grav && !grav) { b2k_set_error("%s: grav is NULL (pass -robot.gravity like DHRobot.rne)", fn); return B2K_ERR_INVALID; }
+    int rc;
+    if ((rc = check_out(fn, "q", in0, N)) || (nin >= 2 && (rc = check_out(fn, "second input", in1, N))) ||
+        (nin >= 3 && (rc = check_out(fn, "third input", in2, N))) || (rc = check_out(fn, "output", out, N)))
+        return rc;
+    if (N == 0) return B2K_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == B2K_F64) return b2k_rne_fan_launch_f64(r, mode, in0, in1, in2, N, grav, out, st);
+    return b2k_rne_fan_launch_f32(r, mode, in0, in1, in2, N, grav, out, st);
+}
+
+extern "C" int b2k_rne_inertia(b2k_rne_t r, int dtype, const void *q, int64_t N, void *M, void *stream)
+{
+    return fan_dispatch("b2k_rne_inertia", r, dtype, FAN_INERTIA, q, nullptr, nullptr, 1, N, nullptr, false, M, stream);
+}
+extern "C" int b2k_rne_gravload(b2k_rne_t r, int dtype, const void *q, int64_t N, const double *grav, void *taug, void *stream)
+{
+    return fan_dispatch("b2k_rne_gravload", r, dtype, FAN_GRAVLOAD, q, nullptr, nullptr, 1, N, grav, true, taug, stream);
+}
+extern "C" int b2k_rne_itorque(b2k_rne_t r, int dtype, const void *q, const void *qdd, int64_t N, void *taui, void *stream)
+{
+    return fan_dispatch("b2k_rne_itorque", r, dtype, FAN_ITORQUE, q, qdd, nullptr, 2, N, nullptr, false, taui, stream);
+}
+extern "C" int b2k_rne_coriolis(b2k_rne_t r, int dtype, const void *q, const void *qd, int64_t N, void *Cm, void *stream)
+{
+    return fan_dispatch("b2k_rne_coriolis", r, dtype, FAN_CORIOLIS, q, qd, nullptr, 2, N, nullptr, false, Cm, stream);
+}
+extern "C" int b2k_rne_accel(b2k_rne_t r, int dtype, const void *q, const void *qd, const void *torque, int64_t N,
+                             const double *grav, void *qdd, void *stream)
+{
+    return fan_dispatch("b2k_rne_accel", r, dtype, FAN_ACCEL, q, qd, torque, 3, N, grav, true, qdd, stream);
+}

@@ -133,6 +133,25 @@ def main():
     pack["ncases"] = np.array(ncase)
     np.savez(os.path.join(out, "random_rne.npz"), **pack)
 
+    # ---------------- dynamics fan-outs (Dynamics.py loops over the compiled frne), Puma560
+    from oracle import oracle as orc_mod
+
+    links = ch.puma560_links()
+    L = ch.pack_rne(links)
+    Rf = ref.RefRNE(6, 0, L, g)
+    Rnf = ref.RefRNE(6, 0, orc_mod.nofriction_L(L), g)
+    f_fric = lambda q, qd, qdd, grav: Rf.rne(q, qd, qdd, gravity=grav)      # noqa: E731
+    f_nofr = lambda q, qd, qdd, grav: Rnf.rne(q, qd, qdd, gravity=grav)     # noqa: E731
+    rng = np.random.default_rng(11)
+    Nd = 24
+    q = rng.uniform(-2.5, 2.5, (Nd, 6)); qd = rng.normal(size=(Nd, 6)); qdd = rng.normal(size=(Nd, 6))
+    torque = rng.normal(size=(Nd, 6)) * 5
+    q[0] = ch.PUMA_QN
+    np.savez(os.path.join(out, "puma_dynamics.npz"), L=L, gravity=g, q=q, qd=qd, qdd=qdd, torque=torque,
+             inertia=orc_mod.dyn_inertia(f_fric, 6, q), gravload=orc_mod.dyn_gravload(f_fric, 6, q, g),
+             itorque=orc_mod.dyn_itorque(f_fric, 6, q, qdd), coriolis=orc_mod.dyn_coriolis(f_nofr, 6, q, qd),
+             accel=orc_mod.dyn_accel(f_fric, 6, q, qd, torque, g))
+
     # ---------------- Panda IK (config 4 protocol: reachable targets Tep = FK(q*))
     d = ch.panda_ets()
     R = ref.RefETS(d)

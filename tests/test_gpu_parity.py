@@ -202,6 +202,64 @@ def test_fixture_rne_random_links():
         np.testing.assert_allclose(host(tau), z[p + "tau"], rtol=1e-9, atol=1e-9, err_msg=f"case {c}")
 
 
+def test_dynamics_fanouts():
+    """inertia / gravload / itorque / coriolis / accel: reference KATs
+    (tests/test_DHRobot.py:1092-1200), the fixture produced through the compiled frne, and the oracle on
+    a larger random batch incl. an MDH robot and a robot with prismatic joints."""
+    k = KAT["puma560_dynamics"]
+    puma = rtb.models.Puma560()
+    qn = puma.qn
+    dec = k["decimal"]
+    M = puma.inertia(qn)
+    assert M.shape == (6, 6)
+    np.testing.assert_array_almost_equal(M, np.array(k["inertia"]), decimal=dec)
+    np.testing.assert_array_almost_equal(puma.gravload(qn), np.array(k["gravload"], dtype=float), decimal=dec)
+    np.testing.assert_array_almost_equal(puma.itorque(qn, k["itorque"]["qdd"]), k["itorque"]["taui"], decimal=dec)
+    np.testing.assert_array_almost_equal(puma.coriolis(qn, k["coriolis"]["qd"]), np.array(k["coriolis"]["C"], dtype=float), decimal=dec)
+    np.testing.assert_array_almost_equal(puma.accel(qn, k["accel"]["qd"], k["accel"]["torque"]), k["accel"]["qdd"], decimal=dec)
+    q2 = np.c_[qn, qn].T  # trajectory forms of the same tests
+    a2 = puma.accel(q2, np.tile(k["accel"]["qd"], (2, 1)), np.tile(k["accel"]["torque"], (2, 1)))
+    assert a2.shape == (2, 6)
+    np.testing.assert_array_almost_equal(a2[1], k["accel"]["qdd"], decimal=dec)
+    assert puma.coriolis(q2, np.tile(k["coriolis"]["qd"], (2, 1))).shape == (2, 6, 6)
+    z = np.load(os.path.join(G, "puma_dynamics.npz"))
+    tol = dict(rtol=1e-10, atol=1e-10)
+    np.testing.assert_allclose(host(puma.inertia(dev(z["q"]))), z["inertia"], **tol)
+    np.testing.assert_allclose(host(puma.gravload(dev(z["q"]))), z["gravload"], **tol)
+    np.testing.assert_allclose(host(puma.itorque(dev(z["q"]), dev(z["qdd"]))), z["itorque"], **tol)
+    np.testing.assert_allclose(host(puma.coriolis(dev(z["q"]), dev(z["qd"]))), z["coriolis"], **tol)
+    np.testing.assert_allclose(host(puma.accel(dev(z["q"]), dev(z["qd"]), dev(z["torque"]))), z["accel"], rtol=1e-9, atol=1e-9)
+    # larger batches against the oracle: MDH Panda (n=7), and a DH robot with prismatic joints
+    rng = np.random.default_rng(31)
+    robots = [rtb.models.PandaMDH(),
+              rtb.DHRobot([rtb.RevoluteDH(d=0.3, a=0.1, alpha=1.2, m=2, r=[0.1, 0, 0.05], I=[0.1, 0.2, 0.15], Jm=1e-4, G=50, B=1e-3, Tc=[0.1, -0.2]),
+                           rtb.PrismaticDH(theta=0.4, a=0.2, alpha=-0.7, m=1.5, r=[0, 0.1, 0], I=[0.05, 0.04, 0.03], Jm=2e-4, G=30, B=2e-3, Tc=[0.05, -0.05]),
+                           rtb.RevoluteDH(d=0.1, a=0.25, alpha=0.0, m=1, r=[0.05, 0.02, 0], I=[0.02, 0.03, 0.01], Jm=1e-4, G=-40, B=1e-3, Tc=[0.02, -0.03])])]
+    for rob in robots:
+        n = rob.n
+        L = rob._pack_rne()
+        mdh = rob.mdh
+        g = rob.gravity
+        f = lambda q, qd, qdd, grav: orc.rne(n, mdh, L, -np.asarray(grav, dtype=float), q, qd, qdd)  # noqa: E731
+        Lnf = orc.nofriction_L(L)
+        fnf = lambda q, qd, qdd, grav: orc.rne(n, mdh, Lnf, -np.asarray(grav, dtype=float), q, qd, qdd)  # noqa: E731
+        N = 333
+        q = rng.uniform(-2, 2, (N, n)); qd = rng.normal(size=(N, n)); qdd = rng.normal(size=(N, n)); tq = rng.normal(size=(N, n))
+        np.testing.assert_allclose(host(rob.inertia(dev(q))), orc.dyn_inertia(f, n, q), **tol)
+        np.testing.assert_allclose(host(rob.gravload(dev(q))), orc.dyn_gravload(f, n, q, g), **tol)
+        np.testing.assert_allclose(host(rob.itorque(dev(q), dev(qdd))), orc.dyn_itorque(f, n, q, qdd), **tol)
+        np.testing.assert_allclose(host(rob.coriolis(dev(q), dev(qd))), orc.dyn_coriolis(fnf, n, q, qd), **tol)
+        np.testing.assert_allclose(host(rob.accel(dev(q), dev(qd), dev(tq))), orc.dyn_accel(f, n, q, qd, tq, g), rtol=1e-8, atol=1e-8)
+        # structural properties: M symmetric positive definite; itorque == M qdd; rne == M qdd + C qd + g + friction
+        Mq = host(rob.inertia(dev(q)))
+        np.testing.assert_allclose(Mq, Mq.transpose(0, 2, 1), atol=1e-10)
+        assert (np.linalg.eigvalsh(Mq) > 0).all()
+        np.testing.assert_allclose(host(rob.itorque(dev(q), dev(qdd))), np.einsum("kij,kj->ki", Mq, qdd), atol=1e-9)
+    # fp32 runs
+    M32 = host(puma.inertia(dev(z["q"], np.float32)))
+    np.testing.assert_allclose(M32, z["inertia"], rtol=2e-4, atol=2e-4)
+
+
 def test_fixture_ik_fp64_explicit_q0():
     """Row i of the batch == the reference called on target i: explicit q0, slimit=1, fp64."""
     z = np.load(os.path.join(G, "panda_ik.npz"))

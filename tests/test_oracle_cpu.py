@@ -142,6 +142,28 @@ def test_fixture_rne():
         np.testing.assert_allclose(tau, z[p + "tau"], rtol=1e-12, atol=1e-11)
 
 
+def test_dynamics_fanouts_kat_and_fixture():
+    """Dynamics fan-outs (reference Dynamics.py loops) on top of the oracle's rne: the reference's own
+    KATs (tests/test_DHRobot.py:1092-1200) and the fixture generated through the compiled frne."""
+    k = KAT["puma560_dynamics"]
+    L = ch.pack_rne(ch.puma560_links())
+    g = np.array([0, 0, -9.81])
+    f = lambda q, qd, qdd, grav: orc.rne(6, 0, L, -np.asarray(grav, dtype=float), q, qd, qdd)  # noqa: E731
+    Lnf = orc.nofriction_L(L)
+    fnf = lambda q, qd, qdd, grav: orc.rne(6, 0, Lnf, -np.asarray(grav, dtype=float), q, qd, qdd)  # noqa: E731
+    qn = ch.PUMA_QN
+    dec = k["decimal"]
+    np.testing.assert_array_almost_equal(orc.dyn_inertia(f, 6, qn)[0], np.array(k["inertia"]), decimal=dec)
+    np.testing.assert_array_almost_equal(orc.dyn_gravload(f, 6, qn, g)[0], np.array(k["gravload"], dtype=float), decimal=dec)
+    np.testing.assert_array_almost_equal(orc.dyn_itorque(f, 6, qn, k["itorque"]["qdd"])[0], k["itorque"]["taui"], decimal=dec)
+    np.testing.assert_array_almost_equal(orc.dyn_coriolis(fnf, 6, qn, k["coriolis"]["qd"])[0], np.array(k["coriolis"]["C"], dtype=float), decimal=dec)
+    np.testing.assert_array_almost_equal(orc.dyn_accel(f, 6, qn, k["accel"]["qd"], k["accel"]["torque"], g)[0], k["accel"]["qdd"], decimal=dec)
+    z = np.load(os.path.join(G, "puma_dynamics.npz"))
+    np.testing.assert_allclose(orc.dyn_inertia(f, 6, z["q"]), z["inertia"], rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(orc.dyn_coriolis(fnf, 6, z["q"], z["qd"]), z["coriolis"], rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(orc.dyn_accel(f, 6, z["q"], z["qd"], z["torque"], g), z["accel"], rtol=1e-10, atol=1e-10)
+
+
 def test_fixture_angle_axis():
     z = np.load(os.path.join(G, "angle_axis.npz"))
     for Te, Tep, e in zip(z["Te"], z["Tep"], z["e"]):
