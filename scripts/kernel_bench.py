@@ -116,6 +116,33 @@ for dt in (np.float64, np.float32):
     report(f"rne_puma_{tag}", timeit(lambda i: L.b2k_rne(puma._rne_ob, code, bufs[i][0].data_ptr(), bufs[i][1].data_ptr(), bufs[i][2].data_ptr(), N, rtb._lib.dptr(g), None, tau.data_ptr(), st), nbuf), N, 24 * es)
     del bufs, tau
 
+# dynamics fan-outs over the RNE recursion: Puma560, fp64
+if want("dyn_"):
+    Nd = max(1, N // 4)
+    ql = puma.qlim
+    qd_ = torch.from_numpy(rng.uniform(ql[0], ql[1], (Nd, 6))).to(dev)
+    v_ = torch.from_numpy(rng.normal(size=(Nd, 6))).to(dev)
+    t_ = torch.from_numpy(rng.normal(size=(Nd, 6))).to(dev)
+    puma.rne(qd_[:4], v_[:4], v_[:4])
+    L = rtb._lib.lib()
+    st = torch.cuda.current_stream().cuda_stream
+    g = np.ascontiguousarray(-puma.gravity)
+    Mo = torch.empty((Nd, 6, 6), dtype=torch.float64, device=dev)
+    vo = torch.empty((Nd, 6), dtype=torch.float64, device=dev)
+    F = rtb._lib.F64
+    h = puma._rne_ob
+    cases = [
+        ("dyn_inertia_puma_f64", lambda i: L.b2k_rne_inertia(h, F, qd_.data_ptr(), Nd, Mo.data_ptr(), st), (6 + 36) * 8, 6),
+        ("dyn_gravload_puma_f64", lambda i: L.b2k_rne_gravload(h, F, qd_.data_ptr(), Nd, rtb._lib.dptr(g), vo.data_ptr(), st), 12 * 8, 1),
+        ("dyn_itorque_puma_f64", lambda i: L.b2k_rne_itorque(h, F, qd_.data_ptr(), v_.data_ptr(), Nd, vo.data_ptr(), st), 18 * 8, 1),
+        ("dyn_coriolis_puma_f64", lambda i: L.b2k_rne_coriolis(h, F, qd_.data_ptr(), v_.data_ptr(), Nd, Mo.data_ptr(), st), (12 + 36) * 8, 21),
+        ("dyn_accel_puma_f64", lambda i: L.b2k_rne_accel(h, F, qd_.data_ptr(), v_.data_ptr(), t_.data_ptr(), Nd, rtb._lib.dptr(g), vo.data_ptr(), st), 24 * 8, 7),
+    ]
+    for name, fn, bpr, nrec in cases:
+        if want(name):
+            ms = timeit(fn, 1)
+            report(name, ms, Nd, bpr, {"recursions_per_row": nrec, "recursions_per_s": nrec * Nd / (ms * 1e-3)})
+
 # IK (config 4): reachable targets, chan
 if want("ik_"):
     from oracle import oracle as orc
