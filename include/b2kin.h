@@ -178,6 +178,15 @@ int b2k_rne_coriolis(b2k_rne_t rne, int dtype, const void *q, const void *qd, in
 int b2k_rne_accel(b2k_rne_t rne, int dtype, const void *q, const void *qd, const void *torque, int64_t N,
                   const double *grav, void *qdd, void *stream);
 
+/* ---------------------------------------------------------------- pure functions of the Jacobian
+ * b2k_hessian replaces fknm.ETS_hessian0 / ETS_hessiane (fknm.cpp:583-783 -> _ETS_hessian
+ * methods.cpp:16-32): H (N,n,6,n) from J (N,6,n); pass jacob0 for hessian0, jacobe for hessiane.
+ * b2k_manipulability is the Yoshikawa measure of ETS.manipulability (ETS.py:1780-1787):
+ * m = sqrt|det(Ja Ja^T)| over the Cartesian rows selected by axes_mask (bit k = row k of J;
+ * 63 = all, 7 = translational, 56 = rotational); |det Ja| when Ja is square. */
+int b2k_hessian(int dtype, int n, const void *J, int64_t N, void *H, void *stream);
+int b2k_manipulability(int dtype, int n, const void *J, int64_t N, uint32_t axes_mask, void *m, void *stream);
+
 /* ---------------------------------------------------------------- host-buffer front ends
  * The same operations for callers that hold HOST arrays (what the reference's API takes):
  * the library streams row chunks host->device, runs the kernel and streams results back on

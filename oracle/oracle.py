@@ -238,3 +238,26 @@ def nofriction_L(L):
     L[:, 21] = 0.0
     L[:, 22:24] = 0.0
     return L.ravel()
+
+
+def hessian(J):
+    """_ETS_hessian, methods.cpp:16-32: H (n,6,n) from J (6,n)."""
+    J = np.asarray(J, dtype=np.float64)
+    n = J.shape[1]
+    H = np.zeros((n, 6, n))
+    for j in range(n):
+        for i in range(j, n):
+            H[j, :3, i] = np.cross(J[3:, j], J[:3, i])
+            H[j, 3:, i] = np.cross(J[3:, j], J[3:, i])
+            if i != j:
+                H[i, :3, j] = H[j, :3, i]
+                H[i, 3:, j] = 0.0
+    return H
+
+
+def yoshikawa(J, axes=(True,) * 6):
+    """ETS.py:1780-1787"""
+    Ja = np.asarray(J, dtype=np.float64)[np.asarray(axes, dtype=bool), :]
+    if Ja.shape[0] == Ja.shape[1]:
+        return abs(np.linalg.det(Ja))
+    return np.sqrt(abs(np.linalg.det(Ja @ Ja.T)))

@@ -101,6 +101,16 @@ class RefETS:
         f = fknm()
         return np.stack([np.asarray(f.ETS_jacobe(self.ets, q[i], tool)) for i in range(q.shape[0])])
 
+    def hessian0(self, q, tool=None):
+        q = np.atleast_2d(np.ascontiguousarray(q, dtype=np.float64))
+        f = fknm()
+        return np.stack([np.asarray(f.ETS_hessian0(self.ets, q[i], None, tool)) for i in range(q.shape[0])])
+
+    def hessiane(self, q, tool=None):
+        q = np.atleast_2d(np.ascontiguousarray(q, dtype=np.float64))
+        f = fknm()
+        return np.stack([np.asarray(f.ETS_hessiane(self.ets, q[i], None, tool)) for i in range(q.shape[0])])
+
     def ik_lm(self, Tep, q0=None, ilimit=30, slimit=100, tol=1e-6, joint_limits=True, mask=None,
               k=1.0, method="chan"):
         """Per-target loop over fknm.IK_LM_c (the reference has no batched IK)."""

@@ -349,6 +349,66 @@ class ETS:
             self._chain, B.code(np.dtype(dt)), q.ctypes.data, N, q.shape[1], _lib.dptr(_mat44(base, "base")),
             _lib.dptr(_mat44(tool, "tool")), T.ctypes.data, J.ctypes.data, t.cuda.current_device()))
 
+    # ------------------------------------------------------------------ functions of the Jacobian
+    def _hess(self, q, J, tool, jac, dtype):
+        if q is None and J is None:
+            raise ValueError("one of q or the Jacobian must be supplied")
+        if J is None:
+            J = jac(q, tool=tool, dtype=dtype)
+        host = not B.is_tensor(J)
+        dt = B.pick_dtype(J, dtype)
+        Jd = B.to_device(J, dt)
+        single = Jd.dim() == 2
+        Jd = (Jd.reshape(1, 6, -1) if single else Jd).contiguous()
+        n = self.n
+        if tuple(Jd.shape[1:]) != (6, n):
+            raise ValueError(f"the Jacobian must be (6,{n}) or (N,6,{n})")
+        N = Jd.shape[0]
+        H = B.empty((N, n, 6, n), dt, like=Jd)
+        _lib.check(_lib.lib().b2k_hessian(B.code(dt), n, B.ptr(Jd), N, B.ptr(H), B.stream_ptr(Jd)))
+        if host:
+            H = B.to_host(H)
+        return H[0] if single else H
+
+    def hessian0(self, q=None, J0=None, tool=None, dtype=None):
+        """Manipulator Hessian in the base frame, (n,6,n) or (N,n,6,n), from q or from a given jacob0
+        (reference ETS.hessian0, ETS.py:1334-1450 -> fknm.ETS_hessian0)."""
+        return self._hess(q, J0, tool, self.jacob0, dtype)
+
+    def hessiane(self, q=None, Je=None, tool=None, dtype=None):
+        """Manipulator Hessian in the end-effector frame (reference ETS.hessiane, ETS.py:1452-1568)."""
+        return self._hess(q, Je, tool, self.jacobe, dtype)
+
+    def manipulability(self, q=None, J=None, method: str = "yoshikawa", axes="all", dtype=None):
+        """Yoshikawa manipulability index, scalar or (N,) (reference ETS.manipulability, ETS.py:1687-1820;
+        only the default `yoshikawa` measure is on the accelerated path)."""
+        if method != "yoshikawa":
+            raise NotImplementedError("only method='yoshikawa' is accelerated (minsingular / invcondition need an SVD)")
+        if isinstance(axes, str):
+            mask = {"all": 63, "trans": 7, "rot": 56}.get(axes)
+            if mask is None:
+                raise ValueError("axes must be all, trans, rot or a 6-element bool list")
+        else:
+            ax = [bool(a) for a in axes]
+            if len(ax) != 6:
+                raise ValueError("axes must be all, trans, rot or a 6-element bool list")
+            mask = sum(1 << k for k, a in enumerate(ax) if a)
+        if q is None and J is None:
+            raise ValueError("one of q or J must be supplied")
+        if J is None:
+            J = self.jacob0(q, dtype=dtype)
+        host = not B.is_tensor(J)
+        dt = B.pick_dtype(J, dtype)
+        Jd = B.to_device(J, dt)
+        single = Jd.dim() == 2
+        Jd = (Jd.reshape(1, 6, -1) if single else Jd).contiguous()
+        N = Jd.shape[0]
+        m = B.empty((N,), dt, like=Jd)
+        _lib.check(_lib.lib().b2k_manipulability(B.code(dt), self.n, B.ptr(Jd), N, mask, B.ptr(m), B.stream_ptr(Jd)))
+        if host:
+            m = B.to_host(m)
+        return float(m[0]) if single else m
+
     # ------------------------------------------------------------------ inverse kinematics
     def _ik(self, Tep, q0, ilimit, slimit, tol, mask, joint_limits, k, method, seed, semantics, rng_per_row, dtype):
         Tep = getattr(Tep, "A", Tep)

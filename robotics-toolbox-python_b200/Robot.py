@@ -117,6 +117,15 @@ class Robot:
     def fkine_jacob0(self, q, tool=None, **kw):
         return self.ets().fkine_jacob0(q, base=self._base_arg(), tool=self._tool_arg(tool), **kw)
 
+    def hessian0(self, q=None, J0=None, end=None, start=None, tool=None, **kw):
+        return self.ets(start, end).hessian0(q, J0=J0, tool=self._tool_arg(tool), **kw)
+
+    def hessiane(self, q=None, Je=None, end=None, start=None, tool=None, **kw):
+        return self.ets(start, end).hessiane(q, Je=Je, tool=self._tool_arg(tool), **kw)
+
+    def manipulability(self, q=None, J=None, method="yoshikawa", axes="all", **kw):
+        return self.ets().manipulability(q, J=J, method=method, axes=axes, **kw)
+
     def ik_LM(self, Tep, end=None, start=None, **kw):
         return self.ets(start, end).ik_LM(Tep, **kw)
 

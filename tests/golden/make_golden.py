@@ -152,6 +152,31 @@ def main():
              itorque=orc_mod.dyn_itorque(f_fric, 6, q, qdd), coriolis=orc_mod.dyn_coriolis(f_nofr, 6, q, qd),
              accel=orc_mod.dyn_accel(f_fric, 6, q, qd, torque, g))
 
+    # ---------------- manipulator Hessians: compiled fknm + the literal golden of the reference's own test
+    d = ch.panda_ets()
+    R = ref.RefETS(d)
+    Qh = np.random.default_rng(5).uniform(-np.pi, np.pi, (40, 7))
+    Qh[0] = [1.4, 0.2, 1.8, 0.7, 0.1, 3.1, 2.9]
+    toolh = ch.trotx(0.3) @ ch.transl(0.1, 0.2, 0.3)
+    kat = np.zeros((0,))
+    tpath = "/root/reference/tests/test_ETS.py"
+    if os.path.exists(tpath):  # transcribe `ans` of test_hessian0 (tests/test_ETS.py:718-1111) mechanically
+        src = open(tpath).read()
+        a = src.index("def test_hessian0(self)")
+        a = src.index("ans = np.array(", a) + len("ans = ")
+        depth, b = 0, a + len("np.array")
+        while True:
+            ch_ = src[b]
+            depth += ch_ == "("
+            depth -= ch_ == ")"
+            b += 1
+            if depth == 0:
+                break
+        ans = eval(src[a:b], {"np": np})
+        kat = np.stack([ans[:, :, i] for i in range(7)])  # ans_new of tests/test_ETS.py:1113-1116
+    np.savez(os.path.join(out, "panda_hessian.npz"), Q=Qh, tool=toolh, **desc_arrays(d), J0=R.jacob0(Qh), Je=R.jacobe(Qh),
+             H0=R.hessian0(Qh), He=R.hessiane(Qh), H0_tool=R.hessian0(Qh, toolh), kat_hessian0_q1=kat)
+
     # ---------------- Panda IK (config 4 protocol: reachable targets Tep = FK(q*))
     d = ch.panda_ets()
     R = ref.RefETS(d)

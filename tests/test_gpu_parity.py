@@ -260,6 +260,41 @@ def test_dynamics_fanouts():
     np.testing.assert_allclose(M32, z["inertia"], rtol=2e-4, atol=2e-4)
 
 
+def test_hessian_and_manipulability():
+    """hessian0 / hessiane / manipulability: fknm.ETS_hessian0/e fixture, the reference test's
+    literal golden (tests/test_ETS.py:718-1128: q as array, list, (1,n), (n,1) and J0=J), and the oracle."""
+    z = np.load(os.path.join(G, "panda_hessian.npz"))
+    e = ets_from_desc(z)
+    tol = dict(rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(host(e.hessian0(dev(z["Q"]))), z["H0"], **tol)
+    np.testing.assert_allclose(host(e.hessiane(dev(z["Q"]))), z["He"], **tol)
+    np.testing.assert_allclose(host(e.hessian0(dev(z["Q"]), tool=z["tool"])), z["H0_tool"], **tol)
+    np.testing.assert_allclose(host(e.hessian0(J0=dev(z["J0"]))), z["H0"], **tol)
+    q1 = z["Q"][0]
+    ans = z["kat_hessian0_q1"]
+    for qq in (q1, list(q1), q1[None, :], q1[:, None]):
+        H = e.hessian0(qq)
+        assert H.shape == (7, 6, 7)
+        np.testing.assert_array_almost_equal(H, ans, decimal=6)
+    np.testing.assert_array_almost_equal(e.hessian0(J0=e.jacob0(q1)), ans, decimal=6)
+    with pytest.raises(ValueError):
+        e.hessian0()
+    H32 = host(e.hessian0(dev(z["Q"], np.float32)))
+    np.testing.assert_allclose(H32, z["H0"], rtol=1e-4, atol=1e-5)
+    # manipulability (yoshikawa) for all / trans / rot / explicit axes, and the square case on a 6-joint arm
+    J = z["J0"]
+    for axes, mask in (("all", [1] * 6), ("trans", [1, 1, 1, 0, 0, 0]), ("rot", [0, 0, 0, 1, 1, 1]), ([1, 0, 1, 0, 1, 1], [1, 0, 1, 0, 1, 1])):
+        want = np.array([orc.yoshikawa(Jk, mask) for Jk in J])
+        np.testing.assert_allclose(host(e.manipulability(dev(z["Q"]), axes=axes)), want, rtol=1e-9, atol=1e-12)
+    assert isinstance(e.manipulability(q1), float)
+    ur = rtb.models.UR10().ets()
+    Q6 = np.random.default_rng(6).uniform(-3, 3, (50, 6))
+    J6 = host(ur.jacob0(dev(Q6)))
+    np.testing.assert_allclose(host(ur.manipulability(dev(Q6))), [orc.yoshikawa(Jk) for Jk in J6], rtol=1e-9, atol=1e-12)
+    with pytest.raises(NotImplementedError):
+        e.manipulability(q1, method="minsingular")
+
+
 def test_fixture_ik_fp64_explicit_q0():
     """Row i of the batch == the reference called on target i: explicit q0, slimit=1, fp64."""
     z = np.load(os.path.join(G, "panda_ik.npz"))

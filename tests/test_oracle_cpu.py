@@ -164,6 +164,20 @@ def test_dynamics_fanouts_kat_and_fixture():
     np.testing.assert_allclose(orc.dyn_accel(f, 6, z["q"], z["qd"], z["torque"], g), z["accel"], rtol=1e-10, atol=1e-10)
 
 
+def test_hessian_and_manipulability_restatements():
+    """oracle.hessian (methods.cpp:16-32) against the compiled fknm.ETS_hessian0/e fixture and the literal
+    golden of the reference's own test (tests/test_ETS.py:718-1116, transcribed by make_golden.py)."""
+    z = np.load(os.path.join(G, "panda_hessian.npz"))
+    for k in range(z["Q"].shape[0]):
+        np.testing.assert_allclose(orc.hessian(z["J0"][k]), z["H0"][k], rtol=0, atol=1e-14)
+        np.testing.assert_allclose(orc.hessian(z["Je"][k]), z["He"][k], rtol=0, atol=1e-14)
+    assert z["kat_hessian0_q1"].shape == (7, 6, 7)
+    np.testing.assert_array_almost_equal(orc.hessian(z["J0"][0]), z["kat_hessian0_q1"], decimal=6)
+    J = z["J0"][3]
+    assert abs(orc.yoshikawa(J) - np.sqrt(abs(np.linalg.det(J @ J.T)))) < 1e-15
+    assert abs(orc.yoshikawa(J[:, :6]) - abs(np.linalg.det(J[:, :6]))) < 1e-15
+
+
 def test_fixture_angle_axis():
     z = np.load(os.path.join(G, "angle_axis.npz"))
     for Te, Tep, e in zip(z["Te"], z["Tep"], z["e"]):
