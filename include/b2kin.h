@@ -56,6 +56,9 @@ extern "C" {
 #define B2K_LM_CHAN 0     /* Wn = lambda * E * I   */
 #define B2K_LM_WAMPLER 1  /* Wn = lambda * I       */
 #define B2K_LM_SUGIHARA 2 /* Wn = (E + lambda) * I */
+/* the other two solvers of the fknm module ride the same loop and entry point (method argument of b2k_ik_lm) */
+#define B2K_IK_NR 3 /* Newton-Raphson, dq = pinv_d(J) e, lambda = pinv_damping: fknm.IK_NR_c, ik.cpp:121-155 */
+#define B2K_IK_GN 4 /* Gauss-Newton, min-norm solution of (J^T We J) dq = J^T We e: fknm.IK_GN_c, ik.cpp:79-119 */
 
 /* which of the reference's two LM loops to reproduce */
 #define B2K_IK_SEM_CPP 0    /* fknm.IK_LM_c -> _IK_loop, ik.cpp:19-75 (ETS.ik_LM)       */
@@ -138,6 +141,10 @@ int b2k_fkine_jacobe(b2k_chain_t chain, int dtype, const void *q, int64_t N, int
  * Outputs (device): q_out (N,n), success/iterations/searches int32 (N), residual (N) in dtype
  * -- the tuple IK_LM_c returns (fknm.cpp:516), one entry per target.
  * Requires jindex == 0..n-1 in chain order (the reference C++ loop assumes it, ik.cpp:34-35).
+ * method = B2K_IK_NR / B2K_IK_GN select fknm.IK_NR_c / IK_GN_c (fknm.cpp:164-392) and, with the
+ * Python semantics, IK_NR.step / IK_GN.step (IK.py:714-762, 1154-1219; both take pinv(J) e there).
+ * The pseudo-inverse step is evaluated as Jw^T (Jw Jw^T + d^2)^-1 ew (6x6 Cholesky); pinv = False
+ * on a square chain (J.inverse() e) is the same vector and is not a separate code path.
  */
 int b2k_ik_lm(b2k_chain_t chain, int dtype, const void *Tep, int64_t N, const void *q0,
               int ilimit, int slimit, double tol, int reject_jl, const double *we, double lambda,

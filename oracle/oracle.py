@@ -126,7 +126,8 @@ class Chain:
         if q0 is not None:
             q0 = np.ascontiguousarray(np.broadcast_to(_f64(q0).reshape(-1, n), (N, n)))
         we = None if mask is None else _f64(mask)
-        meth = {"c": 0, "w": 1, "s": 2}[method[0].lower()]
+        # chan / wampler / sugihara (LM, k = lambda); nr (k = pinv_damping); gn
+        meth = {"c": 0, "w": 1, "s": 2, "n": 3, "g": 4}[method[0].lower()]
         q = np.empty((N, n))
         succ = np.empty(N, dtype=np.int32)
         its = np.empty(N, dtype=np.int32)

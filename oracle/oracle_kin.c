@@ -26,7 +26,7 @@
  *   orc_jacob0      <- _ETS_jacob0 methods.cpp:112-216
  *   orc_jacobe      <- _ETS_jacobe methods.cpp:219-316
  *   orc_angle_axis  <- _angle_axis ik.cpp:241-286
- *   orc_ik_lm       <- _IK_loop ik.cpp:19-75, _IK_LM_* ik.cpp:157-209,
+ *   orc_ik_lm       <- _IK_loop ik.cpp:19-75, _IK_LM_* ik.cpp:157-209, _IK_NR/_IK_GN ik.cpp:79-155,
  *                      IK_LM_c fknm.cpp:394-525 (semantics 0);
  *                      IKSolver._solve IK.py:297-367 + IK_LM.step IK.py:994-1017
  *                      (semantics 1)
@@ -360,6 +360,123 @@ static int lm_step(const orc_chain *c, const double *we, double lambda, int meth
     return lu_solve(n, A, dq);
 }
 
+/* One-sided (Hestenes) Jacobi SVD of W (rows x cols, row-major, cols <= 6 <= rows or cols <= rows):
+ * rotates column pairs until they are mutually orthogonal.  On return W = (input) * V, so the
+ * columns of W are u_i * s_i and V (cols x cols) holds the right singular vectors. */
+static void onesided_jacobi(int rows, int cols, double *W, double *V)
+{
+    for (int i = 0; i < cols; i++)
+        for (int j = 0; j < cols; j++) V[i * cols + j] = (i == j);
+    for (int sweep = 0; sweep < 60; sweep++) {
+        int rotated = 0;
+        for (int p = 0; p < cols - 1; p++)
+            for (int q = p + 1; q < cols; q++) {
+                double al = 0.0, be = 0.0, ga = 0.0;
+                for (int r = 0; r < rows; r++) {
+                    al += W[r * cols + p] * W[r * cols + p];
+                    be += W[r * cols + q] * W[r * cols + q];
+                    ga += W[r * cols + p] * W[r * cols + q];
+                }
+                if (ga == 0.0 || fabs(ga) <= 1e-17 * sqrt(al * be)) continue;
+                rotated = 1;
+                double zeta = (be - al) / (2.0 * ga);
+                double t = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+                double c = 1.0 / sqrt(1.0 + t * t), sn = c * t;
+                for (int r = 0; r < rows; r++) {
+                    double wp = W[r * cols + p], wq = W[r * cols + q];
+                    W[r * cols + p] = c * wp - sn * wq;
+                    W[r * cols + q] = sn * wp + c * wq;
+                }
+                for (int r = 0; r < cols; r++) {
+                    double vp = V[r * cols + p], vq = V[r * cols + q];
+                    V[r * cols + p] = c * vp - sn * vq;
+                    V[r * cols + q] = sn * vp + c * vq;
+                }
+            }
+        if (!rotated) break;
+    }
+}
+
+/* Newton-Raphson step dq = pinv_d(J) e (ik.cpp:121-155; _pseudo_inverse ik.cpp:211-224:
+ * J = U S V^T, pinv_d = V diag(s / (s^2 + d^2)) U^T), through a one-sided Jacobi SVD (the
+ * reference uses Eigen's two-sided JacobiSVD; the pseudo-inverse is unique, so any accurate SVD
+ * gives the same operator).  For n >= 6 the SVD of B = J^T (n x 6): B Vb = W, w_i = u_i s_i, and
+ * pinv_d(J) e = sum_i w_i (Vb[:,i] . e) / (s_i^2 + d^2).  For n < 6 the SVD of J (6 x n): J Vj = W and
+ * pinv_d(J) e = sum_i Vj[:,i] (w_i . e) / (s_i^2 + d^2).
+ * (NR without pinv on n == 6, J.inverse()*e, is the same vector wherever J is invertible.)
+ * Gauss-Newton step (ik.cpp:79-119): the minimum-norm least-squares solution of
+ * (J^T We J) dq = J^T We e (BDCSVD::solve), i.e. pinv(We^1/2 J) We^1/2 e -- same routine on the
+ * weighted J and e, no damping (the reference ignores pinv_damping there), singular values below
+ * eps * k * s_max treated as zero as Eigen's rank threshold does. */
+static int pinv_step(const orc_chain *c, const double *ws, double damping, int truncate, const double *q,
+                     const double *e, double *dq, double *work)
+{
+    int n = c->n;
+    double *J = work;          /* 6n, (6, n) row-major */
+    double *tJ = work + 6 * n;
+    jacob0_one(c->m, n, c->isjoint, c->axis, c->flip, c->jindex, c->Tc, q, NULL, J, tJ);
+    double ew[6], V[36], s2[6];
+    for (int a = 0; a < 6; a++) {
+        ew[a] = ws[a] * e[a];
+        for (int j = 0; j < n; j++) J[a * n + j] *= ws[a];
+    }
+    int k = n >= 6 ? 6 : n;
+    double *W = tJ; /* reuse: n x 6 (n >= 6) or 6 x n */
+    if (n >= 6) {
+        for (int j = 0; j < n; j++)
+            for (int a = 0; a < 6; a++) W[j * 6 + a] = J[a * n + j];
+        onesided_jacobi(n, 6, W, V);
+    } else {
+        memcpy(W, J, sizeof(double) * 6 * n);
+        onesided_jacobi(6, n, W, V);
+    }
+    int rows = n >= 6 ? n : 6;
+    double smax2 = 0.0;
+    for (int i = 0; i < k; i++) {
+        double t = 0.0;
+        for (int r = 0; r < rows; r++) t += W[r * k + i] * W[r * k + i];
+        s2[i] = t;
+        if (t > smax2) smax2 = t;
+    }
+    double rel = 2.220446049250313e-16 * (n > 6 ? n : 6);
+    double thr = truncate ? rel * rel * smax2 : 0.0; /* threshold on s^2 */
+    for (int j = 0; j < n; j++) dq[j] = 0.0;
+    for (int i = 0; i < k; i++) {
+        double den = s2[i] + damping * damping;
+        if (!(s2[i] > thr) || !(den > 0.0)) continue;
+        if (n >= 6) {
+            double t = 0.0;
+            for (int a = 0; a < 6; a++) t += V[a * 6 + i] * ew[a];
+            t /= den;
+            for (int j = 0; j < n; j++) dq[j] += W[j * 6 + i] * t;
+        } else {
+            double t = 0.0;
+            for (int a = 0; a < 6; a++) t += W[a * n + i] * ew[a];
+            t /= den;
+            for (int j = 0; j < n; j++) dq[j] += V[j * n + i] * t;
+        }
+    }
+    for (int j = 0; j < n; j++)
+        if (!isfinite(dq[j])) return 0;
+    return 1;
+}
+
+/* one solver update: LM (methods 0-2), Newton-Raphson (3), Gauss-Newton (4) */
+static int ik_step(const orc_chain *c, const double *we, double lambda, int method,
+                   const double *q, const double *e, double E, double *dq, double *work)
+{
+    if (method == 3) {
+        const double one[6] = {1, 1, 1, 1, 1, 1};
+        return pinv_step(c, one, lambda, 0, q, e, dq, work);
+    }
+    if (method == 4) {
+        double ws[6];
+        for (int a = 0; a < 6; a++) ws[a] = sqrt(we[a]);
+        return pinv_step(c, ws, 0.0, 1, q, e, dq, work);
+    }
+    return lm_step(c, we, lambda, method, q, e, E, dq, work);
+}
+
 static int check_lim(int n, const double *q, const double *ql, const double *qh)
 {
     for (int i = 0; i < n; i++)
@@ -369,7 +486,8 @@ static int check_lim(int n, const double *q, const double *ql, const double *qh)
 }
 
 /*
- * Batched LM IK.  method: 0 chan, 1 wampler, 2 sugihara.
+ * Batched IK.  method: 0 chan, 1 wampler, 2 sugihara (LM); 3 Newton-Raphson with the damped
+ * pseudo-inverse (lambda = pinv_damping, _IK_NR ik.cpp:121-155); 4 Gauss-Newton (_IK_GN ik.cpp:79-119).
  * semantics 0 = the C++ loop (fknm.IK_LM_c): test E before stepping, wrap with fmod,
  *               counters as ik.cpp:39-69 (it, search start at 0/1; iter restarts at 0).
  * semantics 1 = the Python IK_LM solver (ikine_LM): step first, test the pre-step E,
@@ -411,7 +529,7 @@ void orc_ik_lm(int m, int n, const int *isjoint, const int *axis, const int *fli
                             solution = reject_jl ? check_lim(n, q, qlim_l, qlim_h) : 1;
                             break;
                         }
-                        int ok = lm_step(&c, we, lambda, method, q, e, E, dq, work);
+                        int ok = ik_step(&c, we, lambda, method, q, e, E, dq, work);
                         if (!ok) { iter++; break; } /* singular normal matrix: abandon this search */
                         for (int i = 0; i < n; i++) q[i] += dq[i];
                         iter++;
@@ -433,7 +551,7 @@ void orc_ik_lm(int m, int n, const int *isjoint, const int *axis, const int *fli
                     while (i < ilimit) {
                         i++;
                         lm_error(&c, T, we, q, e, &E);
-                        int ok = lm_step(&c, we, lambda, method, q, e, E, dq, work);
+                        int ok = ik_step(&c, we, lambda, method, q, e, E, dq, work);
                         if (!ok) break; /* numpy LinAlgError: abandon search (IK.py:321-324) */
                         for (int k = 0; k < n; k++) q[k] += dq[k];
                         if (E < tol) {

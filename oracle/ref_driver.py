@@ -129,6 +129,33 @@ class RefETS:
         return q, succ, its, srch, E
 
 
+def _ik_pinv(ets, fn, Tep, q0, ilimit, slimit, tol, joint_limits, mask, pinv, pinv_damping):
+    """Per-target loop over fknm.IK_NR_c / IK_GN_c (fknm.cpp:164-392): args
+    (ets, Tep, q0, ilimit, slimit, tol, reject_jl, we, use_pinv, pinv_damping)."""
+    Tep = np.ascontiguousarray(Tep, dtype=np.float64).reshape(-1, 4, 4)
+    N = Tep.shape[0]
+    q = np.empty((N, ets.n)); succ = np.empty(N, np.int32); its = np.empty(N, np.int32)
+    srch = np.empty(N, np.int32); E = np.empty(N)
+    if q0 is not None:
+        q0 = np.broadcast_to(np.asarray(q0, dtype=np.float64).reshape(-1, ets.n), (N, ets.n))
+    for i in range(N):
+        qi0 = None if q0 is None else np.ascontiguousarray(q0[i])
+        q[i], succ[i], its[i], srch[i], E[i] = fn(ets.ets, Tep[i], qi0, ilimit, slimit, tol,
+                                                  int(bool(joint_limits)), mask, int(bool(pinv)),
+                                                  float(pinv_damping))
+    return q, succ, its, srch, E
+
+
+def ik_nr(ets, Tep, q0=None, ilimit=30, slimit=100, tol=1e-6, joint_limits=True, mask=None, pinv=True,
+          pinv_damping=0.0):
+    return _ik_pinv(ets, fknm().IK_NR_c, Tep, q0, ilimit, slimit, tol, joint_limits, mask, pinv, pinv_damping)
+
+
+def ik_gn(ets, Tep, q0=None, ilimit=30, slimit=100, tol=1e-6, joint_limits=True, mask=None, pinv=True,
+          pinv_damping=0.0):
+    return _ik_pinv(ets, fknm().IK_GN_c, Tep, q0, ilimit, slimit, tol, joint_limits, mask, pinv, pinv_damping)
+
+
 def angle_axis(Te, Tep):
     return np.asarray(fknm().Angle_Axis(np.ascontiguousarray(Te, dtype=np.float64),
                                         np.ascontiguousarray(Tep, dtype=np.float64)))

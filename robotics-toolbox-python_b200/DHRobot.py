@@ -139,6 +139,31 @@ class DHRobot:
     def ik_LM(self, Tep, **kwargs):
         return self.ets().ik_LM(Tep, **kwargs)
 
+    def ik_NR(self, Tep, **kwargs):
+        return self.ets().ik_NR(Tep, **kwargs)
+
+    def ik_GN(self, Tep, **kwargs):
+        return self.ets().ik_GN(Tep, **kwargs)
+
+    # reference DHRobot.py:1923-2452: positional wrappers over the C++ solvers.  (In the reference they
+    # forward to ETS methods of the same lower-case names, which ETS does not define; here they work.)
+    def ik_lm_chan(self, Tep, q0=None, ilimit=30, slimit=100, tol=1e-6, reject_jl=True, we=None, λ=1.0):
+        return self.ets().ik_LM(Tep, q0, ilimit, slimit, tol, we, reject_jl, λ, "chan")
+
+    def ik_lm_wampler(self, Tep, q0=None, ilimit=30, slimit=100, tol=1e-6, reject_jl=True, we=None, λ=1.0):
+        return self.ets().ik_LM(Tep, q0, ilimit, slimit, tol, we, reject_jl, λ, "wampler")
+
+    def ik_lm_sugihara(self, Tep, q0=None, ilimit=30, slimit=100, tol=1e-6, reject_jl=True, we=None, λ=1.0):
+        return self.ets().ik_LM(Tep, q0, ilimit, slimit, tol, we, reject_jl, λ, "sugihara")
+
+    def ik_nr(self, Tep, q0=None, ilimit=30, slimit=100, tol=1e-6, reject_jl=True, we=None, use_pinv=True,
+              pinv_damping=0.0):
+        return self.ets().ik_NR(Tep, q0, ilimit, slimit, tol, we, reject_jl, use_pinv, pinv_damping)
+
+    def ik_gn(self, Tep, q0=None, ilimit=30, slimit=100, tol=1e-6, reject_jl=True, we=None, use_pinv=True,
+              pinv_damping=0.0):
+        return self.ets().ik_GN(Tep, q0, ilimit, slimit, tol, we, reject_jl, use_pinv, pinv_damping)
+
     # ---- inverse dynamics
     def dynchanged(self, what=None):
         """Mark the packed dynamic parameters stale (reference BaseRobot.py:383-398)."""

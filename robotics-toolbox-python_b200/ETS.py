@@ -436,8 +436,11 @@ class ETS:
             elif tuple(q0d.shape) != (N, n):
                 raise ValueError(f"q0 must have {n} elements or shape ({N},{n})")
         we = None if mask is None else np.ascontiguousarray(np.asarray(mask, dtype=np.float64).reshape(6))
-        m = str(method).lower()
-        meth = 2 if m.startswith("s") else (1 if m.startswith("w") else 0)  # fknm.cpp:481-495: 's', 'w', else chan
+        if isinstance(method, int):
+            meth = method  # _lib.IK_NR / _lib.IK_GN
+        else:
+            m = str(method).lower()
+            meth = 2 if m.startswith("s") else (1 if m.startswith("w") else 0)  # fknm.cpp:481-495: 's', 'w', else chan
         q = B.empty((N, n), dt, like=Td)
         succ = B.empty_i32((N,), like=Td)
         its = B.empty_i32((N,), like=Td)
@@ -465,16 +468,35 @@ class ETS:
             return q[0], int(s[0]), int(it[0]), int(sr[0]), float(E[0])
         return q, s, it, sr, E
 
-    def ikine_LM(self, Tep, q0=None, ilimit: int = 30, slimit: int = 100, tol: float = 1e-6, mask=None,
-                 joint_limits: bool = True, seed: Optional[int] = None, k: float = 1.0, method: str = "chan",
-                 kq: float = 0.0, km: float = 0.0, ps: float = 0.0, pi=0.3, dtype=None, **kwargs) -> IKSolution:
-        """Levenberg-Marquardt IK with the semantics of the reference's Python solver class
-        (ETS.ikine_LM, ETS.py:2443-2637 -> IK_LM.solve, IK.py:174-367, 912-1017): returns an
-        :class:`IKSolution`; for an (N,4,4) trajectory q is (N,n), success is the conjunction,
-        iterations / searches are summed and residual is the minimum (IK.py:263-290)."""
+    def _ik_tuple(self, r):
+        q, s, it, sr, E, single = r
+        if single:
+            return q[0], int(s[0]), int(it[0]), int(sr[0]), float(E[0])
+        return q, s, it, sr, E
+
+    def ik_NR(self, Tep, q0=None, ilimit: int = 30, slimit: int = 100, tol: float = 1e-6, mask=None,
+              joint_limits: bool = True, pinv: int = True, pinv_damping: float = 0.0, seed: Optional[int] = 0,
+              dtype=None):
+        """Newton-Raphson IK with the semantics of the reference's C++ solver (ETS.ik_NR,
+        ETS.py:2172-2298 -> fknm.IK_NR_c -> _IK_NR ik.cpp:121-155): dq = pinv_d(J) e.  Same return
+        convention as :meth:`ik_LM`.  ``pinv=False`` (J.inverse() e, square chains only in the reference)
+        yields the same step wherever J is invertible and is not a separate code path."""
+        return self._ik_tuple(self._ik(Tep, q0, ilimit, slimit, tol, mask, joint_limits, pinv_damping, _lib.IK_NR,
+                                       seed, _lib.SEM_CPP, True, dtype))
+
+    def ik_GN(self, Tep, q0=None, ilimit: int = 30, slimit: int = 100, tol: float = 1e-6, mask=None,
+              joint_limits: bool = True, pinv: int = True, pinv_damping: float = 0.0, seed: Optional[int] = 0,
+              dtype=None):
+        """Gauss-Newton IK with the semantics of the reference's C++ solver (ETS.ik_GN,
+        ETS.py:2300-2430 -> fknm.IK_GN_c -> _IK_GN ik.cpp:79-119): the minimum-norm solution of
+        (J^T We J) dq = J^T We e.  ``pinv_damping`` is accepted and ignored, as in the reference."""
+        return self._ik_tuple(self._ik(Tep, q0, ilimit, slimit, tol, mask, joint_limits, 0.0, _lib.IK_GN,
+                                       seed, _lib.SEM_CPP, True, dtype))
+
+    def _ikine(self, meth, Tep, q0, ilimit, slimit, tol, mask, joint_limits, seed, k, kq, km, dtype) -> IKSolution:
         if kq != 0.0 or km != 0.0:
             raise NotImplementedError("null-space terms (kq, km) are outside the accelerated path (SURVEY 2.1 row 5)")
-        q, s, it, sr, E, single = self._ik(Tep, q0, ilimit, slimit, tol, mask, joint_limits, k, method, seed,
+        q, s, it, sr, E, single = self._ik(Tep, q0, ilimit, slimit, tol, mask, joint_limits, k, meth, seed,
                                            _lib.SEM_PYTHON, False, dtype)
         if B.is_tensor(q):
             q, s, it, sr, E = (B.to_host(x) for x in (q, s, it, sr, E))
@@ -486,3 +508,26 @@ class ETS:
         ok = bool(s.all())
         return IKSolution(q=q, success=ok, iterations=int(it.sum()), searches=int(sr.sum()),
                           residual=float(E.min()), reason="" if ok else fail)
+
+    def ikine_NR(self, Tep, q0=None, ilimit: int = 30, slimit: int = 100, tol: float = 1e-6, mask=None,
+                 joint_limits: bool = True, seed: Optional[int] = None, pinv: bool = False, kq: float = 0.0,
+                 km: float = 0.0, ps: float = 0.0, pi=0.3, dtype=None, **kwargs) -> IKSolution:
+        """Newton-Raphson IK with the semantics of the reference's Python solver class (ETS.ikine_NR,
+        ETS.py:2639-2776 -> IK_NR, IK.py:579-762: q += pinv(J) e or inv(J) e -- the same vector)."""
+        return self._ikine(_lib.IK_NR, Tep, q0, ilimit, slimit, tol, mask, joint_limits, seed, 0.0, kq, km, dtype)
+
+    def ikine_GN(self, Tep, q0=None, ilimit: int = 30, slimit: int = 100, tol: float = 1e-6, mask=None,
+                 joint_limits: bool = True, seed: Optional[int] = None, pinv: bool = False, kq: float = 0.0,
+                 km: float = 0.0, ps: float = 0.0, pi=0.3, dtype=None, **kwargs) -> IKSolution:
+        """Gauss-Newton IK with the semantics of the reference's Python solver class (ETS.ikine_GN,
+        ETS.py:2778-2930 -> IK_GN, IK.py:1020-1219; its step is also q += pinv(J) e, IK.py:1214-1217)."""
+        return self._ikine(_lib.IK_NR, Tep, q0, ilimit, slimit, tol, mask, joint_limits, seed, 0.0, kq, km, dtype)
+
+    def ikine_LM(self, Tep, q0=None, ilimit: int = 30, slimit: int = 100, tol: float = 1e-6, mask=None,
+                 joint_limits: bool = True, seed: Optional[int] = None, k: float = 1.0, method: str = "chan",
+                 kq: float = 0.0, km: float = 0.0, ps: float = 0.0, pi=0.3, dtype=None, **kwargs) -> IKSolution:
+        """Levenberg-Marquardt IK with the semantics of the reference's Python solver class
+        (ETS.ikine_LM, ETS.py:2443-2637 -> IK_LM.solve, IK.py:174-367, 912-1017): returns an
+        :class:`IKSolution`; for an (N,4,4) trajectory q is (N,n), success is the conjunction,
+        iterations / searches are summed and residual is the minimum (IK.py:263-290)."""
+        return self._ikine(method, Tep, q0, ilimit, slimit, tol, mask, joint_limits, seed, k, kq, km, dtype)

@@ -56,3 +56,40 @@ class IK_LM:
         return ets.ikine_LM(Tep, q0=q0, ilimit=self.ilimit, slimit=self.slimit, tol=self.tol, mask=self.mask,
                             joint_limits=self.joint_limits, seed=self.seed, k=self.k, method=self.method,
                             kq=self.kq, km=self.km, ps=self.ps, pi=self.pi)
+
+
+class _IK_pinv:
+    def __init__(self, name: str = "IK Solver", ilimit: int = 30, slimit: int = 100, tol: float = 1e-6,
+                 mask=None, joint_limits: bool = True, seed: Optional[int] = None, pinv: bool = False,
+                 kq: float = 0.0, km: float = 0.0, ps: float = 0.0, pi=0.3, **kwargs):
+        self.ilimit, self.slimit, self.tol = ilimit, slimit, tol
+        self.mask = mask
+        self.We = np.diag(np.ones(6) if mask is None else np.asarray(mask, dtype=float))
+        self.joint_limits = joint_limits
+        self.seed = seed
+        self.pinv = pinv
+        self.kq, self.km, self.ps, self.pi = kq, km, ps, pi
+        self.name = f"{self._tag} (pinv={pinv})"
+
+    def _args(self):
+        return dict(ilimit=self.ilimit, slimit=self.slimit, tol=self.tol, mask=self.mask,
+                    joint_limits=self.joint_limits, seed=self.seed, pinv=self.pinv, kq=self.kq, km=self.km,
+                    ps=self.ps, pi=self.pi)
+
+
+class IK_NR(_IK_pinv):
+    """Newton-Raphson solver object (reference IK.py:579-762); ``solve`` runs the fused GPU kernel."""
+    _tag = "NR"
+
+    def solve(self, ets, Tep, q0=None) -> IKSolution:
+        ets = ets.ets() if hasattr(ets, "ets") and callable(ets.ets) else ets
+        return ets.ikine_NR(Tep, q0=q0, **self._args())
+
+
+class IK_GN(_IK_pinv):
+    """Gauss-Newton solver object (reference IK.py:1020-1219); ``solve`` runs the fused GPU kernel."""
+    _tag = "GN"
+
+    def solve(self, ets, Tep, q0=None) -> IKSolution:
+        ets = ets.ets() if hasattr(ets, "ets") and callable(ets.ets) else ets
+        return ets.ikine_GN(Tep, q0=q0, **self._args())

@@ -132,5 +132,18 @@ class Robot:
     def ikine_LM(self, Tep, end=None, start=None, **kw):
         return self.ets(start, end).ikine_LM(Tep, **kw)
 
+    # reference RobotKinematics.py:748-1027 (ik_NR, ik_GN), 1228-1525 (ikine_NR, ikine_GN)
+    def ik_NR(self, Tep, end=None, start=None, **kw):
+        return self.ets(start, end).ik_NR(Tep, **kw)
+
+    def ik_GN(self, Tep, end=None, start=None, **kw):
+        return self.ets(start, end).ik_GN(Tep, **kw)
+
+    def ikine_NR(self, Tep, end=None, start=None, **kw):
+        return self.ets(start, end).ikine_NR(Tep, **kw)
+
+    def ikine_GN(self, Tep, end=None, start=None, **kw):
+        return self.ets(start, end).ikine_GN(Tep, **kw)
+
 
 ERobot = Robot

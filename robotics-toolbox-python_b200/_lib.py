@@ -19,6 +19,7 @@ MAX_JOINTS = 10
 MAX_QWIDTH = 16
 LM_METHODS = {"chan": 0, "wampler": 1, "sugihara": 2}
 SEM_CPP, SEM_PYTHON = 0, 1
+IK_NR, IK_GN = 3, 4  # method codes of b2k_ik_lm beyond the three LM damping rules
 
 _lib = None
 

@@ -366,6 +366,11 @@ int b2k_ik_launch_f32(const b2k_chain_s *, const void *, long long, const void *
 int b2k_ik_launch_f64(const b2k_chain_s *, const void *, long long, const void *, int, int, double, int, const double *,
                       double, int, unsigned long long, int, int, void *, int *, int *, int *, void *, cudaStream_t);
 
+int b2k_ik_nr_launch_f32(const b2k_chain_s *, const void *, long long, const void *, int, int, double, int, const double *,
+                         double, int, unsigned long long, int, int, void *, int *, int *, int *, void *, cudaStream_t);
+int b2k_ik_nr_launch_f64(const b2k_chain_s *, const void *, long long, const void *, int, int, double, int, const double *,
+                         double, int, unsigned long long, int, int, void *, int *, int *, int *, void *, cudaStream_t);
+
 extern "C" int b2k_ik_lm(b2k_chain_t c, int dtype, const void *Tep, int64_t N, const void *q0, int ilimit, int slimit,
                          double tol, int reject_jl, const double *we, double lambda, int method, uint64_t seed,
                          int semantics, int rng_per_row, void *q_out, int32_t *success, int32_t *iterations,
@@ -380,7 +385,7 @@ extern "C" int b2k_ik_lm(b2k_chain_t c, int dtype, const void *Tep, int64_t N, c
         return B2K_ERR_INVALID;
     }
     if (ilimit < 1 || slimit < 1) { b2k_set_error("%s: ilimit and slimit must be >= 1", fn); return B2K_ERR_INVALID; }
-    if (method != B2K_LM_CHAN && method != B2K_LM_WAMPLER && method != B2K_LM_SUGIHARA) { b2k_set_error("%s: bad method %d", fn, method); return B2K_ERR_INVALID; }
+    if (method < B2K_LM_CHAN || method > B2K_IK_GN) { b2k_set_error("%s: bad method %d", fn, method); return B2K_ERR_INVALID; }
     if (semantics != B2K_IK_SEM_CPP && semantics != B2K_IK_SEM_PYTHON) { b2k_set_error("%s: bad semantics %d", fn, semantics); return B2K_ERR_INVALID; }
     int rc;
     if ((rc = check_out(fn, "Tep", Tep, N)) || (rc = check_out(fn, "q_out", q_out, N)) ||
@@ -389,6 +394,12 @@ extern "C" int b2k_ik_lm(b2k_chain_t c, int dtype, const void *Tep, int64_t N, c
         return rc;
     if (N == 0) return B2K_OK;
     cudaStream_t st = (cudaStream_t)stream;
+    if (method == B2K_IK_NR || method == B2K_IK_GN) {
+        if (lambda < 0) { b2k_set_error("%s: pinv_damping is negative", fn); return B2K_ERR_INVALID; }
+        auto nr = dtype == B2K_F64 ? b2k_ik_nr_launch_f64 : b2k_ik_nr_launch_f32;
+        return nr(c, Tep, N, q0, ilimit, slimit, tol, reject_jl, we, method == B2K_IK_GN ? 0.0 : lambda, method, seed,
+                  semantics, rng_per_row, q_out, success, iterations, searches, residual, st);
+    }
     if (dtype == B2K_F64)
         return b2k_ik_launch_f64(c, Tep, N, q0, ilimit, slimit, tol, reject_jl, we, lambda, method, seed, semantics,
                                  rng_per_row, q_out, success, iterations, searches, residual, st);

@@ -23,6 +23,7 @@ template <typename real, int N>
 struct IkP {
     real qlim_l[N], qlim_h[N];
     real we[6];
+    real ws[6]; // step weights of the pseudo-inverse solvers: 1 (NR) or sqrt(we) (GN)
     real lambda, tol;
     int ilimit, slimit, method, reject_jl, semantics, rng_per_row, has_q0, unit_w;
     unsigned long long seed;
@@ -148,7 +149,67 @@ __device__ __forceinline__ bool ik_chol_solve(real *A, real *b)
 // Evaluates the pose error e and cost E at q, then forms the Jacobian, the normal equations and the
 // damped update dq (left in g).  Returns false when A cannot be factorised.
 // (K.unit_w: We = I, the common case -- the weights are then left out of the 35 inner products)
-template <typename real, int N, int PROF>
+// Pseudo-inverse update of the Newton-Raphson / Gauss-Newton solvers (STEP = 1), dq left in g:
+//   NR (_IK_NR ik.cpp:121-155, _pseudo_inverse ik.cpp:211-224):  dq = V diag(s/(s^2+d^2)) U^T e
+//   GN (_IK_GN ik.cpp:79-119): minimum-norm solution of (J^T We J) dq = J^T We e = pinv(We^1/2 J) We^1/2 e
+// Both are  Jw^T (Jw Jw^T + d^2 I)^-1 ew  for n >= 6 (6x6 SPD, Cholesky) and
+// (Jw^T Jw + d^2 I)^-1 Jw^T ew for n < 6 (n x n), Jw = diag(ws) J, ew = diag(ws) e -- the same operator
+// as the reference's SVD wherever the factorisation exists; where it does not (a singular
+// configuration with d = 0) the search is abandoned, where the reference takes a wild step.
+template <typename real, int N>
+__device__ __forceinline__ bool ik_pinv_step(const IkP<real, N> &K, real (*J)[6], const real *e, real *g)
+{
+    real ew[6];
+    const real d2 = K.lambda * K.lambda;
+#pragma unroll
+    for (int a = 0; a < 6; a++) {
+        ew[a] = K.ws[a] * e[a];
+        if (!K.unit_w) {
+#pragma unroll
+            for (int j = 0; j < N; j++) J[j][a] *= K.ws[a];
+        }
+    }
+    if (N >= 6) {
+        real A[21];
+#pragma unroll
+        for (int a = 0; a < 6; a++)
+#pragma unroll
+            for (int b = 0; b <= a; b++) {
+                real s = (a == b) ? (d2 + (K.ws[a] == (real)0 ? (real)1 : (real)0)) : (real)0; // a masked row decouples
+#pragma unroll
+                for (int j = 0; j < N; j++) s = fma(J[j][a], J[j][b], s);
+                A[a * (a + 1) / 2 + b] = s;
+            }
+        const bool ok = ik_chol_solve<real, 6>(A, ew);
+#pragma unroll
+        for (int j = 0; j < N; j++) {
+            real s = 0;
+#pragma unroll
+            for (int a = 0; a < 6; a++) s = fma(J[j][a], ew[a], s);
+            g[j] = s;
+        }
+        return ok;
+    } else {
+        real A[N * (N + 1) / 2];
+#pragma unroll
+        for (int i = 0; i < N; i++) {
+            real s = 0;
+#pragma unroll
+            for (int a = 0; a < 6; a++) s = fma(J[i][a], ew[a], s);
+            g[i] = s;
+#pragma unroll
+            for (int j = 0; j <= i; j++) {
+                real t = (i == j) ? d2 : (real)0;
+#pragma unroll
+                for (int a = 0; a < 6; a++) t = fma(J[i][a], J[j][a], t);
+                A[i * (i + 1) / 2 + j] = t;
+            }
+        }
+        return ik_chol_solve<real, N>(A, g);
+    }
+}
+
+template <typename real, int N, int PROF, int STEP = 0>
 __device__ __forceinline__ bool ik_eval(const ChainP<real, N> &P, const IkP<real, N> &K, const real *Tp, const real *q,
                                         real &Ecur, real *g, bool skip_step_if_converged)
 {
@@ -183,6 +244,7 @@ __device__ __forceinline__ bool ik_eval(const ChainP<real, N> &P, const IkP<real
             J[j][3] = 0; J[j][4] = 0; J[j][5] = 0;
         }
     }
+    if (STEP == 1) return ik_pinv_step<real, N>(K, J, e, g);
     const real wn = (K.method == B2K_LM_CHAN) ? K.lambda * E : (K.method == B2K_LM_WAMPLER) ? K.lambda : (E + K.lambda);
     real A[N * (N + 1) / 2];
     if (K.unit_w) {
@@ -244,7 +306,7 @@ __device__ __forceinline__ bool ik_wrap_and_check(const IkP<real, N> &K, real *q
 // iteration the lane is at, so the lanes of a warp never leave the common code.  With
 // two_phase != 0 a lane does only the FIRST search of a problem; a problem whose first search
 // fails is appended to the hard list (with its iteration contribution) for k_ik_restarts.
-template <typename real, int N, int PROF>
+template <typename real, int N, int PROF, int STEP = 0>
 __global__ void __launch_bounds__(B2K_THREADS)
 k_ik_lm(const __grid_constant__ ChainP<real, N> P, const __grid_constant__ IkP<real, N> K,
         const real *__restrict__ Tep, const real *__restrict__ q0, long long nprob, real *__restrict__ q_out,
@@ -310,7 +372,7 @@ k_ik_lm(const __grid_constant__ ChainP<real, N> P, const __grid_constant__ IkP<r
         real g[N], Ecur;
         if (cpp) {
             // test before stepping (ik.cpp:44-58)
-            const bool ok = ik_eval<real, N, PROF>(P, K, Tp, q, Ecur, g, true);
+            const bool ok = ik_eval<real, N, PROF, STEP>(P, K, Tp, q, Ecur, g, true);
             E = Ecur;
             if (Ecur < K.tol) {
                 const bool inlim = ik_wrap_and_check<real, N>(K, q);
@@ -326,7 +388,7 @@ k_ik_lm(const __grid_constant__ ChainP<real, N> P, const __grid_constant__ IkP<r
             if (!ok || iter > K.ilimit) search_failed();
         } else {
             // count the step, apply it, then test the PRE-step E (IK.py:314-348)
-            const bool ok = ik_eval<real, N, PROF>(P, K, Tp, q, Ecur, g, false);
+            const bool ok = ik_eval<real, N, PROF, STEP>(P, K, Tp, q, Ecur, g, false);
             E = Ecur;
             iter++;
             if (!ok) { search_failed(); continue; } // numpy LinAlgError: abandon the search (IK.py:321-324)
@@ -350,7 +412,7 @@ k_ik_lm(const __grid_constant__ ChainP<real, N> P, const __grid_constant__ IkP<r
 // is the sum of the contributions of all lower-numbered searches plus its own -- exactly what
 // the sequential loop reports, but the latency of a problem needing k restarts drops from
 // k x ilimit LM iterations to ceil(k / G) x ilimit.
-template <typename real, int N, int PROF, int G>
+template <typename real, int N, int PROF, int G, int STEP = 0>
 __global__ void __launch_bounds__(B2K_THREADS)
 k_ik_restarts(const __grid_constant__ ChainP<real, N> P, const __grid_constant__ IkP<real, N> K,
               const real *__restrict__ Tep, real *__restrict__ q_out, int *__restrict__ success,
@@ -388,7 +450,7 @@ k_ik_restarts(const __grid_constant__ ChainP<real, N> P, const __grid_constant__
                 if (going) {
                     real g[N], Ecur;
                     if (cpp) {
-                        const bool ok = ik_eval<real, N, PROF>(P, K, Tp, q, Ecur, g, true);
+                        const bool ok = ik_eval<real, N, PROF, STEP>(P, K, Tp, q, Ecur, g, true);
                         E = Ecur;
                         if (Ecur < K.tol) {
                             const bool inlim = ik_wrap_and_check<real, N>(K, q);
@@ -403,7 +465,7 @@ k_ik_restarts(const __grid_constant__ ChainP<real, N> P, const __grid_constant__
                             if (!ok || iters > K.ilimit) going = false;
                         }
                     } else {
-                        const bool ok = ik_eval<real, N, PROF>(P, K, Tp, q, Ecur, g, false);
+                        const bool ok = ik_eval<real, N, PROF, STEP>(P, K, Tp, q, Ecur, g, false);
                         E = Ecur;
                         iters++;
                         if (!ok) going = false;
@@ -461,7 +523,7 @@ k_ik_restarts(const __grid_constant__ ChainP<real, N> P, const __grid_constant__
     }
 }
 
-template <typename real, int N>
+template <typename real, int N, int STEP>
 int ik_launch_n(const b2k_chain_s *c, const real *Tep, long long nprob, const real *q0, int ilimit, int slimit,
                 double tol, int reject_jl, const double *we, double lambda, int method, unsigned long long seed,
                 int semantics, int rng_per_row, real *q_out, int *success, int *iterations, int *searches,
@@ -472,7 +534,12 @@ int ik_launch_n(const b2k_chain_s *c, const real *Tep, long long nprob, const re
     IkP<real, N> K;
     for (int i = 0; i < N; i++) { K.qlim_l[i] = (real)c->qlim_l[i]; K.qlim_h[i] = (real)c->qlim_h[i]; }
     K.unit_w = 1;
-    for (int k = 0; k < 6; k++) { K.we[k] = we ? (real)we[k] : (real)1; if (K.we[k] != (real)1) K.unit_w = 0; }
+    for (int k = 0; k < 6; k++) {
+        K.we[k] = we ? (real)we[k] : (real)1;
+        if (K.we[k] != (real)1) K.unit_w = 0;
+        // NR weighs only the cost E, never the step (ik.cpp:141-146); GN weighs both (ik.cpp:102-103)
+        K.ws[k] = (method == B2K_IK_GN && we) ? (real)sqrt(we[k] > 0 ? we[k] : 0.0) : (real)1;
+    }
     K.lambda = (real)lambda; K.tol = (real)tol;
     K.ilimit = ilimit; K.slimit = slimit; K.method = method; K.reject_jl = reject_jl ? 1 : 0;
     K.semantics = semantics; K.rng_per_row = rng_per_row ? 1 : 0; K.has_q0 = q0 ? 1 : 0; K.seed = seed;
@@ -513,8 +580,9 @@ int ik_launch_n(const b2k_chain_s *c, const real *Tep, long long nprob, const re
         B2K_CUDA(cudaGetLastError());
         return B2K_OK;
     };
-    int rc = c->dh_like ? launch_a(k_ik_lm<real, N, 1>) : launch_a(k_ik_lm<real, N, 0>);
-    if (rc == B2K_OK && two_phase) rc = c->dh_like ? launch_b(k_ik_restarts<real, N, 1, G>) : launch_b(k_ik_restarts<real, N, 0, G>);
+    int rc = c->dh_like ? launch_a(k_ik_lm<real, N, 1, STEP>) : launch_a(k_ik_lm<real, N, 0, STEP>);
+    if (rc == B2K_OK && two_phase)
+        rc = c->dh_like ? launch_b(k_ik_restarts<real, N, 1, G, STEP>) : launch_b(k_ik_restarts<real, N, 0, G, STEP>);
     if (scratch) {
         cudaError_t e = cudaFreeAsync(scratch, st);
         if (e != cudaSuccess && rc == B2K_OK) rc = b2k_cuda_fail(e, "cudaFreeAsync");
@@ -522,7 +590,7 @@ int ik_launch_n(const b2k_chain_s *c, const real *Tep, long long nprob, const re
     return rc;
 }
 
-template <typename real>
+template <typename real, int STEP = 0>
 int ik_launch(const b2k_chain_s *c, const void *Tep, long long nprob, const void *q0, int ilimit, int slimit, double tol,
               int reject_jl, const double *we, double lambda, int method, unsigned long long seed, int semantics,
               int rng_per_row, void *q_out, int *success, int *iterations, int *searches, void *residual,
@@ -530,7 +598,7 @@ int ik_launch(const b2k_chain_s *c, const void *Tep, long long nprob, const void
 {
 #define B2K_CASE(NN)                                                                                                   \
     case NN:                                                                                                           \
-        return ik_launch_n<real, NN>(c, (const real *)Tep, nprob, (const real *)q0, ilimit, slimit, tol, reject_jl, we, \
+        return ik_launch_n<real, NN, STEP>(c, (const real *)Tep, nprob, (const real *)q0, ilimit, slimit, tol, reject_jl, we, \
                                      lambda, method, seed, semantics, rng_per_row, (real *)q_out, success, iterations, \
                                      searches, (real *)residual, st);
     switch (c->n) {

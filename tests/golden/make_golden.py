@@ -19,6 +19,8 @@ puma_rne.npz       frne.frne, Puma560 standard DH               3
 panda_mdh_rne.npz  frne.frne, Panda modified DH
 random_rne.npz     frne.frne, random DH/MDH links incl. prismatic
 panda_ik.npz       fknm.IK_LM_c (explicit q0, slimit=1; and with restarts)
+ik_nr_gn.npz       fknm.IK_NR_c / IK_GN_c (explicit q0, slimit=1): Panda n=7, UR10 n=6, a 3-joint chain
+                   (`python make_golden.py iknr` regenerates this file alone)
 """
 import os
 import sys
@@ -41,8 +43,45 @@ def fkj(desc, Q, base=None, tool=None):
     return dict(Tfk=R.fkine_rows(Q, base, tool), J0=R.jacob0(Q, tool), Je=R.jacobe(Q, tool))
 
 
+def ik_nr_gn(out):
+    """Newton-Raphson / Gauss-Newton fixtures.  With pinv_damping > 0 the iteration is well conditioned and
+    the outputs are reproducible to rounding; undamped runs are chaotic near singular configurations, so
+    consumers compare those statistically (success rate, iteration histogram)."""
+    pack = {}
+    ur = ch.dh_to_ets(ch.ur10_links())
+    m3 = len(ur["isjoint"])
+    # first three joints of the UR10 chain: cut after the ET that precedes joint 4
+    jpos = [i for i in range(m3) if ur["isjoint"][i]]
+    cut = jpos[3]
+    ur3 = {k: (np.asarray(v)[:cut] if k != "n" else 3) for k, v in ur.items()}
+    for name, d, n in (("panda", ch.panda_ets(), 7), ("ur10", ur, 6), ("ur3", ur3, 3)):
+        R = ref.RefETS(d)
+        rng = np.random.default_rng(11)
+        N = 160
+        qs = rng.uniform(-2.6, 2.6, (N, n))
+        Tep = R.fkine_rows(qs)
+        q0 = qs + rng.normal(0, 0.35, (N, n))
+        q0[N // 2:] = rng.uniform(-np.pi, np.pi, (N - N // 2, n))  # second half: unrelated starts
+        pack.update({f"{name}_{k}": v for k, v in desc_arrays(d).items()})
+        pack.update({f"{name}_qs": qs, f"{name}_Tep": Tep, f"{name}_q0": q0})
+        mask = np.array([1, 1, 1, 0, 0, 0.0])
+        runs = [("nr_d", ref.ik_nr, dict(pinv_damping=0.1)), ("nr", ref.ik_nr, dict(pinv_damping=0.0)),
+                ("gn", ref.ik_gn, {}), ("gn_mask", ref.ik_gn, dict(mask=mask)),
+                ("nr_d_mask", ref.ik_nr, dict(pinv_damping=0.1, mask=mask))]
+        if n == 6:
+            runs.append(("nr_inv", ref.ik_nr, dict(pinv=False)))
+        for tag, fn, kw in runs:
+            q, s, it, sr, E = fn(R, Tep, q0=q0, ilimit=30, slimit=1, tol=1e-6, joint_limits=False, **kw)
+            pack.update({f"{name}_{tag}_q": q, f"{name}_{tag}_success": s, f"{name}_{tag}_it": it, f"{name}_{tag}_E": E})
+    pack["mask"] = mask
+    np.savez(os.path.join(out, "ik_nr_gn.npz"), **pack)
+
+
 def main():
     out = HERE
+    if len(sys.argv) > 1 and sys.argv[1] == "iknr":
+        ik_nr_gn(out)
+        return
     # ---------------- Panda (config 1/2 inputs: default_rng(0).uniform(-pi,pi,(N,7)))
     d = ch.panda_ets()
     Q = np.random.default_rng(0).uniform(-np.pi, np.pi, (1024, 7))[:256]
@@ -201,6 +240,8 @@ def main():
     q, s, it, sr, E = R.ik_lm(Tep, q0=None, ilimit=30, slimit=100, tol=1e-6, joint_limits=True, k=1.0, method="chan")
     pack.update(rs_success=s, rs_it=it, rs_search=sr, rs_E=E, rs_q=q)
     np.savez(os.path.join(out, "panda_ik.npz"), **pack)
+
+    ik_nr_gn(out)
 
     # angle-axis corner cases (ik.cpp:261-277)
     Ts = [np.eye(4), ch.trotx(np.pi), ch.troty(np.pi) @ ch.transl(1, 2, 3), ch.trotz(np.pi), ch.trotx(1e-7),

@@ -317,6 +317,87 @@ def test_fixture_ik_fp64_explicit_q0():
     assert (pos_err[s == 1] < 5e-3).all()
 
 
+IKNR_CASES = [("nr_d", "nr", 0.1, False), ("nr_d_mask", "nr", 0.1, True), ("nr", "nr", 0.0, False),
+              ("gn", "gn", 0.0, False), ("gn_mask", "gn", 0.0, True), ("nr_inv", "nr", 0.0, False)]
+
+
+def test_fixture_ik_nr_gn():
+    """fknm.IK_NR_c / IK_GN_c (explicit q0, slimit=1, fp64) on Panda (n=7), UR10 (n=6) and a 3-joint chain:
+    damped Newton-Raphson reproduces the reference row for row; undamped runs (chaotic near singular
+    configurations, and the kernel uses a 6x6 Cholesky where the reference uses an SVD) are held to outcome
+    statistics, to the well-started half of the batch, and to the oracle."""
+    z = np.load(os.path.join(G, "ik_nr_gn.npz"))
+    for name in ("panda", "ur10", "ur3"):
+        e = ets_from_desc(z, name + "_")
+        C = orc.Chain(e.describe())
+        Tep, q0 = z[name + "_Tep"], z[name + "_q0"]
+        half = len(Tep) // 2
+        for tag, meth, damp, masked in IKNR_CASES:
+            if f"{name}_{tag}_q" not in z:
+                continue
+            mask = z["mask"] if masked else None
+            fn = e.ik_GN if meth == "gn" else e.ik_NR
+            q, s, it, sr, E = (host(x) for x in fn(dev(Tep), q0=dev(q0), slimit=1, joint_limits=False, mask=mask,
+                                                    pinv_damping=damp))
+            rs, rit, rq = z[f"{name}_{tag}_success"], z[f"{name}_{tag}_it"], z[f"{name}_{tag}_q"]
+            want = C.ik_lm(Tep, q0, 30, 1, 1e-6, False, mask, damp, meth)
+            if damp > 0:
+                same = (s == rs) & (it == rit)
+                assert same.mean() >= 0.99, (name, tag, same.mean())
+                ok = same & (s == 1)
+                np.testing.assert_allclose(q[ok], rq[ok], atol=1e-7)
+                np.testing.assert_allclose(E[ok], z[f"{name}_{tag}_E"][ok], atol=1e-11)
+                assert ((s == want[1]) & (it == want[2])).mean() >= 0.99
+            else:
+                assert abs(s.mean() - rs.mean()) < 0.06, (name, tag, s.mean(), rs.mean())
+                assert abs(s.mean() - want[1].mean()) < 0.06, (name, tag, s.mean(), want[1].mean())
+                near = ((s == rs) & (it == rit))[:half]
+                assert near.mean() >= 0.9, (name, tag, near.mean())
+            okr = s == 1  # whatever path it took, a reported success is a solution
+            Tq = C.fkine(q[okr])
+            if not masked:
+                assert np.abs(Tq - Tep[okr]).max() < 5e-3
+            else:
+                assert np.abs(Tq[:, :3, 3] - Tep[okr][:, :3, 3]).max() < 5e-3
+
+
+def test_ik_nr_gn_restarts_and_python_semantics():
+    """Multi-start Newton-Raphson / Gauss-Newton (both loops, both precisions) against the oracle run with
+    the same counter-based restart stream, plus the solver-class entry points."""
+    e = rtb.models.Panda().ets()
+    C = orc.Chain(e.describe())
+    rng = np.random.default_rng(4)
+    qs = rng.uniform(-2.8, 2.8, (1500, 7))
+    Tep = C.fkine(qs)
+    for sem in (0, 1):
+        for meth, code in (("nr", rtb._lib.IK_NR), ("gn", rtb._lib.IK_GN)):
+            damp = 0.1 if meth == "nr" else 0.0
+            want = C.ik_lm(Tep, None, 30, 20, 1e-6, True, None, damp, meth, seed=9, semantics=sem, rng_per_row=True)
+            got = e._ik(dev(Tep), None, 30, 20, 1e-6, None, True, damp, code, 9, sem, True, None)[:5]
+            q, s, it, sr, E = (host(x) for x in got)
+            assert abs(s.mean() - want[1].mean()) < 0.02, (sem, meth, s.mean(), want[1].mean())
+            if damp > 0:
+                same = (s == want[1]) & (it == want[2]) & (sr == want[3])
+                assert same.mean() >= 0.97, (sem, meth, same.mean())
+                ok = same & (s == 1)
+                np.testing.assert_allclose(q[ok], want[0][ok], atol=1e-6)
+            ok = s == 1
+            assert np.abs(C.fkine(q[ok]) - Tep[ok]).max() < 5e-3
+            assert (np.abs(q[ok]) <= np.pi + 1e-9).all()
+    q32, s32, *_ = (host(x) for x in e.ik_NR(dev(Tep, np.float32), pinv_damping=0.1, seed=2))
+    assert s32.mean() > 0.99
+    sol = rtb.IK_NR(seed=3).solve(e, Tep[:200])
+    assert sol.q.shape == (200, 7) and sol.searches >= 200
+    sol = rtb.IK_GN(seed=3, slimit=50).solve(rtb.models.Panda(), Tep[0])
+    assert sol.q.shape == (7,)
+    if sol.success:
+        assert np.abs(C.fkine(sol.q[None])[0] - Tep[0]).max() < 5e-3
+    ur = rtb.models.UR10()
+    Tu = ur.eval(rng.uniform(-2, 2, (64, 6)))
+    q, s, *_ = ur.ik_nr(Tu, None, 30, 100, 1e-6, False, None, True, 0.05)
+    assert s.mean() > 0.95
+
+
 def test_ik_restarts_match_oracle_stream():
     """With the documented counter-based restart generator the whole multi-start run is
     reproducible: same (seed,row,search,joint) draws as oracle_kin.c, so counters agree."""

@@ -207,6 +207,36 @@ def test_fixture_ik():
     assert abs(sr.mean() - z["rs_search"].mean()) < 0.5
 
 
+IKNR_CASES = [("nr_d", "nr", 0.1, False), ("nr_d_mask", "nr", 0.1, True), ("nr", "nr", 0.0, False),
+              ("gn", "gn", 0.0, False), ("gn_mask", "gn", 0.0, True), ("nr_inv", "nr", 0.0, False)]
+
+
+def test_fixture_ik_nr_gn():
+    """Newton-Raphson / Gauss-Newton restatements vs fknm.IK_NR_c / IK_GN_c.  The oracle takes the
+    pseudo-inverse through a one-sided Jacobi SVD, the reference through Eigen's JacobiSVD / BDCSVD:
+    damped runs reproduce the reference row for row; undamped Newton steps are chaotic near singular
+    configurations, so those are held to outcome statistics and to the well-started half of the batch."""
+    z = np.load(os.path.join(G, "ik_nr_gn.npz"))
+    for name in ("panda", "ur10", "ur3"):
+        C = orc.Chain(load_desc(z, name + "_"))
+        Tep, q0 = z[name + "_Tep"], z[name + "_q0"]
+        half = len(Tep) // 2
+        for tag, meth, damp, masked in IKNR_CASES:
+            if f"{name}_{tag}_q" not in z:
+                continue
+            q, s, it, sr, E = C.ik_lm(Tep, q0, 30, 1, 1e-6, False, z["mask"] if masked else None, damp, meth)
+            rs, rit, rq = z[f"{name}_{tag}_success"], z[f"{name}_{tag}_it"], z[f"{name}_{tag}_q"]
+            if damp > 0:
+                assert (s == rs).all() and (it == rit).all(), (name, tag)
+                ok = s == 1
+                np.testing.assert_allclose(q[ok], rq[ok], atol=1e-8)
+                np.testing.assert_allclose(E[ok], z[f"{name}_{tag}_E"][ok], atol=1e-12)
+            else:
+                assert abs(s.mean() - rs.mean()) < 0.06, (name, tag, s.mean(), rs.mean())
+                near = ((s == rs) & (it == rit))[:half]
+                assert near.mean() >= 0.9, (name, tag, near.mean())
+
+
 def test_rng_stream_is_stable():
     """The restart RNG is part of the product's contract: pin a few draws."""
     u = [orc.rand_u01(0, 0, 0, 0), orc.rand_u01(1, 2, 3, 4), orc.rand_u01(2**63, 10**9, 99, 6)]
