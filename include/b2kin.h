@@ -193,6 +193,13 @@ int b2k_rne_accel(b2k_rne_t rne, int dtype, const void *q, const void *qd, const
  * 63 = all, 7 = translational, 56 = rotational); |det Ja| when Ja is square. */
 int b2k_hessian(int dtype, int n, const void *J, int64_t N, void *H, void *stream);
 int b2k_manipulability(int dtype, int n, const void *J, int64_t N, uint32_t axes_mask, void *m, void *stream);
+/* b2k_jacob_dot: Jd (N,6,n) = sum_i H[i] qd[i], the Jacobian time derivative of Robot.jacob0_dot
+ * (Robot.py:964-1099, representation None: np.tensordot(hessian0, qd, (0,0))), from J (N,6,n) and qd (N,n)
+ * without materialising the Hessian.
+ * b2k_jacobm: the manipulability Jacobian dm/dq (N,n) of ETS.jacobm (ETS.py:1628-1685) / Robot.jacobm
+ * (Robot.py:1124-1232) over the Cartesian rows in axes_mask: Jm[i] = m * vec(Ja Ha_i^T) . vec(inv(Ja Ja^T)). */
+int b2k_jacob_dot(int dtype, int n, const void *J, const void *qd, int64_t N, void *Jd, void *stream);
+int b2k_jacobm(int dtype, int n, const void *J, int64_t N, uint32_t axes_mask, void *Jm, void *stream);
 
 /* ---------------------------------------------------------------- host-buffer front ends
  * The same operations for callers that hold HOST arrays (what the reference's API takes):

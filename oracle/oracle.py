@@ -262,3 +262,23 @@ def yoshikawa(J, axes=(True,) * 6):
     if Ja.shape[0] == Ja.shape[1]:
         return abs(np.linalg.det(Ja))
     return np.sqrt(abs(np.linalg.det(Ja @ Ja.T)))
+
+
+def jacobm(J, H, axes=None):
+    """ETS.jacobm ETS.py:1672-1685 / Robot.jacobm Robot.py:1215-1232: J (6,n), H (n,6,n)."""
+    J = _f64(J); H = _f64(H)
+    n = J.shape[1]
+    ax = np.ones(6, bool) if axes is None else np.asarray(axes, bool)
+    m = yoshikawa(J, ax)
+    Ja, Ha = J[ax, :], H[:, ax, :]
+    b = np.linalg.inv(Ja @ Ja.T)
+    Jm = np.zeros((n, 1))
+    for i in range(n):
+        c = Ja @ Ha[i].T
+        Jm[i, 0] = m * c.flatten("F") @ b.flatten("F")
+    return Jm
+
+
+def jacob_dot(H, qd):
+    """Robot.jacob0_dot Robot.py:1099: np.tensordot(H, qd, (0, 0))."""
+    return np.tensordot(_f64(H), _f64(qd), (0, 0))

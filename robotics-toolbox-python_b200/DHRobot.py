@@ -130,6 +130,23 @@ class DHRobot:
     def fkine_jacob0(self, q, **kwargs):
         return self.ets().fkine_jacob0(q, **kwargs)
 
+    # pure functions of the Jacobian (reference DHRobot.py: hessian0 1142-1198 region, manipulability / jacobm /
+    # jacob0_dot exercised by tests/test_DHRobot.py:1246-1283), evaluated on the chain's own ETS
+    def hessian0(self, q=None, J0=None, **kwargs):
+        return self.ets().hessian0(q, J0=J0, **kwargs)
+
+    def hessiane(self, q=None, Je=None, **kwargs):
+        return self.ets().hessiane(q, Je=Je, **kwargs)
+
+    def manipulability(self, q=None, J=None, method="yoshikawa", axes="all", **kwargs):
+        return self.ets().manipulability(q, J=J, method=method, axes=axes, **kwargs)
+
+    def jacobm(self, q=None, J=None, H=None, axes="all", **kwargs):
+        return self.ets().jacobm(q, J=J, H=H, axes=axes, **kwargs)
+
+    def jacob0_dot(self, q=None, qd=None, J0=None, representation=None, **kwargs):
+        return self.ets().jacob0_dot(q, qd, J0=J0, representation=representation, **kwargs)
+
     def ikine_LM(self, Tep, q0=None, ilimit=30, slimit=100, tol=1e-6, joint_limits=False, mask=None, seed=None,
                  **kwargs):
         """reference DHRobot.ikine_LM 2454-2474 (note joint_limits defaults to False here)."""

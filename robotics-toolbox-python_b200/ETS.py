@@ -409,6 +409,71 @@ class ETS:
             m = B.to_host(m)
         return float(m[0]) if single else m
 
+    @staticmethod
+    def _axes_mask(axes):
+        if isinstance(axes, str):
+            mask = 63 if axes.startswith("all") else 7 if axes.startswith("trans") else 56 if axes.startswith("rot") else None
+            if mask is None:
+                raise ValueError("axes must be all, trans, rot or a 6-element bool list")
+            return mask
+        ax = [bool(a) for a in axes]
+        if len(ax) != 6:
+            raise ValueError("axes must be all, trans, rot or a 6-element bool list")
+        return sum(1 << k for k, a in enumerate(ax) if a)
+
+    def _jprep(self, J, dtype):
+        host = not B.is_tensor(J)
+        dt = B.pick_dtype(J, dtype)
+        Jd = B.to_device(J, dt)
+        single = Jd.dim() == 2
+        Jd = (Jd.reshape(1, 6, -1) if single else Jd).contiguous()
+        if tuple(Jd.shape[1:]) != (6, self.n):
+            raise ValueError(f"the Jacobian must be (6,{self.n}) or (N,6,{self.n})")
+        return Jd, dt, host, single
+
+    def jacobm(self, q=None, J=None, H=None, axes="all", dtype=None):
+        """Manipulability Jacobian dm/dq, (n,1) for one configuration like the reference, (N,n) for a batch
+        (reference ETS.jacobm, ETS.py:1628-1685; Robot.jacobm with `axes`, Robot.py:1124-1232).  `H` is
+        accepted for signature compatibility; the kernel forms the Hessian terms from J on the fly."""
+        if q is None and J is None:
+            raise ValueError("one of q or J must be supplied")
+        if J is None:
+            J = self.jacob0(q, dtype=dtype)
+        elif not (B.is_tensor(J) or isinstance(J, np.ndarray)):
+            raise TypeError("J must be an array")
+        if H is not None and not (B.is_tensor(H) or isinstance(H, np.ndarray)):
+            raise TypeError("Hessian must be numpy array of shape 6xnxn")
+        mask = self._axes_mask(axes)
+        Jd, dt, host, single = self._jprep(J, dtype)
+        N = Jd.shape[0]
+        Jm = B.empty((N, self.n), dt, like=Jd)
+        _lib.check(_lib.lib().b2k_jacobm(B.code(dt), self.n, B.ptr(Jd), N, mask, B.ptr(Jm), B.stream_ptr(Jd)))
+        if host:
+            Jm = B.to_host(Jm)
+        return Jm[0].reshape(self.n, 1) if single else Jm
+
+    def jacob0_dot(self, q=None, qd=None, J0=None, representation=None, dtype=None):
+        """Time derivative of the base-frame Jacobian, (6,n) or (N,6,n): sum_i hessian0[i] qd[i]
+        (reference Robot.jacob0_dot, Robot.py:964-1099, representation None; the analytical
+        representations differentiate numerically through spatialmath and are not accelerated)."""
+        if representation is not None:
+            raise NotImplementedError("only representation=None (geometric Jacobian) is accelerated")
+        if qd is None or (q is None and J0 is None):
+            raise ValueError("qd and one of q or J0 must be supplied")
+        if J0 is None:
+            J0 = self.jacob0(q, dtype=dtype)
+        Jd, dt, host, single = self._jprep(J0, dtype)
+        N = Jd.shape[0]
+        B.check_numeric(qd, "qd")
+        qdd = B.to_device(qd, dt).reshape(-1, self.n).contiguous()
+        if qdd.shape[0] != N:
+            raise ValueError(f"qd must have {N} rows of {self.n}")
+        out = B.empty((N, 6, self.n), dt, like=Jd)
+        _lib.check(_lib.lib().b2k_jacob_dot(B.code(dt), self.n, B.ptr(Jd), B.ptr(qdd), N, B.ptr(out), B.stream_ptr(Jd)))
+        if host:
+            out = B.to_host(out)
+        return out[0] if single else out
+
     # ------------------------------------------------------------------ inverse kinematics
     def _ik(self, Tep, q0, ilimit, slimit, tol, mask, joint_limits, k, method, seed, semantics, rng_per_row, dtype):
         Tep = getattr(Tep, "A", Tep)

@@ -126,6 +126,14 @@ class Robot:
     def manipulability(self, q=None, J=None, method="yoshikawa", axes="all", **kw):
         return self.ets().manipulability(q, J=J, method=method, axes=axes, **kw)
 
+    def jacobm(self, q=None, J=None, H=None, end=None, start=None, axes="all", **kw):
+        """reference Robot.jacobm, Robot.py:1101-1232"""
+        return self.ets(start, end).jacobm(q, J=J, H=H, axes=axes, **kw)
+
+    def jacob0_dot(self, q, qd, J0=None, representation=None, **kw):
+        """reference Robot.jacob0_dot, Robot.py:964-1099"""
+        return self.ets().jacob0_dot(q, qd, J0=J0, representation=representation, **kw)
+
     def ik_LM(self, Tep, end=None, start=None, **kw):
         return self.ets(start, end).ik_LM(Tep, **kw)
 

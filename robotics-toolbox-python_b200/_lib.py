@@ -51,6 +51,8 @@ _PROTOS = {
     "b2k_rne_accel": (C.c_int, [vp, C.c_int, vp, vp, vp, i64, dp, vp, vp]),
     "b2k_hessian": (C.c_int, [C.c_int, C.c_int, vp, i64, vp, vp]),
     "b2k_manipulability": (C.c_int, [C.c_int, C.c_int, vp, i64, C.c_uint32, vp, vp]),
+    "b2k_jacob_dot": (C.c_int, [C.c_int, C.c_int, vp, vp, i64, vp, vp]),
+    "b2k_jacobm": (C.c_int, [C.c_int, C.c_int, vp, i64, C.c_uint32, vp, vp]),
     "b2k_host_alloc": (C.c_int, [C.POINTER(vp), i64]),
     "b2k_host_free": (C.c_int, [vp]),
     "b2k_fkine_jacob0_host": (C.c_int, [vp, C.c_int, vp, i64, i64, dp, dp, vp, vp, C.c_int]),

@@ -1,6 +1,7 @@
-// b2k_extra.cu -- pure functions of the Jacobian: manipulator Hessian and Yoshikawa
-// manipulability.  Replaces fknm.ETS_hessian0 / ETS_hessiane (reference fknm.cpp:583-783 ->
-// _ETS_hessian methods.cpp:16-32) and the yoshikawa branch of ETS.manipulability (ETS.py:1780-1787).
+// b2k_extra.cu -- pure functions of the Jacobian: manipulator Hessian, Yoshikawa
+// manipulability, Jacobian time derivative and manipulability Jacobian.  Replaces fknm.ETS_hessian0 /
+// ETS_hessiane (reference fknm.cpp:583-783 -> _ETS_hessian methods.cpp:16-32), the yoshikawa branch of
+// ETS.manipulability (ETS.py:1780-1787), Robot.jacob0_dot (Robot.py:964-1099) and ETS.jacobm (ETS.py:1628-1685).
 #include "b2k_common.cuh"
 
 // H[a, 0:3, b] = Jw_a x Jv_b, H[a, 3:6, b] = Jw_a x Jw_b for b >= a; mirrored translational block and a zero
@@ -76,16 +77,122 @@ __global__ void __launch_bounds__(128) k_yoshikawa(const real *__restrict__ J, l
     m[row] = square ? fabs(det) : sqrt(fabs(det));
 }
 
+// Jd = sum_i H[i] qd[i]  (Robot.jacob0_dot, Robot.py:964-1099: np.tensordot(H, qd, (0, 0))) without
+// materialising H: Jd[r, b] = sum_a qd[a] * H[a, r, b].  Same mapping as k_hessian (warp per row).
+template <typename real, int N>
+__global__ void __launch_bounds__(256) k_jacob_dot(const real *__restrict__ J, const real *__restrict__ qd, long long nrows,
+                                                   real *__restrict__ Jd)
+{
+    __shared__ real sJ[8][6 * N + N];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long wstride = (long long)gridDim.x * 8;
+    for (long long row = (long long)blockIdx.x * 8 + warp; row < nrows; row += wstride) {
+        for (int e = lane; e < 6 * N; e += 32) sJ[warp][e] = J[row * (6 * N) + e];
+        for (int e = lane; e < N; e += 32) sJ[warp][6 * N + e] = qd[row * N + e];
+        __syncwarp();
+        const real *j = sJ[warp], *v = sJ[warp] + 6 * N;
+        for (int e = lane; e < 6 * N; e += 32) {
+            const int r = e / N, b = e % N;
+            const int c = r % 3, c1 = (c + 1) % 3, c2 = (c + 2) % 3, wrow = r < 3 ? 0 : 3;
+            real acc = 0;
+            for (int a = 0; a < N; a++) {
+                if (b >= a || r < 3) {
+                    const int lo = b >= a ? a : b, hi = b >= a ? b : a;
+                    const real u1 = j[(3 + c1) * N + lo], u2 = j[(3 + c2) * N + lo];
+                    const real w1 = j[(wrow + c1) * N + hi], w2 = j[(wrow + c2) * N + hi];
+                    acc += v[a] * (u1 * w2 - u2 * w1);
+                }
+            }
+            Jd[row * (6 * N) + e] = acc;
+        }
+        __syncwarp();
+    }
+}
+
+// Manipulability Jacobian dm/dq (ETS.jacobm ETS.py:1628-1685, Robot.jacobm Robot.py:1124-1232):
+//   Jm[i] = m * sum_{a,b} (Ja Ha_i^T)[a,b] * inv(Ja Ja^T)[a,b],  Ja / Ha = the selected Cartesian rows, m = Yoshikawa.
+// One lane per row; the na x na Gram matrix is inverted by Gauss-Jordan with partial pivoting (its determinant
+// gives m on the way).
+template <typename real, int N>
+__global__ void __launch_bounds__(128) k_jacobm(const real *__restrict__ J, long long nrows, unsigned axes_mask,
+                                                real *__restrict__ Jm)
+{
+    const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= nrows) return;
+    int sel[6], na = 0;
+    for (int k = 0; k < 6; k++)
+        if (axes_mask & (1u << k)) sel[na++] = k;
+    const real *jr = J + row * (6 * N);
+    real j[6 * N];
+    for (int e = 0; e < 6 * N; e++) j[e] = jr[e];
+    real A[36], Bi[36];
+    for (int a = 0; a < na; a++)
+        for (int b = 0; b < na; b++) {
+            real s = 0;
+            for (int k = 0; k < N; k++) s += j[sel[a] * N + k] * j[sel[b] * N + k];
+            A[a * na + b] = s;
+            Bi[a * na + b] = (a == b) ? (real)1 : (real)0;
+        }
+    // m as k_yoshikawa computes it: |det Ja| for a square selection, sqrt|det(Ja Ja^T)| otherwise
+    real det = 1;
+    for (int c = 0; c < na; c++) {
+        int p = c;
+        real best = fabs(A[c * na + c]);
+        for (int r = c + 1; r < na; r++)
+            if (fabs(A[r * na + c]) > best) { best = fabs(A[r * na + c]); p = r; }
+        if (p != c) {
+            for (int k = 0; k < na; k++) {
+                real t = A[c * na + k]; A[c * na + k] = A[p * na + k]; A[p * na + k] = t;
+                t = Bi[c * na + k]; Bi[c * na + k] = Bi[p * na + k]; Bi[p * na + k] = t;
+            }
+            det = -det;
+        }
+        const real piv = A[c * na + c];
+        det *= piv;
+        const real inv = (real)1 / piv; // a singular Gram matrix gives inf/nan, as numpy's inv raises / returns garbage
+        for (int k = 0; k < na; k++) { A[c * na + k] *= inv; Bi[c * na + k] *= inv; }
+        for (int r = 0; r < na; r++) {
+            if (r == c) continue;
+            const real f = A[r * na + c];
+            for (int k = 0; k < na; k++) { A[r * na + k] -= f * A[c * na + k]; Bi[r * na + k] -= f * Bi[c * na + k]; }
+        }
+    }
+    const real m = sqrt(fabs(det));
+    for (int i = 0; i < N; i++) {
+        real acc = 0;
+        for (int a = 0; a < na; a++)
+            for (int b = 0; b < na; b++) {
+                // c[a][b] = sum_k Ja[a][k] * H[i][sel b][k]
+                const int r = sel[b], cc = r % 3, c1 = (cc + 1) % 3, c2 = (cc + 2) % 3, wrow = r < 3 ? 0 : 3;
+                real cab = 0;
+                for (int k = 0; k < N; k++) {
+                    if (k >= i || r < 3) {
+                        const int lo = k >= i ? i : k, hi = k >= i ? k : i;
+                        const real u1 = j[(3 + c1) * N + lo], u2 = j[(3 + c2) * N + lo];
+                        const real w1 = j[(wrow + c1) * N + hi], w2 = j[(wrow + c2) * N + hi];
+                        cab += j[sel[a] * N + k] * (u1 * w2 - u2 * w1);
+                    }
+                }
+                acc += cab * Bi[a * na + b];
+            }
+        Jm[row * N + i] = m * acc;
+    }
+}
+
 template <typename real>
-static int extra_launch(int what, int n, const void *J, long long N, unsigned axes_mask, void *out, cudaStream_t st)
+static int extra_launch(int what, int n, const void *J, long long N, unsigned axes_mask, void *out, cudaStream_t st,
+                        const void *aux = nullptr)
 {
 #define B2K_CASE(NN)                                                                                                  \
     case NN:                                                                                                          \
-        if (what == 0) {                                                                                              \
+        if (what == 0 || what == 2) {                                                                                 \
             long long blocks = (N + 7) / 8;                                                                           \
             const long long cap = (long long)b2k_num_sms() * 16;                                                      \
             if (blocks > cap) blocks = cap;                                                                           \
-            k_hessian<real, NN><<<(unsigned)blocks, 256, 0, st>>>((const real *)J, N, (real *)out);                   \
+            if (what == 0) k_hessian<real, NN><<<(unsigned)blocks, 256, 0, st>>>((const real *)J, N, (real *)out);    \
+            else k_jacob_dot<real, NN><<<(unsigned)blocks, 256, 0, st>>>((const real *)J, (const real *)aux, N, (real *)out); \
+        } else if (what == 3) {                                                                                       \
+            k_jacobm<real, NN><<<(unsigned)((N + 127) / 128), 128, 0, st>>>((const real *)J, N, axes_mask, (real *)out); \
         } else {                                                                                                      \
             k_yoshikawa<real, NN><<<(unsigned)((N + 127) / 128), 128, 0, st>>>((const real *)J, N, axes_mask, (real *)out); \
         }                                                                                                             \
@@ -120,4 +227,24 @@ extern "C" int b2k_manipulability(int dtype, int n, const void *J, int64_t N, ui
     if (N == 0) return B2K_OK;
     return dtype == B2K_F64 ? extra_launch<double>(1, n, J, N, axes_mask & 63u, m, (cudaStream_t)stream)
                             : extra_launch<float>(1, n, J, N, axes_mask & 63u, m, (cudaStream_t)stream);
+}
+
+
+extern "C" int b2k_jacob_dot(int dtype, int n, const void *J, const void *qd, int64_t N, void *Jd, void *stream)
+{
+    if (N < 0 || (N > 0 && (!J || !qd || !Jd))) { b2k_set_error("b2k_jacob_dot: bad arguments"); return B2K_ERR_INVALID; }
+    if (dtype != B2K_F32 && dtype != B2K_F64) { b2k_set_error("b2k_jacob_dot: bad dtype"); return B2K_ERR_INVALID; }
+    if (N == 0) return B2K_OK;
+    return dtype == B2K_F64 ? extra_launch<double>(2, n, J, N, 0, Jd, (cudaStream_t)stream, qd)
+                            : extra_launch<float>(2, n, J, N, 0, Jd, (cudaStream_t)stream, qd);
+}
+
+extern "C" int b2k_jacobm(int dtype, int n, const void *J, int64_t N, uint32_t axes_mask, void *Jm, void *stream)
+{
+    if (N < 0 || (N > 0 && (!J || !Jm))) { b2k_set_error("b2k_jacobm: bad arguments"); return B2K_ERR_INVALID; }
+    if (dtype != B2K_F32 && dtype != B2K_F64) { b2k_set_error("b2k_jacobm: bad dtype"); return B2K_ERR_INVALID; }
+    if ((axes_mask & 63u) == 0) { b2k_set_error("b2k_jacobm: no Cartesian axis selected"); return B2K_ERR_INVALID; }
+    if (N == 0) return B2K_OK;
+    return dtype == B2K_F64 ? extra_launch<double>(3, n, J, N, axes_mask & 63u, Jm, (cudaStream_t)stream)
+                            : extra_launch<float>(3, n, J, N, axes_mask & 63u, Jm, (cudaStream_t)stream);
 }

@@ -293,6 +293,39 @@ def test_hessian_and_manipulability():
     np.testing.assert_allclose(host(ur.manipulability(dev(Q6))), [orc.yoshikawa(Jk) for Jk in J6], rtol=1e-9, atol=1e-12)
     with pytest.raises(NotImplementedError):
         e.manipulability(q1, method="minsingular")
+    # manipulability Jacobian: reference test literal (tests/test_ERobot.py:28-52: q as array, list, (1,n), (n,1), J=)
+    kat = KAT["panda_jacobm"]
+    pe = rtb.models.Panda().ets()
+    qk = np.array(kat["q"])
+    for qq in (qk, list(qk), qk[None, :], qk[:, None]):
+        Jm = pe.jacobm(qq)
+        assert Jm.shape == (7, 1)
+        np.testing.assert_array_almost_equal(Jm.ravel(), kat["Jm"], decimal=kat["decimal"])
+    np.testing.assert_array_almost_equal(pe.jacobm(J=pe.jacob0(qk)).ravel(), kat["Jm"], decimal=kat["decimal"])
+    with pytest.raises(TypeError):
+        pe.jacobm([1, 3], "qwe")
+    with pytest.raises(TypeError):
+        pe.jacobm("Wfgsrth")
+    with pytest.raises(ValueError):
+        pe.jacobm(qk, axes="abcdef")
+    sel = np.abs(np.linalg.det(z["J0"] @ z["J0"].transpose(0, 2, 1))) > 1e-8  # away from singular configurations
+    for axes, mask in (("all", [1] * 6), ("trans", [1, 1, 1, 0, 0, 0]), ("rot", [0, 0, 0, 1, 1, 1])):
+        want = np.stack([orc.jacobm(Jk, Hk, mask).ravel() for Jk, Hk in zip(z["J0"], z["H0"])])
+        got = host(e.jacobm(dev(z["Q"]), axes=axes))
+        np.testing.assert_allclose(got[sel], want[sel], rtol=1e-7, atol=1e-10)
+    np.testing.assert_allclose(host(rtb.models.Panda().jacobm(dev(z["Q"]), axes="trans")),
+                               host(e.jacobm(J=dev(z["J0"]), axes="trans")), rtol=1e-9, atol=1e-12)
+    # Jacobian time derivative = tensordot(hessian0, qd) (Robot.py:1099)
+    QD = np.random.default_rng(8).normal(size=z["Q"].shape)
+    want = np.stack([orc.jacob_dot(Hk, v) for Hk, v in zip(z["H0"], QD)])
+    np.testing.assert_allclose(host(e.jacob0_dot(dev(z["Q"]), dev(QD))), want, rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(e.jacob0_dot(z["Q"][2], QD[2]), want[2], rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(host(e.jacob0_dot(dev(z["Q"], np.float32), dev(QD, np.float32))), want, rtol=2e-4, atol=2e-4)
+    puma = rtb.models.Puma560()
+    assert puma.jacob0_dot(puma.qn, [0.1, -0.2, 0.3, -0.4, 0.5, -0.6]).shape == (6, 6)
+    assert abs(puma.manipulability(puma.qn) - 0.0786) < 1e-4  # tests/test_DHRobot.py:1262-1279
+    assert abs(puma.manipulability(puma.qn, axes="trans") - 0.111181) < 1e-4
+    assert abs(puma.manipulability(puma.qn, axes="rot") - 2.44949) < 1e-4
 
 
 def test_fixture_ik_fp64_explicit_q0():

@@ -176,6 +176,15 @@ def test_hessian_and_manipulability_restatements():
     J = z["J0"][3]
     assert abs(orc.yoshikawa(J) - np.sqrt(abs(np.linalg.det(J @ J.T)))) < 1e-15
     assert abs(orc.yoshikawa(J[:, :6]) - abs(np.linalg.det(J[:, :6]))) < 1e-15
+    # manipulability Jacobian (ETS.py:1672-1685) on the reference's J and H: the reference test's literal golden
+    kat = KAT["panda_jacobm"]
+    np.testing.assert_allclose(z["Q"][0], kat["q"])
+    np.testing.assert_array_almost_equal(orc.jacobm(z["J0"][0], z["H0"][0]).ravel(), kat["Jm"], decimal=kat["decimal"])
+    # Jacobian time derivative (Robot.py:1099) against a central difference of the reference's own jacob0
+    C = orc.Chain(load_desc(z))
+    q, qd, h = z["Q"][1], np.array([0.1, -0.2, 0.3, -0.4, 0.5, -0.6, 0.7]), 1e-6
+    num = (C.jacob0((q + h * qd)[None])[0] - C.jacob0((q - h * qd)[None])[0]) / (2 * h)
+    np.testing.assert_allclose(orc.jacob_dot(z["H0"][1], qd), num, atol=1e-8)
 
 
 def test_fixture_angle_axis():
