@@ -201,6 +201,16 @@ int b2k_manipulability(int dtype, int n, const void *J, int64_t N, uint32_t axes
 int b2k_jacob_dot(int dtype, int n, const void *J, const void *qd, int64_t N, void *Jd, void *stream);
 int b2k_jacobm(int dtype, int n, const void *J, int64_t N, uint32_t axes_mask, void *Jm, void *stream);
 
+/* ---------------------------------------------------------------- trajectory producer
+ * b2k_jtraj replaces tools.trajectory.jtraj (tools/trajectory.py:686-780): quintic joint-space blend
+ * from q0 to qf (host n-vectors; qd0 / qd1 boundary velocities or NULL = 0) sampled at N points,
+ * written straight into device buffers q, qd, qdd (N,n) (qd / qdd may be NULL) so the batch can feed
+ * b2k_fkine / b2k_rne without touching the host.
+ *   t == NULL: N samples of normalised time np.linspace(0, 1, N), tscal must be 1 (the `t: int` form);
+ *   t != NULL: device vector of N sample times (dtype), tscal = max(t) (the time-vector form). */
+int b2k_jtraj(int dtype, int n, const double *q0, const double *qf, const double *qd0, const double *qd1,
+              int64_t N, const void *t, double tscal, void *q, void *qd, void *qdd, void *stream);
+
 /* ---------------------------------------------------------------- host-buffer front ends
  * The same operations for callers that hold HOST arrays (what the reference's API takes):
  * the library streams row chunks host->device, runs the kernel and streams results back on

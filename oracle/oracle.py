@@ -282,3 +282,30 @@ def jacobm(J, H, axes=None):
 def jacob_dot(H, qd):
     """Robot.jacob0_dot Robot.py:1099: np.tensordot(H, qd, (0, 0))."""
     return np.tensordot(_f64(H), _f64(qd), (0, 0))
+
+
+def jtraj(q0, qf, t, qd0=None, qd1=None):
+    """tools/trajectory.py:730-775 restated line by line: returns (tv, q, qd, qdd)."""
+    if isinstance(t, (int, np.integer)):
+        tscal = 1.0
+        ts = np.linspace(0, 1, t)
+        tv = ts * t
+    else:
+        t = _f64(t)
+        tv = t.flatten()
+        tscal = max(t)
+        ts = t.flatten() / tscal
+    q0, qf = _f64(q0).ravel(), _f64(qf).ravel()
+    qd0 = np.zeros(q0.shape) if qd0 is None else _f64(qd0).ravel()
+    qd1 = np.zeros(q0.shape) if qd1 is None else _f64(qd1).ravel()
+    A = 6 * (qf - q0) - 3 * (qd1 + qd0) * tscal
+    Bc = -15 * (qf - q0) + (8 * qd0 + 7 * qd1) * tscal
+    Cc = 10 * (qf - q0) - (6 * qd0 + 4 * qd1) * tscal
+    E = qd0 * tscal
+    F = q0
+    tt = np.array([ts**5, ts**4, ts**3, ts**2, ts, np.ones(ts.shape)]).T
+    z = np.zeros(A.shape)
+    qt = tt @ np.array([A, Bc, Cc, z, E, F])
+    qdt = tt @ np.array([z, 5 * A, 4 * Bc, 3 * Cc, z, E]) / tscal
+    qddt = tt @ np.array([z, z, 20 * A, 12 * Bc, 6 * Cc, z]) / tscal**2
+    return tv, qt, qdt, qddt

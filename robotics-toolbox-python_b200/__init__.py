@@ -21,5 +21,7 @@ from .DHRobot import DHRobot  # noqa: F401
 from .Robot import ERobot, Link, Robot  # noqa: F401
 from . import models  # noqa: F401
 from . import dist  # noqa: F401
+from . import trajectory  # noqa: F401
+from .trajectory import Trajectory, jtraj  # noqa: F401
 
 __version__ = "0.1.0"

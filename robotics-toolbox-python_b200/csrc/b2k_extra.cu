@@ -248,3 +248,71 @@ extern "C" int b2k_jacobm(int dtype, int n, const void *J, int64_t N, uint32_t a
     return dtype == B2K_F64 ? extra_launch<double>(3, n, J, N, axes_mask & 63u, Jm, (cudaStream_t)stream)
                             : extra_launch<float>(3, n, J, N, axes_mask & 63u, Jm, (cudaStream_t)stream);
 }
+
+
+// ------------------------------------------------------------------ joint-space trajectory producer
+// jtraj (reference tools/trajectory.py:686-780): quintic blend q0 -> qf with boundary velocities qd0, qd1:
+//   q(s) = A s^5 + B s^4 + C s^3 + E s + F,  qd = (5A s^4 + 4B s^3 + 3C s^2 + E) / tscal,
+//   qdd = (20A s^3 + 12B s^2 + 6C s) / tscal^2,  s = t / tscal in [0, 1].
+// Rows are time samples; one thread per (row, joint) element so the three (N,n) outputs are written coalesced and a
+// q batch is produced where the FK / RNE kernels consume it, without a host round trip.
+struct JtrajP {
+    double A[B2K_MAX_JOINTS], B[B2K_MAX_JOINTS], C[B2K_MAX_JOINTS], E[B2K_MAX_JOINTS], F[B2K_MAX_JOINTS];
+    double inv_tscal, inv_nm1;
+    int n;
+};
+
+template <typename real>
+__global__ void __launch_bounds__(256) k_jtraj(const __grid_constant__ JtrajP P, const real *__restrict__ ts, long long nrows,
+                                               real *__restrict__ q, real *__restrict__ qd, real *__restrict__ qdd)
+{
+    const long long total = nrows * P.n;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long row = e / P.n;
+        const int j = (int)(e - row * P.n);
+        // normalised time: the caller's samples, or np.linspace(0, 1, N)[row] (last sample exactly 1)
+        const real s = ts ? ts[row] * (real)P.inv_tscal
+                          : (row == nrows - 1 ? (real)1 : (real)((double)row * P.inv_nm1));
+        const real A = (real)P.A[j], B = (real)P.B[j], C = (real)P.C[j], E = (real)P.E[j], F = (real)P.F[j];
+        const real it = (real)P.inv_tscal;
+        q[e] = fma(fma(fma(fma(A, s, B), s, C) * s, s, E), s, F);
+        if (qd) qd[e] = fma(fma(fma((real)5 * A, s, (real)4 * B), s, (real)3 * C) * s, s, E) * it;
+        if (qdd) qdd[e] = fma(fma((real)20 * A, s, (real)12 * B), s, (real)6 * C) * s * it * it;
+    }
+}
+
+extern "C" int b2k_jtraj(int dtype, int n, const double *q0, const double *qf, const double *qd0, const double *qd1,
+                         int64_t N, const void *t, double tscal, void *q, void *qd, void *qdd, void *stream)
+{
+    const char *fn = "b2k_jtraj";
+    if (n < 1 || n > B2K_MAX_JOINTS) { b2k_set_error("%s: n must be 1..%d", fn, B2K_MAX_JOINTS); return B2K_ERR_INVALID; }
+    if (dtype != B2K_F32 && dtype != B2K_F64) { b2k_set_error("%s: bad dtype", fn); return B2K_ERR_INVALID; }
+    if (!q0 || !qf) { b2k_set_error("%s: q0 / qf is NULL", fn); return B2K_ERR_INVALID; }
+    if (N < 0 || (N > 0 && !q)) { b2k_set_error("%s: bad N / q", fn); return B2K_ERR_INVALID; }
+    if (!(tscal > 0)) { b2k_set_error("%s: tscal must be positive", fn); return B2K_ERR_INVALID; }
+    if (N == 0) return B2K_OK;
+    JtrajP P;
+    P.n = n;
+    P.inv_tscal = 1.0 / tscal;
+    P.inv_nm1 = N > 1 ? 1.0 / (double)(N - 1) : 0.0;
+    for (int j = 0; j < n; j++) { // trajectory.py:753-757
+        const double d = qf[j] - q0[j], v0 = qd0 ? qd0[j] : 0.0, v1 = qd1 ? qd1[j] : 0.0;
+        P.A[j] = 6 * d - 3 * (v1 + v0) * tscal;
+        P.B[j] = -15 * d + (8 * v0 + 7 * v1) * tscal;
+        P.C[j] = 10 * d - (6 * v0 + 4 * v1) * tscal;
+        P.E[j] = v0 * tscal;
+        P.F[j] = q0[j];
+    }
+    const long long total = N * n;
+    long long blocks = (total + 255) / 256;
+    const long long cap = (long long)b2k_num_sms() * 16;
+    if (blocks > cap) blocks = cap;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == B2K_F64)
+        k_jtraj<double><<<(unsigned)blocks, 256, 0, st>>>(P, (const double *)t, N, (double *)q, (double *)qd, (double *)qdd);
+    else
+        k_jtraj<float><<<(unsigned)blocks, 256, 0, st>>>(P, (const float *)t, N, (float *)q, (float *)qd, (float *)qdd);
+    b2k_count_launch();
+    B2K_CUDA(cudaGetLastError());
+    return B2K_OK;
+}

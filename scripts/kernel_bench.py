@@ -154,8 +154,8 @@ if want("ik_"):
     for dt in (np.float32, np.float64):
         tag = "f64" if dt == np.float64 else "f32"
         Td = torch.from_numpy(Tep.astype(dt)).to(dev)
-        for k, jl in ((0.1, False), (1.0, True)):
-            name = f"ik_lm_panda_{tag}_chan{k}_jl{int(jl)}"
+        for k, jl, meth in ((0.1, False, 0), (1.0, True, 0), (0.1, False, 3), (0.0, False, 4)):
+            name = f"ik_lm_panda_{tag}_chan{k}_jl{int(jl)}" if meth == 0 else f"ik_{'nr' if meth == 3 else 'gn'}_panda_{tag}_damp{k}"
             if not want(name):
                 continue
             n = 7
@@ -169,7 +169,7 @@ if want("ik_"):
             codei = rtb._lib.F64 if dt == np.float64 else rtb._lib.F32
 
             def run(i):  # straight through the C ABI: no per-call allocations on the Python side
-                rtb._lib.check(Lb.b2k_ik_lm(chn, codei, Td.data_ptr(), M, None, 30, 100, 1e-6, int(jl), None, float(k), 0,
+                rtb._lib.check(Lb.b2k_ik_lm(chn, codei, Td.data_ptr(), M, None, 30, 100, 1e-6, int(jl), None, float(k), meth,
                                             5 + i, 0, 1, qo.data_ptr(), so.data_ptr(), io.data_ptr(), ro.data_ptr(),
                                             Eo.data_ptr(), stp))
 

@@ -415,7 +415,9 @@ def test_ik_nr_gn_restarts_and_python_semantics():
                 ok = same & (s == 1)
                 np.testing.assert_allclose(q[ok], want[0][ok], atol=1e-6)
             ok = s == 1
-            assert np.abs(C.fkine(q[ok]) - Tep[ok]).max() < 5e-3
+            # the C++ loop returns the q it tested (E < tol <=> |e| < 1.4e-3); the Python loop returns q AFTER one more
+            # step (IK.py:314-348), which for a pseudo-inverse step near a singularity can move the pose by ~1e-2
+            assert np.abs(C.fkine(q[ok]) - Tep[ok]).max() < (5e-3 if sem == 0 else 5e-2)
             assert (np.abs(q[ok]) <= np.pi + 1e-9).all()
     q32, s32, *_ = (host(x) for x in e.ik_NR(dev(Tep, np.float32), pinv_damping=0.1, seed=2))
     assert s32.mean() > 0.99
@@ -720,3 +722,40 @@ def test_launch_counter_moves():
     n0 = rtb.launch_count()
     e.eval(dev(np.zeros((10, 7))))
     assert rtb.launch_count() == n0 + 1
+
+
+def test_jtraj_producer():
+    """jtraj on the device: the reference's own test properties (tests/test_trajectory.py:420-520)
+    and the restated numpy formula, for the `t: int` and time-vector forms, with boundary velocities."""
+    q1 = np.r_[1, 2, 3, 4, 5, 6].astype(float)
+    q2 = -q1
+    tg = rtb.jtraj(q1, q2, 11)
+    assert tg.q.shape == tg.qd.shape == tg.qdd.shape == (11, 6) and len(tg) == 11 and tg.naxes == 6
+    assert np.allclose(tg.q[0], q1) and np.allclose(tg.q[-1], q2) and np.allclose(tg.q[5], 0)
+    assert np.allclose(tg.qd[0], 0) and np.allclose(tg.qd[-1], 0)
+    assert np.allclose(tg.qdd[0], 0) and np.allclose(tg.qdd[-1], 0) and np.allclose(tg.qdd[5], 0)
+    tv, q, qd, qdd = orc.jtraj(q1, q2, 11)
+    np.testing.assert_allclose(tg.t, tv)
+    for a, b in ((tg.q, q), (tg.qd, qd), (tg.qdd, qdd)):
+        np.testing.assert_allclose(a, b, rtol=1e-12, atol=1e-12)
+    # time vector + boundary velocities, on the device, feeding FK without leaving it
+    t = np.linspace(0, 2.5, 5001)
+    v0, v1 = 0.1 * q1, -0.2 * q1
+    tg = rtb.jtraj(q1, q2, dev(t), qd0=v0, qd1=v1)
+    assert tg.q.is_cuda
+    tv, q, qd, qdd = orc.jtraj(q1, q2, t, v0, v1)
+    for a, b in ((tg.q, q), (tg.qd, qd), (tg.qdd, qdd)):
+        np.testing.assert_allclose(host(a), b, rtol=1e-11, atol=1e-11)
+    np.testing.assert_allclose(host(tg.qd[0]), v0, atol=1e-12)
+    np.testing.assert_allclose(host(tg.qd[-1]), v1, atol=1e-10)
+    puma = rtb.models.Puma560()
+    T = puma.ets().eval(tg.q)
+    np.testing.assert_allclose(host(T), orc.Chain(puma.ets().describe()).fkine(q), rtol=1e-9, atol=1e-10)
+    tau = puma.rne(tg.q, tg.qd, tg.qdd)  # the whole q, qd, qdd -> torque pipeline stays in HBM
+    assert tau.is_cuda and tau.shape == (5001, 6)
+    tg32 = rtb.jtraj(q1, q2, 1000, dtype=np.float32, device=True)
+    np.testing.assert_allclose(host(tg32.q), orc.jtraj(q1, q2, 1000)[1], rtol=1e-5, atol=1e-5)
+    with pytest.raises(ValueError):
+        rtb.jtraj(q1, q2[:5], 10)
+    with pytest.raises(ValueError):
+        rtb.jtraj(q1, q2, 10, qd0=[1, 2])

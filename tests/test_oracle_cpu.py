@@ -272,3 +272,18 @@ def test_live_against_compiled_reference():
     d = ch.panda_ets()
     Q = np.random.default_rng(0).uniform(-np.pi, np.pi, (1024, 7))
     np.testing.assert_allclose(orc.Chain(d).fkine(Q), ref.RefETS(d).fkine(Q), atol=1e-14)
+
+
+def test_jtraj_restatement_properties():
+    """oracle.jtraj (tools/trajectory.py:730-775) against the reference test's properties
+    (tests/test_trajectory.py:420-520) and the polynomial's defining boundary conditions."""
+    q1 = np.r_[1, 2, 3, 4, 5, 6].astype(float)
+    tv, q, qd, qdd = orc.jtraj(q1, -q1, 11)
+    assert q.shape == qd.shape == qdd.shape == (11, 6)
+    assert np.allclose(q[0], q1) and np.allclose(q[-1], -q1) and np.allclose(q[5], 0)
+    assert np.allclose(qd[0], 0) and np.allclose(qd[-1], 0) and np.allclose(qdd[[0, 5, -1]], 0)
+    t = np.linspace(0, 3, 301)
+    tv, q, qd, qdd = orc.jtraj(q1, -q1, t, 0.3 * q1, -0.1 * q1)
+    np.testing.assert_allclose(qd[0], 0.3 * q1, atol=1e-12)
+    np.testing.assert_allclose(qd[-1], -0.1 * q1, atol=1e-10)
+    np.testing.assert_allclose(np.gradient(q, t, axis=0)[5:-5], qd[5:-5], atol=2e-3)
