@@ -35,7 +35,12 @@ def is_tensor(x) -> bool:
 def pick_dtype(x, dtype=None):
     """fp64 unless the caller passes float32 data or dtype=float32 (the reference is fp64-only)."""
     if dtype is not None:
-        d = np.dtype(str(dtype).replace("torch.", "")) if not isinstance(dtype, np.dtype) else dtype
+        if isinstance(dtype, np.dtype):
+            d = dtype
+        elif isinstance(dtype, type):  # np.float32 / np.float64 / float
+            d = np.dtype(dtype)
+        else:  # "float32", torch.float32
+            d = np.dtype(str(dtype).replace("torch.", ""))
         if d not in (np.dtype(np.float32), np.dtype(np.float64)):
             raise TypeError("dtype must be float32 or float64")
         return d
