@@ -201,6 +201,16 @@ int b2k_manipulability(int dtype, int n, const void *J, int64_t N, uint32_t axes
 int b2k_jacob_dot(int dtype, int n, const void *J, const void *qd, int64_t N, void *Jd, void *stream);
 int b2k_jacobm(int dtype, int n, const void *J, int64_t N, uint32_t axes_mask, void *Jm, void *stream);
 
+/* ---------------------------------------------------------------- pose error, position-based servo
+ * b2k_angle_axis replaces fknm.Angle_Axis (fknm.cpp:112-162 -> _angle_axis ik.cpp:241-286), batched:
+ * e (N,6) = [translation error; angle-axis rotation error] between Te (N,4,4) and Tep.
+ * tep_stride = 16: one target per row, Tep (N,4,4); tep_stride = 0: a single (4,4) target for every row.
+ * b2k_p_servo is tools/p_servo.py:46-106 with method="angle-axis": v (N,6) = gain .* e (gain: host
+ * 6-vector or NULL = ones), arrived (N) int32 = sum|e| < threshold. */
+int b2k_angle_axis(int dtype, const void *Te, const void *Tep, int64_t N, int64_t tep_stride, void *e, void *stream);
+int b2k_p_servo(int dtype, const void *Te, const void *Tep, int64_t N, int64_t tep_stride, const double *gain,
+                double threshold, void *v, int32_t *arrived, void *stream);
+
 /* ---------------------------------------------------------------- trajectory producer
  * b2k_jtraj replaces tools.trajectory.jtraj (tools/trajectory.py:686-780): quintic joint-space blend
  * from q0 to qf (host n-vectors; qd0 / qd1 boundary velocities or NULL = 0) sampled at N points,

@@ -3,6 +3,7 @@
 // ETS_hessiane (reference fknm.cpp:583-783 -> _ETS_hessian methods.cpp:16-32), the yoshikawa branch of
 // ETS.manipulability (ETS.py:1780-1787), Robot.jacob0_dot (Robot.py:964-1099) and ETS.jacobm (ETS.py:1628-1685).
 #include "b2k_common.cuh"
+#include "b2k_ik.cuh" // ik_angle_axis
 
 // H[a, 0:3, b] = Jw_a x Jv_b, H[a, 3:6, b] = Jw_a x Jw_b for b >= a; mirrored translational block and a zero
 // rotational block for b < a (methods.cpp:18-31).  One warp per row: the 6n values of J are staged in shared
@@ -315,4 +316,69 @@ extern "C" int b2k_jtraj(int dtype, int n, const double *q0, const double *qf, c
     b2k_count_launch();
     B2K_CUDA(cudaGetLastError());
     return B2K_OK;
+}
+
+
+// ------------------------------------------------------------------ pose error / position-based servo
+// Batched fknm.Angle_Axis (fknm.cpp:112-162 -> _angle_axis ik.cpp:241-286) and tools/p_servo.py:46-106 with
+// method="angle-axis": e = angle_axis(Te, Tep), v = gain .* e, arrived = sum|e| < threshold.
+// Lane per row; tep_stride = 0 broadcasts one target to every row.
+template <typename real>
+__global__ void __launch_bounds__(256) k_pose_error(const real *__restrict__ Te, const real *__restrict__ Tep,
+                                                    long long tep_stride, long long nrows, real g0, real g1, real g2,
+                                                    real g3, real g4, real g5, real threshold, real *__restrict__ out,
+                                                    int *__restrict__ arrived)
+{
+    const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= nrows) return;
+    const real *a = Te + row * 16, *b = Tep + row * tep_stride;
+    Pose<real> T;
+    pose_from_const<real>(T, a);
+    real Tp[12], e[6];
+#pragma unroll
+    for (int k = 0; k < 12; k++) Tp[k] = b[k];
+    ik_angle_axis<real>(T, Tp, e);
+    const real g[6] = {g0, g1, g2, g3, g4, g5};
+    real sum = 0;
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        sum += fabs(e[k]);
+        out[row * 6 + k] = g[k] * e[k];
+    }
+    if (arrived) arrived[row] = sum < threshold ? 1 : 0;
+}
+
+static int pose_error_launch(const char *fn, int dtype, const void *Te, const void *Tep, int64_t N, int64_t tep_stride,
+                             const double *gain, double threshold, void *out, int32_t *arrived, void *stream)
+{
+    if (dtype != B2K_F32 && dtype != B2K_F64) { b2k_set_error("%s: bad dtype", fn); return B2K_ERR_INVALID; }
+    if (N < 0 || (N > 0 && (!Te || !Tep || !out))) { b2k_set_error("%s: bad arguments", fn); return B2K_ERR_INVALID; }
+    if (tep_stride != 0 && tep_stride != 16) { b2k_set_error("%s: tep_stride must be 0 (one target) or 16", fn); return B2K_ERR_INVALID; }
+    if (N == 0) return B2K_OK;
+    double g[6];
+    for (int k = 0; k < 6; k++) g[k] = gain ? gain[k] : 1.0;
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned blocks = (unsigned)((N + 255) / 256);
+    if (dtype == B2K_F64)
+        k_pose_error<double><<<blocks, 256, 0, st>>>((const double *)Te, (const double *)Tep, tep_stride, N, g[0], g[1], g[2],
+                                                     g[3], g[4], g[5], threshold, (double *)out, arrived);
+    else
+        k_pose_error<float><<<blocks, 256, 0, st>>>((const float *)Te, (const float *)Tep, tep_stride, N, (float)g[0],
+                                                    (float)g[1], (float)g[2], (float)g[3], (float)g[4], (float)g[5],
+                                                    (float)threshold, (float *)out, arrived);
+    b2k_count_launch();
+    B2K_CUDA(cudaGetLastError());
+    return B2K_OK;
+}
+
+extern "C" int b2k_angle_axis(int dtype, const void *Te, const void *Tep, int64_t N, int64_t tep_stride, void *e, void *stream)
+{
+    return pose_error_launch("b2k_angle_axis", dtype, Te, Tep, N, tep_stride, nullptr, 0.0, e, nullptr, stream);
+}
+
+extern "C" int b2k_p_servo(int dtype, const void *Te, const void *Tep, int64_t N, int64_t tep_stride, const double *gain,
+                           double threshold, void *v, int32_t *arrived, void *stream)
+{
+    if (N > 0 && !arrived) { b2k_set_error("b2k_p_servo: arrived is NULL"); return B2K_ERR_INVALID; }
+    return pose_error_launch("b2k_p_servo", dtype, Te, Tep, N, tep_stride, gain, threshold, v, arrived, stream);
 }

@@ -281,3 +281,28 @@ def test_gather_rows_world_size_2_gloo(tmp_path):
         outs.append(o)
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0 and f"RANK_OK {r}" in o, o
+
+
+def test_plain_c_program_links_and_fails_loudly_without_a_gpu(tmp_path):
+    """examples/cabi_host.c needs nothing but include/b2kin.h and libb2kin.so (no Python, torch or CUDA headers);
+    on a box without a CUDA device the library call must return an error code and a message, not fall back."""
+    import shutil
+    import subprocess
+
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    libdir = os.path.join(ROOT, "robotics-toolbox-python_b200", "lib")
+    exe = str(tmp_path / "cabi_host")
+    subprocess.run(["gcc", "-O2", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "cabi_host.c"),
+                    "-L", libdir, "-lb2kin", f"-Wl,-rpath,{libdir}", "-lm", "-o", exe], check=True)
+    try:
+        import torch
+
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    r = subprocess.run([exe, "4"], capture_output=True, text=True)
+    if has_gpu:
+        assert r.returncode == 0 and len(r.stdout.strip().splitlines()) == 4
+    else:
+        assert r.returncode == 2 and "CUDA error" in r.stderr and r.stdout == ""

@@ -759,3 +759,52 @@ def test_jtraj_producer():
         rtb.jtraj(q1, q2[:5], 10)
     with pytest.raises(ValueError):
         rtb.jtraj(q1, q2, 10, qd0=[1, 2])
+
+
+def test_angle_axis_and_p_servo():
+    """Batched fknm.Angle_Axis against the compiled-reference fixture (corner cases of ik.cpp:261-277) and p_servo
+    (tools/p_servo.py:46-106, angle-axis method): v = gain .* e, arrived = sum|e| < threshold."""
+    z = np.load(os.path.join(G, "angle_axis.npz"))
+    e = rtb.angle_axis(z["Te"], z["Tep"])
+    np.testing.assert_allclose(e, z["e"], rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(rtb.angle_axis(z["Te"][5], z["Tep"][5]), z["e"][5], rtol=1e-10, atol=1e-12)
+    one = rtb.angle_axis(dev(z["Te"]), dev(z["Tep"][3]))  # a single target for every row
+    want = np.stack([orc.angle_axis(a, z["Tep"][3]) for a in z["Te"]])
+    np.testing.assert_allclose(host(one), want, rtol=1e-10, atol=1e-12)
+    e32 = rtb.angle_axis(z["Te"].astype(np.float32), z["Tep"].astype(np.float32))
+    far = np.abs(z["e"]).max(axis=1) < 3.0  # away from the angle = pi discontinuity, where fp32 rounding picks a branch
+    np.testing.assert_allclose(e32[far], z["e"][far], rtol=2e-3, atol=2e-3)
+    gain = np.array([1, 2, 3, 0.5, 0.25, 4.0])
+    v, arrived = rtb.p_servo(z["Te"], z["Tep"], gain=gain, threshold=0.4)
+    np.testing.assert_allclose(v, z["e"] * gain, rtol=1e-10, atol=1e-12)
+    assert (arrived == (np.abs(z["e"]).sum(axis=1) < 0.4)).all()
+    v1, a1 = rtb.p_servo(z["Te"][0], z["Tep"][0], gain=2.0)
+    assert v1.shape == (6,) and a1 is True
+    panda = rtb.models.Panda()
+    Q = dev(np.random.default_rng(1).uniform(-2, 2, (4096, 7)))
+    T = panda.ets().eval(Q)
+    v, arr = rtb.p_servo(T, T[7], gain=1.5)  # servo every pose of the batch towards one target, all on the device
+    assert v.is_cuda and v.shape == (4096, 6) and bool(arr[7]) and float(v[7].abs().max()) == 0.0
+    with pytest.raises(NotImplementedError):
+        rtb.p_servo(z["Te"][0], z["Tep"][0], method="rpy")
+
+
+def test_c_program_through_the_c_abi(tmp_path):
+    """examples/cabi_host.c: a plain C program (no Python, no torch, no CUDA headers) linked against libb2kin.so
+    builds a 3R chain, calls b2k_fkine_jacob0_host and prints the rows; compare them with the oracle."""
+    import subprocess
+
+    root = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+    libdir = os.path.join(root, "robotics-toolbox-python_b200", "lib")
+    exe = str(tmp_path / "cabi_host")
+    subprocess.run(["gcc", "-O2", "-I", os.path.join(root, "include"), os.path.join(root, "examples", "cabi_host.c"),
+                    "-L", libdir, "-lb2kin", f"-Wl,-rpath,{libdir}", "-lm", "-o", exe], check=True)
+    r = subprocess.run([exe, "3001"], check=True, capture_output=True, text=True)
+    rows = np.array([[float(x) for x in ln.split()] for ln in r.stdout.strip().splitlines()])
+    assert rows.shape == (3001, 3 + 16 + 18)
+    links = [dict(d=0.4, a=0.0, alpha=np.pi / 2), dict(d=0.0, a=0.35, alpha=0.0), dict(d=0.1, a=0.25, alpha=-np.pi / 2)]
+    e = rtb.DHRobot([rtb.RevoluteDH(**lk) for lk in links]).ets()
+    C = orc.Chain(e.describe())
+    Q = rows[:, :3]
+    np.testing.assert_allclose(rows[:, 3:19].reshape(-1, 4, 4), C.fkine(Q), rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(rows[:, 19:].reshape(-1, 6, 3), C.jacob0(Q), rtol=1e-10, atol=1e-12)
