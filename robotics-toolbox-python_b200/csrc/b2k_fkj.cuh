@@ -674,6 +674,75 @@ k_fkj_forward(const __grid_constant__ ChainP<real, N> P, const real *__restrict_
     if (WJ) TileStage<real, 6 * N>::wait_all();
 }
 
+// ------------------------------------------------------------------ forward walk, lean form for the common call
+// k_fkj_forward above is general: any row stride / jindex permutation / alignment, ragged tiles, several tiles per
+// warp, measurement skeletons.  ncu on the pose-only fp32 kernel (profiles/r01_fkine_f32.txt) showed what that
+// generality costs on a one-shot grid, where every warp pays the prologue for a single tile: ~300 of 714 issued
+// instructions per tile were integer / control (IMAD, ISETP, LOP3, BRA, BSSY ...), and the kernel was issue-bound.
+// This kernel is the same walk with everything about the call fixed at compile time: DH-like chain (PROF 1),
+// q rows exactly N wide with jindex j = column j, 16-byte aligned q, one FULL tile per warp.  The launcher uses it
+// for the full tiles of such calls and hands a ragged tail (nrows % 32 rows) to the general kernel.
+template <typename real, int N>
+struct FkjFast {
+    static constexpr int QBYTES = 32 * N * (int)sizeof(real);          // multiple of 128
+    static constexpr int QUNITS = QBYTES / 16;
+    static constexpr int WB_POSE = QBYTES;                                  // per-warp shared memory, pose only
+    static constexpr int WB_JAC = QBYTES + TileStage<real, 6 * N>::BYTES;   // with the Jacobian stage
+};
+
+template <typename real, int N, bool WT, bool WJ>
+__global__ void __launch_bounds__(B2K_THREADS, FkjBounds<real, N, WJ>::MINB)
+k_fkj_fast(const __grid_constant__ ChainP<real, N> P, const real *__restrict__ q, int ntiles, real *__restrict__ Tout,
+           real *__restrict__ Jout)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    typedef FkjFast<real, N> F;
+    constexpr int WB = WJ ? F::WB_JAC : F::WB_POSE;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int tile = blockIdx.x * B2K_WARPS_PER_BLOCK + warp;
+    if (tile >= ntiles) return;
+    unsigned char *wbase = smem_raw + warp * WB;
+    real *sq = reinterpret_cast<real *>(wbase);
+    {
+        const uint4 *g = reinterpret_cast<const uint4 *>(q + (size_t)tile * (32 * N));
+        uint4 *sdst = reinterpret_cast<uint4 *>(sq);
+#pragma unroll
+        for (int u = 0; u < (F::QUNITS + 31) / 32; u++) {
+            const int idx = u * 32 + lane;
+            if (F::QUNITS % 32 == 0 || idx < F::QUNITS) cp_async16(sdst + idx, g + idx);
+        }
+    }
+    cp_async_wait_all();
+    __syncwarp();
+    real qrow[N];
+#pragma unroll
+    for (int j = 0; j < N; j++) qrow[j] = sq[lane * N + j];
+    Pose<real> T;
+    real zj[WJ ? N : 1][3], pj[WJ ? N : 1][3];
+    chain_forward<real, N, WJ, 1>(P, [&](int j, int) { return qrow[j]; }, T, zj, pj);
+    const size_t row = (size_t)tile * 32 + lane;
+    if (WT) {
+        Pose<real> Tb = T;
+        if (P.has_base) pose_mul_const_left(Tb, P.B, AK_GEN | AK_TX | AK_TY | AK_TZ);
+        store_pose_row<real>(Tb, Tout + row * 16);
+    }
+    if (WJ) {
+        typedef TileStage<real, 6 * N> JS;
+        unsigned char *so = wbase + F::QBYTES;
+        real jrow[6 * N];
+        jacob0_row<real, N, 1>(P, T, zj, pj, jrow);
+        JS::put_row(so, lane, jrow);
+        real *gout = Jout + (size_t)tile * (32 * 6 * N);
+        if (!JS::drain_async(so, gout, 32, lane)) {
+            __syncwarp();
+            JS::drain(so, gout, 32, lane);
+        } else {
+            JS::wait_all(); // the bulk copy reads this warp's shared memory: it must finish before the block may retire
+        }
+    }
+}
+
 // ------------------------------------------------------------------ backward walk: end-effector-frame Jacobian (+ pose)
 // Reference _ETS_jacobe, methods.cpp:219-316: U starts at the tool and is left-multiplied by
 // each ET walking from the tip to the base; column j is read off U before joint j is applied.
@@ -808,10 +877,7 @@ int fkj_launch_n(const b2k_chain_s *c, int mode, const real *q, long long nrows,
     const size_t qb = fkj_q_bytes<real>(ldq);
     const size_t wsm = (fkj_warp_smem<real, N>(ldq, wt, wj0 || wje) + 15) & ~(size_t)15;
     const size_t smem = wsm * B2K_WARPS_PER_BLOCK;
-    const long long ntiles = (nrows + 31) / 32;
-    const long long nblk_needed = (ntiles + B2K_WARPS_PER_BLOCK - 1) / B2K_WARPS_PER_BLOCK;
     const float inv_ldq = 1.0f / (float)ldq;
-    const int qmode = fkj_qmode<real>(q, ldq);
     if (wt && (((uintptr_t)T) & 31)) { b2k_set_error("fkj: T must be 32-byte aligned"); return B2K_ERR_INVALID; }
     if ((wj0 || wje) && (((uintptr_t)J) % TileStage<real, 6 * N>::UB)) {
         b2k_set_error("fkj: J must be %d-byte aligned", TileStage<real, 6 * N>::UB);
@@ -821,6 +887,10 @@ int fkj_launch_n(const b2k_chain_s *c, int mode, const real *q, long long nrows,
     const int variant = b2k_get_variant();
     const int dbg = variant == 2 ? 1 : (variant == 3 ? 2 : 0);
     auto launch_impl = [&](auto kern, auto... extra) -> int {
+        // (q, nrows, T, J are read here, at launch time: the lean path below may have advanced them to the ragged tail)
+        const long long ntiles = (nrows + 31) / 32;
+        const long long nblk_needed = (ntiles + B2K_WARPS_PER_BLOCK - 1) / B2K_WARPS_PER_BLOCK;
+        const int qmode = fkj_qmode<real>(q, ldq);
         int per_sm = b2k_blocks_per_sm((const void *)kern, B2K_THREADS, smem);
         if (per_sm < 1) return per_sm < 0 ? per_sm : (b2k_set_error("fkj kernel does not fit on an SM (smem %zu B)", smem), B2K_ERR_INVALID);
         // One-shot grid, a few consecutive tiles per warp: the hardware block scheduler hands out
@@ -844,6 +914,32 @@ int fkj_launch_n(const b2k_chain_s *c, int mode, const real *q, long long nrows,
     auto launch = [&](auto kern) -> int { return launch_impl(kern, dbg); };   // forward kernels take dbg
     auto launch_b = [&](auto kern) -> int { return launch_impl(kern); };      // backward kernels do not
 
+    // Lean kernel for the common call (see k_fkj_fast): full tiles there, a ragged tail through the general kernel.
+    if (!wje && c->dh_like && c->dense_jindex && ldq == N && variant == 0 && !(((uintptr_t)q) & 15) && nrows >= 32 &&
+        nrows / 32 <= 0x7fffffffLL / 2) {
+        const int nfull = (int)(nrows / 32);
+        auto launch_fast = [&](auto kern, size_t fsmem) -> int {
+            int per_sm = b2k_blocks_per_sm((const void *)kern, B2K_THREADS, fsmem);
+            if (per_sm < 1) return per_sm < 0 ? per_sm : (b2k_set_error("fkj fast kernel does not fit on an SM (smem %zu B)", fsmem), B2K_ERR_INVALID);
+            const unsigned grid = (unsigned)((nfull + B2K_WARPS_PER_BLOCK - 1) / B2K_WARPS_PER_BLOCK);
+            kern<<<grid, B2K_THREADS, fsmem, st>>>(P, q, nfull, T, J);
+            b2k_count_launch();
+            B2K_CUDA(cudaGetLastError());
+            return B2K_OK;
+        };
+        typedef FkjFast<real, N> F;
+        int rc;
+        if (wt && wj0) rc = launch_fast(k_fkj_fast<real, N, true, true>, (size_t)F::WB_JAC * B2K_WARPS_PER_BLOCK);
+        else if (wt) rc = launch_fast(k_fkj_fast<real, N, true, false>, (size_t)F::WB_POSE * B2K_WARPS_PER_BLOCK);
+        else rc = launch_fast(k_fkj_fast<real, N, false, true>, (size_t)F::WB_JAC * B2K_WARPS_PER_BLOCK);
+        const long long done = (long long)nfull * 32;
+        if (rc != B2K_OK || done == nrows) return rc;
+        // ragged tail: the last nrows % 32 rows, general kernel on the slices that start at row `done`
+        q += done * ldq;
+        if (wt) T += done * 16;
+        if (wj0) J += done * (6 * N);
+        nrows -= done;
+    }
     if (wje) {
         if (c->dh_like) return wt ? launch_b(k_fkj_backward<real, N, true, 1>) : launch_b(k_fkj_backward<real, N, false, 1>);
         return wt ? launch_b(k_fkj_backward<real, N, true, 0>) : launch_b(k_fkj_backward<real, N, false, 0>);
