@@ -674,6 +674,37 @@ k_fkj_forward(const __grid_constant__ ChainP<real, N> P, const real *__restrict_
     if (WJ) TileStage<real, 6 * N>::wait_all();
 }
 
+// Backward walk of a DH-like chain (unflipped Rz joints, Rx-form inter-joint constants): U starts at the tail
+// constant and is left-multiplied towards the base; column j of Je is read off U before joint j is applied
+// (reference _ETS_jacobe, methods.cpp:219-316).  row = Je, row-major 6 x N.
+template <typename real, int N>
+__device__ __forceinline__ void backward_walk_dh(const ChainP<real, N> &P, const real *eta, Pose<real> &U, real *row)
+{
+    real sn[N], cs[N];
+    b2k_sincos_batch<real, N>(eta, P.trig, sn, cs);
+#pragma unroll
+    for (int j = N - 1; j >= 0; j--) {
+        real col[6];
+        je_col_rev<real, 2>(U, (real)1, col);
+#pragma unroll
+        for (int k = 0; k < 6; k++) row[k * N + j] = col[k];
+        rot_rows<real, 0, 1>(U, sn[j], cs[j]);
+        if (j > 0) { // left-multiply by the Rx-form constant A_j
+            const real *A = P.A[j];
+            real *cols[4] = {U.c0, U.c1, U.c2, U.p};
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                real a = cols[k][1], b = cols[k][2];
+                cols[k][1] = fma(A[5], a, A[6] * b);
+                cols[k][2] = fma(A[9], a, A[10] * b);
+            }
+            U.p[0] += A[3]; U.p[1] += A[7]; U.p[2] += A[11];
+        } else {
+            pose_mul_const_left(U, P.A[0], P.akind[0]);
+        }
+    }
+}
+
 // ------------------------------------------------------------------ forward walk, lean form for the common call
 // k_fkj_forward above is general: any row stride / jindex permutation / alignment, ragged tiles, several tiles per
 // warp, measurement skeletons.  ncu on the pose-only fp32 kernel (profiles/r01_fkine_f32.txt) showed what that
@@ -743,6 +774,55 @@ k_fkj_fast(const __grid_constant__ ChainP<real, N> P, const real *__restrict__ q
     }
 }
 
+// lean form of the backward walk (end-effector-frame Jacobian, optional pose): same contract as k_fkj_fast
+template <typename real, int N, bool WT>
+__global__ void __launch_bounds__(B2K_THREADS, FkjBounds<real, N, true>::MINB)
+k_fkj_back_fast(const __grid_constant__ ChainP<real, N> P, const real *__restrict__ q, int ntiles, real *__restrict__ Tout,
+                real *__restrict__ Jout)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    typedef FkjFast<real, N> F;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int tile = blockIdx.x * B2K_WARPS_PER_BLOCK + warp;
+    if (tile >= ntiles) return;
+    unsigned char *wbase = smem_raw + warp * F::WB_JAC;
+    real *sq = reinterpret_cast<real *>(wbase);
+    {
+        const uint4 *g = reinterpret_cast<const uint4 *>(q + (size_t)tile * (32 * N));
+        uint4 *sdst = reinterpret_cast<uint4 *>(sq);
+#pragma unroll
+        for (int u = 0; u < (F::QUNITS + 31) / 32; u++) {
+            const int idx = u * 32 + lane;
+            if (F::QUNITS % 32 == 0 || idx < F::QUNITS) cp_async16(sdst + idx, g + idx);
+        }
+    }
+    cp_async_wait_all();
+    __syncwarp();
+    real eta[N];
+#pragma unroll
+    for (int j = 0; j < N; j++) eta[j] = sq[lane * N + j];
+    Pose<real> U;
+    real jrow[6 * N];
+    pose_from_const(U, P.A[N]);
+    backward_walk_dh<real, N>(P, eta, U, jrow);
+    if (WT) {
+        Pose<real> Tb = U;
+        if (P.has_base) pose_mul_const_left(Tb, P.B, AK_GEN | AK_TX | AK_TY | AK_TZ);
+        store_pose_row<real>(Tb, Tout + ((size_t)tile * 32 + lane) * 16);
+    }
+    typedef TileStage<real, 6 * N> JS;
+    unsigned char *so = wbase + F::QBYTES;
+    JS::put_row(so, lane, jrow);
+    real *gout = Jout + (size_t)tile * (32 * 6 * N);
+    if (!JS::drain_async(so, gout, 32, lane)) {
+        __syncwarp();
+        JS::drain(so, gout, 32, lane);
+    } else {
+        JS::wait_all();
+    }
+}
+
 // ------------------------------------------------------------------ backward walk: end-effector-frame Jacobian (+ pose)
 // Reference _ETS_jacobe, methods.cpp:219-316: U starts at the tool and is left-multiplied by
 // each ET walking from the tip to the base; column j is read off U before joint j is applied.
@@ -779,31 +859,10 @@ k_fkj_backward(const __grid_constant__ ChainP<real, N> P, const real *__restrict
         real row[6 * N]; // Je, row-major 6 x N
         pose_from_const(U, P.A[N]);
         if constexpr (PROF == 1) { // DH-like chain: straight-line walk, batched sincos
-            real eta[N], sn[N], cs[N];
+            real eta[N];
 #pragma unroll
             for (int j = 0; j < N; j++) eta[j] = myq[P.jidx[j]];
-            b2k_sincos_batch<real, N>(eta, P.trig, sn, cs);
-#pragma unroll
-            for (int j = N - 1; j >= 0; j--) {
-                real col[6];
-                je_col_rev<real, 2>(U, (real)1, col);
-#pragma unroll
-                for (int k = 0; k < 6; k++) row[k * N + j] = col[k];
-                rot_rows<real, 0, 1>(U, sn[j], cs[j]);
-                if (j > 0) { // left-multiply by the Rx-form constant A_j
-                    const real *A = P.A[j];
-                    real *cols[4] = {U.c0, U.c1, U.c2, U.p};
-#pragma unroll
-                    for (int k = 0; k < 4; k++) {
-                        real a = cols[k][1], b = cols[k][2];
-                        cols[k][1] = fma(A[5], a, A[6] * b);
-                        cols[k][2] = fma(A[9], a, A[10] * b);
-                    }
-                    U.p[0] += A[3]; U.p[1] += A[7]; U.p[2] += A[11];
-                } else {
-                    pose_mul_const_left(U, P.A[0], P.akind[0]);
-                }
-            }
+            backward_walk_dh<real, N>(P, eta, U, row);
         } else {
 #pragma unroll
             for (int j = N - 1; j >= 0; j--) {
@@ -915,7 +974,7 @@ int fkj_launch_n(const b2k_chain_s *c, int mode, const real *q, long long nrows,
     auto launch_b = [&](auto kern) -> int { return launch_impl(kern); };      // backward kernels do not
 
     // Lean kernel for the common call (see k_fkj_fast): full tiles there, a ragged tail through the general kernel.
-    if (!wje && c->dh_like && c->dense_jindex && ldq == N && variant == 0 && !(((uintptr_t)q) & 15) && nrows >= 32 &&
+    if (c->dh_like && c->dense_jindex && ldq == N && variant == 0 && !(((uintptr_t)q) & 15) && nrows >= 32 &&
         nrows / 32 <= 0x7fffffffLL / 2) {
         const int nfull = (int)(nrows / 32);
         auto launch_fast = [&](auto kern, size_t fsmem) -> int {
@@ -929,7 +988,9 @@ int fkj_launch_n(const b2k_chain_s *c, int mode, const real *q, long long nrows,
         };
         typedef FkjFast<real, N> F;
         int rc;
-        if (wt && wj0) rc = launch_fast(k_fkj_fast<real, N, true, true>, (size_t)F::WB_JAC * B2K_WARPS_PER_BLOCK);
+        if (wje) rc = wt ? launch_fast(k_fkj_back_fast<real, N, true>, (size_t)F::WB_JAC * B2K_WARPS_PER_BLOCK)
+                         : launch_fast(k_fkj_back_fast<real, N, false>, (size_t)F::WB_JAC * B2K_WARPS_PER_BLOCK);
+        else if (wt && wj0) rc = launch_fast(k_fkj_fast<real, N, true, true>, (size_t)F::WB_JAC * B2K_WARPS_PER_BLOCK);
         else if (wt) rc = launch_fast(k_fkj_fast<real, N, true, false>, (size_t)F::WB_POSE * B2K_WARPS_PER_BLOCK);
         else rc = launch_fast(k_fkj_fast<real, N, false, true>, (size_t)F::WB_JAC * B2K_WARPS_PER_BLOCK);
         const long long done = (long long)nfull * 32;
@@ -937,7 +998,7 @@ int fkj_launch_n(const b2k_chain_s *c, int mode, const real *q, long long nrows,
         // ragged tail: the last nrows % 32 rows, general kernel on the slices that start at row `done`
         q += done * ldq;
         if (wt) T += done * 16;
-        if (wj0) J += done * (6 * N);
+        if (wj0 || wje) J += done * (6 * N);
         nrows -= done;
     }
     if (wje) {
