@@ -362,7 +362,7 @@ def run_b200(args):
             "config": {"workload": WORKLOAD, "rows_per_gpu": ROWS_PER_GPU, "global_batch": ROWS_PER_GPU * world,
                        "parallelism": f"rows sharded over {world} rank(s), no data-path collective",
                        "l2": "4 distinct 56 MB q batches rotated + 464 MB written per step (> 126 MB L2)",
-                       "kernel": "k_fkj_forward<double,7,T,J0,allRz> (1 launch per step)"},
+                       "kernel": "k_fkj_fast<double,7,T,J0> (1 launch per step)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": load_traffic(), "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": BYTES_PER_EVAL * ROWS_PER_GPU},
