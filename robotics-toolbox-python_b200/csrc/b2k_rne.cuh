@@ -28,6 +28,7 @@ struct RneP {
     real c_tcp[N]; // |G|*Tc+
     real c_tcm[N]; // |G|*Tc-
     int prismatic[N];
+    real psrc[N][3]; // p* + r (standard DH backward recursion, ne.c:415-417), summed on the host
     real ps[N][3]; // p* of a revolute link: (a, d sin(alpha), d cos(alpha)) for DH, (a, -d sin(alpha), d cos(alpha)) for MDH
     real grav[3];
     real fext[6];
@@ -42,6 +43,11 @@ template <typename real> __device__ __forceinline__ V3<real> vadd(V3<real> a, V3
 template <typename real> __device__ __forceinline__ V3<real> vcross(V3<real> a, V3<real> b)
 {
     return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
+}
+// a x b + c with the addition folded into the products (2 FMA per component instead of MUL + FMA + ADD)
+template <typename real> __device__ __forceinline__ V3<real> vcross_acc(V3<real> a, V3<real> b, V3<real> c)
+{
+    return {fma(a.y, b.z, fma(-a.z, b.y, c.x)), fma(a.z, b.x, fma(-a.x, b.z, c.y)), fma(a.x, b.y, fma(-a.y, b.x, c.z))};
 }
 template <typename real> __device__ __forceinline__ V3<real> vscale(V3<real> a, real s) { return {s * a.x, s * a.y, s * a.z}; }
 template <typename real> __device__ __forceinline__ real vdot(V3<real> a, V3<real> b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
@@ -101,6 +107,27 @@ struct FRot { // factored link rotation
             return {u, fma(ca, w, -(sa * v.z)), fma(sa, w, ca * v.z)};
         }
     }
+    // R^T v + c and R v + c with c folded into the last stage of FMAs (no separate additions)
+    __device__ __forceinline__ V3<real> tmul_acc(V3<real> v, V3<real> c) const
+    {
+        if (!MDH) {
+            const real w = fma(ct, v.y, -(st * v.x));
+            return {fma(ct, v.x, fma(st, v.y, c.x)), fma(ca, w, fma(sa, v.z, c.y)), fma(ca, v.z, fma(-sa, w, c.z))};
+        } else {
+            const real wy = fma(ca, v.y, sa * v.z);
+            return {fma(ct, v.x, fma(st, wy, c.x)), fma(ct, wy, fma(-st, v.x, c.y)), fma(ca, v.z, fma(-sa, v.y, c.z))};
+        }
+    }
+    __device__ __forceinline__ V3<real> mul_acc(V3<real> v, V3<real> c) const
+    {
+        if (!MDH) {
+            const real m = fma(ca, v.y, -(sa * v.z));
+            return {fma(ct, v.x, fma(-st, m, c.x)), fma(st, v.x, fma(ct, m, c.y)), fma(sa, v.y, fma(ca, v.z, c.z))};
+        } else {
+            const real w = fma(st, v.x, ct * v.y);
+            return {fma(ct, v.x, fma(-st, v.y, c.x)), fma(ca, w, fma(-sa, v.z, c.y)), fma(sa, w, fma(ca, v.z, c.z))};
+        }
+    }
 };
 
 template <typename real>
@@ -149,8 +176,8 @@ __device__ __forceinline__ void rne_row_allrev(const RneP<real, N> &P, const rea
                 const V3<real> t3 = R.tmul(wd);
                 wdn = {fma(t1.y, qd, t3.x), fma(-t1.x, qd, t3.y), t3.z + qdd}; // t1 x (0,0,qd) + t3 + (0,0,qdd)
                 V3<real> a = vcross(w, ps);
-                a = vcross(w, a);
-                a = vadd(vadd(vcross(wd, ps), a), acc);
+                a = vcross_acc(w, a, acc);
+                a = vcross_acc(wd, ps, a);
                 accn = R.tmul(a);
             }
         } else { // ne.c:252-288
@@ -162,15 +189,13 @@ __device__ __forceinline__ void rne_row_allrev(const RneP<real, N> &P, const rea
                 wdn = R.tmul(V3<real>{fma(w.y, qd, wd.x), fma(-w.x, qd, wd.y), wd.z + qdd});
             }
             const V3<real> t2 = vcross(wn, ps);
-            accn = vadd(vcross(wdn, ps), vcross(wn, t2));
-            accn = vadd(accn, R.tmul(j == 0 ? gravity : acc));
+            accn = R.tmul_acc(j == 0 ? gravity : acc, vcross_acc(wdn, ps, vcross(wn, t2)));
         }
         w = wn; wd = wdn; acc = accn;
         const V3<real> rc = {P.r[j][0], P.r[j][1], P.r[j][2]};
-        V3<real> abar = vadd(vcross(wd, rc), vcross(w, vcross(w, rc)));
-        abar = vadd(abar, acc);
+        const V3<real> abar = vcross_acc(wd, rc, vcross_acc(w, vcross(w, rc), acc));
         Fm[j] = vscale(abar, P.m[j]);
-        Nm[j] = vadd(imul(P.I[j], wd), vcross(w, imul(P.I[j], w)));
+        Nm[j] = vcross_acc(w, imul(P.I[j], w), imul(P.I[j], wd));
     }
     V3<real> f = {0, 0, 0}, nn = {0, 0, 0};
     const V3<real> f_tip = {P.fext[0], P.fext[1], P.fext[2]}, n_tip = {P.fext[3], P.fext[4], P.fext[5]};
@@ -181,28 +206,29 @@ __device__ __forceinline__ void rne_row_allrev(const RneP<real, N> &P, const rea
         if (MDH) { // ne.c:358-398
             if (j == N - 1) {
                 fj = vadd(f_tip, Fm[j]);
-                nj = n_tip;
+                nj = vadd(n_tip, Nm[j]);
             } else {
                 const FRot<real, MDH> Rn = {sth[j + 1], cth[j + 1], P.sa[j + 1], P.ca[j + 1]};
                 const V3<real> psn = {P.ps[j + 1][0], P.ps[j + 1][1], P.ps[j + 1][2]};
                 const V3<real> Rf = Rn.mul(f);
                 fj = vadd(Rf, Fm[j]);
-                nj = vadd(Rn.mul(nn), vcross(psn, Rf));
+                nj = Rn.mul_acc(nn, vcross_acc(psn, Rf, Nm[j]));
             }
-            nj = vadd(vadd(nj, vcross(rc, Fm[j])), Nm[j]);
+            nj = vcross_acc(rc, Fm[j], nj);
         } else { // ne.c:409-453
             const V3<real> ps = {P.ps[j][0], P.ps[j][1], P.ps[j][2]};
-            V3<real> t1 = vcross(vadd(ps, rc), Fm[j]);
+            const V3<real> psrc = {P.psrc[j][0], P.psrc[j][1], P.psrc[j][2]};
+            V3<real> t1 = vcross_acc(psrc, Fm[j], Nm[j]);
             if (j != N - 1) {
                 const FRot<real, MDH> Rn = {sth[j + 1], cth[j + 1], P.sa[j + 1], P.ca[j + 1]};
-                fj = vadd(Fm[j], Rn.mul(f));
-                const V3<real> t3 = vadd(vcross(Rn.tmul(ps), f), nn);
-                t1 = vadd(t1, Rn.mul(t3));
+                fj = Rn.mul_acc(f, Fm[j]);
+                const V3<real> t3 = vcross_acc(Rn.tmul(ps), f, nn);
+                t1 = Rn.mul_acc(t3, t1);
             } else {
                 fj = vadd(Fm[j], f_tip);
-                t1 = vadd(vadd(t1, vcross(ps, f_tip)), n_tip);
+                t1 = vadd(vcross_acc(ps, f_tip, t1), n_tip);
             }
-            nj = vadd(t1, Nm[j]);
+            nj = t1;
         }
         f = fj; nn = nj;
         real t = MDH ? nj.z : fma(nj.y, P.sa[j], nj.z * P.ca[j]); // n . (R^T z0)
@@ -648,6 +674,7 @@ void rne_fill_params(const b2k_rne_s *r, const double *grav, const double *fext,
         P.ps[j][0] = (real)A;
         P.ps[j][1] = (real)(r->mdh ? -D * sin(alpha) : D * sin(alpha));
         P.ps[j][2] = (real)(D * cos(alpha));
+        for (int k = 0; k < 3; k++) P.psrc[j][k] = (real)((double)P.ps[j][k] + (double)P.r[j][k]);
     }
     for (int k = 0; k < 3; k++) P.grav[k] = grav ? (real)grav[k] : (real)0;
     for (int k = 0; k < 6; k++) P.fext[k] = fext ? (real)fext[k] : (real)0;
