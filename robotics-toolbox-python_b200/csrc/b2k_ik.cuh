@@ -560,7 +560,8 @@ int ik_launch_n(const b2k_chain_s *c, const real *Tep, long long nprob, const re
         if (per_sm < 1) return per_sm < 0 ? per_sm : (b2k_set_error("ik kernel does not fit on an SM"), B2K_ERR_INVALID);
         long long grid = (long long)b2k_num_sms() * per_sm;
         long long need = (nprob + B2K_THREADS - 1) / B2K_THREADS;
-        if (grid > need) grid = need;
+        static const int oneshot = getenv("B2K_IK_ONESHOT") ? atoi(getenv("B2K_IK_ONESHOT")) : 0; // experiment
+        if (grid > need || (oneshot && two_phase)) grid = need;
         if (grid < 1) grid = 1;
         kern<<<(unsigned)grid, B2K_THREADS, 0, st>>>(P, K, Tep, q0, nprob, q_out, success, iterations, searches, residual,
                                                      two_phase ? 1 : 0, hard_idx, hard_count);
