@@ -93,6 +93,40 @@ def test_rne_create_validation():
     assert lib.b2k_rne_create(0, 0, L.ctypes.data_as(rtb._lib.dp), C.byref(h)) == -1
 
 
+def test_widened_entry_points_validate_before_launching():
+    """The entry points of the widened rows reject bad arguments with a status code and a message
+    before any CUDA call, like the core ones."""
+    lib = rtb._lib.lib()
+    dp = rtb._lib.dp
+    q0 = np.zeros(6)
+    buf = np.zeros(64)  # stands in for a (never dereferenced) device pointer
+    p = buf.ctypes.data
+    assert lib.b2k_jtraj(1, 0, q0.ctypes.data_as(dp), q0.ctypes.data_as(dp), None, None, 8, None, 1.0, p, p, p, None) == -1
+    assert b"n must be" in lib.b2k_last_error()
+    assert lib.b2k_jtraj(1, 6, q0.ctypes.data_as(dp), q0.ctypes.data_as(dp), None, None, 8, None, 0.0, p, p, p, None) == -1
+    assert b"tscal" in lib.b2k_last_error()
+    assert lib.b2k_jtraj(7, 6, q0.ctypes.data_as(dp), q0.ctypes.data_as(dp), None, None, 8, None, 1.0, p, p, p, None) == -1
+    assert lib.b2k_jtraj(1, 6, q0.ctypes.data_as(dp), q0.ctypes.data_as(dp), None, None, 0, None, 1.0, None, None, None, None) == 0
+    assert lib.b2k_hessian(1, 7, None, 4, None, None) == -1
+    assert lib.b2k_manipulability(1, 7, p, 4, 0, p, None) == -1 and b"axis" in lib.b2k_last_error()
+    assert lib.b2k_jacobm(1, 7, p, 4, 0, p, None) == -1
+    assert lib.b2k_jacob_dot(3, 7, p, p, 4, p, None) == -1
+    assert lib.b2k_angle_axis(1, p, p, 4, 5, p, None) == -1 and b"tep_stride" in lib.b2k_last_error()
+    assert lib.b2k_p_servo(1, p, p, 4, 16, None, 0.1, p, None, None) == -1 and b"arrived" in lib.b2k_last_error()
+    # IK: unknown method code, negative damping for the pseudo-inverse solvers
+    d = ch.panda_ets()
+    h = C.c_void_p()
+    ip = rtb._lib.ip
+    assert lib.b2k_chain_create(len(d["isjoint"]), d["isjoint"].ctypes.data_as(ip), d["axis"].ctypes.data_as(ip),
+                                d["flip"].ctypes.data_as(ip), d["jindex"].ctypes.data_as(ip),
+                                np.ascontiguousarray(d["T"]).ctypes.data_as(dp), np.ascontiguousarray(d["qlim"]).ctypes.data_as(dp),
+                                C.byref(h)) == 0
+    ik = lambda lam, meth: lib.b2k_ik_lm(h, 1, p, 2, None, 30, 100, 1e-6, 0, None, lam, meth, 0, 0, 1, p, p, p, p, p, None)  # noqa: E731
+    assert ik(1.0, 5) == -1 and b"method" in lib.b2k_last_error()
+    assert ik(-0.5, rtb._lib.IK_NR) == -1 and b"damping" in lib.b2k_last_error()
+    assert lib.b2k_chain_destroy(h) == 0
+
+
 # ------------------------------------------------------------------ host-side mirror of the reference interface
 def test_models_match_the_reference_tables():
     """Product model tables == the independent restatement used to generate the goldens."""
