@@ -58,7 +58,8 @@ def report(name, ms, rows, bytes_per_row, extra=None):
 
 
 def want(name):
-    return args.only in name
+    # `name` is a case name or the prefix of a block of cases ("ik_", "dyn_", "probe_")
+    return args.only in name or (name.endswith("_") and args.only.startswith(name))
 
 
 N = args.rows
