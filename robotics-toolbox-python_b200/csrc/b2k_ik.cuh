@@ -311,21 +311,38 @@ __global__ void __launch_bounds__(B2K_THREADS)
 k_ik_lm(const __grid_constant__ ChainP<real, N> P, const __grid_constant__ IkP<real, N> K,
         const real *__restrict__ Tep, const real *__restrict__ q0, long long nprob, real *__restrict__ q_out,
         int *__restrict__ success, int *__restrict__ iterations, int *__restrict__ searches,
-        real *__restrict__ residual, int two_phase, int *__restrict__ hard_idx, int *__restrict__ hard_count)
+        real *__restrict__ residual, int two_phase, int *__restrict__ hard_idx, int *__restrict__ hard_count,
+        int iter_cap, const int *__restrict__ in_list, const int *__restrict__ in_count, int *__restrict__ cont_idx,
+        int *__restrict__ cont_count)
 {
+    // Segmented first search (two_phase only): with iter_cap > 0 a problem that is still iterating after iter_cap
+    // evaluations in THIS launch parks its state (q in q_out, the search's evaluation count in iterations) and is
+    // appended to cont_idx; a later launch with in_list = that list resumes it.  Quick problems then never share a
+    // warp with slow ones for long, and the slow ones are re-packed into full warps.
     const long long stride = (long long)gridDim.x * blockDim.x;
-    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long pos = (long long)blockIdx.x * blockDim.x + threadIdx.x; // position in the work list
+    const long long nwork = in_list ? (long long)*in_count : nprob;
     const bool cpp = K.semantics == B2K_IK_SEM_CPP;
 
     real q[N], Tp[12], E = 0;
     int it = 0, search = 0, iter = 0; // search is 0-based here; reported 1-based (cpp: ik.cpp:39-69, python: IK.py:299-348)
-    bool active = idx < nprob;
+    int evals = 0;                    // evaluations of the current problem in this launch
+    bool active = pos < nwork;
+    long long idx = active ? (in_list ? (long long)in_list[pos] : pos) : 0;
 
     auto begin_problem = [&]() {
         const real *t = Tep + idx * 16;
 #pragma unroll
         for (int k = 0; k < 12; k++) Tp[k] = t[k];
         const unsigned long long row = K.rng_per_row ? (unsigned long long)idx : 0ULL;
+        evals = 0;
+        if (in_list) { // resume a parked first search
+#pragma unroll
+            for (int i = 0; i < N; i++) q[i] = q_out[idx * N + i];
+            E = 0; it = 0; search = 0;
+            iter = iterations[idx];
+            return;
+        }
         if (K.has_q0) {
 #pragma unroll
             for (int i = 0; i < N; i++) q[i] = q0[idx * N + i];
@@ -336,9 +353,22 @@ k_ik_lm(const __grid_constant__ ChainP<real, N> P, const __grid_constant__ IkP<r
         iter = cpp ? 1 : 0; // the C++ loop's first search starts counting at 1 (ik.cpp:39), later ones at 0 (ik.cpp:67)
     };
     auto next_problem = [&]() {
-        idx += stride;
-        active = idx < nprob;
-        if (active) begin_problem();
+        pos += stride;
+        active = pos < nwork;
+        if (active) {
+            idx = in_list ? (long long)in_list[pos] : pos;
+            begin_problem();
+        }
+    };
+    // park the running first search when this launch's evaluation budget for it is used up
+    auto maybe_yield = [&]() {
+        if (iter_cap > 0 && ++evals >= iter_cap) {
+#pragma unroll
+            for (int i = 0; i < N; i++) q_out[idx * N + i] = q[i];
+            iterations[idx] = iter;
+            cont_idx[atomicAdd(cont_count, 1)] = (int)idx;
+            next_problem();
+        }
     };
     auto finish = [&](int ok, int its, int srch) {
 #pragma unroll
@@ -386,6 +416,7 @@ k_ik_lm(const __grid_constant__ ChainP<real, N> P, const __grid_constant__ IkP<r
                 for (int i = 0; i < N; i++) q[i] += g[i];
             }
             if (!ok || iter > K.ilimit) search_failed();
+            else maybe_yield();
         } else {
             // count the step, apply it, then test the PRE-step E (IK.py:314-348)
             const bool ok = ik_eval<real, N, PROF, STEP>(P, K, Tp, q, Ecur, g, false);
@@ -400,6 +431,8 @@ k_ik_lm(const __grid_constant__ ChainP<real, N> P, const __grid_constant__ IkP<r
                 else search_failed();
             } else if (iter >= K.ilimit) {
                 search_failed();
+            } else {
+                maybe_yield();
             }
         }
     }
@@ -548,25 +581,39 @@ int ik_launch_n(const b2k_chain_s *c, const real *Tep, long long nprob, const re
     // failed it with B2K_IK_GROUP lanes per problem.  Scratch (hard list + counter) is stream-ordered.
     constexpr int G = 8;
     const bool two_phase = slimit > 1 && nprob >= 1024 && b2k_get_variant() != 4;
+    // first-search scheduling (B2K_IK_MODE, default 2): 0 = persistent lanes pulling problems, 1 = one problem per lane,
+    // 2 = one problem per lane in two segments (IK_SEG1 evaluations, then the rest for the problems still running)
+    static const int mode_env = getenv("B2K_IK_MODE") ? atoi(getenv("B2K_IK_MODE")) : 2;
+    const int mode = two_phase ? mode_env : 0;
+    constexpr int IK_SEG1 = 10;
     int *scratch = nullptr;
     if (two_phase) {
         b2k_keep_mempool(); // do not hand the pool's memory back to the OS at every synchronisation
-        B2K_CUDA(cudaMallocAsync((void **)&scratch, sizeof(int) * (size_t)(nprob + 1), st));
-        B2K_CUDA(cudaMemsetAsync(scratch, 0, sizeof(int), st));
+        B2K_CUDA(cudaMallocAsync((void **)&scratch, sizeof(int) * (size_t)(2 * nprob + 2), st));
+        B2K_CUDA(cudaMemsetAsync(scratch, 0, 2 * sizeof(int), st));
     }
-    int *hard_count = scratch, *hard_idx = scratch ? scratch + 1 : nullptr;
+    int *hard_count = scratch, *cont_count = scratch ? scratch + 1 : nullptr;
+    int *hard_idx = scratch ? scratch + 2 : nullptr, *cont_idx = scratch ? scratch + 2 + nprob : nullptr;
     auto launch_a = [&](auto kern) -> int {
         int per_sm = b2k_blocks_per_sm((const void *)kern, B2K_THREADS, 0);
         if (per_sm < 1) return per_sm < 0 ? per_sm : (b2k_set_error("ik kernel does not fit on an SM"), B2K_ERR_INVALID);
         long long grid = (long long)b2k_num_sms() * per_sm;
         long long need = (nprob + B2K_THREADS - 1) / B2K_THREADS;
-        static const int oneshot = getenv("B2K_IK_ONESHOT") ? atoi(getenv("B2K_IK_ONESHOT")) : 0; // experiment
-        if (grid > need || (oneshot && two_phase)) grid = need;
+        if (grid > need || mode >= 1) grid = need;
         if (grid < 1) grid = 1;
+        const bool seg = mode == 2 && ilimit > IK_SEG1 + 2;
         kern<<<(unsigned)grid, B2K_THREADS, 0, st>>>(P, K, Tep, q0, nprob, q_out, success, iterations, searches, residual,
-                                                     two_phase ? 1 : 0, hard_idx, hard_count);
+                                                     two_phase ? 1 : 0, hard_idx, hard_count, seg ? IK_SEG1 : 0, nullptr,
+                                                     nullptr, cont_idx, cont_count);
         b2k_count_launch();
         B2K_CUDA(cudaGetLastError());
+        if (seg) { // second segment: the parked problems, re-packed (the list length is only known on the device)
+            kern<<<(unsigned)grid, B2K_THREADS, 0, st>>>(P, K, Tep, q0, nprob, q_out, success, iterations, searches,
+                                                         residual, 1, hard_idx, hard_count, 0, cont_idx, cont_count, nullptr,
+                                                         nullptr);
+            b2k_count_launch();
+            B2K_CUDA(cudaGetLastError());
+        }
         return B2K_OK;
     };
     auto launch_b = [&](auto kern) -> int {
