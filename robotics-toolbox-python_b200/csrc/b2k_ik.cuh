@@ -450,8 +450,13 @@ __global__ void __launch_bounds__(B2K_THREADS)
 k_ik_restarts(const __grid_constant__ ChainP<real, N> P, const __grid_constant__ IkP<real, N> K,
               const real *__restrict__ Tep, real *__restrict__ q_out, int *__restrict__ success,
               int *__restrict__ iterations, int *__restrict__ searches, real *__restrict__ residual,
-              const int *__restrict__ hard_idx, const int *__restrict__ hard_count)
+              const int *__restrict__ hard_idx, const int *__restrict__ hard_count, int s_first, int max_batches,
+              int *__restrict__ out_idx, int *__restrict__ out_count)
 {
+    // s_first: first (0-based) search of this launch; max_batches: batches of G searches a problem may run here.
+    // A problem still unsolved after max_batches batches is appended to out_idx (its iteration total parked in
+    // iterations[]) for a later launch with a wider group -- most hard problems need one or two restarts, so a
+    // narrow first round (G = 2) does a quarter of the work of running G = 8 searches for every one of them.
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const int sub = lane % G, gbase = lane - sub;
@@ -470,8 +475,10 @@ k_ik_restarts(const __grid_constant__ ChainP<real, N> P, const __grid_constant__
         for (int k = 0; k < 12; k++) Tp[k] = Tep[idx * 16 + k];
         int it_total = have ? iterations[idx] : 0;
         bool done = !have;
-        for (int s0 = 1; s0 < K.slimit; s0 += G) { // batch of searches s0 .. s0+G-1 (0-based; search 0 was phase A)
+        int batches = 0;
+        for (int s0 = s_first; s0 < K.slimit; s0 += G, batches++) { // batch of searches s0 .. s0+G-1 (0-based; search 0 was phase A)
             if (__all_sync(FULL, done)) break;
+            if (batches >= max_batches) break;
             const int s = s0 + sub;
             const bool run = !done && s < K.slimit;
             real q[N], E = 0;
@@ -553,6 +560,10 @@ k_ik_restarts(const __grid_constant__ ChainP<real, N> P, const __grid_constant__
                 }
             }
         }
+        if (!done && sub == 0 && out_idx) { // out of batches for this launch: hand the problem to the next round
+            iterations[idx] = it_total;
+            out_idx[atomicAdd(out_count, 1)] = (int)idx;
+        }
     }
 }
 
@@ -616,21 +627,37 @@ int ik_launch_n(const b2k_chain_s *c, const real *Tep, long long nprob, const re
         }
         return B2K_OK;
     };
-    auto launch_b = [&](auto kern) -> int {
+    // restarts in two rounds: G = 4 lanes per hard problem for searches 1-4, then G = 8 for whatever is still unsolved
+    auto launch_b = [&](auto kern, int g, const int *list, const int *count, int s_first, int max_batches, int *out_list,
+                        int *out_cnt) -> int {
         int per_sm = b2k_blocks_per_sm((const void *)kern, B2K_THREADS, 0);
         if (per_sm < 1) return per_sm < 0 ? per_sm : (b2k_set_error("ik restart kernel does not fit on an SM"), B2K_ERR_INVALID);
         long long grid = (long long)b2k_num_sms() * per_sm;
-        long long need = (nprob * G + B2K_THREADS - 1) / B2K_THREADS; // upper bound: every problem hard
+        long long need = (nprob * g + B2K_THREADS - 1) / B2K_THREADS; // upper bound: every problem hard
         if (grid > need) grid = need;
         if (grid < 1) grid = 1;
-        kern<<<(unsigned)grid, B2K_THREADS, 0, st>>>(P, K, Tep, q_out, success, iterations, searches, residual, hard_idx, hard_count);
+        kern<<<(unsigned)grid, B2K_THREADS, 0, st>>>(P, K, Tep, q_out, success, iterations, searches, residual, list, count,
+                                                     s_first, max_batches, out_list, out_cnt);
         b2k_count_launch();
         B2K_CUDA(cudaGetLastError());
         return B2K_OK;
     };
     int rc = c->dh_like ? launch_a(k_ik_lm<real, N, 1, STEP>) : launch_a(k_ik_lm<real, N, 0, STEP>);
-    if (rc == B2K_OK && two_phase)
-        rc = c->dh_like ? launch_b(k_ik_restarts<real, N, 1, G, STEP>) : launch_b(k_ik_restarts<real, N, 0, G, STEP>);
+    if (rc == B2K_OK && two_phase) {
+        static const int rounds_env = getenv("B2K_IK_ROUNDS") ? atoi(getenv("B2K_IK_ROUNDS")) : 2; // 1: single G = 8 round
+        constexpr int G1 = 4;
+        if (rounds_env >= 2 && slimit > 1 + G1) {
+            B2K_CUDA(cudaMemsetAsync(cont_count, 0, sizeof(int), st)); // the parked-problem list of phase A is free again
+            rc = c->dh_like ? launch_b(k_ik_restarts<real, N, 1, G1, STEP>, G1, hard_idx, hard_count, 1, 1, cont_idx, cont_count)
+                            : launch_b(k_ik_restarts<real, N, 0, G1, STEP>, G1, hard_idx, hard_count, 1, 1, cont_idx, cont_count);
+            if (rc == B2K_OK)
+                rc = c->dh_like ? launch_b(k_ik_restarts<real, N, 1, G, STEP>, G, cont_idx, cont_count, 1 + G1, 0x7fffffff, nullptr, nullptr)
+                                : launch_b(k_ik_restarts<real, N, 0, G, STEP>, G, cont_idx, cont_count, 1 + G1, 0x7fffffff, nullptr, nullptr);
+        } else {
+            rc = c->dh_like ? launch_b(k_ik_restarts<real, N, 1, G, STEP>, G, hard_idx, hard_count, 1, 0x7fffffff, nullptr, nullptr)
+                            : launch_b(k_ik_restarts<real, N, 0, G, STEP>, G, hard_idx, hard_count, 1, 0x7fffffff, nullptr, nullptr);
+        }
+    }
     if (scratch) {
         cudaError_t e = cudaFreeAsync(scratch, st);
         if (e != cudaSuccess && rc == B2K_OK) rc = b2k_cuda_fail(e, "cudaFreeAsync");
