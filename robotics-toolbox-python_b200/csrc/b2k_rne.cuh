@@ -423,7 +423,7 @@ __device__ __forceinline__ void rne_row_generic(const RneP<real, N> &P, const re
 // ALLREV: every joint is revolute (the usual case) -- strips the prismatic code, which the compiler
 // would otherwise if-convert into always-executed select chains.
 template <typename real, int N, bool MDH, bool ALLREV>
-__global__ void __launch_bounds__(B2K_THREADS, (sizeof(real) == 4) ? 4 : 3)
+__global__ void __launch_bounds__(B2K_THREADS, (sizeof(real) == 4 || (ALLREV && N <= 6)) ? 4 : 3)
 k_rne(const __grid_constant__ RneP<real, N> P, const real *__restrict__ q, const real *__restrict__ qd,
       const real *__restrict__ qdd, long long nrows, real *__restrict__ tau, int warp_smem_bytes, int in_bytes,
       int qmode)
