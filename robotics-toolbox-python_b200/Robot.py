@@ -45,6 +45,7 @@ class Robot:
         else:
             raise TypeError("arg must be an ETS or a list of Link")
         self.name, self.manufacturer = name, manufacturer
+        self._sub_ets = {}
         self._T = np.eye(4) if base is None else _mat44(base, "base")
         self._tool = None if tool is None else _mat44(tool, "tool")
         self._ets = None
@@ -83,14 +84,41 @@ class Robot:
         self._configs[name] = np.asarray(q, dtype=np.float64)
         setattr(self, name, self._configs[name])
 
+    def _getlink(self, link, default):
+        """Link reference or name -> index into self.links (reference BaseRobot._getlink 1377-1424)."""
+        if link is None:
+            return default
+        if isinstance(link, str):
+            for i, l in enumerate(self.links):
+                if l.name == link:
+                    return i
+            raise ValueError(f"no link named {link}")
+        if isinstance(link, Link):
+            for i, l in enumerate(self.links):
+                if l is link:
+                    return i
+            raise ValueError("link not in robot links")
+        raise TypeError("unknown argument")
+
     def ets(self, start=None, end=None) -> ETS:
-        """The chain from the base link to the end-effector (reference BaseRobot.ets 1554-1652); only
-        the full serial chain is supported here (branched trees are SURVEY 8f-4)."""
-        if start is not None or end is not None:
-            raise NotImplementedError("sub-chain extraction is outside the accelerated path (SURVEY 8f row 4)")
+        """``robot.ets()``: the chain from the base link to the end-effector; ``robot.ets(start=l1, end=l2)``: the
+        kinematics from link ``l1`` to link ``l2`` (Link reference or name), start link included -- reference
+        BaseRobot.ets 1554-1652 / _find_ets 1426-1467 for an unbranched tree.  The joints of a sub-chain keep the
+        jindex they have in the whole robot, so q stays the robot's full joint vector.  Paths that run towards the
+        base (inverted link transforms) and branched trees are outside this repository's scope."""
         if self._ets is None:
             self._ets = ETS.from_links([l.ets for l in self.links])
-        return self._ets
+        if start is None and end is None:
+            return self._ets
+        i = self._getlink(start, 0)
+        j = self._getlink(end, len(self.links) - 1)
+        if i > j:
+            raise NotImplementedError("paths towards the base need inverted link transforms (SURVEY 8f row 4)")
+        key = (i, j)
+        if key not in self._sub_ets:
+            offs = np.cumsum([0] + [len(l.ets) for l in self.links])
+            self._sub_ets[key] = ETS([et.copy() for et in self._ets._ets[offs[i]:offs[j + 1]]])
+        return self._sub_ets[key]
 
     def _base_arg(self):
         return None if np.array_equal(self._T, np.eye(4)) else self._T

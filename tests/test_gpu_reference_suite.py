@@ -224,3 +224,27 @@ def test_ik_solver_classes_on_a_trajectory():
         assert sol.q.shape == (16, 7)
         assert sol.success and sol.searches >= 16
         nt.assert_array_almost_equal(panda.ets().eval(sol.q), Tep, decimal=2)
+
+
+def test_sub_chain_ets_start_end():
+    """BaseRobot.ets(start, end) (BaseRobot.py:1554-1652) on the serial Panda: the chain splits into link ranges whose
+    poses multiply back to the whole, joints keep their robot-wide jindex (q stays the full joint vector)."""
+    panda = rtb.models.Panda()
+    Q = np.random.default_rng(12).uniform(-2, 2, (64, 7))
+    L = panda.links
+    head = panda.ets(end=L[3])                 # base .. link3
+    tail = panda.ets(start=L[4], end=L[-1])    # link4 .. end-effector
+    assert [et.jindex for et in tail if et.isjoint] == [4, 5, 6]
+    assert panda.ets(end=L[3].name).n == head.n == 4
+    T_head, T_tail = head.eval(Q[:, :4]), tail.eval(Q)
+    nt.assert_allclose(T_head @ T_tail, panda.ets().eval(Q), rtol=1e-10, atol=1e-12)
+    # Jacobian of a sub-chain = numerical derivative of its own pose
+    q = Q[0]
+    Jt = tail.jacob0(q)
+    full = numjac(lambda x: tail.eval(x), q)
+    nt.assert_array_almost_equal(Jt, full[:, 4:], decimal=5)
+    nt.assert_array_almost_equal(panda.jacob0(q, end=L[3]), numjac(lambda x: head.eval(x), q[:4]), decimal=5)
+    with pytest.raises(ValueError):
+        panda.ets(end="no_such_link")
+    with pytest.raises(NotImplementedError):
+        panda.ets(start=L[5], end=L[2])
