@@ -1,6 +1,7 @@
 #!/usr/bin/env python3
 """The reference's own CPU implementation of the OTHER BASELINE.json configs, timed on the host cores
-(bench.py --impl reference covers configs[1]).  TEST/MEASUREMENT INFRASTRUCTURE: drives oracle/_ref
+(bench.py --impl reference covers configs[1]).  TEST / MEASUREMENT INFRASTRUCTURE (lives under oracle/ for that
+reason; nothing in the product imports it): drives oracle/_ref
 (the reference's fknm/frne, built from /root/reference) or, when that is absent, the oracle port.
 
 One JSON line per case, all host threads (one process per core, like bench.py's RefArm) and one core:
@@ -8,7 +9,7 @@ One JSON line per case, all host threads (one process per core, like bench.py's 
   panda_ik_lm_f64      configs[3]  fknm.IK_LM_c per target (reference ETS.py ik_LM -> fknm.cpp:81-139)
   ur10_fkine_jacob0    configs[4]  fknm.ETS_fkine batch + per-row ETS_jacob0 (fp64: the reference has no fp32)
 
-Usage: python scripts/cpu_ref_bench.py [--seconds 5]
+Usage: python -m oracle.cpu_ref_bench [--seconds 5]   (from the repository root)
 """
 import argparse
 import json

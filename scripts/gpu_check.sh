@@ -11,7 +11,7 @@ echo "== pytest -m gpu" ; timeout 1500 python -m pytest tests -m gpu -x -q > gpu
 echo "== bench" ; timeout 900 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err ; echo "bench rc=$?" ; cat gpurun_out/bench.json ; tail -3 gpurun_out/bench.err
 if [ "${1:-}" != "quick" ]; then
 echo "== bench reference arm" ; timeout 900 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err ; cat gpurun_out/bench_ref.json
-echo "== reference CPU arm, other configs" ; timeout 600 python scripts/cpu_ref_bench.py --seconds 0.5 > gpurun_out/cpu_ref.jsonl 2> gpurun_out/cpu_ref.err ; cat gpurun_out/cpu_ref.jsonl
+echo "== reference CPU arm, other configs" ; timeout 600 python -m oracle.cpu_ref_bench --seconds 0.5 > gpurun_out/cpu_ref.jsonl 2> gpurun_out/cpu_ref.err ; cat gpurun_out/cpu_ref.jsonl
 echo "== ncu launch list" ; timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches.csv python bench.py --steps 4 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_list.log 2>&1 ; echo "rc=$?"
 echo "== ncu full capture (fused fkine+jacob0 kernel)" ; timeout 1200 ncu --set full --clock-control none --import-source on -k regex:k_fkj_fast -s 3 -c 2 -f -o gpurun_out/prof_fkj python bench.py --steps 4 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1 ; echo "rc=$?"
 fi

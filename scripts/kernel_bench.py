@@ -146,12 +146,10 @@ if want("dyn_"):
 
 # IK (config 4): reachable targets, chan
 if want("ik_"):
-    from oracle import oracle as orc
-
     panda = rtb.models.Panda().ets()
     M = args.ik_rows
     qs = np.random.default_rng(2).uniform(-np.pi, np.pi, (M, 7))
-    Tep = orc.Chain(panda.describe()).fkine(qs)
+    Tep = panda.eval(qs)  # reachable targets: Tep = FK(q*)
     for dt in (np.float32, np.float64):
         tag = "f64" if dt == np.float64 else "f32"
         Td = torch.from_numpy(Tep.astype(dt)).to(dev)
