@@ -596,7 +596,7 @@ int ik_launch_n(const b2k_chain_s *c, const real *Tep, long long nprob, const re
     // 2 = one problem per lane in two segments (IK_SEG1 evaluations, then the rest for the problems still running)
     static const int mode_env = getenv("B2K_IK_MODE") ? atoi(getenv("B2K_IK_MODE")) : 2;
     const int mode = two_phase ? mode_env : 0;
-    constexpr int IK_SEG1 = 10;
+    static const int IK_SEG1 = getenv("B2K_IK_SEG1") ? atoi(getenv("B2K_IK_SEG1")) : 10; // evaluations in the first segment
     int *scratch = nullptr;
     if (two_phase) {
         b2k_keep_mempool(); // do not hand the pool's memory back to the OS at every synchronisation
