@@ -168,6 +168,23 @@ def test_ets_composition_and_jindex_numbering():
         ET.Rx("theta")  # symbolic values have no GPU path (reference raises TypeError("Symbolic value"))
 
 
+def test_robot_sub_chain_ets():
+    """Robot.ets(start, end) for a serial robot (reference BaseRobot.ets 1554-1652): link ranges, names, jindex kept."""
+    panda = rtb.models.Panda()
+    L = panda.links
+    assert panda.ets() is panda.ets()
+    head, tail = panda.ets(end=L[3]), panda.ets(start=L[4], end=L[-1])
+    assert len(head) + len(tail) == len(panda.ets()) and head.n == 4 and tail.n == 3
+    assert [et.jindex for et in tail if et.isjoint] == [4, 5, 6]
+    assert panda.ets(end=L[3].name).n == 4 and panda.ets(start=L[2], end=L[2]).n == L[2].ets.n
+    with pytest.raises(ValueError):
+        panda.ets(end="nope")
+    with pytest.raises(TypeError):
+        panda.ets(end=3.5)
+    with pytest.raises(NotImplementedError):
+        panda.ets(start=L[5], end=L[2])
+
+
 def test_dh_link_expansion_matches_reference_rule():
     for kw in (dict(d=0.2, a=0.3, alpha=0.4, offset=0.5), dict(d=0.0, a=0.0, alpha=0.0), dict(d=0.1, a=0, alpha=-1.0, flip=True)):
         for cls, mdh, sigma in ((rtb.RevoluteDH, False, 0), (rtb.RevoluteMDH, True, 0)):
