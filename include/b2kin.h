@@ -221,6 +221,17 @@ int b2k_p_servo(int dtype, const void *Te, const void *Tep, int64_t N, int64_t t
 int b2k_jtraj(int dtype, int n, const double *q0, const double *qf, const double *qd0, const double *qd1,
               int64_t N, const void *t, double tscal, void *q, void *qd, void *qdd, void *stream);
 
+/* b2k_mtraj replaces tools.trajectory.quintic (trajectory.py:271-416), trapezoidal (429-615) and their
+ * multi-axis form mtraj (617-684): n axes, each following a quintic (kind 0; boundary velocities qd0 / qdf
+ * or NULL = 0) or trapezoidal (kind 1; V = per-axis velocity of the linear segment, NULL or NaN = the
+ * reference's default 1.5 (qf - q0) / tf) profile from q0[j] to qf[j]; outputs s, sd, sdd (N,n) device
+ * (sd / sdd may be NULL).  t == NULL: sample times 0, 1, ..., N-1 (the `t: int` form, tf must be N-1);
+ * t != NULL: device vector of N sample times, tf = max(t).  tblend (host, n doubles or NULL) receives the
+ * blend times of the trapezoidal profile.  "V too small" / "V too big" (trajectory.py:555-558) -> B2K_ERR_INVALID. */
+int b2k_mtraj(int dtype, int kind, int n, const double *q0, const double *qf, const double *qd0, const double *qdf,
+              const double *V, int64_t N, const void *t, double tf, void *s, void *sd, void *sdd, double *tblend,
+              void *stream);
+
 /* ---------------------------------------------------------------- host-buffer front ends
  * The same operations for callers that hold HOST arrays (what the reference's API takes):
  * the library streams row chunks host->device, runs the kernel and streams results back on

@@ -309,3 +309,49 @@ def jtraj(q0, qf, t, qd0=None, qd1=None):
     qdt = tt @ np.array([z, 5 * A, 4 * Bc, 3 * Cc, z, E]) / tscal
     qddt = tt @ np.array([z, z, 20 * A, 12 * Bc, 6 * Cc, z]) / tscal**2
     return tv, qt, qdt, qddt
+
+
+def quintic(q0, qf, t, qd0=0, qdf=0):
+    """tools/trajectory.py:329-345 + quintic_func 385-416, restated: returns (t, s, sd, sdd)."""
+    t = np.arange(0, t) if isinstance(t, (int, np.integer)) else _f64(t).ravel()
+    T = max(t)
+    X = [[0.0, 0.0, 0.0, 0.0, 0.0, 1.0], [T**5, T**4, T**3, T**2, T, 1.0], [0.0, 0.0, 0.0, 0.0, 1.0, 0.0],
+         [5.0 * T**4, 4.0 * T**3, 3.0 * T**2, 2.0 * T, 1.0, 0.0], [0.0, 0.0, 0.0, 2.0, 0.0, 0.0],
+         [20.0 * T**3, 12.0 * T**2, 6.0 * T, 2.0, 0.0, 0.0]]
+    coeffs = np.linalg.lstsq(X, np.r_[q0, qf, qd0, qdf, 0, 0], rcond=None)[0]
+    coeffs_d = coeffs[0:5] * np.arange(5, 0, -1)
+    coeffs_dd = coeffs_d[0:4] * np.arange(4, 0, -1)
+    return t, np.polyval(coeffs, t), np.polyval(coeffs_d, t), np.polyval(coeffs_dd, t)
+
+
+def trapezoidal(q0, qf, t, V=None):
+    """tools/trajectory.py:488-505 + trapezoidal_func 552-607, restated: returns (t, s, sd, sdd, tb)."""
+    t = np.arange(0, t) if isinstance(t, (int, np.integer)) else _f64(t).ravel()
+    T = max(t)
+    if V is None:
+        V = (qf - q0) / T * 1.5
+    else:
+        V = abs(V) * np.sign(qf - q0)
+        if abs(V) < (abs(qf - q0) / T):
+            raise ValueError("V too small")
+        elif abs(V) > (2 * abs(qf - q0) / T):
+            raise ValueError("V too big")
+    if V == 0:
+        tb, a = np.inf, 0
+    else:
+        tb = (q0 - qf + V * T) / V
+        a = V / tb
+    p, pd, pdd = [], [], []
+    for tk in t:
+        if tk < 0:
+            pk, pdk, pddk = q0, 0, 0
+        elif tk <= tb:
+            pk, pdk, pddk = q0 + a / 2 * tk**2, a * tk, a
+        elif tk <= (T - tb):
+            pk, pdk, pddk = (qf + q0 - V * T) / 2 + V * tk, V, 0
+        elif tk <= T:
+            pk, pdk, pddk = qf - a / 2 * T**2 + a * T * tk - a / 2 * tk**2, a * T - a * tk, -a
+        else:
+            pk, pdk, pddk = qf, 0, 0
+        p.append(pk); pd.append(pdk); pdd.append(pddk)
+    return t, np.array(p), np.array(pd), np.array(pdd), tb

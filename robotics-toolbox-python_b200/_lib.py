@@ -56,6 +56,7 @@ _PROTOS = {
     "b2k_angle_axis": (C.c_int, [C.c_int, vp, vp, i64, i64, vp, vp]),
     "b2k_p_servo": (C.c_int, [C.c_int, vp, vp, i64, i64, dp, C.c_double, vp, vp, vp]),
     "b2k_jtraj": (C.c_int, [C.c_int, C.c_int, dp, dp, dp, dp, i64, vp, C.c_double, vp, vp, vp, vp]),
+    "b2k_mtraj": (C.c_int, [C.c_int, C.c_int, C.c_int, dp, dp, dp, dp, dp, i64, vp, C.c_double, vp, vp, vp, dp, vp]),
     "b2k_host_alloc": (C.c_int, [C.POINTER(vp), i64]),
     "b2k_host_free": (C.c_int, [vp]),
     "b2k_fkine_jacob0_host": (C.c_int, [vp, C.c_int, vp, i64, i64, dp, dp, vp, vp, C.c_int]),

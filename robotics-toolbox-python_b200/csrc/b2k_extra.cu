@@ -382,3 +382,121 @@ extern "C" int b2k_p_servo(int dtype, const void *Te, const void *Tep, int64_t N
     if (N > 0 && !arrived) { b2k_set_error("b2k_p_servo: arrived is NULL"); return B2K_ERR_INVALID; }
     return pose_error_launch("b2k_p_servo", dtype, Te, Tep, N, tep_stride, gain, threshold, v, arrived, stream);
 }
+
+// ------------------------------------------------------------------ scalar / multi-axis trajectory profiles
+// quintic (tools/trajectory.py:271-416), trapezoidal (429-615) and their multi-axis form mtraj (617-684): every axis
+// follows the same kind of profile between its own end points.  The per-axis parameters are worked out on the host in
+// fp64 (quintic: the 6x6 boundary-condition system of quintic_func; trapezoidal: V, blend time tb and acceleration a of
+// trapezoidal_func); one thread per (sample, axis) element evaluates position, velocity and acceleration.
+struct MtrajP {
+    double c[B2K_MAX_JOINTS][6]; // quintic: polynomial coefficients, highest power first; trapezoidal: q0, qf, V, tb, a, T
+    int n, kind;
+};
+
+template <typename real>
+__global__ void __launch_bounds__(256) k_mtraj(const __grid_constant__ MtrajP P, const real *__restrict__ t, long long nrows,
+                                               real *__restrict__ s, real *__restrict__ sd, real *__restrict__ sdd)
+{
+    const long long total = nrows * P.n;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long row = e / P.n;
+        const int j = (int)(e - row * P.n);
+        const real tk = t ? t[row] : (real)row; // `t: int` means t = arange(0, t) (trajectory.py:330, 489)
+        real p, pd, pdd;
+        if (P.kind == 0) { // np.polyval of coeffs, coeffs_d, coeffs_dd (trajectory.py:405-415)
+            const real c5 = (real)P.c[j][0], c4 = (real)P.c[j][1], c3 = (real)P.c[j][2], c2 = (real)P.c[j][3],
+                       c1 = (real)P.c[j][4], c0 = (real)P.c[j][5];
+            p = fma(fma(fma(fma(fma(c5, tk, c4), tk, c3), tk, c2), tk, c1), tk, c0);
+            pd = fma(fma(fma(fma((real)5 * c5, tk, (real)4 * c4), tk, (real)3 * c3), tk, (real)2 * c2), tk, c1);
+            pdd = fma(fma(fma((real)20 * c5, tk, (real)12 * c4), tk, (real)6 * c3), tk, (real)2 * c2);
+        } else { // trapezoidalfunc (trajectory.py:566-600)
+            const real q0 = (real)P.c[j][0], qf = (real)P.c[j][1], V = (real)P.c[j][2], tb = (real)P.c[j][3],
+                       a = (real)P.c[j][4], T = (real)P.c[j][5];
+            if (tk < 0) { p = q0; pd = 0; pdd = 0; }
+            else if (tk <= tb) { p = q0 + a / 2 * tk * tk; pd = a * tk; pdd = a; }
+            else if (tk <= T - tb) { p = (qf + q0 - V * T) / 2 + V * tk; pd = V; pdd = 0; }
+            else if (tk <= T) { p = qf - a / 2 * T * T + a * T * tk - a / 2 * tk * tk; pd = a * T - a * tk; pdd = -a; }
+            else { p = qf; pd = 0; pdd = 0; }
+        }
+        s[e] = p;
+        if (sd) sd[e] = pd;
+        if (sdd) sdd[e] = pdd;
+    }
+}
+
+// solve the 6x6 system of quintic_func (Gaussian elimination with partial pivoting, fp64)
+static bool quintic_coeffs(double q0, double qf, double T, double v0, double vf, double *c)
+{
+    const double T2 = T * T, T3 = T2 * T, T4 = T3 * T, T5 = T4 * T;
+    double X[6][7] = {{0, 0, 0, 0, 0, 1, q0},          {T5, T4, T3, T2, T, 1, qf},         {0, 0, 0, 0, 1, 0, v0},
+                      {5 * T4, 4 * T3, 3 * T2, 2 * T, 1, 0, vf}, {0, 0, 0, 2, 0, 0, 0}, {20 * T3, 12 * T2, 6 * T, 2, 0, 0, 0}};
+    for (int k = 0; k < 6; k++) {
+        int p = k;
+        for (int i = k + 1; i < 6; i++)
+            if (fabs(X[i][k]) > fabs(X[p][k])) p = i;
+        if (X[p][k] == 0.0) return false;
+        if (p != k)
+            for (int j = 0; j < 7; j++) { double tmp = X[k][j]; X[k][j] = X[p][j]; X[p][j] = tmp; }
+        for (int i = k + 1; i < 6; i++) {
+            const double f = X[i][k] / X[k][k];
+            for (int j = k; j < 7; j++) X[i][j] -= f * X[k][j];
+        }
+    }
+    for (int i = 5; i >= 0; i--) {
+        double acc = X[i][6];
+        for (int j = i + 1; j < 6; j++) acc -= X[i][j] * c[j];
+        c[i] = acc / X[i][i];
+    }
+    return true;
+}
+
+extern "C" int b2k_mtraj(int dtype, int kind, int n, const double *q0, const double *qf, const double *qd0, const double *qdf,
+                         const double *V, int64_t N, const void *t, double tf, void *s, void *sd, void *sdd, double *tblend,
+                         void *stream)
+{
+    const char *fn = "b2k_mtraj";
+    if (n < 1 || n > B2K_MAX_JOINTS) { b2k_set_error("%s: n must be 1..%d", fn, B2K_MAX_JOINTS); return B2K_ERR_INVALID; }
+    if (dtype != B2K_F32 && dtype != B2K_F64) { b2k_set_error("%s: bad dtype", fn); return B2K_ERR_INVALID; }
+    if (kind != 0 && kind != 1) { b2k_set_error("%s: kind must be 0 (quintic) or 1 (trapezoidal)", fn); return B2K_ERR_INVALID; }
+    if (!q0 || !qf) { b2k_set_error("%s: q0 / qf is NULL", fn); return B2K_ERR_INVALID; }
+    if (N < 0 || (N > 0 && !s)) { b2k_set_error("%s: bad N / output", fn); return B2K_ERR_INVALID; }
+    if (!(tf > 0)) { b2k_set_error("%s: the final time must be positive (at least two samples)", fn); return B2K_ERR_INVALID; }
+    MtrajP P;
+    P.n = n;
+    P.kind = kind;
+    for (int j = 0; j < n; j++) {
+        if (kind == 0) {
+            if (!quintic_coeffs(q0[j], qf[j], tf, qd0 ? qd0[j] : 0.0, qdf ? qdf[j] : 0.0, P.c[j])) {
+                b2k_set_error("%s: singular boundary-condition system", fn);
+                return B2K_ERR_INVALID;
+            }
+        } else { // trapezoidal_func, trajectory.py:552-565
+            double v;
+            if (!V || V[j] != V[j]) v = (qf[j] - q0[j]) / tf * 1.5; // NaN = not given
+            else {
+                const double d = qf[j] - q0[j];
+                v = fabs(V[j]) * (d > 0 ? 1.0 : (d < 0 ? -1.0 : 0.0));
+                if (fabs(v) < fabs(d) / tf) { b2k_set_error("V too small"); return B2K_ERR_INVALID; }
+                if (fabs(v) > 2 * fabs(d) / tf) { b2k_set_error("V too big"); return B2K_ERR_INVALID; }
+            }
+            double tb, a;
+            if (v == 0) { tb = INFINITY; a = 0; }
+            else { tb = (q0[j] - qf[j] + v * tf) / v; a = v / tb; }
+            P.c[j][0] = q0[j]; P.c[j][1] = qf[j]; P.c[j][2] = v; P.c[j][3] = tb; P.c[j][4] = a; P.c[j][5] = tf;
+            if (tblend) tblend[j] = tb;
+        }
+    }
+    if (N == 0) return B2K_OK;
+    const long long total = N * n;
+    long long blocks = (total + 255) / 256;
+    const long long cap = (long long)b2k_num_sms() * 16;
+    if (blocks > cap) blocks = cap;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == B2K_F64)
+        k_mtraj<double><<<(unsigned)blocks, 256, 0, st>>>(P, (const double *)t, N, (double *)s, (double *)sd, (double *)sdd);
+    else
+        k_mtraj<float><<<(unsigned)blocks, 256, 0, st>>>(P, (const float *)t, N, (float *)s, (float *)sd, (float *)sdd);
+    b2k_count_launch();
+    B2K_CUDA(cudaGetLastError());
+    return B2K_OK;
+}

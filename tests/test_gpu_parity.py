@@ -808,3 +808,51 @@ def test_c_program_through_the_c_abi(tmp_path):
     Q = rows[:, :3]
     np.testing.assert_allclose(rows[:, 3:19].reshape(-1, 4, 4), C.fkine(Q), rtol=1e-10, atol=1e-12)
     np.testing.assert_allclose(rows[:, 19:].reshape(-1, 6, 3), C.jacob0(Q), rtol=1e-10, atol=1e-12)
+
+
+def test_quintic_trapezoidal_mtraj_producers():
+    """quintic / trapezoidal / mtraj on the device against the restated numpy formulas and the
+    reference tests' properties (tests/test_trajectory.py:19-153, 209-260): int and time-vector forms,
+    boundary velocities, explicit V with its two error cases, multi-axis form."""
+    for targ in (11, np.linspace(0, 1, 11), np.linspace(0, 2.5, 1001)):
+        for args in ((1, 2), (1, 2, -1, 1), (2, -0.5, 0.3, 0.0)):
+            tg = rtb.quintic(args[0], args[1], targ, *args[2:])
+            t, s, sd, sdd = orc.quintic(args[0], args[1], targ, *args[2:])
+            assert tg.s.shape == s.shape and tg.naxes == 1
+            np.testing.assert_allclose(tg.t, t)
+            scale = max(1.0, np.abs(sdd).max())
+            for a, b in ((tg.s, s), (tg.sd, sd), (tg.sdd, sdd)):
+                np.testing.assert_allclose(a, b, rtol=1e-9, atol=1e-9 * scale)
+        for V in (None, 0.12 if isinstance(targ, int) else 1.2 * 1.0 / float(np.max(targ))):
+            tg = rtb.trapezoidal(1, 2, targ, V)
+            t, s, sd, sdd, tb = orc.trapezoidal(1, 2, targ, V)
+            for a, b in ((tg.s, s), (tg.sd, sd), (tg.sdd, sdd)):
+                np.testing.assert_allclose(a, b, rtol=1e-12, atol=1e-12)
+            assert abs(tg.tblend - tb) < 1e-12
+    tg = rtb.quintic(1, 2, 11)
+    assert np.all(np.diff(tg.s) > 0) and abs(tg.s[5] - 1.5) < 1e-9 and abs(tg.sdd.sum()) < 1e-9
+    tg = rtb.trapezoidal(1, 2, 11)
+    assert np.all(np.diff(tg.s) > 0) and abs(tg.s[5] - 1.5) < 1e-12 and abs(tg.sd[0]) < 1e-12
+    assert rtb.trapezoidal(2, 2, 11).sd.max() == 0.0  # q0 == qf: V = 0, tb = inf
+    with pytest.raises(ValueError, match="V too small"):
+        rtb.trapezoidal(1, 2, 11, 0.01)
+    with pytest.raises(ValueError, match="V too big"):
+        rtb.trapezoidal(1, 2, 11, 1.0)
+    with pytest.raises(TypeError):
+        rtb.quintic(1, 2, 3.5)
+    # multi-axis
+    q0, qf = np.array([1.0, -2.0, 0.5, 3.0]), np.array([2.0, 1.0, 0.5, -1.0])
+    for f, o in ((rtb.quintic, orc.quintic), (rtb.trapezoidal, orc.trapezoidal)):
+        tg = rtb.mtraj(f, q0, qf, 50, device=True)
+        assert tg.q.is_cuda and tg.q.shape == (50, 4) and tg.name == "mtraj" and not tg.istime
+        for j in range(4):
+            ref = o(q0[j], qf[j], 50)
+            np.testing.assert_allclose(host(tg.q[:, j]), ref[1], rtol=1e-9, atol=1e-9)
+            np.testing.assert_allclose(host(tg.qd[:, j]), ref[2], rtol=1e-9, atol=1e-9)
+            np.testing.assert_allclose(host(tg.qdd[:, j]), ref[3], rtol=1e-9, atol=1e-9)
+    tg32 = rtb.mtraj(rtb.quintic, q0, qf, dev(np.linspace(0, 2, 300), np.float32))
+    np.testing.assert_allclose(host(tg32.q[:, 0]), orc.quintic(q0[0], qf[0], np.linspace(0, 2, 300))[1], rtol=1e-4, atol=1e-4)
+    with pytest.raises(TypeError):
+        rtb.mtraj("quintic", q0, qf, 10)
+    with pytest.raises(ValueError):
+        rtb.mtraj(rtb.quintic, q0, qf[:3], 10)

@@ -287,3 +287,19 @@ def test_jtraj_restatement_properties():
     np.testing.assert_allclose(qd[0], 0.3 * q1, atol=1e-12)
     np.testing.assert_allclose(qd[-1], -0.1 * q1, atol=1e-10)
     np.testing.assert_allclose(np.gradient(q, t, axis=0)[5:-5], qd[5:-5], atol=2e-3)
+
+
+def test_quintic_trapezoidal_restatements():
+    """oracle.quintic / trapezoidal against the reference tests' properties (tests/test_trajectory.py:19-153)."""
+    t, s, sd, sdd = orc.quintic(1, 2, 11)
+    assert np.all(np.diff(s) > 0) and abs(s[0] - 1) < 1e-9 and abs(s[-1] - 2) < 1e-9 and abs(s[5] - 1.5) < 1e-9
+    assert abs(sd[0]) < 1e-9 and abs(sd[-1]) < 1e-9 and abs(sdd[[0, 5, -1]]).max() < 1e-9 and abs(sdd.sum()) < 1e-9
+    t, s, sd, sdd = orc.quintic(1, 2, 11, -1, 1)
+    assert abs(sd[0] + 1) < 1e-9 and abs(sd[-1] - 1) < 1e-9 and abs(sdd[0]) < 1e-9 and abs(sdd[-1]) < 1e-9
+    t, s, sd, sdd, tb = orc.trapezoidal(1, 2, 11)
+    assert np.all(np.diff(s) > 0) and abs(s[0] - 1) < 1e-12 and abs(s[-1] - 2) < 1e-12 and abs(s[5] - 1.5) < 1e-12
+    assert abs(sd[0]) < 1e-12 and abs(sd[-1]) < 1e-12 and abs(sd[5] - 0.15) < 1e-12  # V = 1.5 (qf-q0)/T
+    with pytest.raises(ValueError):
+        orc.trapezoidal(1, 2, 11, 0.01)
+    with pytest.raises(ValueError):
+        orc.trapezoidal(1, 2, 11, 1.0)
