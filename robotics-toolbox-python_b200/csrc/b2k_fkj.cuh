@@ -7,11 +7,14 @@
 // an immediate c[0x0][..] operand of the FMA).  The warp as a whole moves the tile's q block and
 // its T / J blocks between HBM and registers through a per-warp shared-memory stage so that
 // every global access is a fully coalesced warp transaction:
-//     q tile  (32 x ldq)  : 16-byte cp.async (LDGSTS) straight into smem, issued for tile t+1
-//                           while tile t's results drain; one row per lane read back
-//     T tile  (32 x 16)   : registers -> 16-byte vector STS (odd row stride in 16-byte units,
-//                           conflict free) -> LDS.128 + STG.128 (512 B per warp instruction)
-//     J tile  (32 x 6n)   : same; for Panda fp64 the stage is the exact image of the output block
+//     q tile  (32 x ldq)  : 16-byte cp.async (LDGSTS) straight into smem; one row per lane read back
+//     T tile  (32 x 16)   : one pose row per lane, 256-bit stores straight from registers
+//                           (a row is 128 B / 64 B contiguous: full sectors without staging)
+//     J tile  (32 x 6n)   : registers -> 16-byte vector STS into a stage that is the exact image of
+//                           the output block -> ONE TMA bulk copy (cp.async.bulk, SASS UBLKCP)
+// Two forms of every walk: the general kernels (k_fkj_forward / k_fkj_backward: any row stride, jindex
+// permutation, alignment, chain shape, ragged tiles) and the lean kernels (k_fkj_fast / k_fkj_back_fast)
+// the launcher picks for the common call, with all of that fixed at compile time.
 // No tensor cores: the products are 3x3 / 6xn (far below an MMA tile) -- this is HBM-bound
 // streaming work (520 B per evaluation for Panda fp64).
 //
