@@ -166,6 +166,18 @@ class ET:
         e._qlim = None if self._qlim is None else self._qlim.copy()
         return e
 
+    def inv(self) -> "ET":
+        """Inverse of this ET (reference ET.inv, ET.py:506-539): a joint moves the other way (flip toggled), a
+        constant gets the inverse matrix (and -eta)."""
+        e = self.copy()
+        if e._joint:
+            e._flip = not e._flip
+        else:
+            e._T = np.linalg.inv(e._T)
+            if e._eta is not None:
+                e._eta = -e._eta
+        return e
+
     def __mul__(self, other):
         from .ETS import ETS
         return ETS([self]) * other

@@ -108,6 +108,11 @@ class ETS:
 
     __add__ = __mul__
 
+    def inv(self) -> "ETS":
+        """Inverse of the ETS: the inverses of the individual ETs in reverse order (reference ETS.inv,
+        ETS.py:545-576).  Joints keep their jindex, so explicit joint indices are essential."""
+        return ETS([et.inv() for et in reversed(self._ets)])
+
     def __len__(self):
         return len(self._ets)
 

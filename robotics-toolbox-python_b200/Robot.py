@@ -104,20 +104,22 @@ class Robot:
         """``robot.ets()``: the chain from the base link to the end-effector; ``robot.ets(start=l1, end=l2)``: the
         kinematics from link ``l1`` to link ``l2`` (Link reference or name), start link included -- reference
         BaseRobot.ets 1554-1652 / _find_ets 1426-1467 for an unbranched tree.  The joints of a sub-chain keep the
-        jindex they have in the whole robot, so q stays the robot's full joint vector.  Paths that run towards the
-        base (inverted link transforms) and branched trees are outside this repository's scope."""
+        jindex they have in the whole robot, so q stays the robot's full joint vector.  A path that runs towards the
+        base is the inverse of the corresponding forward range.  Branched trees are outside this repository's scope
+        (SURVEY 8f row 4)."""
         if self._ets is None:
             self._ets = ETS.from_links([l.ets for l in self.links])
         if start is None and end is None:
             return self._ets
         i = self._getlink(start, 0)
         j = self._getlink(end, len(self.links) - 1)
-        if i > j:
-            raise NotImplementedError("paths towards the base need inverted link transforms (SURVEY 8f row 4)")
         key = (i, j)
         if key not in self._sub_ets:
             offs = np.cumsum([0] + [len(l.ets) for l in self.links])
-            self._sub_ets[key] = ETS([et.copy() for et in self._ets._ets[offs[i]:offs[j + 1]]])
+            if i <= j:  # towards the tip: start link's own transform included (_find_ets 1445-1453)
+                self._sub_ets[key] = ETS([et.copy() for et in self._ets._ets[offs[i]:offs[j + 1]]])
+            else:       # towards the base: inverted link transforms of links i .. j+1 (_find_ets 1457-1467)
+                self._sub_ets[key] = ETS([et.copy() for et in self._ets._ets[offs[j + 1]:offs[i + 1]]]).inv()
         return self._sub_ets[key]
 
     def _base_arg(self):

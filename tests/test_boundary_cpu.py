@@ -181,8 +181,19 @@ def test_robot_sub_chain_ets():
         panda.ets(end="nope")
     with pytest.raises(TypeError):
         panda.ets(end=3.5)
-    with pytest.raises(NotImplementedError):
-        panda.ets(start=L[5], end=L[2])
+    # towards the base: the inverse of the forward range, ET by ET (reference ETS.inv 545-576, ET.inv 506-539);
+    # checked with the CPU oracle, which evaluates any chain description
+    from oracle import oracle as orc
+
+    q = np.random.default_rng(0).uniform(-2, 2, (5, 7))
+    fwd, back = panda.ets(start=L[3], end=L[6]), panda.ets(start=L[6], end=L[2])
+    assert [(e.jindex, e.isflip) for e in back if e.isjoint] == [(6, True), (5, True), (4, True), (3, True)]
+    prod = orc.Chain(fwd.describe()).fkine(q) @ orc.Chain(back.describe()).fkine(q)
+    np.testing.assert_allclose(prod, np.broadcast_to(np.eye(4), prod.shape), atol=1e-14)
+    e = rtb.ET.Rz(jindex=2) * rtb.ET.tx(1) * rtb.ET.Rx(jindex=3, flip=True) * rtb.ET.tx(1)
+    prod = orc.Chain(e.describe()).fkine(q[:, :4]) @ orc.Chain(e.inv().describe()).fkine(q[:, :4])
+    np.testing.assert_allclose(prod, np.broadcast_to(np.eye(4), prod.shape), atol=1e-14)
+    assert rtb.ET.tx(0.3).inv().eta == -0.3 and rtb.ET.Rz(jindex=1).inv().isflip
 
 
 def test_dh_link_expansion_matches_reference_rule():

@@ -246,5 +246,9 @@ def test_sub_chain_ets_start_end():
     nt.assert_array_almost_equal(panda.jacob0(q, end=L[3]), numjac(lambda x: head.eval(x), q[:4]), decimal=5)
     with pytest.raises(ValueError):
         panda.ets(end="no_such_link")
-    with pytest.raises(NotImplementedError):
-        panda.ets(start=L[5], end=L[2])
+    # a path towards the base is the inverse of the forward range (reference _find_ets, BaseRobot.py:1457-1467)
+    back = panda.ets(start=L[6], end=L[2])
+    fwd = panda.ets(start=L[3], end=L[6])
+    nt.assert_allclose(fwd.eval(Q) @ back.eval(Q), np.broadcast_to(np.eye(4), (64, 4, 4)), rtol=0, atol=1e-12)
+    e = rtb.ET.Rz(jindex=2) * rtb.ET.tx(1) * rtb.ET.Rx(jindex=3, flip=True) * rtb.ET.tx(1)  # docstring example of ETS.inv
+    nt.assert_allclose(e.eval(Q[:, :4]) @ e.inv().eval(Q[:, :4]), np.broadcast_to(np.eye(4), (64, 4, 4)), rtol=0, atol=1e-12)
