@@ -15,9 +15,17 @@ the launching stream, MAX over ranks.  Inputs are resident in HBM; four distinct
 
 Extra objects in the JSON line (see DESIGN.md "Measurement"):
   roofline      algorithmic bytes (520 B/eval) / average kernel time vs MEASURED_PEAKS hbm_gbs
+  step_ms       median / min / max of K individually timed steps (a second pass, outside `value`)
   cpu_baseline  the reference's own fknm (oracle/_ref, built from /root/reference) on the host cores,
-                bounded sample, rank 0 at N=1 only
-  e2e           same metric through the public API with pinned HOST buffers (H2D + kernel + D2H)
+                bounded sample, rank 0 at N=1 only; `effective_cores` = all-core / single-core throughput
+  e2e           same metric through the public API with pinned HOST buffers (H2D + kernel + D2H);
+                e2e.pageable = the same with the caller's q in ordinary (pageable) numpy memory
+  configs       the other BASELINE.json configs, each device-timed with roofline, cpu_baseline and a parity
+                record against the reference on a sampled subset: rne_puma_f64_1M (configs[2]),
+                ik_lm_panda_f32_100k_* (configs[3], both protocols of SURVEY 8d), fkj_ur10_f32_1M (configs[4]
+                per-GPU shard; at N > 1 it runs on every rank with seed 3 + rank: fkj_ur10_f32_sharded)
+  gather        (N > 1) NCCL reassembly of the UR10 result shards, outside the metric: one all-gather of the
+                packed (T|J) buffer and a gather to rank 0, achieved GB/s into a rank against 900 GB/s
   clocks        SM clocks / throttle reasons sampled through NVML during the timed region
   gpu_launches  kernels this library launched inside the timed region
 """
@@ -35,101 +43,90 @@ if ROOT not in sys.path:
 import numpy as np  # noqa: E402
 
 ROWS_PER_GPU = 1_000_000
+IK_ROWS = 100_000
 N_JOINTS = 7
 BYTES_PER_EVAL = (7 + 16 + 42) * 8  # q + T + J0, fp64
 METRIC = "Panda 7-DOF fkine+jacob0 evals/sec @ batch 1M"
 WORKLOAD = "panda_ets_fkine_jacob0_f64_batch1M"
+NVLINK_GBS = 900.0  # nominal NVLink 5 bandwidth per direction per GPU (B200_PROFILING.md)
+PARITY_ROWS = 4096
+IK_PARITY_ROWS = 1024
+IK_PROTOCOLS = {  # the notebook protocol and the API default
+    "ik_lm_panda_f32_100k_chan0.1": dict(k=0.1, jl=False),
+    "ik_lm_panda_f32_100k_chan1.0_jl": dict(k=1.0, jl=True),
+}
 
 
-def make_q(seed, rows=ROWS_PER_GPU):
-    return np.random.default_rng(seed).uniform(-np.pi, np.pi, (rows, N_JOINTS))
+def make_q(seed, rows=ROWS_PER_GPU, n=N_JOINTS):
+    return np.random.default_rng(seed).uniform(-np.pi, np.pi, (rows, n))
 
 
-# ------------------------------------------------------------------ reference CPU arm
-_W = {}
+def make_config(world):
+    """The workload description, identical for both arms (the driver compares them)."""
+    return {"workload": WORKLOAD, "rows_per_gpu": ROWS_PER_GPU, "global_batch": ROWS_PER_GPU * world,
+            "parallelism": f"rows sharded over {world} rank(s), no data-path collective",
+            "l2": "4 distinct 56 MB q batches rotated + 464 MB written per step (> 126 MB L2)"}
 
 
-def _ref_worker_init(use_ref):
-    from oracle import chains as ch
-
-    d = ch.panda_ets()
-    if use_ref:
-        from oracle import ref_driver as ref
-
-        _W["ets"] = ref.RefETS(d)
-        _W["f"] = ref.fknm()
-    else:
-        from oracle import oracle as orc
-
-        orc.set_threads(1)
-        _W["chain"] = orc.Chain(d)
-    _W["use_ref"] = use_ref
+# ------------------------------------------------------------------ parity-sample inputs (shared by both legs)
+PUMA_QLIM = np.deg2rad(np.array([[-160, 160], [-110, 110], [-135, 135], [-266, 266], [-100, 100], [-266, 266]], float)).T
 
 
-def _ref_worker_run(args):
-    """One worker's slice of a step: the reference's own way to get N poses + N Jacobians --
-    one batched ETS_fkine call plus a per-row ETS_jacob0 loop (the reference has no batched
-    Jacobian: SURVEY 3.2).  Returns a checksum so the work cannot be optimised away."""
-    seed, rows = args
-    Q = make_q(seed, rows)
-    if _W["use_ref"]:
-        f, ets = _W["f"], _W["ets"].ets
-        T = f.ETS_fkine(ets, Q, None, None, 1)
-        s = float(T[-1, 0, 3])
-        jac = f.ETS_jacob0
-        for i in range(rows):
-            J = jac(ets, Q[i], None)
-        return s + float(J[0, 0])
-    C = _W["chain"]
-    return float(C.fkine(Q)[-1, 0, 3]) + float(C.jacob0(Q)[-1, 0, 0])
+def rne_inputs(seed, rows):
+    """q ~ U(qlim) (reference Puma560.py:112-177), qd, qdd ~ N(0,1), exact zeros in a tail
+    block of qd so the Coulomb `qd == 0` branch (ne.c:487-490) is exercised."""
+    rng = np.random.default_rng(seed)
+    q = rng.uniform(PUMA_QLIM[0], PUMA_QLIM[1], (rows, 6))
+    qd = rng.normal(size=(rows, 6))
+    qdd = rng.normal(size=(rows, 6))
+    qd[-max(1, rows // 64):] = 0.0
+    return q, qd, qdd
 
 
-class RefArm:
-    """The reference implementation of the path on the host cores (all of them)."""
-
-    def __init__(self, cores=None):
-        import multiprocessing as mp
-        from oracle import ref_driver as ref
-
-        self.use_ref = ref.available()
-        self.kind = "reference" if self.use_ref else "port"
-        self.cores = cores or len(os.sched_getaffinity(0))
-        self.pool = mp.get_context("fork").Pool(self.cores, initializer=_ref_worker_init, initargs=(self.use_ref,))
-        self.pool.map(_ref_worker_run, [(i, 64) for i in range(self.cores)])  # spin up + build chains
-
-    def step(self, rows_per_core, seed0=0):
-        t = time.perf_counter()
-        self.pool.map(_ref_worker_run, [(seed0 + i, rows_per_core) for i in range(self.cores)])
-        return time.perf_counter() - t
-
-    def close(self):
-        self.pool.close()
-        self.pool.join()
+def ik_parity_inputs():
+    rng = np.random.default_rng(22)
+    qt = rng.uniform(-np.pi, np.pi, (IK_PARITY_ROWS, 7))
+    q0 = rng.uniform(-np.pi, np.pi, (IK_PARITY_ROWS, 7))
+    return qt, q0
 
 
-def cpu_baseline(rows_per_core=100_000, reps=3):
-    arm = RefArm()
-    best = min(arm.step(rows_per_core, seed0=100 * r) for r in range(reps))
-    total = rows_per_core * arm.cores
-    # single-core figure: what the (single-threaded, GIL-holding) reference delivers out of the box
-    one = RefArm(cores=1)
-    t1 = min(one.step(rows_per_core // 2, seed0=7 + r) for r in range(2))
-    one.close()
-    arm.close()
-    return {
-        "value": total / best, "unit": "evals/s", "cores": arm.cores, "kind": arm.kind,
-        "sample": f"{total} rows ({rows_per_core}/core x {arm.cores} processes), best of {reps}: "
-                  "fknm.ETS_fkine batch call + per-row fknm.ETS_jacob0 loop (the reference has no batched Jacobian)",
-        "single_core_value": (rows_per_core // 2) / t1,
-    }
+# ------------------------------------------------------------------ CPU leg (reference implementation on the host cores)
+def cpu_leg(secondary=True):
+    """Runs BEFORE CUDA is initialised in this process (the worker pools fork).  Returns the cpu_baseline
+    objects and the reference's outputs on the parity samples.  This is the one place bench.py touches oracle/."""
+    from oracle import cpu_arm as ca
+
+    out = {"headline": ca.baseline("panda_fkj", seconds=0.12, reps=3), "configs": {}, "refs": {}}
+    if not secondary:
+        return out
+    out["configs"]["rne_puma_f64_1M"] = ca.baseline("puma_rne", seconds=0.3, reps=2)
+    out["configs"]["fkj_ur10_f32_1M"] = ca.baseline("ur10_fkj", seconds=0.12, reps=2)
+    for name, o in IK_PROTOCOLS.items():
+        out["configs"][name] = ca.baseline("panda_ik", opts=o, seconds=0.5, reps=2)
+    # reference outputs on the parity samples (same seeded inputs the GPU leg will evaluate)
+    Q = make_q(4242, PARITY_ROWS, 7)
+    out["refs"]["panda_fkj"] = ca.evaluate("panda_fkj", (Q,))
+    Qu = make_q(4243, PARITY_ROWS, 6).astype(np.float32).astype(np.float64)  # the fp32-rounded inputs the GPU sees
+    out["refs"]["ur10_fkj"] = ca.evaluate("ur10_fkj", (Qu,))
+    out["refs"]["puma_rne"] = ca.evaluate("puma_rne", rne_inputs(4244, PARITY_ROWS))
+    qt, q0 = ik_parity_inputs()
+    Tep = ca.evaluate("panda_fkj", (qt,))[0]
+    for name, o in IK_PROTOCOLS.items():
+        out["refs"][name] = (Tep,) + tuple(ca.evaluate("panda_ik", (Tep, q0), dict(o, slimit=1)))
+    out["modules_loaded"] = ca.loaded_reference_modules()
+    return out
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return 0
-    arm = RefArm()
-    rows_per_core = 20_000
+    from oracle import cpu_arm as ca
+
+    v1 = ca.time_inline("panda_fkj", 100_000, reps=2)  # single core, in this process (maps oracle/_ref/fknm*.so here)
+    arm = ca.CpuArm("panda_fkj")
+    rows_per_core = 100_000  # ~0.12 s of work per process per step
     for _ in range(args.warmup):
         arm.step(rows_per_core)
     t = 0.0
@@ -139,17 +136,21 @@ def run_reference(args):
     total = rows_per_core * arm.cores
     ms = 1e3 * t / args.steps
     value = total / (t / args.steps)
+    n_sched, quota = ca.effective_cores()
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": "evals/s", "n_gpus": args.gpus,
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "evals/s", "n_gpus": max(args.gpus, world),
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample_rows_per_step": total,
-                   "note": "reference CPU implementation (fknm built from /root/reference) on the host cores; "
-                           "a step is a bounded sample of the 1M-row workload"},
+        "config": make_config(max(args.gpus, world)),
         "cpu_baseline": {"value": value, "unit": "evals/s", "cores": arm.cores, "kind": arm.kind,
-                         "sample": f"{total} rows per step ({rows_per_core}/core x {arm.cores} processes)"},
+                         "sample": f"{total} rows per step ({rows_per_core}/process x {arm.cores} processes): "
+                                   + ca.DESCRIBE["panda_fkj"],
+                         "single_core_value": v1, "effective_cores": round(value / v1, 2),
+                         "cgroup_cpu_quota_cores": quota, "modules_loaded": ca.loaded_reference_modules()},
         "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "note": "reference CPU implementation (fknm built from /root/reference) on the host cores; a step is a "
+                "bounded sample of the 1M-row workload",
     }
     print(json.dumps(line))
     return 0
@@ -161,7 +162,6 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.period = period
         self.samples = []  # (t, sm_mhz, reasons_bitmask)
-        self.windows = []
         self._stop = threading.Event()
         self.h = None
         self.max_mhz = None
@@ -201,14 +201,16 @@ class ClockSampler(threading.Thread):
     def stop(self):
         self._stop.set()
 
-    def summary(self, t0, t1):
+    def summary(self, windows):
+        """windows: list of (t0, t1) perf_counter intervals during which the GPU ran timed work."""
         names = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
                  0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
                  0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
-        inwin = [s for s in self.samples if t0 <= s[0] <= t1]
+        inwin = [s for s in self.samples if any(a <= s[0] <= b for a, b in windows)]
         note = None
-        if not inwin:  # timed region shorter than one sampling period: use the closest samples
-            inwin = sorted(self.samples, key=lambda s: abs(s[0] - 0.5 * (t0 + t1)))[:3]
+        if not inwin and windows:  # timed regions shorter than one sampling period: use the closest samples
+            mid = 0.5 * (windows[0][0] + windows[0][1])
+            inwin = sorted(self.samples, key=lambda s: abs(s[0] - mid))[:3]
             note = "timed region shorter than the sampling period; nearest samples used"
         if not inwin:
             return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "note": "NVML unavailable"}
@@ -234,28 +236,35 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
 
 
-def load_traffic():
-    """dram bytes per launch of the fused kernel from the committed ncu --set full capture, if any."""
+def load_traffic(key=WORKLOAD):
+    """dram bytes per launch from the committed ncu --set full capture of that kernel, if any."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(p):
         try:
-            return json.load(open(p)).get(WORKLOAD)
+            return json.load(open(p)).get(key)
         except Exception:
             return None
     return None
+
+
+def err_stats(got, ref, atol):
+    """max |got - ref| over a sample, and max |got - ref| / |ref| over its entries that are not (analytically)
+    zero (|ref| >= 1e-6: entries like cos(pi/2) products come out as +-1e-17 on both sides)."""
+    got = np.asarray(got, dtype=np.float64)
+    ref = np.asarray(ref, dtype=np.float64)
+    d = np.abs(got - ref)
+    big = np.abs(ref) >= 1e-6
+    return float(d.max()), float((d[big] / np.abs(ref[big])).max()) if big.any() else 0.0
 
 
 def run_b200(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    n_gpus = args.gpus
-    if world != n_gpus and world > 1:
-        n_gpus = world
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_baseline()  # before CUDA is initialised in this process (the pool forks)
+        cpu = cpu_leg(secondary=not args.headline_only)  # before CUDA is initialised in this process (the pools fork)
 
     import torch
 
@@ -264,6 +273,7 @@ def run_b200(args):
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = rtb.dist.bind_to_gpu_numa(local)  # CPU affinity + first-touch placement of pinned buffers next to this GPU
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -271,66 +281,240 @@ def run_b200(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
 
-    ets = rtb.models.Panda().ets()
-    NBUF = 4
-    lo, hi = rtb.dist.shard_bounds(ROWS_PER_GPU * world, world, rank)  # this rank's rows of the global batch
-    assert hi - lo == ROWS_PER_GPU
-    qs = [torch.from_numpy(make_q(1000 * b + rank)).to(dev) for b in range(NBUF)]
-    T = torch.empty((ROWS_PER_GPU, 4, 4), dtype=torch.float64, device=dev)
-    J = torch.empty((ROWS_PER_GPU, 6, N_JOINTS), dtype=torch.float64, device=dev)
+    peak, peak_src = load_peaks()
     L = rtb._lib.lib()
-    chain = ets._chain
+    F32, F64 = rtb._lib.F32, rtb._lib.F64
     stream = torch.cuda.current_stream(dev)
-
-    def step(i):
-        q = qs[i % NBUF]
-        rtb._lib.check(L.b2k_fkine_jacob0(chain, rtb._lib.F64, q.data_ptr(), ROWS_PER_GPU, N_JOINTS, None, None,
-                                          T.data_ptr(), J.data_ptr(), stream.cuda_stream))
+    sp = stream.cuda_stream
+    windows = []
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    def rank_max(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def time_steps(step, steps, warmup, per_step=False):
+        """W warm-up steps, then K steps between CUDA events on the launching stream, barrier + synchronize on
+        both sides, max over ranks -> ms per step.  per_step=True: every step individually (a distribution)."""
+        for i in range(warmup):
+            step(i)
+        barrier()
+        w0 = time.perf_counter()
+        if per_step:
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+            ev[0].record(stream)
+            for i in range(steps):
+                step(i)
+                ev[i + 1].record(stream)
+            barrier()
+            windows.append((w0, time.perf_counter()))
+            return [ev[i].elapsed_time(ev[i + 1]) for i in range(steps)]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for i in range(steps):
+            step(i)
+        e1.record(stream)
+        barrier()
+        windows.append((w0, time.perf_counter()))
+        return rank_max(e0.elapsed_time(e1)) / steps
+
     sampler = ClockSampler(local)
     sampler.start()
-    for i in range(max(args.warmup, 3)):
-        step(i)
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    W = max(args.warmup, 3)
+
+    # ================================================================ headline: Panda ETS fkine+jacob0 fp64
+    panda = rtb.models.Panda()
+    ets = panda.ets()
+    NBUF = 4
+    lo, hi = rtb.dist.shard_bounds(ROWS_PER_GPU * world, world, rank)  # this rank's rows of the global batch
+    assert hi - lo == ROWS_PER_GPU
+    qs = [torch.from_numpy(make_q(1000 * b + rank)).to(dev) for b in range(NBUF)]
+    T = torch.empty((ROWS_PER_GPU, 4, 4), dtype=torch.float64, device=dev)
+    J = torch.empty((ROWS_PER_GPU, 6, N_JOINTS), dtype=torch.float64, device=dev)
+    chain = ets._chain
+
+    def step(i):
+        q = qs[i % NBUF]
+        rtb._lib.check(L.b2k_fkine_jacob0(chain, F64, q.data_ptr(), ROWS_PER_GPU, N_JOINTS, None, None,
+                                          T.data_ptr(), J.data_ptr(), sp))
+
     n0 = rtb.launch_count()
-    t0 = time.perf_counter()
-    e0.record(stream)
-    for i in range(args.steps):
-        step(i)
-    e1.record(stream)
-    barrier()
-    t1 = time.perf_counter()
-    launches = rtb.launch_count() - n0
-    ms_total = e0.elapsed_time(e1)
-    tt = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    ms_total = float(tt.item())
-    ms_step = ms_total / args.steps
+    ms_step = time_steps(step, args.steps, W)
+    launches = rtb.launch_count() - n0 - W
     value = ROWS_PER_GPU * world / (ms_step * 1e-3)
-    clocks = sampler.summary(t0, t1)
+    clocks = sampler.summary(windows[-1:])
+    per = time_steps(step, min(args.steps, 200), 0, per_step=True)  # distribution, outside `value`
+    step_ms = {"median": float(np.median(per)), "min": float(np.min(per)), "max": float(np.max(per)), "n": len(per),
+               "note": "each step between its own pair of events (second pass; the event records add ~1 us per step)"}
+    del qs
 
-    # ---- optional reassembly of the shards (reported separately; not part of the metric)
-    gather_ms = None
-    if dist is not None and args.gather:
-        barrier()
-        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        g0.record(stream)
-        rtb.dist.gather_rows(T, ROWS_PER_GPU * world)
-        rtb.dist.gather_rows(J, ROWS_PER_GPU * world)
-        g1.record(stream)
-        barrier()
-        gt = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device=dev)
-        dist.all_reduce(gt, op=dist.ReduceOp.MAX)
-        gather_ms = float(gt.item())
+    configs = {}
 
-    # ---- end to end through the public API with pinned host buffers (H2D + kernel + D2H per step)
+    def parity_fkj(e, key, Q, dt, rtol, atol):
+        if cpu is None or key not in cpu["refs"]:
+            return None
+        Tr, Jr = cpu["refs"][key]
+        Tg, Jg = e.fkine_jacob0(torch.from_numpy(Q.astype(dt)).to(dev))
+        eT, rT = err_stats(Tg.cpu().numpy(), Tr, atol)
+        eJ, rJ = err_stats(Jg.cpu().numpy(), Jr, atol)
+        ok = bool(np.allclose(Tg.cpu().numpy(), Tr, rtol=rtol, atol=atol) and np.allclose(Jg.cpu().numpy(), Jr, rtol=rtol, atol=atol))
+        return {"rows": int(Q.shape[0]), "vs": "reference fknm (ETS_fkine, ETS_jacob0) on the same seeded rows",
+                "max_abs_err": max(eT, eJ), "max_rel_err_nonzero_entries": max(rT, rJ), "rtol": rtol, "atol": atol, "pass": ok}
+
+    headline_parity = parity_fkj(ets, "panda_fkj", make_q(4242, PARITY_ROWS, 7), np.float64, 1e-10, 1e-12)
+
+    # ================================================================ the other BASELINE configs
+    def roof(bytes_per_row, rows, ms, bound="hbm", note=None):
+        a = bytes_per_row * rows / (ms * 1e-3) / 1e9
+        r = {"bound": bound, "achieved": a, "peak": peak, "unit": "GB/s", "frac": a / peak,
+             "algorithmic_bytes_per_launch": bytes_per_row * rows}
+        if note:
+            r["note"] = note
+        return r
+
+    KS = max(5, min(args.steps, 30))
+    if not args.headline_only:
+        # ---- config 5 / configs[4]: UR10 DH fkine+jacob0 fp32, 1M rows per GPU, seed 3 + rank
+        ur10 = rtb.models.UR10().ets()
+        uq = [torch.from_numpy(make_q(3 + rank + 100 * b, ROWS_PER_GPU, 6).astype(np.float32)).to(dev) for b in range(8)]
+        # packed result buffer [T | J] so the reassembly is ONE collective (see `gather` below)
+        TJ = torch.empty(ROWS_PER_GPU * 52, dtype=torch.float32, device=dev)
+        Tu, Ju = TJ[:ROWS_PER_GPU * 16].view(ROWS_PER_GPU, 4, 4), TJ[ROWS_PER_GPU * 16:].view(ROWS_PER_GPU, 6, 6)
+        uch = ur10._chain
+
+        def ustep(i):
+            rtb._lib.check(L.b2k_fkine_jacob0(uch, F32, uq[i % 8].data_ptr(), ROWS_PER_GPU, 6, None, None, Tu.data_ptr(),
+                                              Ju.data_ptr(), sp))
+
+        ms = time_steps(ustep, KS, 3)
+        name = "fkj_ur10_f32_1M" if world == 1 else "fkj_ur10_f32_sharded"
+        configs[name] = {
+            "baseline_config": "configs[4]: UR10 fkine+jacob0 fp32, 1M rows per GPU (8M over 8 GPUs), seed 3 + rank",
+            "ms": ms, "value": ROWS_PER_GPU * world / (ms * 1e-3), "unit": "evals/s", "rows": ROWS_PER_GPU * world,
+            "dtype": "f32", "steps": KS, "kernel": "k_fkj_fast<float,6,T,J0>",
+            "roofline": roof((6 + 16 + 36) * 4, ROWS_PER_GPU, ms),
+            "cpu_baseline": cpu["configs"].get("fkj_ur10_f32_1M") if cpu else None,
+            "parity": parity_fkj(ur10, "ur10_fkj", make_q(4243, PARITY_ROWS, 6), np.float32, 1e-4, 1e-5),
+        }
+        if configs[name]["parity"]:
+            configs[name]["parity"]["note"] = "fp32 results against the reference's fp64 on the fp32-rounded inputs"
+
+        # ---- reassembly of the shards (outside the metric)
+        gather = None
+        if dist is not None:
+            full = torch.empty(world * TJ.numel(), dtype=torch.float32, device=dev)
+            recv = (world - 1) * TJ.numel() * 4
+
+            def ag(i):
+                dist.all_gather_into_tensor(full, TJ)
+
+            ag_ms = time_steps(ag, 5, 2)
+            del full
+            parts = [torch.empty_like(TJ) for _ in range(world)] if rank == 0 else None
+
+            def g0(i):
+                dist.gather(TJ, parts, dst=0)
+
+            g_ms = time_steps(g0, 5, 2)
+            del parts
+            gather = {
+                "what": "UR10 fp32 result shards, packed [T | J] per rank: one NCCL all-gather; and a gather to rank 0",
+                "bytes_per_rank_shard": TJ.numel() * 4, "bytes_received_per_rank": recv,
+                "all_gather_ms": ag_ms, "gather_to_root_ms": g_ms,
+                "GBps": recv / (ag_ms * 1e-3) / 1e9, "frac_of_900GBps": recv / (ag_ms * 1e-3) / 1e9 / NVLINK_GBS,
+                "gather_to_root_GBps": recv / (g_ms * 1e-3) / 1e9,
+                "gather_to_root_frac_of_900GBps": recv / (g_ms * 1e-3) / 1e9 / NVLINK_GBS,
+                "kernel_ms": ms, "note": "GB/s = bytes received by one rank / time; the kernel that produced the shard "
+                                         "takes kernel_ms, so the reassembly cannot be hidden behind it (SURVEY 8e)",
+            }
+        del uq, TJ, Tu, Ju
+
+    if not args.headline_only and world == 1:
+        # ---- configs[2]: Puma560 DH rne fp64, 1M rows
+        puma = rtb.models.Puma560()
+        rb = [tuple(torch.from_numpy(a).to(dev) for a in rne_inputs(1 + 10 * b, ROWS_PER_GPU)) for b in range(3)]
+        tau = torch.empty((ROWS_PER_GPU, 6), dtype=torch.float64, device=dev)
+        puma.rne(rb[0][0][:8], rb[0][1][:8], rb[0][2][:8])  # builds the handle
+        g = np.ascontiguousarray(-puma.gravity)
+        h = puma._rne_ob
+
+        def rstep(i):
+            a, b, c = rb[i % 3]
+            rtb._lib.check(L.b2k_rne(h, F64, a.data_ptr(), b.data_ptr(), c.data_ptr(), ROWS_PER_GPU, rtb._lib.dptr(g), None,
+                                     tau.data_ptr(), sp))
+
+        ms = time_steps(rstep, KS, 3)
+        par = None
+        if cpu is not None:
+            a, b, c = rne_inputs(4244, PARITY_ROWS)
+            tg = puma.rne(torch.from_numpy(a).to(dev), torch.from_numpy(b).to(dev), torch.from_numpy(c).to(dev)).cpu().numpy()
+            e_abs, e_rel = err_stats(tg, cpu["refs"]["puma_rne"], 1e-10)
+            par = {"rows": PARITY_ROWS, "vs": "reference frne.frne on the same seeded rows", "max_abs_err": e_abs,
+                   "max_rel_err_nonzero_entries": e_rel, "rtol": 1e-10, "atol": 1e-10,
+                   "pass": bool(np.allclose(tg, cpu["refs"]["puma_rne"], rtol=1e-10, atol=1e-10))}
+        configs["rne_puma_f64_1M"] = {
+            "baseline_config": "configs[2]: Puma560 DHRobot rne (q, qd, qdd) batch 1M fp64",
+            "ms": ms, "value": ROWS_PER_GPU / (ms * 1e-3), "unit": "rows/s", "rows": ROWS_PER_GPU, "dtype": "f64",
+            "steps": KS, "kernel": rtb.rne_kernel_name(puma) if hasattr(rtb, "rne_kernel_name") else "k_rne<double,6,DH,allrev>",
+            "roofline": roof(24 * 8, ROWS_PER_GPU, ms, note="FP64-pipe co-limited: see DESIGN 3.4"),
+            "cpu_baseline": cpu["configs"].get("rne_puma_f64_1M") if cpu else None, "parity": par,
+        }
+        del rb, tau
+
+        # ---- configs[3]: Panda ikine_LM, 100k reachable targets, fp32, both protocols of SURVEY 8d
+        qstar = torch.from_numpy(make_q(2, IK_ROWS, 7)).to(dev)
+        Tep64 = ets.eval(qstar)  # reachable by construction: Tep = FK(q*)
+        Tep32 = Tep64.float().contiguous()
+        qo = torch.empty((IK_ROWS, 7), dtype=torch.float32, device=dev)
+        so, io, ro = (torch.empty(IK_ROWS, dtype=torch.int32, device=dev) for _ in range(3))
+        Eo = torch.empty(IK_ROWS, dtype=torch.float32, device=dev)
+        for name, o in IK_PROTOCOLS.items():
+            def istep(i, o=o):
+                rtb._lib.check(L.b2k_ik_lm(chain, F32, Tep32.data_ptr(), IK_ROWS, None, 30, 100, 1e-6, int(o["jl"]), None,
+                                           float(o["k"]), 0, 5 + i, 0, 1, qo.data_ptr(), so.data_ptr(), io.data_ptr(),
+                                           ro.data_ptr(), Eo.data_ptr(), sp))
+
+            n_before = rtb.launch_count()
+            ms = time_steps(istep, 5, 2)
+            ik_launches = (rtb.launch_count() - n_before) / 7.0
+            ok = so.bool()
+            Tg = ets.eval(qo.double())
+            pose_err = float((Tg - Tep64).abs().amax(dim=(1, 2))[ok].max()) if bool(ok.any()) else None
+            par = {"targets": IK_ROWS, "success_rate": float(ok.float().mean()), "mean_iterations": float(io.float().mean()),
+                   "max_iterations": int(io.max()), "mean_searches": float(ro.float().mean()), "max_searches": int(ro.max()),
+                   "max_residual_E_of_successes": float(Eo[ok].max()) if bool(ok.any()) else None, "tol": 1e-6,
+                   "max_pose_err_of_successes": pose_err,
+                   "pose_err_note": "max |FK(q) - Tep| (fp64 FK of the fp32 solution) over the successful targets"}
+            if cpu is not None:
+                Tp, qr, sr_, itr, srr, Er = cpu["refs"][name]
+                _, q0 = ik_parity_inputs()
+                qg, sg, itg, srg, Eg = ets.ik_LM(torch.from_numpy(Tp).to(dev), q0=torch.from_numpy(q0).to(dev), ilimit=30,
+                                                 slimit=1, tol=1e-6, joint_limits=o["jl"], k=o["k"], method="chan")
+                sg, itg, qg = sg.cpu().numpy(), itg.cpu().numpy(), qg.cpu().numpy()
+                same = (sg == sr_) & (itg == itr)
+                both = same & (sr_ == 1)
+                par["counters_vs_reference"] = {
+                    "targets": IK_PARITY_ROWS, "protocol": "fp64, explicit q0, slimit 1 (deterministic in the reference)",
+                    "vs": "reference fknm.IK_LM_c", "identical_success_and_iterations": float(same.mean()),
+                    "max_abs_q_diff_where_identical": float(np.abs(qg[both] - qr[both]).max()) if both.any() else None}
+            configs[name] = {
+                "baseline_config": "configs[3]: Panda ikine_LM fused kernel, 100k random reachable SE(3) targets, fp32",
+                "protocol": f"ilimit 30, slimit 100, tol 1e-6, chan lambda={o['k']}, joint-limit check {o['jl']}, random restarts",
+                "ms": ms, "value": IK_ROWS / (ms * 1e-3), "unit": "solves/s", "rows": IK_ROWS, "dtype": "f32", "steps": 5,
+                "kernel": "k_ik_lm + k_ik_restarts", "launches_per_step": ik_launches,
+                "roofline": roof((16 + 7 + 4) * 4, IK_ROWS, ms, bound="latency",
+                                 note="serial LM iterations per target: latency / issue bound, HBM fraction reported for completeness"),
+                "cpu_baseline": cpu["configs"].get(name) if cpu else None, "parity": par,
+            }
+        del qstar, Tep64, Tep32
+
+    # ================================================================ end to end through the public API (host buffers)
     e2e_steps = max(2, min(args.steps, 5))
     qp = [rtb.pinned_empty((ROWS_PER_GPU, N_JOINTS)) for _ in range(2)]
     for b in range(2):
@@ -345,36 +529,52 @@ def run_b200(args):
         ets.fkine_jacob0_into(qp[i % 2], Tp, Jp)  # synchronous: results are in Tp / Jp on return
     torch.cuda.synchronize(dev)
     w1 = time.perf_counter()
-    et = torch.tensor([(w1 - w0) / e2e_steps], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(et, op=dist.ReduceOp.MAX)
-    e2e_value = ROWS_PER_GPU * world / float(et.item())
+    e2e_value = ROWS_PER_GPU * world / rank_max((w1 - w0) / e2e_steps)
     checksum = float(Tp[-1, 0, 3]) + float(Jp[-1, 0, 0])
+    # the reference's calling convention: q is an ordinary (pageable) numpy array, results are fresh arrays
+    qpage = [np.array(qp[b]) for b in range(2)]
+    for b in range(2):
+        Th, Jh = ets.fkine_jacob0(qpage[b])
+    barrier()
+    w0 = time.perf_counter()
+    for i in range(e2e_steps):
+        Th, Jh = ets.fkine_jacob0(qpage[i % 2])
+    torch.cuda.synchronize(dev)
+    w1 = time.perf_counter()
+    e2e_page = ROWS_PER_GPU * world / rank_max((w1 - w0) / e2e_steps)
+    page_ok = bool(np.array_equal(Th, Tp) and np.array_equal(Jh, Jp))  # both loops ended on the same q batch
     sampler.stop()
 
     if rank == 0:
-        peak, peak_src = load_peaks()
         achieved = BYTES_PER_EVAL * ROWS_PER_GPU / (ms_step * 1e-3) / 1e9
+        hb = cpu["headline"] if cpu else None
         line = {
             "metric": METRIC, "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "warmup": W, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "rows_per_gpu": ROWS_PER_GPU, "global_batch": ROWS_PER_GPU * world,
-                       "parallelism": f"rows sharded over {world} rank(s), no data-path collective",
-                       "l2": "4 distinct 56 MB q batches rotated + 464 MB written per step (> 126 MB L2)",
-                       "kernel": "k_fkj_fast<double,7,T,J0> (1 launch per step)"},
+            "config": make_config(world),
+            "kernel": "k_fkj_fast<double,7,T,J0> (1 launch per step)",
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": load_traffic(), "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": BYTES_PER_EVAL * ROWS_PER_GPU},
-            "cpu_baseline": cpu,
+            "step_ms": step_ms,
+            "cpu_baseline": hb,
+            "parity": headline_parity,
             "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": ROWS_PER_GPU * N_JOINTS * 8 * world,
                     "d2h_bytes_per_step": ROWS_PER_GPU * (16 + 42) * 8 * world, "steps": e2e_steps,
-                    "api": "ETS.fkine_jacob0_into(pinned q, T, J) -> b2k_fkine_jacob0_host", "checksum": checksum},
+                    "api": "ETS.fkine_jacob0_into(pinned q, T, J) -> b2k_fkine_jacob0_host", "checksum": checksum,
+                    "pageable": {"value": e2e_page, "unit": "evals/s",
+                                 "api": "ETS.fkine_jacob0(pageable numpy q) -> fresh result arrays (pooled pinned memory)",
+                                 "identical_to_pinned_path": page_ok},
+                    "numa": numa},
             "clocks": clocks, "gpu_launches": int(launches),
         }
-        if gather_ms is not None:
-            line["gather"] = {"ms": gather_ms, "bytes_received_per_rank": ROWS_PER_GPU * (world - 1) * 58 * 8,
-                              "note": "NCCL all-gather of T and J shards, outside the metric"}
+        if configs:
+            line["configs"] = configs
+        if not args.headline_only and dist is not None and gather is not None:
+            line["gather"] = gather
+        if cpu and cpu.get("modules_loaded") is not None:
+            line["reference_modules_loaded"] = cpu["modules_loaded"]
         print(json.dumps(line))
     if dist is not None:
         dist.barrier()
@@ -388,7 +588,7 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--gather", action="store_true", help="also time an NCCL all-gather of the result shards (N>1)")
+    ap.add_argument("--headline-only", action="store_true", help="skip the secondary configs and the gather")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -167,6 +167,20 @@ int b2k_rne_destroy(b2k_rne_t rne);
 int b2k_rne(b2k_rne_t rne, int dtype, const void *q, const void *qd, const void *qdd, int64_t N,
             const double *grav, const double *fext, void *tau, void *stream);
 
+/* Robot-specialised kernels.  For all-revolute arms b2k_rne (and the dynamics entry points below) run a kernel that is
+ * generated for THIS robot's link table and compiled for sm_100a at first use (NVRTC): terms whose link parameter is zero
+ * are never emitted, alpha = k pi/2 turns rotations into permutations, constants are folded (csrc/b2k_rne_gen.cpp,
+ * b2k_rne_spec.cu).  Results equal the generic kernel's to rounding.  Environment: B2K_RNE_SPEC=0 disables it, =2 makes a
+ * failure to specialise an error; B2K_NVRTC_PATH names libnvrtc.so.12 when it is not on the loader path.
+ *   b2k_rne_spec_info  writes a one-line description of the kernel that serves (mode, dtype, grav pattern, has_fext) for
+ *                      this robot into buf -- mode: 0 rne, 1 inertia, 2 gravload, 3 itorque, 4 coriolis, 5 accel.
+ *   b2k_rne_codegen    returns the generated row function (plain C in terms of `real`; also valid host C++) and its
+ *                      constant bank, so the generator can be checked against the oracle without a GPU;
+ *                      counts[3] = multiplications, fused multiply-adds, additions per row. */
+int b2k_rne_spec_info(b2k_rne_t rne, int mode, int dtype, const double *grav, int has_fext, char *buf, int64_t cap);
+int b2k_rne_codegen(b2k_rne_t rne, int mode, int grav_mask, int has_fext, char *src, int64_t src_cap, double *consts,
+                    int32_t consts_cap, int32_t *n_consts, int32_t *counts);
+
 /* ---------------------------------------------------------------- dynamics built on the recursion
  * The reference's DynamicsMixin (robot/Dynamics.py) obtains these by looping frne calls in
  * Python; here each is ONE kernel in which a lane performs all the recursions of its row

@@ -33,14 +33,15 @@ class DHLink:
 
     def __init__(self, d=0.0, alpha=0.0, theta=0.0, a=0.0, sigma=0, mdh=False, offset=0.0, flip=False,
                  qlim=None, m=None, r=None, I=None, Jm=None, B=None, Tc=None, G=None, name=None):
-        self.d, self.alpha, self.theta, self.a = float(d), float(alpha), float(theta), float(a)
-        self.sigma = int(sigma)
-        self.mdh = bool(mdh)
-        self.offset = float(offset)
-        self.flip = bool(flip)
-        self.qlim = None if qlim is None else np.asarray(qlim, dtype=np.float64).reshape(2)
-        self.name = name
         self._robot = None
+        self.ets = None  # built at the end of __init__; the kinematic setters below rebuild it
+        self._d, self._alpha, self._theta, self._a = float(d), float(alpha), float(theta), float(a)
+        self._sigma = int(sigma)
+        self._mdh = bool(mdh)
+        self._offset = float(offset)
+        self._flip = bool(flip)
+        self._qlim = None if qlim is None else np.asarray(qlim, dtype=np.float64).reshape(2)
+        self.name = name
         # dynamic parameters with the reference defaults (Link.py:172-184)
         self._m = 0.0 if m is None else float(m)
         self._r = np.zeros(3) if r is None else np.asarray(r, dtype=np.float64).reshape(3)
@@ -73,6 +74,34 @@ class DHLink:
             self._dirty()
 
         return property(get, set)
+
+    # Kinematic parameters: the reference decorates theta, d, a, alpha, sigma, mdh (and offset) with
+    # @_listen_dyn (DHLink.py:448-563) so a change re-serialises the frne table.  Here a change must ALSO
+    # rebuild this link's elementary transforms and drop the robot's compiled chain (its device handle is
+    # released with the old ETS object), otherwise fkine / jacob / ik would keep walking the old geometry.
+    def _kinprop(name, conv):  # noqa: N805
+        def get(self):
+            return getattr(self, "_" + name)
+
+        def set(self, v):
+            setattr(self, "_" + name, conv(v))
+            if self.ets is not None:
+                self.ets = self._to_ets()
+            if self._robot is not None:
+                self._robot._kinchanged()
+
+        return property(get, set)
+
+    d = _kinprop("d", float)
+    a = _kinprop("a", float)
+    alpha = _kinprop("alpha", float)
+    theta = _kinprop("theta", float)
+    offset = _kinprop("offset", float)
+    sigma = _kinprop("sigma", int)
+    mdh = _kinprop("mdh", bool)
+    flip = _kinprop("flip", bool)
+    qlim = _kinprop("qlim", lambda v: None if v is None else np.asarray(v, dtype=np.float64).reshape(2))
+    del _kinprop
 
     m = _dynprop("m", float)
     r = _dynprop("r", lambda v: np.asarray(v, dtype=np.float64).reshape(3))

@@ -182,6 +182,12 @@ class DHRobot:
         return self.ets().ik_GN(Tep, q0, ilimit, slimit, tol, we, reject_jl, use_pinv, pinv_damping)
 
     # ---- inverse dynamics
+    def _kinchanged(self):
+        """A link's DH parameter changed: the cached ETS (and with it the compiled chain handle) and the
+        packed RNE table are both stale (reference DHLink.py:448-563 @_listen_dyn on theta/d/a/alpha/sigma/mdh)."""
+        self._ets_cache = None
+        self._dynchanged = True
+
     def dynchanged(self, what=None):
         """Mark the packed dynamic parameters stale (reference BaseRobot.py:383-398)."""
         self._dynchanged = True
@@ -256,7 +262,7 @@ class DHRobot:
         if host:
             t = B.require_cuda()
             qh, qdh, qddh = (np.ascontiguousarray(x, dtype=dt) for x in (q2, qd2, qdd2))
-            tau = np.empty((N, n), dtype=dt)
+            tau = _lib.host_result((N, n), dt)
             _lib.check(L.b2k_rne_host(self._rne_ob, B.code(dt), qh.ctypes.data, qdh.ctypes.data, qddh.ctypes.data, N,
                                       _lib.dptr(ng), _lib.dptr(fx), tau.ctypes.data, t.cuda.current_device()))
         else:

@@ -272,7 +272,7 @@ class ETS:
         if not B.is_tensor(q2):
             t = B.require_cuda()
             qh = np.ascontiguousarray(q2, dtype=dt)
-            T = np.empty((N, 4, 4), dtype=dt)
+            T = _lib.host_result((N, 4, 4), dt)
             _lib.check(L.b2k_fkine_host(self._chain, B.code(dt), qh.ctypes.data, N, qh.shape[1], _lib.dptr(base),
                                         _lib.dptr(tool), T.ctypes.data, t.cuda.current_device()))
             return T[0] if single else T
@@ -325,8 +325,8 @@ class ETS:
         if not B.is_tensor(q2):
             t = B.require_cuda()
             qh = np.ascontiguousarray(q2, dtype=dt)
-            T = np.empty((N, 4, 4), dtype=dt)
-            J = np.empty((N, 6, n), dtype=dt)
+            T = _lib.host_result((N, 4, 4), dt)
+            J = _lib.host_result((N, 6, n), dt)
             _lib.check(L.b2k_fkine_jacob0_host(self._chain, B.code(dt), qh.ctypes.data, N, qh.shape[1],
                                                _lib.dptr(base), _lib.dptr(tool), T.ctypes.data, J.ctypes.data,
                                                t.cuda.current_device()))

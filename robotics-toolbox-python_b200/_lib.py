@@ -44,6 +44,8 @@ _PROTOS = {
     "b2k_rne_create": (C.c_int, [C.c_int, C.c_int, dp, C.POINTER(vp)]),
     "b2k_rne_destroy": (C.c_int, [vp]),
     "b2k_rne": (C.c_int, [vp, C.c_int, vp, vp, vp, i64, dp, dp, vp, vp]),
+    "b2k_rne_codegen": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_char_p, i64, dp, C.c_int32, ip, ip]),
+    "b2k_rne_spec_info": (C.c_int, [vp, C.c_int, C.c_int, dp, C.c_int, C.c_char_p, i64]),
     "b2k_rne_inertia": (C.c_int, [vp, C.c_int, vp, i64, vp, vp]),
     "b2k_rne_gravload": (C.c_int, [vp, C.c_int, vp, i64, dp, vp, vp]),
     "b2k_rne_itorque": (C.c_int, [vp, C.c_int, vp, vp, i64, vp, vp]),
@@ -127,26 +129,86 @@ def set_variant(v: int):
     check(lib().b2k_set_variant(int(v)))
 
 
-def pinned_empty(shape, dtype=np.float64):
+class _PinnedPool:
+    """Recycles page-locked host blocks: cudaHostAlloc of a few hundred MB costs ~100 ms, so result arrays
+    handed to numpy callers come from (and return to) this cache.  At most B2K_PINNED_CACHE_MB (default
+    2048) of freed blocks are kept; anything beyond is released to the driver."""
+
+    GRAN = 1 << 20
+
+    def __init__(self):
+        import threading
+
+        self.free = {}  # rounded size -> [ptr values]
+        self.cached = 0
+        self.limit = int(os.environ.get("B2K_PINNED_CACHE_MB", "2048")) << 20
+        self.mu = threading.Lock()
+
+    def take(self, nbytes):
+        size = max(self.GRAN, (nbytes + self.GRAN - 1) // self.GRAN * self.GRAN)
+        with self.mu:
+            lst = self.free.get(size)
+            if lst:
+                self.cached -= size
+                return lst.pop(), size
+        p = vp()
+        check(lib().b2k_host_alloc(C.byref(p), size))
+        return p.value, size
+
+    def give(self, ptr, size):
+        with self.mu:
+            if self.cached + size <= self.limit:
+                self.free.setdefault(size, []).append(ptr)
+                self.cached += size
+                return
+        try:
+            lib().b2k_host_free(vp(ptr))
+        except Exception:
+            pass
+
+
+_pool = None
+
+
+def pinned_empty(shape, dtype=np.float64, pooled=False):
     """A numpy array backed by page-locked host memory (cudaHostAlloc), so the host-buffer
-    front ends move it at full PCIe / C2C bandwidth.  The memory is released when the array
-    (and all views of it) are garbage collected."""
+    front ends move it at full PCIe / C2C bandwidth.  The memory is released (pooled=True: returned to
+    the recycling cache) when the array and all views of it are garbage collected."""
+    global _pool
     dtype = np.dtype(dtype)
-    n = int(np.prod(shape)) * dtype.itemsize
-    p = vp()
-    check(lib().b2k_host_alloc(C.byref(p), max(n, 1)))
+    count = int(np.prod(shape))
+    n = count * dtype.itemsize
+    if pooled:
+        if _pool is None:
+            _pool = _PinnedPool()
+        addr, size = _pool.take(max(n, 1))
+    else:
+        p = vp()
+        check(lib().b2k_host_alloc(C.byref(p), max(n, 1)))
+        addr, size = p.value, None
 
     class _Owner:
-        def __init__(self, ptr):
-            self.ptr = ptr
+        def __init__(self, addr, size):
+            self.addr, self.size = addr, size
 
         def __del__(self):
             try:
-                lib().b2k_host_free(self.ptr)
+                if self.size is None:
+                    lib().b2k_host_free(vp(self.addr))
+                else:
+                    _pool.give(self.addr, self.size)
             except Exception:
                 pass
 
-    buf = (C.c_char * max(n, 1)).from_address(p.value)
-    buf._owner = _Owner(p)  # keep-alive chain: ndarray -> buf -> owner
-    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
-    return arr
+    buf = (C.c_char * max(n, 1)).from_address(addr)
+    buf._owner = _Owner(addr, size)  # keep-alive chain: ndarray -> buf -> owner
+    return np.frombuffer(buf, dtype=dtype, count=count).reshape(shape)
+
+
+def host_result(shape, dtype):
+    """Result array of a host-buffer call: pooled pinned memory once it is large enough for the copy
+    bandwidth to matter (>= 1 MB), plain numpy memory otherwise."""
+    n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    if n >= (1 << 20):
+        return pinned_empty(shape, dtype, pooled=True)
+    return np.empty(shape, dtype=dtype)

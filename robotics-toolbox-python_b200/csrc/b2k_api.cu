@@ -119,7 +119,10 @@ extern "C" int b2k_set_variant(int v)
 }
 
 // ------------------------------------------------------------------ validation helpers
-static int check_common(const char *fn, const b2k_chain_s *c, int dtype, const void *q, int64_t N, int64_t ldq)
+// q_on_device: the pointer is read by a kernel (element-wise at worst: only the natural alignment of the element
+// type is needed); host pointers of the *_host front ends only go through cudaMemcpy and need none.
+static int check_common(const char *fn, const b2k_chain_s *c, int dtype, const void *q, int64_t N, int64_t ldq,
+                        bool q_on_device = true)
 {
     if (!c) { b2k_set_error("%s: chain handle is NULL", fn); return B2K_ERR_INVALID; }
     if (dtype != B2K_F32 && dtype != B2K_F64) { b2k_set_error("%s: dtype must be B2K_F32 or B2K_F64", fn); return B2K_ERR_INVALID; }
@@ -130,14 +133,15 @@ static int check_common(const char *fn, const b2k_chain_s *c, int dtype, const v
                       c->q_width, B2K_MAX_QWIDTH, c->q_width - 1);
         return B2K_ERR_INVALID;
     }
-    if (((uintptr_t)q) & 7) { b2k_set_error("%s: q must be 8-byte aligned", fn); return B2K_ERR_INVALID; }
+    const unsigned es = dtype == B2K_F64 ? 8u : 4u;
+    if (q_on_device && (((uintptr_t)q) & (es - 1))) { b2k_set_error("%s: q must be %u-byte aligned", fn, es); return B2K_ERR_INVALID; }
     return B2K_OK;
 }
 
-static int check_out(const char *fn, const char *name, const void *p, int64_t N)
+static int check_out(const char *fn, const char *name, const void *p, int64_t N, unsigned align = 8)
 {
     if (N > 0 && !p) { b2k_set_error("%s: %s is NULL", fn, name); return B2K_ERR_INVALID; }
-    if (((uintptr_t)p) & 7) { b2k_set_error("%s: %s must be 8-byte aligned", fn, name); return B2K_ERR_INVALID; }
+    if (align > 1 && (((uintptr_t)p) & (align - 1))) { b2k_set_error("%s: %s must be %u-byte aligned", fn, name, align); return B2K_ERR_INVALID; }
     return B2K_OK;
 }
 
@@ -159,6 +163,7 @@ static int fkj_dispatch(const char *fn, b2k_chain_t c, int dtype, int mode, cons
     if ((mode & (FKJ_J0 | FKJ_JE)) && (rc = check_out(fn, "J", J, N))) return rc;
     if ((rc = check_affine(fn, "base", base)) || (rc = check_affine(fn, "tool", tool))) return rc;
     if (N == 0) return B2K_OK;
+    B2K_ON_DEVICE_OF(q);
     cudaStream_t st = (cudaStream_t)stream;
     if (b2k_get_variant() == 1 && !(mode & FKJ_JE))
         return b2k_fkw_launch(c, dtype, mode, q, N, ldq, base, tool, T, J, st);
@@ -205,11 +210,19 @@ extern "C" int b2k_rne(b2k_rne_t r, int dtype, const void *q, const void *qd, co
     if (N < 0) { b2k_set_error("%s: N is negative", fn); return B2K_ERR_INVALID; }
     if (!grav) { b2k_set_error("%s: grav is NULL (pass -robot.gravity like DHRobot.rne)", fn); return B2K_ERR_INVALID; }
     int rc;
-    if ((rc = check_out(fn, "q", q, N)) || (rc = check_out(fn, "qd", qd, N)) || (rc = check_out(fn, "qdd", qdd, N)) ||
-        (rc = check_out(fn, "tau", tau, N)))
+    const unsigned es = dtype == B2K_F64 ? 8u : 4u;
+    if ((rc = check_out(fn, "q", q, N, es)) || (rc = check_out(fn, "qd", qd, N, es)) || (rc = check_out(fn, "qdd", qdd, N, es)) ||
+        (rc = check_out(fn, "tau", tau, N, es)))
         return rc;
     if (N == 0) return B2K_OK;
-    return b2k_rne_launch(r, dtype, q, qd, qdd, N, grav, fext, tau, (cudaStream_t)stream);
+    B2K_ON_DEVICE_OF(q);
+    // the robot-specialised kernel (b2k_rne_spec.cu) serves the full 32-row tiles, the generic one the ragged tail
+    const long long done = b2k_rne_spec_launch(r, 0 /* B2K_GEN_RNE */, dtype, q, qd, qdd, N, grav, fext, tau, (cudaStream_t)stream);
+    if (done < 0) return (int)done;
+    if (done == N) return B2K_OK;
+    const size_t off = (size_t)done * r->n * es;
+    return b2k_rne_launch(r, dtype, (const char *)q + off, (const char *)qd + off, (const char *)qdd + off, N - done, grav, fext,
+                          (char *)tau + off, (cudaStream_t)stream);
 }
 
 // ------------------------------------------------------------------ host-buffer front ends
@@ -232,15 +245,18 @@ namespace {
 // A small pool of per-device pipeline slots (device staging buffers + stream), reused across calls.
 struct Slot {
     cudaStream_t st = nullptr;
+    cudaEvent_t h2d_done = nullptr; // recorded behind the slot's H2D copies: its bounce buffers are free again after it
     void *d_in[3] = {nullptr, nullptr, nullptr};
     void *d_out[2] = {nullptr, nullptr};
-    size_t in_cap[3] = {0, 0, 0}, out_cap[2] = {0, 0};
+    void *h_stage[3] = {nullptr, nullptr, nullptr}; // pinned bounce buffers for PAGEABLE caller inputs
+    size_t in_cap[3] = {0, 0, 0}, out_cap[2] = {0, 0}, stage_cap[3] = {0, 0, 0};
+    bool h2d_pending = false;
 };
 struct Pipe {
-    int device = -1;
+    std::mutex mu; // one pass at a time per device; passes on different devices run concurrently
     std::vector<Slot> slots;
 };
-std::mutex g_pipe_mu;
+std::mutex g_pipe_mu; // guards the map only
 std::map<int, Pipe> g_pipes;
 
 int ensure(void **p, size_t *cap, size_t need)
@@ -254,25 +270,66 @@ int ensure(void **p, size_t *cap, size_t need)
     return B2K_OK;
 }
 
+int ensure_host(void **p, size_t *cap, size_t need)
+{
+    if (*cap >= need) return B2K_OK;
+    if (*p) cudaFreeHost(*p);
+    *p = nullptr;
+    *cap = 0;
+    B2K_CUDA(cudaHostAlloc(p, need, cudaHostAllocPortable));
+    *cap = need;
+    return B2K_OK;
+}
+
+// true when the driver cannot DMA from this host pointer directly (ordinary malloc / numpy memory)
+bool is_pageable(const void *p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return true; }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+
 constexpr int kSlots = 3;
 constexpr long long kChunkRows = 1 << 17; // 128k rows per chunk: ~60 MB of Panda fp64 output
 
 // Generic chunked pipeline: for each chunk, H2D the inputs, run `kernel`, D2H the outputs, round-robin
-// over kSlots streams so the copy engines and the SMs overlap.
+// over kSlots streams so the copy engines and the SMs overlap.  Inputs in pageable memory (what a numpy
+// caller of the reference API holds) are staged by this thread into a pinned bounce buffer of the slot
+// and copied from there: a cudaMemcpyAsync straight from pageable memory would block the host until the
+// driver has staged it, serialising the pipeline; the explicit stage costs one memcpy that hides behind
+// the D2H traffic of the previous chunks.
 template <typename F>
 int run_pipeline(int device, long long N, int n_in, const void *const *h_in, const size_t *in_row_bytes, int n_out,
                  void *const *h_out, const size_t *out_row_bytes, F kernel)
 {
-    int prev = 0;
-    B2K_CUDA(cudaGetDevice(&prev));
-    B2K_CUDA(cudaSetDevice(device));
-    std::lock_guard<std::mutex> lk(g_pipe_mu);
-    Pipe &P = g_pipes[device];
-    if (P.slots.empty()) {
-        P.device = device;
-        P.slots.resize(kSlots);
-        for (auto &s : P.slots) B2K_CUDA(cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking));
+    DeviceGuard guard(device, true); // restores the caller's device on every exit path
+    if (guard.rc) return guard.rc;
+    Pipe *pp;
+    {
+        std::lock_guard<std::mutex> lk(g_pipe_mu);
+        pp = &g_pipes[device]; // std::map nodes are stable
     }
+    Pipe &P = *pp;
+    std::lock_guard<std::mutex> lk(P.mu);
+    if (P.slots.empty()) { // create every stream / event first; publish the slots only when all of them exist
+        std::vector<Slot> fresh(kSlots);
+        cudaError_t e = cudaSuccess;
+        for (auto &s : fresh) {
+            e = cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s.h2d_done, cudaEventDisableTiming);
+            if (e != cudaSuccess) break;
+        }
+        if (e != cudaSuccess) {
+            for (auto &t : fresh) {
+                if (t.h2d_done) cudaEventDestroy(t.h2d_done);
+                if (t.st) cudaStreamDestroy(t.st);
+            }
+            return b2k_cuda_fail(e, "creating the pipeline streams");
+        }
+        P.slots = std::move(fresh);
+    }
+    bool pageable[3] = {false, false, false};
+    for (int i = 0; i < n_in; i++) pageable[i] = is_pageable(h_in[i]);
     const long long chunk = N < kChunkRows ? N : kChunkRows;
     int rc = B2K_OK;
     long long done = 0;
@@ -280,12 +337,30 @@ int run_pipeline(int device, long long N, int n_in, const void *const *h_in, con
     while (done < N && rc == B2K_OK) {
         Slot &s = P.slots[k % kSlots];
         const long long rows = (N - done) < chunk ? (N - done) : chunk;
+        bool staged = false;
         for (int i = 0; i < n_in && rc == B2K_OK; i++) {
             rc = ensure(&s.d_in[i], &s.in_cap[i], (size_t)chunk * in_row_bytes[i]);
             if (rc) break;
-            cudaError_t e = cudaMemcpyAsync(s.d_in[i], (const char *)h_in[i] + (size_t)done * in_row_bytes[i],
-                                            (size_t)rows * in_row_bytes[i], cudaMemcpyHostToDevice, s.st);
+            const char *src = (const char *)h_in[i] + (size_t)done * in_row_bytes[i];
+            const size_t bytes = (size_t)rows * in_row_bytes[i];
+            if (pageable[i]) {
+                if ((rc = ensure_host(&s.h_stage[i], &s.stage_cap[i], (size_t)chunk * in_row_bytes[i]))) break;
+                if (s.h2d_pending) { // the previous chunk of this slot may still be reading the bounce buffers
+                    cudaError_t e = cudaEventSynchronize(s.h2d_done);
+                    if (e != cudaSuccess) { rc = b2k_cuda_fail(e, "cudaEventSynchronize"); break; }
+                    s.h2d_pending = false;
+                }
+                memcpy(s.h_stage[i], src, bytes);
+                src = (const char *)s.h_stage[i];
+                staged = true;
+            }
+            cudaError_t e = cudaMemcpyAsync(s.d_in[i], src, bytes, cudaMemcpyHostToDevice, s.st);
             if (e != cudaSuccess) rc = b2k_cuda_fail(e, "cudaMemcpyAsync H2D");
+        }
+        if (staged && rc == B2K_OK) {
+            cudaError_t e = cudaEventRecord(s.h2d_done, s.st);
+            if (e != cudaSuccess) rc = b2k_cuda_fail(e, "cudaEventRecord");
+            s.h2d_pending = true;
         }
         for (int i = 0; i < n_out && rc == B2K_OK; i++) rc = ensure(&s.d_out[i], &s.out_cap[i], (size_t)chunk * out_row_bytes[i]);
         if (rc == B2K_OK) rc = kernel(s, rows);
@@ -300,8 +375,8 @@ int run_pipeline(int device, long long N, int n_in, const void *const *h_in, con
     for (auto &s : P.slots) {
         cudaError_t e = cudaStreamSynchronize(s.st);
         if (e != cudaSuccess && rc == B2K_OK) rc = b2k_cuda_fail(e, "cudaStreamSynchronize");
+        s.h2d_pending = false;
     }
-    cudaSetDevice(prev);
     return rc;
 }
 } // namespace
@@ -310,9 +385,9 @@ extern "C" int b2k_fkine_jacob0_host(b2k_chain_t c, int dtype, const void *q, in
                                      const double *tool, void *T, void *J, int device)
 {
     const char *fn = "b2k_fkine_jacob0_host";
-    int rc = check_common(fn, c, dtype, q, N, ldq);
+    int rc = check_common(fn, c, dtype, q, N, ldq, false);
     if (rc) return rc;
-    if ((rc = check_out(fn, "T", T, N)) || (rc = check_out(fn, "J", J, N))) return rc;
+    if ((rc = check_out(fn, "T", T, N, 1)) || (rc = check_out(fn, "J", J, N, 1))) return rc;
     if (N == 0) return B2K_OK;
     const size_t es = dtype == B2K_F64 ? 8 : 4;
     const void *h_in[1] = {q};
@@ -328,9 +403,9 @@ extern "C" int b2k_fkine_host(b2k_chain_t c, int dtype, const void *q, int64_t N
                               const double *tool, void *T, int device)
 {
     const char *fn = "b2k_fkine_host";
-    int rc = check_common(fn, c, dtype, q, N, ldq);
+    int rc = check_common(fn, c, dtype, q, N, ldq, false);
     if (rc) return rc;
-    if ((rc = check_out(fn, "T", T, N))) return rc;
+    if ((rc = check_out(fn, "T", T, N, 1))) return rc;
     if (N == 0) return B2K_OK;
     const size_t es = dtype == B2K_F64 ? 8 : 4;
     const void *h_in[1] = {q};
@@ -392,10 +467,11 @@ extern "C" int b2k_ik_lm(b2k_chain_t c, int dtype, const void *Tep, int64_t N, c
         (rc = check_out(fn, "success", success, N)) || (rc = check_out(fn, "iterations", iterations, N)) ||
         (rc = check_out(fn, "searches", searches, N)) || (rc = check_out(fn, "residual", residual, N)))
         return rc;
+    if ((method == B2K_IK_NR || method == B2K_IK_GN) && lambda < 0) { b2k_set_error("%s: pinv_damping is negative", fn); return B2K_ERR_INVALID; }
     if (N == 0) return B2K_OK;
+    B2K_ON_DEVICE_OF(Tep);
     cudaStream_t st = (cudaStream_t)stream;
     if (method == B2K_IK_NR || method == B2K_IK_GN) {
-        if (lambda < 0) { b2k_set_error("%s: pinv_damping is negative", fn); return B2K_ERR_INVALID; }
         auto nr = dtype == B2K_F64 ? b2k_ik_nr_launch_f64 : b2k_ik_nr_launch_f32;
         return nr(c, Tep, N, q0, ilimit, slimit, tol, reject_jl, we, method == B2K_IK_GN ? 0.0 : lambda, method, seed,
                   semantics, rng_per_row, q_out, success, iterations, searches, residual, st);
@@ -420,11 +496,23 @@ static int fan_dispatch(const char *fn, b2k_rne_t r, int dtype, int mode, const 
     if (N < 0) { b2k_set_error("%s: N is negative", fn); return B2K_ERR_INVALID; }
     if (need_grav && !grav) { b2k_set_error("%s: grav is NULL (pass -robot.gravity like DHRobot.rne)", fn); return B2K_ERR_INVALID; }
     int rc;
-    if ((rc = check_out(fn, "q", in0, N)) || (nin >= 2 && (rc = check_out(fn, "second input", in1, N))) ||
-        (nin >= 3 && (rc = check_out(fn, "third input", in2, N))) || (rc = check_out(fn, "output", out, N)))
+    const unsigned es = dtype == B2K_F64 ? 8u : 4u;
+    if ((rc = check_out(fn, "q", in0, N, es)) || (nin >= 2 && (rc = check_out(fn, "second input", in1, N, es))) ||
+        (nin >= 3 && (rc = check_out(fn, "third input", in2, N, es))) || (rc = check_out(fn, "output", out, N, es)))
         return rc;
     if (N == 0) return B2K_OK;
+    B2K_ON_DEVICE_OF(in0);
     cudaStream_t st = (cudaStream_t)stream;
+    const long long done = b2k_rne_spec_launch(r, mode + 1 /* FAN_* -> B2K_GEN_* */, dtype, in0, in1, in2, N, grav, nullptr, out, st);
+    if (done < 0) return (int)done;
+    if (done == N) return B2K_OK;
+    const size_t off = (size_t)done * r->n * es;
+    const size_t out_per_row = (mode == FAN_INERTIA || mode == FAN_CORIOLIS) ? (size_t)r->n * r->n : (size_t)r->n;
+    in0 = (const char *)in0 + off;
+    if (in1) in1 = (const char *)in1 + off;
+    if (in2) in2 = (const char *)in2 + off;
+    out = (char *)out + (size_t)done * out_per_row * es;
+    N -= done;
     if (dtype == B2K_F64) return b2k_rne_fan_launch_f64(r, mode, in0, in1, in2, N, grav, out, st);
     return b2k_rne_fan_launch_f32(r, mode, in0, in1, in2, N, grav, out, st);
 }

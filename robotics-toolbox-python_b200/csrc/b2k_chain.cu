@@ -160,12 +160,14 @@ extern "C" int b2k_rne_create(int n, int mdh, const double *L, b2k_rne_t *out)
             return B2K_ERR_INVALID;
         }
     }
+    b2k_rne_spec_attach(r);
     *out = r;
     return B2K_OK;
 }
 
 extern "C" int b2k_rne_destroy(b2k_rne_t r)
 {
+    if (r) b2k_rne_spec_detach(r);
     free(r);
     return B2K_OK;
 }

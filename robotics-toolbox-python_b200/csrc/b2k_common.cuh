@@ -100,7 +100,14 @@ struct b2k_chain_s {
 struct b2k_rne_s {
     int n, mdh;
     double L[B2K_MAX_JOINTS][24];
+    void *spec; // cache of run-time compiled, robot-specialised kernels (b2k_rne_spec.cu)
 };
+void b2k_rne_spec_attach(b2k_rne_s *r);
+void b2k_rne_spec_detach(b2k_rne_s *r);
+// mode = B2K_GEN_* (b2k_rne_gen.h); returns the rows served by the specialised kernel (a multiple of 32, possibly 0)
+// or a negative b2k_status
+long long b2k_rne_spec_launch(const b2k_rne_s *r, int mode, int dtype, const void *in0, const void *in1, const void *in2,
+                              long long nrows, const double *grav, const double *fext, void *out, cudaStream_t st);
 
 // ---- error plumbing (b2k_api.cu)
 void b2k_set_error(const char *fmt, ...);
@@ -121,6 +128,47 @@ int b2k_tiles_per_warp(bool with_jacobian);
         cudaError_t _e = (call);                         \
         if (_e != cudaSuccess) return b2k_cuda_fail(_e, #call); \
     } while (0)
+
+// Every device-pointer entry point runs on the device that owns its first array argument: a caller
+// whose current device is cuda:0 may hand in buffers (and a stream) of cuda:1.  The guard looks the
+// pointer up (cudaPointerGetAttributes), switches the calling thread to that device for the duration
+// of the call and restores the previous one on every exit path.
+struct DeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    int rc = B2K_OK;
+    explicit DeviceGuard(const void *devptr) { rc = enter_ptr(devptr); }
+    DeviceGuard(int device, bool) { rc = enter(device); }
+    ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
+    DeviceGuard(const DeviceGuard &) = delete;
+    DeviceGuard &operator=(const DeviceGuard &) = delete;
+    inline int enter(int device)
+    {
+        cudaError_t e = cudaGetDevice(&prev);
+        if (e != cudaSuccess) return b2k_cuda_fail(e, "cudaGetDevice");
+        if (device == prev) return B2K_OK;
+        e = cudaSetDevice(device);
+        if (e != cudaSuccess) return b2k_cuda_fail(e, "cudaSetDevice");
+        switched = true;
+        return B2K_OK;
+    }
+    inline int enter_ptr(const void *p)
+    {
+        if (!p) return B2K_OK;
+        cudaPointerAttributes a;
+        cudaError_t e = cudaPointerGetAttributes(&a, p);
+        if (e != cudaSuccess) { cudaGetLastError(); return b2k_cuda_fail(e, "cudaPointerGetAttributes"); }
+        if (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged) return enter(a.device);
+        if (a.type == cudaMemoryTypeUnregistered) {
+            b2k_set_error("array argument %p is not a CUDA device pointer (host arrays go through the *_host entry points)", p);
+            return B2K_ERR_INVALID;
+        }
+        return B2K_OK; // pinned host memory is device-accessible from the current device
+    }
+};
+#define B2K_ON_DEVICE_OF(ptr)  \
+    DeviceGuard _guard(ptr);   \
+    if (_guard.rc) return _guard.rc
 
 // ---- small host helpers shared by launchers
 void b2k_mat_to34(const double *T16, double *A12);          // row-major 4x4 -> 3x4

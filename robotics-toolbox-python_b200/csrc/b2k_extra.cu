@@ -216,6 +216,7 @@ extern "C" int b2k_hessian(int dtype, int n, const void *J, int64_t N, void *H, 
     if (N < 0 || (N > 0 && (!J || !H))) { b2k_set_error("b2k_hessian: bad arguments"); return B2K_ERR_INVALID; }
     if (dtype != B2K_F32 && dtype != B2K_F64) { b2k_set_error("b2k_hessian: bad dtype"); return B2K_ERR_INVALID; }
     if (N == 0) return B2K_OK;
+    B2K_ON_DEVICE_OF(J);
     return dtype == B2K_F64 ? extra_launch<double>(0, n, J, N, 0, H, (cudaStream_t)stream)
                             : extra_launch<float>(0, n, J, N, 0, H, (cudaStream_t)stream);
 }
@@ -226,6 +227,7 @@ extern "C" int b2k_manipulability(int dtype, int n, const void *J, int64_t N, ui
     if (dtype != B2K_F32 && dtype != B2K_F64) { b2k_set_error("b2k_manipulability: bad dtype"); return B2K_ERR_INVALID; }
     if ((axes_mask & 63u) == 0) { b2k_set_error("b2k_manipulability: no Cartesian axis selected"); return B2K_ERR_INVALID; }
     if (N == 0) return B2K_OK;
+    B2K_ON_DEVICE_OF(J);
     return dtype == B2K_F64 ? extra_launch<double>(1, n, J, N, axes_mask & 63u, m, (cudaStream_t)stream)
                             : extra_launch<float>(1, n, J, N, axes_mask & 63u, m, (cudaStream_t)stream);
 }
@@ -236,6 +238,7 @@ extern "C" int b2k_jacob_dot(int dtype, int n, const void *J, const void *qd, in
     if (N < 0 || (N > 0 && (!J || !qd || !Jd))) { b2k_set_error("b2k_jacob_dot: bad arguments"); return B2K_ERR_INVALID; }
     if (dtype != B2K_F32 && dtype != B2K_F64) { b2k_set_error("b2k_jacob_dot: bad dtype"); return B2K_ERR_INVALID; }
     if (N == 0) return B2K_OK;
+    B2K_ON_DEVICE_OF(J);
     return dtype == B2K_F64 ? extra_launch<double>(2, n, J, N, 0, Jd, (cudaStream_t)stream, qd)
                             : extra_launch<float>(2, n, J, N, 0, Jd, (cudaStream_t)stream, qd);
 }
@@ -246,6 +249,7 @@ extern "C" int b2k_jacobm(int dtype, int n, const void *J, int64_t N, uint32_t a
     if (dtype != B2K_F32 && dtype != B2K_F64) { b2k_set_error("b2k_jacobm: bad dtype"); return B2K_ERR_INVALID; }
     if ((axes_mask & 63u) == 0) { b2k_set_error("b2k_jacobm: no Cartesian axis selected"); return B2K_ERR_INVALID; }
     if (N == 0) return B2K_OK;
+    B2K_ON_DEVICE_OF(J);
     return dtype == B2K_F64 ? extra_launch<double>(3, n, J, N, axes_mask & 63u, Jm, (cudaStream_t)stream)
                             : extra_launch<float>(3, n, J, N, axes_mask & 63u, Jm, (cudaStream_t)stream);
 }
@@ -292,6 +296,7 @@ extern "C" int b2k_jtraj(int dtype, int n, const double *q0, const double *qf, c
     if (N < 0 || (N > 0 && !q)) { b2k_set_error("%s: bad N / q", fn); return B2K_ERR_INVALID; }
     if (!(tscal > 0)) { b2k_set_error("%s: tscal must be positive", fn); return B2K_ERR_INVALID; }
     if (N == 0) return B2K_OK;
+    B2K_ON_DEVICE_OF(q);
     JtrajP P;
     P.n = n;
     P.inv_tscal = 1.0 / tscal;
@@ -355,6 +360,7 @@ static int pose_error_launch(const char *fn, int dtype, const void *Te, const vo
     if (N < 0 || (N > 0 && (!Te || !Tep || !out))) { b2k_set_error("%s: bad arguments", fn); return B2K_ERR_INVALID; }
     if (tep_stride != 0 && tep_stride != 16) { b2k_set_error("%s: tep_stride must be 0 (one target) or 16", fn); return B2K_ERR_INVALID; }
     if (N == 0) return B2K_OK;
+    B2K_ON_DEVICE_OF(Te);
     double g[6];
     for (int k = 0; k < 6; k++) g[k] = gain ? gain[k] : 1.0;
     cudaStream_t st = (cudaStream_t)stream;
@@ -487,6 +493,7 @@ extern "C" int b2k_mtraj(int dtype, int kind, int n, const double *q0, const dou
         }
     }
     if (N == 0) return B2K_OK;
+    B2K_ON_DEVICE_OF(s);
     const long long total = N * n;
     long long blocks = (total + 255) / 256;
     const long long cap = (long long)b2k_num_sms() * 16;

@@ -398,7 +398,7 @@ struct TileStage {
     {
         if constexpr (EXACT) {
             const unsigned bytes = (unsigned)rows_here * ROW_BYTES;
-            if (bytes & 15u) return false;
+            if ((bytes & 15u) || (reinterpret_cast<uintptr_t>(gout) & 15)) return false; // cp.async.bulk needs 16-byte size and address
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
             if (lane == 0) {
@@ -408,6 +408,7 @@ struct TileStage {
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             return true;
         } else if constexpr (UB == 16) {
+            if (reinterpret_cast<uintptr_t>(gout) & 15) return false;
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
             if (lane < rows_here) {

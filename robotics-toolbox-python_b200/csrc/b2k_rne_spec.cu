@@ -1,0 +1,572 @@
+// b2k_rne_spec.cu -- run-time compilation and launch of the robot-specialised RNE kernels.
+//
+// b2k_rne_gen.cpp turns one robot's 24-double link table into straight-line CUDA C for the recursion
+// (and for the dynamics fan-outs built on it).  Here that text is wrapped in the tile I/O of the RNE
+// kernels (a warp owns 32 rows: cp.async tiles in, one row per lane, results staged and written by one
+// TMA bulk copy), compiled for sm_100a with NVRTC the first time a (robot, operation, dtype, gravity
+// pattern) is used, loaded through the driver API and launched on the caller's stream.  Both libraries
+// are found with dlopen at run time (libnvrtc.so.12 of the CUDA toolkit, libcuda.so.1 of the driver):
+// libb2kin.so itself links neither.  When either is missing, or the chain has a prismatic joint, the
+// pre-compiled generic kernels of b2k_rne.cuh serve the call -- still on the GPU; nothing here ever
+// computes on the host.  B2K_RNE_SPEC=0 disables the specialised path, B2K_RNE_SPEC=2 turns a failure
+// to specialise into an error (tests use it to prove which kernel ran).
+#include <cuda.h>
+#include <dlfcn.h>
+#include <nvrtc.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <map>
+#include <mutex>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "b2k_rne_gen.h"
+
+namespace {
+
+// ------------------------------------------------------------------ the fixed part of the kernel source
+// Macros supplied on the NVRTC command line: REAL, NJ (joints), NC (constant-bank entries), MODE
+// (B2K_GEN_*), NIN (input arrays), NOUT (reals written per row), NRES (reals the row function returns),
+// PADIN (1: padded input rows, element-wise tile load), MINB (resident blocks per SM to aim for).
+const char *kPrologue = R"B2KSRC(
+typedef REAL real;
+typedef unsigned long long u64;
+struct TrigC { real two_over_pi, magic, pio2_hi, pio2_mid, pio2_lo, fast_limit; real s[6]; real c[6]; };
+struct SpecP { real C[NC]; real grav[3]; real fext[6]; real offset[NJ]; TrigC trig; };
+
+__device__ __forceinline__ real b2k_abs(real x) { return x < (real)0 ? -x : x; }
+
+// sincos of the NJ joint angles as one interleaved batch: three-FMA Cody-Waite reduction by pi/2, fdlibm minimax
+// kernels on [-pi/4, pi/4], integer quadrant logic; every coefficient comes from the parameter bank (csrc/b2k_trig.cuh
+// is the same code; measured <= 1.6 ulp).  fp32 rows with every |angle| < 8 take the special-function unit.
+struct SC { real s, c; };
+__device__ __noinline__ SC sincos_slow(real x)
+{ // by value: taking the address of the caller's arrays would pin them to local memory on the fast path too
+    SC r;
+#if REAL_IS_F64
+    sincos(x, &r.s, &r.c);
+#else
+    sincosf(x, &r.s, &r.c);
+#endif
+    return r;
+}
+__device__ __forceinline__ void sincos_batch(const real *x, const TrigC &t, real *s, real *c)
+{
+#if !REAL_IS_F64
+    {
+        bool all_small = true;
+#pragma unroll
+        for (int j = 0; j < NJ; j++) all_small = all_small && (b2k_abs(x[j]) < 8.0f);
+        if (all_small) {
+#pragma unroll
+            for (int j = 0; j < NJ; j++) { s[j] = __sinf(x[j]); c[j] = __cosf(x[j]); }
+            return;
+        }
+    }
+#endif
+    bool all_fast = true;
+#pragma unroll
+    for (int j = 0; j < NJ; j++) all_fast = all_fast && (b2k_abs(x[j]) < t.fast_limit);
+    if (!all_fast) { // rare: huge / non-finite angles somewhere in this row
+#pragma unroll
+        for (int j = 0; j < NJ; j++) { const SC r = sincos_slow(x[j]); s[j] = r.s; c[j] = r.c; }
+        return;
+    }
+    real r[NJ], z[NJ], ps[NJ], pc[NJ];
+    int q[NJ];
+#pragma unroll
+    for (int j = 0; j < NJ; j++) {
+        const real tt = fma(x[j], t.two_over_pi, t.magic);
+#if REAL_IS_F64
+        q[j] = __double2loint(tt);
+#else
+        q[j] = __float_as_int(tt);
+#endif
+        const real kd = tt - t.magic;
+        real rr = fma(-kd, t.pio2_hi, x[j]);
+        rr = fma(-kd, t.pio2_mid, rr);
+        r[j] = fma(-kd, t.pio2_lo, rr);
+        z[j] = r[j] * r[j];
+    }
+    const int D = REAL_IS_F64 ? 6 : 3;
+#pragma unroll
+    for (int j = 0; j < NJ; j++) { ps[j] = t.s[D - 1]; pc[j] = t.c[D - 1]; }
+#pragma unroll
+    for (int k = D - 2; k >= 0; k--) {
+#pragma unroll
+        for (int j = 0; j < NJ; j++) { ps[j] = fma(ps[j], z[j], t.s[k]); pc[j] = fma(pc[j], z[j], t.c[k]); }
+    }
+#pragma unroll
+    for (int j = 0; j < NJ; j++) {
+        const real sn = fma(r[j] * z[j], ps[j], r[j]);
+        const real cs = fma(z[j] * z[j], pc[j], fma((real)-0.5, z[j], (real)1));
+        const bool swap = q[j] & 1;
+        const real ss = swap ? cs : sn;
+        const real cc = swap ? sn : cs;
+        const int sflip = (q[j] & 2) << 30;
+        const int cflip = ((q[j] + 1) & 2) << 30;
+#if REAL_IS_F64
+        s[j] = __hiloint2double(__double2hiint(ss) ^ sflip, __double2loint(ss));
+        c[j] = __hiloint2double(__double2hiint(cc) ^ cflip, __double2loint(cc));
+#else
+        s[j] = __int_as_float(__float_as_int(ss) ^ sflip);
+        c[j] = __int_as_float(__float_as_int(cc) ^ cflip);
+#endif
+    }
+}
+)B2KSRC";
+
+const char *kKernel = R"B2KSRC(
+#define LDI (PADIN ? (NJ | 1) : NJ)                  /* smem row stride of the input tiles, in reals */
+#define IN_BYTES ((32 * LDI * (int)sizeof(real) + 15) & ~15)
+#define OUT_BYTES (32 * NOUT * (int)sizeof(real))
+#define WARP_BYTES (NIN * IN_BYTES + OUT_BYTES)
+
+__device__ __forceinline__ void load_tile(real *s, const real *g, int lane)
+{
+#if PADIN
+    // padded rows: the exact image would make the one-row-per-lane reads collide on the shared-memory banks
+    for (int i = lane; i < 32 * NJ; i += 32) {
+        const int r = i / NJ, c = i - r * NJ;
+        s[r * LDI + c] = g[i];
+    }
+#else
+    const uint4 *gg = reinterpret_cast<const uint4 *>(g);
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(s);
+    for (int u = lane; u < (32 * NJ * (int)sizeof(real)) / 16; u += 32)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa + 16u * (unsigned)u), "l"(gg + u));
+#endif
+}
+
+// One warp = one tile of 32 rows; one-shot grid of full tiles (the ragged tail of a batch goes to the generic kernel).
+extern "C" __global__ void __launch_bounds__(128, MINB)
+k_rne_spec(const __grid_constant__ SpecP P, const real *__restrict__ in0, const real *__restrict__ in1,
+           const real *__restrict__ in2, real *__restrict__ out, long long ntiles)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long tile = (long long)blockIdx.x * 4 + warp;
+    if (tile >= ntiles) return;
+    unsigned char *wb = smem + (size_t)warp * WARP_BYTES;
+    real *s0 = reinterpret_cast<real *>(wb);
+    real *s1 = reinterpret_cast<real *>(wb + IN_BYTES);
+    real *s2 = reinterpret_cast<real *>(wb + 2 * IN_BYTES);
+    real *so = reinterpret_cast<real *>(wb + NIN * IN_BYTES);
+    const size_t row0 = (size_t)tile * 32;
+    load_tile(s0, in0 + row0 * NJ, lane);
+    if (NIN >= 2) load_tile(s1, in1 + row0 * NJ, lane);
+    if (NIN >= 3) load_tile(s2, in2 + row0 * NJ, lane);
+#if !PADIN
+    asm volatile("cp.async.wait_all;\n" ::: "memory");
+#endif
+    __syncwarp();
+    real th[NJ], st[NJ], ct[NJ], a1[NJ], a2[NJ];
+#pragma unroll
+    for (int j = 0; j < NJ; j++) {
+        th[j] = s0[lane * LDI + j] + P.offset[j];
+        a1[j] = NIN >= 2 ? s1[lane * LDI + j] : (real)0;
+        a2[j] = NIN >= 3 ? s2[lane * LDI + j] : (real)0;
+    }
+    sincos_batch(th, P.trig, st, ct);
+    real res[NRES];
+    rne_row(P.C, P.grav, P.fext, st, ct, a1, a2, res);
+#if MODE == 5
+    // accel: res = [M (NJ x NJ, row i = torques for a unit acceleration of joint i) | torque - rne(q, qd, 0)].
+    // M is the joint-space inertia matrix (symmetric positive definite): LDL^T without pivoting, in registers.
+    {
+        real d[NJ];
+#pragma unroll
+        for (int c = 0; c < NJ; c++) {
+            real dc = res[c * NJ + c];
+#pragma unroll
+            for (int k = 0; k < c; k++) dc = fma(-res[c * NJ + k] * d[k], res[c * NJ + k], dc);
+            d[c] = dc;
+            const real inv = (real)1 / dc;
+#pragma unroll
+            for (int r = c + 1; r < NJ; r++) {
+                real v = res[r * NJ + c];
+#pragma unroll
+                for (int k = 0; k < c; k++) v = fma(-res[r * NJ + k] * d[k], res[c * NJ + k], v);
+                res[r * NJ + c] = v * inv; // L[r][c]
+            }
+        }
+        real *y = res + NJ * NJ;
+#pragma unroll
+        for (int r = 0; r < NJ; r++)
+#pragma unroll
+            for (int k = 0; k < r; k++) y[r] = fma(-res[r * NJ + k], y[k], y[r]);
+#pragma unroll
+        for (int r = 0; r < NJ; r++) y[r] = y[r] / d[r];
+#pragma unroll
+        for (int r = NJ - 1; r >= 0; r--)
+#pragma unroll
+            for (int k = r + 1; k < NJ; k++) y[r] = fma(-res[k * NJ + r], y[k], y[r]);
+#pragma unroll
+        for (int k = 0; k < NOUT; k++) so[lane * NOUT + k] = y[k];
+    }
+#else
+#pragma unroll
+    for (int k = 0; k < NOUT; k++) so[lane * NOUT + k] = res[k];
+#endif
+    // the staged tile is the exact image of the output block: one TMA bulk copy (shared -> global) by lane 0
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    if (lane == 0) {
+        const unsigned ss = (unsigned)__cvta_generic_to_shared(so);
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(out + row0 * NOUT), "r"(ss),
+                     "r"((unsigned)OUT_BYTES) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); // the copy reads this warp's shared memory
+    }
+}
+)B2KSRC";
+
+// ------------------------------------------------------------------ dynamic loading of NVRTC and the driver API
+struct Nvrtc {
+    void *h = nullptr;
+    nvrtcResult (*CreateProgram)(nvrtcProgram *, const char *, const char *, int, const char *const *, const char *const *);
+    nvrtcResult (*CompileProgram)(nvrtcProgram, int, const char *const *);
+    nvrtcResult (*GetCUBINSize)(nvrtcProgram, size_t *);
+    nvrtcResult (*GetCUBIN)(nvrtcProgram, char *);
+    nvrtcResult (*GetProgramLogSize)(nvrtcProgram, size_t *);
+    nvrtcResult (*GetProgramLog)(nvrtcProgram, char *);
+    nvrtcResult (*DestroyProgram)(nvrtcProgram *);
+    const char *(*GetErrorString)(nvrtcResult);
+    std::string why;
+};
+struct Driver {
+    void *h = nullptr;
+    CUresult (*ModuleLoadData)(CUmodule *, const void *);
+    CUresult (*ModuleGetFunction)(CUfunction *, CUmodule, const char *);
+    CUresult (*LaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, CUstream, void **, void **);
+    CUresult (*FuncSetAttribute)(CUfunction, CUfunction_attribute, int);
+    CUresult (*FuncGetAttribute)(int *, CUfunction_attribute, CUfunction);
+    CUresult (*GetErrorString)(CUresult, const char **);
+    std::string why;
+};
+
+template <typename F>
+bool sym(void *h, const char *name, F &fn, std::string &why)
+{
+    fn = reinterpret_cast<F>(dlsym(h, name));
+    if (!fn) { why = std::string("symbol ") + name + " not found"; return false; }
+    return true;
+}
+
+Nvrtc *nvrtc()
+{
+    static Nvrtc N;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        std::vector<std::string> cands;
+        if (const char *e = getenv("B2K_NVRTC_PATH")) cands.push_back(e);
+        for (const char *n : {"libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so"})
+            cands.push_back(n);
+        for (const std::string &c : cands) {
+            N.h = dlopen(c.c_str(), RTLD_NOW | RTLD_LOCAL);
+            if (N.h) break;
+        }
+        if (!N.h) { N.why = "libnvrtc.so.12 not found (set B2K_NVRTC_PATH)"; return; }
+        bool ok = sym(N.h, "nvrtcCreateProgram", N.CreateProgram, N.why) && sym(N.h, "nvrtcCompileProgram", N.CompileProgram, N.why) &&
+                  sym(N.h, "nvrtcGetCUBINSize", N.GetCUBINSize, N.why) && sym(N.h, "nvrtcGetCUBIN", N.GetCUBIN, N.why) &&
+                  sym(N.h, "nvrtcGetProgramLogSize", N.GetProgramLogSize, N.why) && sym(N.h, "nvrtcGetProgramLog", N.GetProgramLog, N.why) &&
+                  sym(N.h, "nvrtcDestroyProgram", N.DestroyProgram, N.why) && sym(N.h, "nvrtcGetErrorString", N.GetErrorString, N.why);
+        if (!ok) { dlclose(N.h); N.h = nullptr; }
+    });
+    return &N;
+}
+
+Driver *driver()
+{
+    static Driver D;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        D.h = dlopen("libcuda.so.1", RTLD_NOW | RTLD_LOCAL);
+        if (!D.h) { D.why = "libcuda.so.1 not found"; return; }
+        bool ok = sym(D.h, "cuModuleLoadData", D.ModuleLoadData, D.why) && sym(D.h, "cuModuleGetFunction", D.ModuleGetFunction, D.why) &&
+                  sym(D.h, "cuLaunchKernel", D.LaunchKernel, D.why) && sym(D.h, "cuFuncSetAttribute", D.FuncSetAttribute, D.why) &&
+                  sym(D.h, "cuFuncGetAttribute", D.FuncGetAttribute, D.why) && sym(D.h, "cuGetErrorString", D.GetErrorString, D.why);
+        if (!ok) { dlclose(D.h); D.h = nullptr; }
+    });
+    return &D;
+}
+
+// ------------------------------------------------------------------ per-robot cache of compiled programs
+struct Program {
+    bool ok = false;
+    std::string why;          // why not, when !ok
+    std::string cubin;        // sm_100a image
+    std::vector<double> consts;
+    int nin = 1, nout = 0, nres = 0, nc = 1;
+    int n_mul = 0, n_fma = 0, n_add = 0, regs = 0;
+    size_t smem = 0;
+    std::map<int, CUfunction> fn; // per device
+};
+typedef std::tuple<int, int, int, int> Key; // mode, dtype, grav_mask, has_fext
+struct SpecCache {
+    std::mutex mu;
+    std::map<Key, Program> progs;
+};
+
+int spec_setting()
+{
+    static const int v = [] { const char *e = getenv("B2K_RNE_SPEC"); return e ? atoi(e) : 1; }();
+    return v;
+}
+
+int gcd_i(int a, int b) { return b ? gcd_i(b, a % b) : a; }
+
+std::string build_source(const b2k_rne_s *r, int mode, int dtype, int grav_mask, int has_fext, Program &p, std::vector<std::string> &defs)
+{
+    b2k_gen_opts o;
+    o.mode = mode; o.grav_mask = grav_mask; o.has_fext = has_fext;
+    b2k_gen_out g;
+    if (b2k_rne_generate(r, o, g)) { p.why = g.error; return std::string(); }
+    const int n = r->n;
+    p.consts = g.consts;
+    p.nc = (int)g.consts.size();
+    p.n_mul = g.n_mul; p.n_fma = g.n_fma; p.n_add = g.n_add;
+    p.nin = (mode == B2K_GEN_RNE || mode == B2K_GEN_ACCEL) ? 3 : ((mode == B2K_GEN_ITORQUE || mode == B2K_GEN_CORIOLIS) ? 2 : 1);
+    p.nout = (mode == B2K_GEN_INERTIA || mode == B2K_GEN_CORIOLIS) ? n * n : n;
+    p.nres = mode == B2K_GEN_ACCEL ? n * n + n : p.nout;
+    const int es = dtype == B2K_F64 ? 8 : 4;
+    // one-row-per-lane reads of an exact-image tile: conflict degree gcd(row words, banks served per wavefront)
+    const int padin = gcd_i(n * es / 4, es == 8 ? 32 : 32) > (es == 8 ? 4 : 2) ? 1 : 0;
+    const int ldi = padin ? (n | 1) : n;
+    const size_t in_bytes = ((size_t)32 * ldi * es + 15) & ~(size_t)15;
+    p.smem = 4 * (p.nin * in_bytes + (size_t)32 * p.nout * es);
+    int minb = (int)((200 * 1024) / (p.smem + 1024));
+    const int want = mode == B2K_GEN_RNE || mode == B2K_GEN_GRAVLOAD || mode == B2K_GEN_ITORQUE ? (es == 8 ? 4 : 6) : (es == 8 ? 2 : 3);
+    if (minb > want) minb = want;
+    if (minb < 1) minb = 1;
+    if (const char *e = getenv("B2K_RNE_SPEC_MINB")) minb = atoi(e) > 0 ? atoi(e) : minb;
+    auto D = [&](const char *k, long long v) { defs.push_back(std::string("-D") + k + "=" + std::to_string(v)); };
+    defs.push_back(std::string("-DREAL=") + (es == 8 ? "double" : "float"));
+    D("REAL_IS_F64", es == 8);
+    D("NJ", n); D("NC", p.nc); D("MODE", mode); D("NIN", p.nin); D("NOUT", p.nout); D("NRES", p.nres); D("PADIN", padin); D("MINB", minb);
+    // in1 / in2 of the generated function are the second / third input rows; the RNE proper names them qd / qdd
+    return std::string(kPrologue) + g.source + kKernel;
+}
+
+void compile(const b2k_rne_s *r, const Key &key, Program &p)
+{
+    const int mode = std::get<0>(key), dtype = std::get<1>(key);
+    Nvrtc *N = nvrtc();
+    if (!N->h) { p.why = N->why; return; }
+    std::vector<std::string> defs;
+    const std::string src = build_source(r, mode, dtype, std::get<2>(key), std::get<3>(key), p, defs);
+    if (src.empty()) return;
+    std::vector<std::string> opts = {"--gpu-architecture=sm_100a", "--std=c++17"};
+    if (getenv("B2K_RNE_SPEC_LINEINFO")) opts.push_back("-lineinfo");
+    for (auto &d : defs) opts.push_back(d);
+    std::vector<const char *> copts;
+    for (auto &s : opts) copts.push_back(s.c_str());
+    nvrtcProgram prog;
+    nvrtcResult rc = N->CreateProgram(&prog, src.c_str(), "b2k_rne_spec.cu", 0, nullptr, nullptr);
+    if (rc != NVRTC_SUCCESS) { p.why = std::string("nvrtcCreateProgram: ") + N->GetErrorString(rc); return; }
+    rc = N->CompileProgram(prog, (int)copts.size(), copts.data());
+    if (rc != NVRTC_SUCCESS) {
+        size_t ls = 0;
+        N->GetProgramLogSize(prog, &ls);
+        std::string log(ls, '\0');
+        if (ls) N->GetProgramLog(prog, &log[0]);
+        p.why = std::string("nvrtcCompileProgram: ") + N->GetErrorString(rc) + "\n" + log.substr(0, 1500);
+        N->DestroyProgram(&prog);
+        return;
+    }
+    size_t cs = 0;
+    N->GetCUBINSize(prog, &cs);
+    p.cubin.assign(cs, '\0');
+    N->GetCUBIN(prog, &p.cubin[0]);
+    N->DestroyProgram(&prog);
+    if (const char *dir = getenv("B2K_RNE_SPEC_DUMP")) { // for cuobjdump / offline inspection
+        char name[512];
+        snprintf(name, sizeof(name), "%s/rne_spec_m%d_%s_n%d_g%d_f%d", dir, mode, dtype == B2K_F64 ? "f64" : "f32", r->n, std::get<2>(key), std::get<3>(key));
+        if (FILE *f = fopen((std::string(name) + ".cubin").c_str(), "wb")) { fwrite(p.cubin.data(), 1, p.cubin.size(), f); fclose(f); }
+        if (FILE *f = fopen((std::string(name) + ".cu").c_str(), "w")) {
+            for (auto &d : defs) fprintf(f, "// %s\n", d.c_str());
+            fputs(src.c_str(), f);
+            fclose(f);
+        }
+    }
+    p.ok = true;
+}
+
+Program *get_program(const b2k_rne_s *r, const Key &key)
+{
+    SpecCache *c = static_cast<SpecCache *>(r->spec);
+    if (!c) return nullptr;
+    std::lock_guard<std::mutex> lk(c->mu);
+    auto it = c->progs.find(key);
+    if (it == c->progs.end()) {
+        Program &p = c->progs[key];
+        compile(r, key, p);
+        if (!p.ok && getenv("B2K_VERBOSE")) fprintf(stderr, "b2kin: RNE specialisation unavailable (%s); using the generic kernel\n", p.why.c_str());
+        return &p;
+    }
+    return &it->second;
+}
+
+int get_function(Program *p, CUfunction *out)
+{
+    Driver *D = driver();
+    if (!D->h) { p->ok = false; p->why = D->why; return -1; }
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+    auto it = p->fn.find(dev);
+    if (it != p->fn.end()) { *out = it->second; return 0; }
+    cudaFree(0); // make sure the runtime's primary context exists and is current on this thread
+    CUmodule mod;
+    CUresult rc = D->ModuleLoadData(&mod, p->cubin.data());
+    const char *es = nullptr;
+    if (rc != CUDA_SUCCESS) { D->GetErrorString(rc, &es); p->ok = false; p->why = std::string("cuModuleLoadData: ") + (es ? es : "?"); return -1; }
+    CUfunction fn;
+    rc = D->ModuleGetFunction(&fn, mod, "k_rne_spec");
+    if (rc != CUDA_SUCCESS) { D->GetErrorString(rc, &es); p->ok = false; p->why = std::string("cuModuleGetFunction: ") + (es ? es : "?"); return -1; }
+    if (p->smem > 48 * 1024) {
+        rc = D->FuncSetAttribute(fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)p->smem);
+        if (rc != CUDA_SUCCESS) { D->GetErrorString(rc, &es); p->ok = false; p->why = std::string("cuFuncSetAttribute: ") + (es ? es : "?"); return -1; }
+    }
+    D->FuncGetAttribute(&p->regs, CU_FUNC_ATTRIBUTE_NUM_REGS, fn);
+    p->fn[dev] = fn;
+    *out = fn;
+    return 0;
+}
+
+template <typename real>
+struct SpecParams { // byte image of the kernel's SpecP for NC constants (built in a buffer)
+};
+
+int grav_mask_of(const double *g)
+{
+    int m = 0;
+    if (g)
+        for (int k = 0; k < 3; k++)
+            if (g[k] != 0.0) m |= 1 << k;
+    return m;
+}
+
+} // namespace
+
+void b2k_rne_spec_attach(b2k_rne_s *r) { r->spec = new SpecCache(); }
+void b2k_rne_spec_detach(b2k_rne_s *r)
+{
+    delete static_cast<SpecCache *>(r->spec);
+    r->spec = nullptr;
+}
+
+// Tries the specialised kernel for the first (N / 32) * 32 rows.  Returns the number of rows it served (0 when the
+// call must go to the generic kernel entirely), or a negative b2k_status when B2K_RNE_SPEC=2 demands it and it failed.
+long long b2k_rne_spec_launch(const b2k_rne_s *r, int mode, int dtype, const void *in0, const void *in1, const void *in2,
+                              long long nrows, const double *grav, const double *fext, void *out, cudaStream_t st)
+{
+    const int setting = spec_setting();
+    if (setting == 0 || !r->spec) return 0;
+    auto refuse = [&](const std::string &why) -> long long {
+        if (setting == 2) { b2k_set_error("RNE specialisation required (B2K_RNE_SPEC=2) but unavailable: %s", why.c_str()); return B2K_ERR_INVALID; }
+        return 0;
+    };
+    for (int j = 0; j < r->n; j++)
+        if ((int)r->L[j][4] != 0) return refuse("prismatic joint");
+    const long long ntiles = nrows / 32;
+    if (ntiles == 0) return 0;
+    const uintptr_t al = (uintptr_t)in0 | (uintptr_t)(in1 ? in1 : in0) | (uintptr_t)(in2 ? in2 : in0) | (uintptr_t)out;
+    if (al & 15) return refuse("arrays are not 16-byte aligned");
+    int has_fext = 0;
+    if (mode == B2K_GEN_RNE && fext)
+        for (int k = 0; k < 6; k++) has_fext |= (fext[k] != 0.0);
+    const bool uses_grav = mode == B2K_GEN_RNE || mode == B2K_GEN_GRAVLOAD || mode == B2K_GEN_ACCEL;
+    const Key key(mode, dtype, uses_grav ? grav_mask_of(grav) : 0, has_fext);
+    Program *p = get_program(r, key);
+    if (!p || !p->ok) return refuse(p ? p->why : "no cache");
+    CUfunction fn;
+    {
+        SpecCache *c = static_cast<SpecCache *>(r->spec);
+        std::lock_guard<std::mutex> lk(c->mu);
+        if (get_function(p, &fn)) return refuse(p->why);
+    }
+    // parameter block: SpecP { real C[NC]; real grav[3]; real fext[6]; real offset[NJ]; TrigC trig; }
+    const int es = dtype == B2K_F64 ? 8 : 4;
+    const int nreal = p->nc + 3 + 6 + r->n + 18;
+    std::vector<unsigned char> pb((size_t)nreal * es);
+    auto put = [&](int idx, double v) {
+        if (es == 8) memcpy(&pb[(size_t)idx * 8], &v, 8);
+        else { float f = (float)v; memcpy(&pb[(size_t)idx * 4], &f, 4); }
+    };
+    int o = 0;
+    for (int k = 0; k < p->nc; k++) put(o++, p->consts[k]);
+    for (int k = 0; k < 3; k++) put(o++, (uses_grav && grav) ? grav[k] : 0.0);
+    for (int k = 0; k < 6; k++) put(o++, (has_fext && fext) ? fext[k] : 0.0);
+    for (int j = 0; j < r->n; j++) put(o++, r->L[j][5]);
+    if (es == 8) {
+        TrigC<double> t;
+        b2k_fill_trig<double>(t);
+        memcpy(&pb[(size_t)o * 8], &t, sizeof(t));
+    } else {
+        TrigC<float> t;
+        b2k_fill_trig<float>(t);
+        memcpy(&pb[(size_t)o * 4], &t, sizeof(t));
+    }
+    long long nt = ntiles;
+    void *args[6] = {pb.data(), (void *)&in0, (void *)&in1, (void *)&in2, (void *)&out, (void *)&nt};
+    const unsigned grid = (unsigned)((ntiles + 3) / 4);
+    CUresult rc = driver()->LaunchKernel(fn, grid, 1, 1, 128, 1, 1, (unsigned)p->smem, (CUstream)st, args, nullptr);
+    if (rc != CUDA_SUCCESS) {
+        const char *es2 = nullptr;
+        driver()->GetErrorString(rc, &es2);
+        b2k_set_error("cuLaunchKernel(k_rne_spec): %s", es2 ? es2 : "?");
+        return B2K_ERR_CUDA;
+    }
+    b2k_count_launch();
+    return ntiles * 32;
+}
+
+// ------------------------------------------------------------------ C ABI: introspection (tests, bench, DESIGN numbers)
+extern "C" int b2k_rne_codegen(b2k_rne_t r, int mode, int grav_mask, int has_fext, char *src, int64_t src_cap, double *consts,
+                               int32_t consts_cap, int32_t *n_consts, int32_t *counts)
+{
+    if (!r) { b2k_set_error("b2k_rne_codegen: rne handle is NULL"); return B2K_ERR_INVALID; }
+    b2k_gen_opts o;
+    o.mode = mode; o.grav_mask = grav_mask; o.has_fext = has_fext;
+    b2k_gen_out g;
+    if (b2k_rne_generate(r, o, g)) { b2k_set_error("b2k_rne_codegen: %s", g.error.c_str()); return B2K_ERR_INVALID; }
+    if (n_consts) *n_consts = (int32_t)g.consts.size();
+    if (counts) { counts[0] = g.n_mul; counts[1] = g.n_fma; counts[2] = g.n_add; }
+    if (src) {
+        if ((int64_t)g.source.size() + 1 > src_cap) { b2k_set_error("b2k_rne_codegen: source needs %zu bytes", g.source.size() + 1); return B2K_ERR_INVALID; }
+        memcpy(src, g.source.c_str(), g.source.size() + 1);
+    }
+    if (consts) {
+        if ((int32_t)g.consts.size() > consts_cap) { b2k_set_error("b2k_rne_codegen: %zu constants", g.consts.size()); return B2K_ERR_INVALID; }
+        memcpy(consts, g.consts.data(), g.consts.size() * sizeof(double));
+    }
+    return B2K_OK;
+}
+
+extern "C" int b2k_rne_spec_info(b2k_rne_t r, int mode, int dtype, const double *grav, int has_fext, char *buf, int64_t cap)
+{
+    if (!r || !buf || cap < 1) { b2k_set_error("b2k_rne_spec_info: bad arguments"); return B2K_ERR_INVALID; }
+    std::string s;
+    if (spec_setting() == 0) s = "generic (B2K_RNE_SPEC=0)";
+    else {
+        bool pris = false;
+        for (int j = 0; j < r->n; j++) pris = pris || ((int)r->L[j][4] != 0);
+        if (pris) s = "generic (prismatic joint)";
+        else {
+            const bool uses_grav = mode == B2K_GEN_RNE || mode == B2K_GEN_GRAVLOAD || mode == B2K_GEN_ACCEL;
+            Program *p = get_program(r, Key(mode, dtype, uses_grav ? grav_mask_of(grav) : 0, has_fext));
+            if (!p || !p->ok) s = std::string("generic (") + (p ? p->why : "no cache") + ")";
+            else {
+                char t[256];
+                snprintf(t, sizeof(t), "k_rne_spec<%s,n=%d,mode=%d>: %d mul + %d fma + %d add per row, %d constants, %d regs, %zu B smem/block",
+                         dtype == B2K_F64 ? "double" : "float", r->n, mode, p->n_mul, p->n_fma, p->n_add, p->nc, p->regs, p->smem);
+                s = t;
+            }
+        }
+    }
+    snprintf(buf, (size_t)cap, "%s", s.c_str());
+    return B2K_OK;
+}

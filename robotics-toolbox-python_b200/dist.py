@@ -12,6 +12,59 @@ from __future__ import annotations
 from typing import List, Tuple
 
 
+def _parse_cpulist(text: str):
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        if "-" in part:
+            a, b = part.split("-")
+            cpus.update(range(int(a), int(b) + 1))
+        else:
+            cpus.add(int(part))
+    return cpus
+
+
+def gpu_numa_node(device_index: int):
+    """NUMA node of the host bridge a GPU hangs off (sysfs), or None when the platform does not say."""
+    import os
+
+    try:
+        import torch
+
+        p = torch.cuda.get_device_properties(device_index)
+        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as f:
+            node = int(f.read())
+        return node if node >= 0 and os.path.isdir(f"/sys/devices/system/node/node{node}") else None
+    except Exception:
+        return None
+
+
+def bind_to_gpu_numa(device_index: int):
+    """Restrict this process to the CPUs of the NUMA node next to its GPU.
+
+    One process per GPU moves ~55 GB/s of results into host memory on the end-to-end path; with eight
+    ranks on a two-socket box the pinned buffers must sit on the socket the GPU's PCIe root belongs to, or
+    half of the traffic crosses the inter-socket link.  Linux places pages on the node of the thread that
+    first touches them, so narrowing the CPU affinity BEFORE the pinned buffers are allocated is enough
+    (no libnuma needed).  Returns {"node", "cpus"} or None when nothing was changed."""
+    import os
+
+    node = gpu_numa_node(device_index)
+    if node is None:
+        return None
+    try:
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = _parse_cpulist(f.read()) & set(os.sched_getaffinity(0))
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return {"node": node, "cpus": len(cpus)}
+    except Exception:
+        return None
+
+
 def shard_bounds(n_rows: int, world_size: int, rank: int) -> Tuple[int, int]:
     """Contiguous, balanced [lo, hi) row range of `rank`; the first n_rows % world_size ranks get
     one extra row."""

@@ -368,3 +368,42 @@ def test_plain_c_program_links_and_fails_loudly_without_a_gpu(tmp_path):
         assert r.returncode == 0 and len(r.stdout.strip().splitlines()) == 4
     else:
         assert r.returncode == 2 and "CUDA error" in r.stderr and r.stdout == ""
+
+
+def test_dh_kinematic_setters_invalidate_the_chain_and_the_rne_table():
+    """Changing a DH parameter after construction must rebuild the link's ETs, drop the robot's cached ETS
+    (whose compiled chain handle goes with it) and mark the packed RNE table dirty -- the reference's
+    @_listen_dyn on theta / d / a / alpha / sigma / mdh / offset (DHLink.py:448-563)."""
+    r = rtb.models.Puma560()
+    e0 = r.ets()
+    d0 = e0.describe()
+    assert r.ets() is e0  # cached
+    r._dynchanged = False
+    r.links[2].d = 0.2
+    assert r._ets_cache is None and r._dynchanged
+    e1 = r.ets()
+    assert e1 is not e0
+    T0 = np.asarray(d0["T"]).reshape(-1, 4, 4)
+    T1 = np.asarray(e1.describe()["T"]).reshape(-1, 4, 4)
+    assert T0.shape == T1.shape and not np.array_equal(T0, T1)
+    assert np.isclose(T1[:, 2, 3], 0.2).any() and not np.isclose(T0[:, 2, 3], 0.2).any()
+    assert r._pack_rne()[24 * 2 + 3] == 0.2
+    # a parameter going to zero drops its elementary transform (DHLink._to_ets omits zero terms)
+    m_before = len(np.asarray(r.ets().describe()["isjoint"]))
+    r.links[2].a = 0.0
+    assert len(np.asarray(r.ets().describe()["isjoint"])) == m_before - 1
+    # qlim feeds the joint ET
+    r.links[0].qlim = [-1.0, 1.0]
+    assert np.allclose(r.qlim[:, 0], [-1.0, 1.0])
+    ql = np.asarray(r.ets().describe()["qlim"]).reshape(-1, 2)
+    assert (np.isclose(ql[:, 0], -1.0) & np.isclose(ql[:, 1], 1.0)).any()
+    # links that are not attached to a robot simply rebuild their own ETS
+    l = rtb.RevoluteDH(d=0.1, a=0.2, alpha=0.3)
+    n0 = len(l.ets)
+    l.alpha = 0.0
+    assert len(l.ets) == n0 - 1
+
+
+def test_numa_helpers_are_safe_without_a_gpu():
+    assert rtb.dist._parse_cpulist("0-2,5,7-8\n") == {0, 1, 2, 5, 7, 8}
+    assert rtb.dist.bind_to_gpu_numa(0) in (None,) or isinstance(rtb.dist.bind_to_gpu_numa(0), dict)
