@@ -140,7 +140,10 @@ int b2k_fkine_jacobe(b2k_chain_t chain, int dtype, const void *q, int64_t N, int
  *            (IKSolver.solve reuses one set of restarts for a whole trajectory, IK.py:222-272)
  * Outputs (device): q_out (N,n), success/iterations/searches int32 (N), residual (N) in dtype
  * -- the tuple IK_LM_c returns (fknm.cpp:516), one entry per target.
- * Requires jindex == 0..n-1 in chain order (the reference C++ loop assumes it, ik.cpp:34-35).
+ * q0 and q_out hold the chain's n joints in chain order, i.e. q[ets.jindices] -- exactly what the reference's Python
+ * solver hands back for an ETS whose jindices are not 0..n-1 (it pads q to max_jindex + 1 internally, IK.py:216-240,
+ * and returns q[ets.jindices], IK.py:346), so sub-chains of a larger robot are served as they are (the reference's
+ * C++ loop assumes dense jindices, ik.cpp:34-35).  Two joints sharing one jindex are rejected.
  * method = B2K_IK_NR / B2K_IK_GN select fknm.IK_NR_c / IK_GN_c (fknm.cpp:164-392) and, with the
  * Python semantics, IK_NR.step / IK_GN.step (IK.py:714-762, 1154-1219; both take pinv(J) e there).
  * The pseudo-inverse step is evaluated as Jw^T (Jw Jw^T + d^2)^-1 ew (6x6 Cholesky); pinv = False
@@ -207,6 +210,10 @@ int b2k_rne_accel(b2k_rne_t rne, int dtype, const void *q, const void *qd, const
  * 63 = all, 7 = translational, 56 = rotational); |det Ja| when Ja is square. */
 int b2k_hessian(int dtype, int n, const void *J, int64_t N, void *H, void *stream);
 int b2k_manipulability(int dtype, int n, const void *J, int64_t N, uint32_t axes_mask, void *m, void *stream);
+/* The singular-value measures of ETS.manipulability (ETS.py:1789-1796) over the Cartesian rows in axes_mask:
+ * kind 0 "minsingular" = numpy svd(Ja)[-1] (the smallest of min(rows, n) singular values), kind 1 "invcondition" =
+ * 1 / numpy.linalg.cond(Ja) = s_min / s_max.  One-sided Jacobi SVD per row, in registers / local memory. */
+int b2k_manipulability_svd(int dtype, int n, const void *J, int64_t N, uint32_t axes_mask, int kind, void *m, void *stream);
 /* b2k_jacob_dot: Jd (N,6,n) = sum_i H[i] qd[i], the Jacobian time derivative of Robot.jacob0_dot
  * (Robot.py:964-1099, representation None: np.tensordot(hessian0, qd, (0,0))), from J (N,6,n) and qd (N,n)
  * without materialising the Hessian.

@@ -355,3 +355,16 @@ def trapezoidal(q0, qf, t, V=None):
             pk, pdk, pddk = qf, 0, 0
         p.append(pk); pd.append(pdk); pdd.append(pddk)
     return t, np.array(p), np.array(pd), np.array(pdd), tb
+
+
+def manip_svd(J, axes=(True,) * 6, kind="minsingular"):
+    """ETS.py:1789-1796: minsingular = svd(Ja)[-1]; invcondition = 1 / cond(Ja)  (numpy, as the reference)."""
+    J = np.asarray(J, dtype=np.float64)
+    if J.ndim == 2:
+        J = J[None]
+    ax = np.asarray(axes, dtype=bool)
+    out = np.empty(J.shape[0])
+    for k, Jk in enumerate(J):
+        s = np.linalg.svd(Jk[ax, :], compute_uv=False)
+        out[k] = s[-1] if kind == "minsingular" else (s[-1] / s[0] if s[0] > 0 else 0.0)
+    return out

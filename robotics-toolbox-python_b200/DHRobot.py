@@ -272,6 +272,22 @@ class DHRobot:
                                  _lib.dptr(fx), B.ptr(tau), B.stream_ptr(qt)))
         return tau[0] if single else tau
 
+    _RNE_MODES = {"rne": 0, "inertia": 1, "gravload": 2, "itorque": 3, "coriolis": 4, "accel": 5}
+
+    def rne_kernel_info(self, op="rne", dtype=np.float64, gravity=None, fext=None) -> str:
+        """Which kernel serves `op` for this robot: the robot-specialised one (generated from the link table and
+        compiled with NVRTC at first use; the line lists its multiply / FMA / add count per row, registers and
+        shared memory) or the pre-compiled generic one, with the reason."""
+        if self._rne_ob is None or self._dynchanged:
+            self.delete_rne()
+            self._init_rne()
+        g = self._gravity if gravity is None else np.asarray(gravity, dtype=np.float64).reshape(3)
+        g = np.ascontiguousarray(-(self._base[:3, :3].T @ g))
+        buf = C.create_string_buffer(2048)
+        _lib.check(_lib.lib().b2k_rne_spec_info(self._rne_ob, self._RNE_MODES[op], B.code(np.dtype(dtype)), _lib.dptr(g),
+                                                int(fext is not None and np.any(np.asarray(fext) != 0)), buf, 2048))
+        return buf.value.decode()
+
     # ---- dynamics built on the recursion (reference DynamicsMixin, Dynamics.py; SURVEY 8f-1)
     def _dyn(self, fn_name, ins, out_tail, gravity=None, use_gravity=False, dtype=None):
         """Shared front end of the fan-out kernels: every input (N,n) or (n,), one launch."""

@@ -385,10 +385,11 @@ class ETS:
         return self._hess(q, Je, tool, self.jacobe, dtype)
 
     def manipulability(self, q=None, J=None, method: str = "yoshikawa", axes="all", dtype=None):
-        """Yoshikawa manipulability index, scalar or (N,) (reference ETS.manipulability, ETS.py:1687-1820;
-        only the default `yoshikawa` measure is on the accelerated path)."""
-        if method != "yoshikawa":
-            raise NotImplementedError("only method='yoshikawa' is accelerated (minsingular / invcondition need an SVD)")
+        """Manipulability measure, scalar or (N,) (reference ETS.manipulability, ETS.py:1687-1820): "yoshikawa"
+        sqrt|det(Ja Ja^T)|, "minsingular" the smallest singular value of Ja, "invcondition" 1 / cond(Ja); Ja = the
+        rows of jacob0 selected by `axes`."""
+        if method not in ("yoshikawa", "minsingular", "invcondition"):
+            raise ValueError("Invalid method chosen")
         if isinstance(axes, str):
             mask = {"all": 63, "trans": 7, "rot": 56}.get(axes)
             if mask is None:
@@ -409,7 +410,11 @@ class ETS:
         Jd = (Jd.reshape(1, 6, -1) if single else Jd).contiguous()
         N = Jd.shape[0]
         m = B.empty((N,), dt, like=Jd)
-        _lib.check(_lib.lib().b2k_manipulability(B.code(dt), self.n, B.ptr(Jd), N, mask, B.ptr(m), B.stream_ptr(Jd)))
+        if method == "yoshikawa":
+            _lib.check(_lib.lib().b2k_manipulability(B.code(dt), self.n, B.ptr(Jd), N, mask, B.ptr(m), B.stream_ptr(Jd)))
+        else:
+            _lib.check(_lib.lib().b2k_manipulability_svd(B.code(dt), self.n, B.ptr(Jd), N, mask, int(method == "invcondition"),
+                                                         B.ptr(m), B.stream_ptr(Jd)))
         if host:
             m = B.to_host(m)
         return float(m[0]) if single else m

@@ -25,4 +25,17 @@ from . import trajectory  # noqa: F401
 from .trajectory import Trajectory, jtraj, lspb, mtraj, quintic, trapezoidal  # noqa: F401
 from .p_servo import angle_axis, p_servo  # noqa: F401
 
+
+
+def rne_kernel_info(robot, op="rne", dtype="float64") -> str:
+    """One line describing the kernel that serves `robot.<op>` (see DHRobot.rne_kernel_info)."""
+    import numpy as _np
+
+    return robot.rne_kernel_info(op, _np.dtype(dtype))
+
+
+def rne_kernel_name(robot) -> str:
+    return rne_kernel_info(robot).split(":")[0]
+
+
 __version__ = "0.1.0"

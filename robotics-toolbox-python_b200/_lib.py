@@ -53,6 +53,7 @@ _PROTOS = {
     "b2k_rne_accel": (C.c_int, [vp, C.c_int, vp, vp, vp, i64, dp, vp, vp]),
     "b2k_hessian": (C.c_int, [C.c_int, C.c_int, vp, i64, vp, vp]),
     "b2k_manipulability": (C.c_int, [C.c_int, C.c_int, vp, i64, C.c_uint32, vp, vp]),
+    "b2k_manipulability_svd": (C.c_int, [C.c_int, C.c_int, vp, i64, C.c_uint32, C.c_int, vp, vp]),
     "b2k_jacob_dot": (C.c_int, [C.c_int, C.c_int, vp, vp, i64, vp, vp]),
     "b2k_jacobm": (C.c_int, [C.c_int, C.c_int, vp, i64, C.c_uint32, vp, vp]),
     "b2k_angle_axis": (C.c_int, [C.c_int, vp, vp, i64, i64, vp, vp]),

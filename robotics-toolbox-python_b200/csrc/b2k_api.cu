@@ -455,8 +455,11 @@ extern "C" int b2k_ik_lm(b2k_chain_t c, int dtype, const void *Tep, int64_t N, c
     if (!c) { b2k_set_error("%s: chain handle is NULL", fn); return B2K_ERR_INVALID; }
     if (dtype != B2K_F32 && dtype != B2K_F64) { b2k_set_error("%s: dtype must be B2K_F32 or B2K_F64", fn); return B2K_ERR_INVALID; }
     if (N < 0) { b2k_set_error("%s: N is negative", fn); return B2K_ERR_INVALID; }
-    if (!c->dense_jindex) {
-        b2k_set_error("%s: the chain's jindices must be 0..n-1 in chain order (the reference C++ solver assumes it, ik.cpp:34-35)", fn);
+    // The solver works on the chain's own joint vector (q0 and q_out hold the n joints in chain order, i.e.
+    // q[ets.jindices] -- what IKSolver.solve hands back, IK.py:216-240,346); a sub-chain of a larger robot
+    // (jindices 3..6, say) is therefore served as it is.  Two joints driven by one coordinate are not.
+    if (!c->distinct_jindex) {
+        b2k_set_error("%s: two joints of the chain share a jindex (coupled joints are outside the solver's model)", fn);
         return B2K_ERR_INVALID;
     }
     if (ilimit < 1 || slimit < 1) { b2k_set_error("%s: ilimit and slimit must be >= 1", fn); return B2K_ERR_INVALID; }

@@ -112,6 +112,10 @@ extern "C" int b2k_chain_create(int m, const int32_t *isjoint, const int32_t *ax
             j++;
         }
     }
+    c->distinct_jindex = 1;
+    for (int a = 0; a < n; a++)
+        for (int b = a + 1; b < n; b++)
+            if (c->jidx[a] == c->jidx[b]) c->distinct_jindex = 0;
     memcpy(c->A[n], acc, sizeof(acc)); // tail constant
     c->dh_like = c->all_rz;
     for (int k = 1; k < n && c->dh_like; k++) {

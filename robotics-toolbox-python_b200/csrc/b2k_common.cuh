@@ -95,6 +95,7 @@ struct b2k_chain_s {
     int all_rz;
     int dh_like;      // all_rz and every inter-joint constant A_1..A_{n-1} has the Rx form (or is a pure translation)
     int dense_jindex; // jidx[j] == j for all j
+    int distinct_jindex; // no two joints read the same column of q
 };
 
 struct b2k_rne_s {

@@ -180,6 +180,60 @@ __global__ void __launch_bounds__(128) k_jacobm(const real *__restrict__ J, long
     }
 }
 
+// Singular-value measures of ETS.manipulability (ETS.py:1789-1796): "minsingular" = the smallest singular value of
+// Ja = the selected rows of J (numpy svd(Ja)[-1]: min(rows, n) values), "invcondition" = 1 / cond(Ja) = s_min / s_max.
+// One lane per row; one-sided (Hestenes) Jacobi on the thinner orientation of Ja (columns = min(rows, n) <= 6,
+// length max(rows, n) <= 10): plane rotations make the columns mutually orthogonal, their norms are the singular
+// values -- accurate to rounding even next to a singularity, where squaring into the Gram matrix would lose half the digits.
+template <typename real, int N>
+__global__ void __launch_bounds__(128) k_singular(const real *__restrict__ J, long long nrows, unsigned axes_mask, int kind,
+                                                  real *__restrict__ m)
+{
+    const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= nrows) return;
+    int sel[6], na = 0;
+    for (int k = 0; k < 6; k++)
+        if (axes_mask & (1u << k)) sel[na++] = k;
+    const real *j = J + row * (6 * N);
+    const bool tall = na >= N;          // Ja itself is tall (or square): orthogonalise its N columns
+    const int p = tall ? na : N, d = tall ? N : na;
+    real W[10 * 6];                     // W[r * d + c], p x d
+    for (int r = 0; r < p; r++)
+        for (int c = 0; c < d; c++) W[r * d + c] = tall ? j[sel[r] * N + c] : j[sel[c] * N + r];
+    const real eps = sizeof(real) == 8 ? (real)1e-15 : (real)1e-6;
+    for (int sweep = 0; sweep < 30; sweep++) {
+        bool rotated = false;
+        for (int a = 0; a < d - 1; a++)
+            for (int b = a + 1; b < d; b++) {
+                real al = 0, be = 0, ga = 0;
+                for (int r = 0; r < p; r++) {
+                    const real x = W[r * d + a], y = W[r * d + b];
+                    al = fma(x, x, al); be = fma(y, y, be); ga = fma(x, y, ga);
+                }
+                if (fabs(ga) <= eps * sqrt(al * be) || ga == 0) continue;
+                rotated = true;
+                const real zeta = (be - al) / (2 * ga);
+                const real t = (zeta >= 0 ? (real)1 : (real)-1) / (fabs(zeta) + sqrt(1 + zeta * zeta));
+                const real cs = 1 / sqrt(1 + t * t), sn = cs * t;
+                for (int r = 0; r < p; r++) {
+                    const real x = W[r * d + a], y = W[r * d + b];
+                    W[r * d + a] = cs * x - sn * y;
+                    W[r * d + b] = sn * x + cs * y;
+                }
+            }
+        if (!rotated) break;
+    }
+    real smin = 0, smax = 0;
+    for (int c = 0; c < d; c++) {
+        real nn = 0;
+        for (int r = 0; r < p; r++) nn = fma(W[r * d + c], W[r * d + c], nn);
+        nn = sqrt(nn);
+        if (c == 0 || nn < smin) smin = nn;
+        if (c == 0 || nn > smax) smax = nn;
+    }
+    m[row] = kind == 0 ? smin : (smax > 0 ? smin / smax : (real)0);
+}
+
 template <typename real>
 static int extra_launch(int what, int n, const void *J, long long N, unsigned axes_mask, void *out, cudaStream_t st,
                         const void *aux = nullptr)
@@ -194,6 +248,8 @@ static int extra_launch(int what, int n, const void *J, long long N, unsigned ax
             else k_jacob_dot<real, NN><<<(unsigned)blocks, 256, 0, st>>>((const real *)J, (const real *)aux, N, (real *)out); \
         } else if (what == 3) {                                                                                       \
             k_jacobm<real, NN><<<(unsigned)((N + 127) / 128), 128, 0, st>>>((const real *)J, N, axes_mask, (real *)out); \
+        } else if (what == 4 || what == 5) {                                                                          \
+            k_singular<real, NN><<<(unsigned)((N + 127) / 128), 128, 0, st>>>((const real *)J, N, axes_mask, what - 4, (real *)out); \
         } else {                                                                                                      \
             k_yoshikawa<real, NN><<<(unsigned)((N + 127) / 128), 128, 0, st>>>((const real *)J, N, axes_mask, (real *)out); \
         }                                                                                                             \
@@ -232,6 +288,18 @@ extern "C" int b2k_manipulability(int dtype, int n, const void *J, int64_t N, ui
                             : extra_launch<float>(1, n, J, N, axes_mask & 63u, m, (cudaStream_t)stream);
 }
 
+
+extern "C" int b2k_manipulability_svd(int dtype, int n, const void *J, int64_t N, uint32_t axes_mask, int kind, void *m, void *stream)
+{
+    if (N < 0 || (N > 0 && (!J || !m))) { b2k_set_error("b2k_manipulability_svd: bad arguments"); return B2K_ERR_INVALID; }
+    if (dtype != B2K_F32 && dtype != B2K_F64) { b2k_set_error("b2k_manipulability_svd: bad dtype"); return B2K_ERR_INVALID; }
+    if ((axes_mask & 63u) == 0) { b2k_set_error("b2k_manipulability_svd: no Cartesian axis selected"); return B2K_ERR_INVALID; }
+    if (kind != 0 && kind != 1) { b2k_set_error("b2k_manipulability_svd: kind must be 0 (minsingular) or 1 (invcondition)"); return B2K_ERR_INVALID; }
+    if (N == 0) return B2K_OK;
+    B2K_ON_DEVICE_OF(J);
+    return dtype == B2K_F64 ? extra_launch<double>(4 + kind, n, J, N, axes_mask & 63u, m, (cudaStream_t)stream)
+                            : extra_launch<float>(4 + kind, n, J, N, axes_mask & 63u, m, (cudaStream_t)stream);
+}
 
 extern "C" int b2k_jacob_dot(int dtype, int n, const void *J, const void *qd, int64_t N, void *Jd, void *stream)
 {

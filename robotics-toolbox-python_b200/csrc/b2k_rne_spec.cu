@@ -123,7 +123,8 @@ const char *kKernel = R"B2KSRC(
 #define LDI (PADIN ? (NJ | 1) : NJ)                  /* smem row stride of the input tiles, in reals */
 #define IN_BYTES ((32 * LDI * (int)sizeof(real) + 15) & ~15)
 #define OUT_BYTES (32 * NOUT * (int)sizeof(real))
-#define WARP_BYTES (NIN * IN_BYTES + OUT_BYTES)
+#define NBUF (TPW > 1 ? 2 : 1)                        /* input buffers per warp */
+#define WARP_BYTES (NBUF * NIN * IN_BYTES + OUT_BYTES)
 
 __device__ __forceinline__ void load_tile(real *s, const real *g, int lane)
 {
@@ -141,42 +142,59 @@ __device__ __forceinline__ void load_tile(real *s, const real *g, int lane)
 #endif
 }
 
-// One warp = one tile of 32 rows; one-shot grid of full tiles (the ragged tail of a batch goes to the generic kernel).
+// A warp owns TPW consecutive tiles of 32 rows (one-shot grid of full tiles; the ragged tail of a batch goes to the
+// generic kernel).  The input tiles are double-buffered: the cp.async loads of tile t+1 are issued before tile t is
+// computed, so a warp always has a tile's worth of reads in flight -- with one tile per warp and 16-20 resident warps
+// per SM the kernel was latency-bound (ncu: long-scoreboard the top stall, FP64 pipe 62 % busy; profiles/r02_rne64s_v1.txt).
 extern "C" __global__ void __launch_bounds__(128, MINB)
 k_rne_spec(const __grid_constant__ SpecP P, const real *__restrict__ in0, const real *__restrict__ in1,
            const real *__restrict__ in2, real *__restrict__ out, long long ntiles)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const long long tile = (long long)blockIdx.x * 4 + warp;
-    if (tile >= ntiles) return;
+    const long long tile0 = ((long long)blockIdx.x * 4 + warp) * TPW;
+    if (tile0 >= ntiles) return;
     unsigned char *wb = smem + (size_t)warp * WARP_BYTES;
-    real *s0 = reinterpret_cast<real *>(wb);
-    real *s1 = reinterpret_cast<real *>(wb + IN_BYTES);
-    real *s2 = reinterpret_cast<real *>(wb + 2 * IN_BYTES);
-    real *so = reinterpret_cast<real *>(wb + NIN * IN_BYTES);
-    const size_t row0 = (size_t)tile * 32;
-    load_tile(s0, in0 + row0 * NJ, lane);
-    if (NIN >= 2) load_tile(s1, in1 + row0 * NJ, lane);
-    if (NIN >= 3) load_tile(s2, in2 + row0 * NJ, lane);
+    real *so = reinterpret_cast<real *>(wb + NBUF * NIN * IN_BYTES);
+    auto load = [&](long long tile, int buf) {
+        unsigned char *b = wb + (size_t)buf * NIN * IN_BYTES;
+        const size_t row0 = (size_t)tile * 32;
+        load_tile(reinterpret_cast<real *>(b), in0 + row0 * NJ, lane);
+        if (NIN >= 2) load_tile(reinterpret_cast<real *>(b + IN_BYTES), in1 + row0 * NJ, lane);
+        if (NIN >= 3) load_tile(reinterpret_cast<real *>(b + 2 * IN_BYTES), in2 + row0 * NJ, lane);
 #if !PADIN
-    asm volatile("cp.async.wait_all;\n" ::: "memory");
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
 #endif
-    __syncwarp();
-    real th[NJ], st[NJ], ct[NJ], a1[NJ], a2[NJ];
+    };
+    load(tile0, 0);
+#pragma unroll 1
+    for (int t = 0; t < TPW; t++) {
+        const long long tile = tile0 + t;
+        if (tile >= ntiles) break;
+        const bool more = (t + 1 < TPW) && (tile + 1 < ntiles);
+        if (more) load(tile + 1, (t + 1) & (NBUF - 1));
+#if !PADIN
+        if (more) asm volatile("cp.async.wait_group 1;\n" ::: "memory");
+        else asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+#endif
+        __syncwarp();
+        const unsigned char *b = wb + (size_t)(t & (NBUF - 1)) * NIN * IN_BYTES;
+        const real *s0 = reinterpret_cast<const real *>(b);
+        const real *s1 = reinterpret_cast<const real *>(b + IN_BYTES);
+        const real *s2 = reinterpret_cast<const real *>(b + 2 * IN_BYTES);
+        real th[NJ], st[NJ], ct[NJ], a1[NJ], a2[NJ];
 #pragma unroll
-    for (int j = 0; j < NJ; j++) {
-        th[j] = s0[lane * LDI + j] + P.offset[j];
-        a1[j] = NIN >= 2 ? s1[lane * LDI + j] : (real)0;
-        a2[j] = NIN >= 3 ? s2[lane * LDI + j] : (real)0;
-    }
-    sincos_batch(th, P.trig, st, ct);
-    real res[NRES];
-    rne_row(P.C, P.grav, P.fext, st, ct, a1, a2, res);
+        for (int j = 0; j < NJ; j++) {
+            th[j] = s0[lane * LDI + j] + P.offset[j];
+            a1[j] = NIN >= 2 ? s1[lane * LDI + j] : (real)0;
+            a2[j] = NIN >= 3 ? s2[lane * LDI + j] : (real)0;
+        }
+        sincos_batch(th, P.trig, st, ct);
+        real res[NRES];
+        rne_row(P.C, P.grav, P.fext, st, ct, a1, a2, res);
 #if MODE == 5
-    // accel: res = [M (NJ x NJ, row i = torques for a unit acceleration of joint i) | torque - rne(q, qd, 0)].
-    // M is the joint-space inertia matrix (symmetric positive definite): LDL^T without pivoting, in registers.
-    {
+        // accel: res = [M (NJ x NJ, row i = torques for a unit acceleration of joint i) | torque - rne(q, qd, 0)].
+        // M is the joint-space inertia matrix (symmetric positive definite): LDL^T without pivoting, in registers.
         real d[NJ];
 #pragma unroll
         for (int c = 0; c < NJ; c++) {
@@ -204,23 +222,28 @@ k_rne_spec(const __grid_constant__ SpecP P, const real *__restrict__ in0, const 
         for (int r = NJ - 1; r >= 0; r--)
 #pragma unroll
             for (int k = r + 1; k < NJ; k++) y[r] = fma(-res[k * NJ + r], y[k], y[r]);
-#pragma unroll
-        for (int k = 0; k < NOUT; k++) so[lane * NOUT + k] = y[k];
-    }
+        const real *o = y;
 #else
-#pragma unroll
-    for (int k = 0; k < NOUT; k++) so[lane * NOUT + k] = res[k];
+        const real *o = res;
 #endif
-    // the staged tile is the exact image of the output block: one TMA bulk copy (shared -> global) by lane 0
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    __syncwarp();
-    if (lane == 0) {
-        const unsigned ss = (unsigned)__cvta_generic_to_shared(so);
-        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(out + row0 * NOUT), "r"(ss),
-                     "r"((unsigned)OUT_BYTES) : "memory");
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); // the copy reads this warp's shared memory
+        // the previous tile's bulk copy must have finished READING the stage before it is overwritten
+        if (t > 0) {
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            __syncwarp();
+        }
+#pragma unroll
+        for (int k = 0; k < NOUT; k++) so[lane * NOUT + k] = o[k];
+        // the staged tile is the exact image of the output block: one TMA bulk copy (shared -> global) by lane 0
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+            const unsigned ss = (unsigned)__cvta_generic_to_shared(so);
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(out + (size_t)tile * 32 * NOUT), "r"(ss),
+                         "r"((unsigned)OUT_BYTES) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
     }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); // the copies read this warp's shared memory
 }
 )B2KSRC";
 
@@ -300,7 +323,7 @@ struct Program {
     std::string why;          // why not, when !ok
     std::string cubin;        // sm_100a image
     std::vector<double> consts;
-    int nin = 1, nout = 0, nres = 0, nc = 1;
+    int nin = 1, nout = 0, nres = 0, nc = 1, tpw = 1;
     int n_mul = 0, n_fma = 0, n_add = 0, regs = 0;
     size_t smem = 0;
     std::map<int, CUfunction> fn; // per device
@@ -312,9 +335,9 @@ struct SpecCache {
 };
 
 int spec_setting()
-{
-    static const int v = [] { const char *e = getenv("B2K_RNE_SPEC"); return e ? atoi(e) : 1; }();
-    return v;
+{ // read at every call so a process can switch (tests run both paths)
+    const char *e = getenv("B2K_RNE_SPEC");
+    return e ? atoi(e) : 1;
 }
 
 int gcd_i(int a, int b) { return b ? gcd_i(b, a % b) : a; }
@@ -337,7 +360,10 @@ std::string build_source(const b2k_rne_s *r, int mode, int dtype, int grav_mask,
     const int padin = gcd_i(n * es / 4, es == 8 ? 32 : 32) > (es == 8 ? 4 : 2) ? 1 : 0;
     const int ldi = padin ? (n | 1) : n;
     const size_t in_bytes = ((size_t)32 * ldi * es + 15) & ~(size_t)15;
-    p.smem = 4 * (p.nin * in_bytes + (size_t)32 * p.nout * es);
+    int tpw = (mode == B2K_GEN_CORIOLIS) ? 1 : 2; // tiles per warp (double-buffered inputs when > 1)
+    if (const char *e = getenv("B2K_RNE_SPEC_TPW")) tpw = atoi(e) > 0 ? atoi(e) : tpw;
+    p.tpw = tpw;
+    p.smem = 4 * ((tpw > 1 ? 2 : 1) * p.nin * in_bytes + (size_t)32 * p.nout * es);
     int minb = (int)((200 * 1024) / (p.smem + 1024));
     const int want = mode == B2K_GEN_RNE || mode == B2K_GEN_GRAVLOAD || mode == B2K_GEN_ITORQUE ? (es == 8 ? 4 : 6) : (es == 8 ? 2 : 3);
     if (minb > want) minb = want;
@@ -346,7 +372,7 @@ std::string build_source(const b2k_rne_s *r, int mode, int dtype, int grav_mask,
     auto D = [&](const char *k, long long v) { defs.push_back(std::string("-D") + k + "=" + std::to_string(v)); };
     defs.push_back(std::string("-DREAL=") + (es == 8 ? "double" : "float"));
     D("REAL_IS_F64", es == 8);
-    D("NJ", n); D("NC", p.nc); D("MODE", mode); D("NIN", p.nin); D("NOUT", p.nout); D("NRES", p.nres); D("PADIN", padin); D("MINB", minb);
+    D("NJ", n); D("NC", p.nc); D("MODE", mode); D("NIN", p.nin); D("NOUT", p.nout); D("NRES", p.nres); D("PADIN", padin); D("MINB", minb); D("TPW", tpw);
     // in1 / in2 of the generated function are the second / third input rows; the RNE proper names them qd / qdd
     return std::string(kPrologue) + g.source + kKernel;
 }
@@ -512,7 +538,8 @@ long long b2k_rne_spec_launch(const b2k_rne_s *r, int mode, int dtype, const voi
     }
     long long nt = ntiles;
     void *args[6] = {pb.data(), (void *)&in0, (void *)&in1, (void *)&in2, (void *)&out, (void *)&nt};
-    const unsigned grid = (unsigned)((ntiles + 3) / 4);
+    const long long per_block = 4LL * p->tpw;
+    const unsigned grid = (unsigned)((ntiles + per_block - 1) / per_block);
     CUresult rc = driver()->LaunchKernel(fn, grid, 1, 1, 128, 1, 1, (unsigned)p->smem, (CUstream)st, args, nullptr);
     if (rc != CUDA_SUCCESS) {
         const char *es2 = nullptr;
@@ -561,8 +588,8 @@ extern "C" int b2k_rne_spec_info(b2k_rne_t r, int mode, int dtype, const double 
             if (!p || !p->ok) s = std::string("generic (") + (p ? p->why : "no cache") + ")";
             else {
                 char t[256];
-                snprintf(t, sizeof(t), "k_rne_spec<%s,n=%d,mode=%d>: %d mul + %d fma + %d add per row, %d constants, %d regs, %zu B smem/block",
-                         dtype == B2K_F64 ? "double" : "float", r->n, mode, p->n_mul, p->n_fma, p->n_add, p->nc, p->regs, p->smem);
+                snprintf(t, sizeof(t), "k_rne_spec<%s,n=%d,mode=%d>: %d mul + %d fma + %d add per row, %d constants, %d regs, %zu B smem/block, %d tiles/warp",
+                         dtype == B2K_F64 ? "double" : "float", r->n, mode, p->n_mul, p->n_fma, p->n_add, p->nc, p->regs, p->smem, p->tpw);
                 s = t;
             }
         }

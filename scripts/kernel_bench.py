@@ -114,7 +114,13 @@ for dt in (np.float64, np.float32):
     st = torch.cuda.current_stream().cuda_stream
     code = rtb._lib.F64 if dt == np.float64 else rtb._lib.F32
     g = np.ascontiguousarray(-puma.gravity)
-    report(f"rne_puma_{tag}", timeit(lambda i: L.b2k_rne(puma._rne_ob, code, bufs[i][0].data_ptr(), bufs[i][1].data_ptr(), bufs[i][2].data_ptr(), N, rtb._lib.dptr(g), None, tau.data_ptr(), st), nbuf), N, 24 * es)
+    for variant, setting in (("", "1"), ("_generic", "0")):  # robot-specialised (NVRTC) kernel vs the pre-compiled generic one
+        if variant and not want(f"rne_puma_{tag}{variant}"):
+            continue
+        os.environ["B2K_RNE_SPEC"] = setting
+        report(f"rne_puma_{tag}{variant}", timeit(lambda i: L.b2k_rne(puma._rne_ob, code, bufs[i][0].data_ptr(), bufs[i][1].data_ptr(), bufs[i][2].data_ptr(), N, rtb._lib.dptr(g), None, tau.data_ptr(), st), nbuf), N, 24 * es,
+               {"kernel": rtb.rne_kernel_info(puma, "rne", dt)})
+    os.environ["B2K_RNE_SPEC"] = "1"
     del bufs, tau
 
 # dynamics fan-outs over the RNE recursion: Puma560, fp64
@@ -140,9 +146,13 @@ if want("dyn_"):
         ("dyn_accel_puma_f64", lambda i: L.b2k_rne_accel(h, F, qd_.data_ptr(), v_.data_ptr(), t_.data_ptr(), Nd, rtb._lib.dptr(g), vo.data_ptr(), st), 24 * 8, 7),
     ]
     for name, fn, bpr, nrec in cases:
-        if want(name):
-            ms = timeit(fn, 1)
-            report(name, ms, Nd, bpr, {"recursions_per_row": nrec, "recursions_per_s": nrec * Nd / (ms * 1e-3)})
+        for variant, setting in (("", "1"), ("_generic", "0")):
+            if want(name + variant) and (not variant or args.only == "" or "generic" in args.only or args.only.startswith("dyn_")):
+                os.environ["B2K_RNE_SPEC"] = setting
+                ms = timeit(fn, 1)
+                report(name + variant, ms, Nd, bpr, {"recursions_per_row": nrec, "recursions_per_s": nrec * Nd / (ms * 1e-3),
+                                                     "kernel": rtb.rne_kernel_info(puma, name.split("_")[1], np.float64)})
+    os.environ["B2K_RNE_SPEC"] = "1"
 
 # IK (config 4): reachable targets, chan
 if want("ik_"):
