@@ -73,6 +73,7 @@ typedef enum {
 
 typedef struct b2k_chain_s *b2k_chain_t; /* replaces the "ETS" PyCapsule, structs.h:25-56 */
 typedef struct b2k_rne_s *b2k_rne_t;     /* replaces the "Robot" PyCapsule, frne.h            */
+typedef struct b2k_tree_s *b2k_tree_t;   /* a rigid-body tree as Robot.rne walks it, Robot.py:1704-1903 */
 
 const char *b2k_last_error(void);
 int b2k_version(void);
@@ -184,6 +185,25 @@ int b2k_rne_spec_info(b2k_rne_t rne, int mode, int dtype, const double *grav, in
 int b2k_rne_codegen(b2k_rne_t rne, int mode, int grav_mask, int has_fext, char *src, int64_t src_cap, double *consts,
                     int32_t consts_cap, int32_t *n_consts, int32_t *counts);
 
+/* ---------------------------------------------------------------- inverse dynamics of ETS / URDF robots (rigid-body trees)
+ * Replaces the pure-Python Robot.rne (Robot.py:1704-1903: Featherstone's recursion over spatial vectors, one Python loop
+ * iteration per trajectory row).  The tree is described the way that function walks it: n joint groups in link order;
+ * group j hangs off group parent[j] (-1 = the base) through the constant transform C[j] (3x4 row-major: the static links
+ * of the group and the constant part of the joint link, folded) followed by ONE joint of kind axis[j] (B2K_RX..B2K_TZ,
+ * flip[j]) that reads q[jindex[j]]; I6[j] (6x6 row-major, [linear; angular] order as spatialmath's SpatialInertia) is the
+ * inertia of the group in the joint link's frame.  b2k_tree_rne: tau (N,n) = rne(q, qd, qdd) rows, arrays (N,n) device,
+ * 16-byte aligned; grav = MINUS the robot's gravity (Robot.rne's a_grav), host 3-vector.  Reference quirks kept: the
+ * joint motion subspace ignores `flip` (ET.s, ET.py:592-608), torques are listed in group order.  The kernel is generated
+ * for the tree at hand and compiled with NVRTC at first use (there is no pre-compiled kernel for an arbitrary tree). */
+int b2k_tree_create(int n, const int32_t *parent, const int32_t *axis, const int32_t *flip, const int32_t *jindex,
+                    const double *C, const double *I6, b2k_tree_t *out);
+int b2k_tree_destroy(b2k_tree_t tree);
+int b2k_tree_rne(b2k_tree_t tree, int dtype, const void *q, const void *qd, const void *qdd, int64_t N, const double *grav,
+                 void *tau, void *stream);
+int b2k_tree_codegen(b2k_tree_t tree, int grav_mask, char *src, int64_t src_cap, double *consts, int32_t consts_cap,
+                     int32_t *n_consts, int32_t *counts);
+int b2k_tree_info(b2k_tree_t tree, int dtype, const double *grav, char *buf, int64_t cap);
+
 /* ---------------------------------------------------------------- dynamics built on the recursion
  * The reference's DynamicsMixin (robot/Dynamics.py) obtains these by looping frne calls in
  * Python; here each is ONE kernel in which a lane performs all the recursions of its row
@@ -232,6 +252,17 @@ int b2k_angle_axis(int dtype, const void *Te, const void *Tep, int64_t N, int64_
 int b2k_p_servo(int dtype, const void *Te, const void *Tep, int64_t N, int64_t tep_stride, const double *gain,
                 double threshold, void *v, int32_t *arrived, void *stream);
 
+/* b2k_p_servo_rpy is tools/p_servo.py:46-106 with the reference's default method="rpy": the error is taken in the
+ * end-effector frame, e = [t(Te^-1 Tep); tr2rpy(Te^-1 Tep, order="zyx")]; arguments as b2k_p_servo.
+ * b2k_jacob0_analytical is ETS.jacob0_analytical (ETS.py:1570-1626): Ja (N,6,n) = blkdiag(I, A^-1(Gamma(R))) J0 from
+ * the poses T (N,4,4) and base-frame Jacobians J (N,6,n); representation 0 "rpy/xyz", 1 "rpy/zyx", 2 "eul", 3 "exp".
+ * tr2rpy / tr2eul / rotvelxform belong to spatialmath-python (not under the reference tree): their documented
+ * conventions are restated in csrc/b2k_pose.cu and pinned by derivative identities in tests/, not by the package. */
+int b2k_p_servo_rpy(int dtype, const void *Te, const void *Tep, int64_t N, int64_t tep_stride, const double *gain,
+                    double threshold, void *v, int32_t *arrived, void *stream);
+int b2k_jacob0_analytical(int dtype, int n, const void *T, const void *J, int64_t N, int representation, void *Ja,
+                          void *stream);
+
 /* ---------------------------------------------------------------- trajectory producer
  * b2k_jtraj replaces tools.trajectory.jtraj (tools/trajectory.py:686-780): quintic joint-space blend
  * from q0 to qf (host n-vectors; qd0 / qd1 boundary velocities or NULL = 0) sampled at N points,
@@ -252,6 +283,17 @@ int b2k_jtraj(int dtype, int n, const double *q0, const double *qf, const double
 int b2k_mtraj(int dtype, int kind, int n, const double *q0, const double *qf, const double *qd0, const double *qdf,
               const double *V, int64_t N, const void *t, double tf, void *s, void *sd, void *sdd, double *tblend,
               void *stream);
+
+/* b2k_ctraj replaces tools.trajectory.ctraj (trajectory.py:782-841 -> SE3.interp): N poses between T0 and T1 (host,
+ * 4x4 row-major) at the path fractions s (device, N values in [0,1], clipped): translation interpolated linearly,
+ * orientation by unit-quaternion slerp along the shorter arc; T (N,4,4) device.
+ * b2k_mstraj evaluates the sample table of tools.trajectory.mstraj (trajectory.py:852-1152): the caller plans the
+ * segments on the host exactly as the reference does and passes the pieces in row order -- kind 0: quintic blend
+ * (jtraj coefficients A B C E F per axis in coef[piece][axis][0..4], sampled at t = (k+1) dt over a blend of length
+ * tscal), kind 1: linear segment (coef = q_prev, q_next; s = (t0 + k dt) / tscal) -- and q (N,n) is written on the device. */
+int b2k_ctraj(int dtype, const double *T0, const double *T1, const void *s, int64_t N, void *T, void *stream);
+int b2k_mstraj(int dtype, int n, int npieces, const int64_t *row0, const int64_t *rows, const int32_t *kind,
+               const double *tscal, const double *t0, const double *dt, const double *coef, int64_t N, void *q, void *stream);
 
 /* ---------------------------------------------------------------- host-buffer front ends
  * The same operations for callers that hold HOST arrays (what the reference's API takes):

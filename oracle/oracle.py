@@ -368,3 +368,307 @@ def manip_svd(J, axes=(True,) * 6, kind="minsingular"):
         s = np.linalg.svd(Jk[ax, :], compute_uv=False)
         out[k] = s[-1] if kind == "minsingular" else (s[-1] / s[0] if s[0] > 0 else 0.0)
     return out
+
+
+# ------------------------------------------------------------------ pose representations (spatialmath conventions, restated)
+# tr2rpy / tr2eul / trlog / rotvelxform / qslerp live in spatialmath-python, which is NOT under /root/reference: these
+# are restatements of its documented definitions (parity unpinned against the package itself; the tests pin them by
+# derivative / end-point identities).
+_EPS = np.finfo(np.float64).eps
+
+
+def tr2rpy(R, order="zyx"):
+    """spatialmath.base.tr2rpy: 'zyx' R = Rz(yaw) Ry(pitch) Rx(roll); 'xyz' R = Rx(yaw) Ry(pitch) Rz(roll); -> (roll, pitch, yaw)"""
+    R = np.asarray(R, dtype=np.float64)[:3, :3]
+    rpy = np.zeros(3)
+    if order == "xyz":
+        if abs(abs(R[0, 2]) - 1) < 10 * _EPS:
+            rpy[0] = 0
+            rpy[2] = np.arctan2(R[2, 1], R[1, 1]) if R[0, 2] > 0 else -np.arctan2(R[1, 0], R[2, 0])
+            rpy[1] = np.arcsin(np.clip(R[0, 2], -1.0, 1.0))
+        else:
+            rpy[0] = -np.arctan2(R[0, 1], R[0, 0])
+            rpy[2] = -np.arctan2(R[1, 2], R[2, 2])
+            k = int(np.argmax(np.abs([R[0, 0], R[0, 1], R[1, 2], R[2, 2]])))
+            if k == 0:
+                rpy[1] = np.arctan(R[0, 2] * np.cos(rpy[0]) / R[0, 0])
+            elif k == 1:
+                rpy[1] = -np.arctan(R[0, 2] * np.sin(rpy[0]) / R[0, 1])
+            elif k == 2:
+                rpy[1] = -np.arctan(R[0, 2] * np.sin(rpy[2]) / R[1, 2])
+            else:
+                rpy[1] = np.arctan(R[0, 2] * np.cos(rpy[2]) / R[2, 2])
+    else:
+        if abs(abs(R[2, 0]) - 1) < 10 * _EPS:
+            rpy[0] = 0
+            rpy[2] = -np.arctan2(R[0, 1], R[0, 2]) if R[2, 0] < 0 else np.arctan2(-R[0, 1], -R[0, 2])
+            rpy[1] = -np.arcsin(np.clip(R[2, 0], -1.0, 1.0))
+        else:
+            rpy[0] = np.arctan2(R[2, 1], R[2, 2])
+            rpy[2] = np.arctan2(R[1, 0], R[0, 0])
+            k = int(np.argmax(np.abs([R[0, 0], R[1, 0], R[2, 1], R[2, 2]])))
+            if k == 0:
+                rpy[1] = -np.arctan(R[2, 0] * np.cos(rpy[2]) / R[0, 0])
+            elif k == 1:
+                rpy[1] = -np.arctan(R[2, 0] * np.sin(rpy[2]) / R[1, 0])
+            elif k == 2:
+                rpy[1] = -np.arctan(R[2, 0] * np.sin(rpy[0]) / R[2, 1])
+            else:
+                rpy[1] = -np.arctan(R[2, 0] * np.cos(rpy[0]) / R[2, 2])
+    return rpy
+
+
+def tr2eul(R):
+    """spatialmath.base.tr2eul: R = Rz(phi) Ry(theta) Rz(psi)"""
+    R = np.asarray(R, dtype=np.float64)[:3, :3]
+    eul = np.zeros(3)
+    if abs(R[0, 2]) < 10 * _EPS and abs(R[1, 2]) < 10 * _EPS:
+        sp, cp = 0.0, 1.0
+    else:
+        eul[0] = np.arctan2(R[1, 2], R[0, 2])
+        sp, cp = np.sin(eul[0]), np.cos(eul[0])
+    eul[1] = np.arctan2(cp * R[0, 2] + sp * R[1, 2], R[2, 2])
+    eul[2] = np.arctan2(-sp * R[0, 0] + cp * R[1, 0], -sp * R[0, 1] + cp * R[1, 1])
+    return eul
+
+
+def trlog(R):
+    """exponential coordinates theta * axis of a rotation matrix"""
+    R = np.asarray(R, dtype=np.float64)[:3, :3]
+    li = np.array([R[2, 1] - R[1, 2], R[0, 2] - R[2, 0], R[1, 0] - R[0, 1]])
+    ln = np.linalg.norm(li)
+    tr = np.trace(R)
+    if ln < 1e-9:
+        if tr > 0:
+            return np.zeros(3)
+        w, V = np.linalg.eigh((R + R.T) / 2)
+        return np.pi * V[:, -1]
+    return np.arctan2(ln, tr - 1) * li / ln
+
+
+def r2x(R, representation):
+    return {"rpy/xyz": lambda: tr2rpy(R, "xyz"), "rpy/zyx": lambda: tr2rpy(R, "zyx"), "eul": lambda: tr2eul(R),
+            "exp": lambda: trlog(R)}[representation]()
+
+
+def rotvelxform_inv(g, representation):
+    """rotvelxform(gamma, inverse=True): angular velocity -> rates of the representation"""
+    if representation == "rpy/zyx":
+        sb, cb, sg, cg = np.sin(g[1]), np.cos(g[1]), np.sin(g[2]), np.cos(g[2])
+        A = np.array([[cb * cg, -sg, 0], [cb * sg, cg, 0], [-sb, 0, 1]])
+        return np.linalg.inv(A)
+    if representation == "rpy/xyz":
+        sb, cb, sg, cg = np.sin(g[1]), np.cos(g[1]), np.sin(g[2]), np.cos(g[2])
+        A = np.array([[sb, 0, 1], [-cb * sg, cg, 0], [cb * cg, sg, 0]])
+        return np.linalg.inv(A)
+    if representation == "eul":
+        sp, cp, st, ct = np.sin(g[0]), np.cos(g[0]), np.sin(g[1]), np.cos(g[1])
+        A = np.array([[0, -sp, cp * st], [0, cp, sp * st], [1, 0, ct]])
+        return np.linalg.inv(A)
+    th = np.linalg.norm(g)
+    sk = np.array([[0, -g[2], g[1]], [g[2], 0, -g[0]], [-g[1], g[0], 0]])
+    if th < 1e-8:
+        return np.eye(3) - sk / 2
+    A = np.eye(3) + sk * (1 - np.cos(th)) / th**2 + sk @ sk * (th - np.sin(th)) / th**3
+    return np.linalg.inv(A)
+
+
+def jacob0_analytical(T, J, representation):
+    """ETS.py:1617-1624: A @ J with A = blkdiag(I, rotvelxform(R, inverse=True))"""
+    T = np.asarray(T).reshape(-1, 4, 4)
+    J = np.asarray(J).reshape(T.shape[0], 6, -1)
+    out = J.copy()
+    for k in range(T.shape[0]):
+        out[k, 3:] = rotvelxform_inv(r2x(T[k, :3, :3], representation), representation) @ J[k, 3:]
+    return out
+
+
+def p_servo_rpy(Te, Tep, gain, threshold):
+    """tools/p_servo.py:80-106, method='rpy'"""
+    Te = np.asarray(Te).reshape(-1, 4, 4)
+    Tep = np.broadcast_to(np.asarray(Tep).reshape(-1, 4, 4), Te.shape)
+    K = np.eye(6) * gain if np.isscalar(gain) else np.diag(gain)
+    v = np.empty((Te.shape[0], 6))
+    arrived = np.empty(Te.shape[0], dtype=bool)
+    for i in range(Te.shape[0]):
+        eTep = np.linalg.inv(Te[i]) @ Tep[i]
+        e = np.r_[eTep[:3, -1], tr2rpy(eTep, "zyx")]
+        v[i] = K @ e
+        arrived[i] = np.sum(np.abs(e)) < threshold
+    return v, arrived
+
+
+def _r2q(R):
+    """unit quaternion (s, v) of a rotation matrix, s >= 0"""
+    R = np.asarray(R, dtype=np.float64)[:3, :3]
+    w, V = np.linalg.eigh(np.array([  # Bar-Itzhack: the dominant eigenvector of K is the quaternion
+        [R[0, 0] + R[1, 1] + R[2, 2], R[2, 1] - R[1, 2], R[0, 2] - R[2, 0], R[1, 0] - R[0, 1]],
+        [R[2, 1] - R[1, 2], R[0, 0] - R[1, 1] - R[2, 2], R[0, 1] + R[1, 0], R[0, 2] + R[2, 0]],
+        [R[0, 2] - R[2, 0], R[0, 1] + R[1, 0], R[1, 1] - R[0, 0] - R[2, 2], R[1, 2] + R[2, 1]],
+        [R[1, 0] - R[0, 1], R[0, 2] + R[2, 0], R[1, 2] + R[2, 1], R[2, 2] - R[0, 0] - R[1, 1]]]) / 3.0)
+    q = V[:, -1]
+    return q if q[0] >= 0 else -q
+
+
+def _q2r(q):
+    s, x, y, z = q
+    return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - s * z), 2 * (x * z + s * y)],
+                     [2 * (x * y + s * z), 1 - 2 * (x * x + z * z), 2 * (y * z - s * x)],
+                     [2 * (x * z - s * y), 2 * (y * z + s * x), 1 - 2 * (x * x + y * y)]])
+
+
+def ctraj_poses(T0, T1, s):
+    """SE3.interp(T1, s) -> trinterp: translation lerp + qslerp(shortest=True); s clipped to [0, 1]"""
+    T0, T1 = np.asarray(T0, dtype=np.float64), np.asarray(T1, dtype=np.float64)
+    q0, q1 = _r2q(T0), _r2q(T1)
+    out = np.zeros((len(s), 4, 4))
+    for i, u in enumerate(np.clip(np.asarray(s, dtype=np.float64), 0, 1)):
+        if u == 0:
+            q = q0
+        elif u == 1:
+            q = q1
+        else:
+            a, dot = q0, float(np.dot(q0, q1))
+            if dot < 0:
+                a, dot = -q0, -dot
+            th = np.arccos(np.clip(dot, -1, 1))
+            q = (a * np.sin((1 - u) * th) + q1 * np.sin(u * th)) / np.sin(th) if abs(th) > 10 * _EPS else a
+        out[i, :3, :3] = _q2r(q)
+        out[i, :3, 3] = T0[:3, 3] * (1 - u) + u * T1[:3, 3]
+        out[i, 3, 3] = 1
+    return out
+
+
+def mstraj(viapoints, dt, tacc, qdmax=None, tsegment=None, q0=None, qd0=None, qdf=None):
+    """tools/trajectory.py:852-1152 restated in numpy (blends through this module's jtraj): returns (t, q, arrive)"""
+    import math
+
+    viapoints = np.asarray(viapoints, dtype=np.float64)
+    if q0 is None:
+        q0, viapoints = viapoints[0, :], viapoints[1:, :]
+    q0 = np.asarray(q0, dtype=np.float64)
+    ns, nj = viapoints.shape
+    if tsegment is None:
+        qdmax = np.tile(float(qdmax), (nj,)) if np.isscalar(qdmax) else np.asarray(qdmax, dtype=np.float64)
+    Tacc = np.tile(float(tacc), (ns,)) if np.isscalar(tacc) else np.asarray(tacc, dtype=np.float64)
+    qd0 = np.zeros(nj) if qd0 is None else np.asarray(qd0, dtype=np.float64)
+    qdf = np.zeros(nj) if qdf is None else np.asarray(qdf, dtype=np.float64)
+
+    def mrange(start, stop, step):
+        return np.arange(round(start / step), round(stop / step) + 1) * step
+
+    q_prev, qd_prev = q0, qd0
+    clock = 0.0
+    arrive = np.zeros(ns)
+    tg = np.zeros((0, nj))
+    tacc2 = 0.0
+    q_next = q_prev
+    for seg in range(ns):
+        q_next = viapoints[seg, :]
+        tacc_ = math.ceil(Tacc[seg] / dt) * dt
+        tacc2 = math.ceil(tacc_ / 2 / dt) * dt
+        taccx = tacc2 if seg == 0 else tacc_
+        dq = q_next - q_prev
+        if qdmax is not None:
+            tl = np.ceil(np.abs(dq) / qdmax / dt) * dt
+            tt = taccx + tl
+            tseg = tt[int(np.argmax(tt))]
+            if tseg <= 2 * tacc_:
+                tseg = 2 * tacc_
+        else:
+            tseg = tsegment[seg]
+        arrive[seg] = clock + tseg + (tacc2 if seg > 0 else 0.0)
+        qd = dq / tseg
+        if taccx > 0:
+            qb = jtraj(q0, q_prev + tacc2 * qd, mrange(0, taccx, dt), qd0=qd_prev, qd1=qd)[1]
+            tg = np.vstack([tg, qb[1:, :]])
+        clock += taccx
+        for t in mrange(tacc2 + dt, tseg - tacc2, dt):
+            s = t / tseg
+            q0 = (1 - s) * q_prev + s * q_next
+            tg = np.vstack([tg, q0])
+            clock += dt
+        q_prev, qd_prev = q_next, qd
+    if tacc2 > 0:
+        qb = jtraj(q0, q_next, mrange(0, tacc2, dt), qd0=qd_prev, qd1=qdf)[1]
+        tg = np.vstack([tg, qb[1:, :]])
+    return dt * np.arange(0, tg.shape[0]), tg, arrive
+
+
+# ------------------------------------------------------------------ Robot.rne (rigid-body trees), reference Robot.py:1704-1903
+# Spatial-vector helpers as spatialmath defines them ([linear; angular] order): SE3.Ad, SpatialVelocity.cross (crm),
+# its force dual (crf = -crm^T), SpatialInertia(m, r) WITHOUT rotational inertia (the reference passes only m and r).
+def _skew(v):
+    return np.array([[0, -v[2], v[1]], [v[2], 0, -v[0]], [-v[1], v[0], 0]], dtype=np.float64)
+
+
+def _Ad(T):
+    R, p = T[:3, :3], T[:3, 3]
+    A = np.zeros((6, 6))
+    A[:3, :3] = R
+    A[:3, 3:] = _skew(p) @ R
+    A[3:, 3:] = R
+    return A
+
+
+def _crm(v):
+    X = np.zeros((6, 6))
+    X[:3, :3] = _skew(v[3:]); X[:3, 3:] = _skew(v[:3]); X[3:, 3:] = _skew(v[3:])
+    return X
+
+
+def spatial_inertia(m, r):
+    C = _skew(np.asarray(r, dtype=np.float64))
+    return np.block([[m * np.eye(3), m * C.T], [m * C, m * C @ C.T]])
+
+
+_AXIS_S = {0: [0, 0, 0, 1, 0, 0], 1: [0, 0, 0, 0, 1, 0], 2: [0, 0, 0, 0, 0, 1], 3: [1, 0, 0, 0, 0, 0], 4: [0, 1, 0, 0, 0, 0],
+           5: [0, 0, 1, 0, 0, 0]}
+
+
+def _joint_T(axis, eta):
+    c, s = np.cos(eta), np.sin(eta)
+    T = np.eye(4)
+    if axis == 0:
+        T[:3, :3] = [[1, 0, 0], [0, c, -s], [0, s, c]]
+    elif axis == 1:
+        T[:3, :3] = [[c, 0, s], [0, 1, 0], [-s, 0, c]]
+    elif axis == 2:
+        T[:3, :3] = [[c, -s, 0], [s, c, 0], [0, 0, 1]]
+    else:
+        T[axis - 3, 3] = eta
+    return T
+
+
+def tree_rne(tree, q, qd, qdd, gravity):
+    """tree: dict(parent (n), axis, flip, jindex, C (n,4,4) constant part of each group, I6 (n,6,6)); gravity = the
+    robot's gravity (NOT negated).  Follows Robot.rne step for step: Xup = (C J(q))^-1, v/a forward, f = I a + v x* I v,
+    Q[j] = s . f, f[parent] += Xup^T f; s ignores flip (ET.s), torques in group order."""
+    q, qd, qdd = (np.atleast_2d(np.asarray(x, dtype=np.float64)) for x in (q, qd, qdd))
+    n = len(tree["parent"])
+    a_grav = -np.r_[np.asarray(gravity, dtype=np.float64), 0, 0, 0]
+    Q = np.zeros((q.shape[0], n))
+    for k in range(q.shape[0]):
+        Xup, v, a, f = [None] * n, [None] * n, [None] * n, [None] * n
+        for j in range(n):
+            ji = tree["jindex"][j]
+            s = np.array(_AXIS_S[tree["axis"][j]], dtype=np.float64)
+            eta = -q[k, ji] if tree["flip"][j] else q[k, ji]
+            T = np.asarray(tree["C"][j]) @ _joint_T(tree["axis"][j], eta)
+            Xup[j] = _Ad(np.linalg.inv(T))
+            vJ = s * qd[k, ji]
+            pa = tree["parent"][j]
+            if pa < 0:
+                v[j] = vJ
+                a[j] = Xup[j] @ a_grav + s * qdd[k, ji]
+            else:
+                v[j] = Xup[j] @ v[pa] + vJ
+                a[j] = Xup[j] @ a[pa] + s * qdd[k, ji] + _crm(v[j]) @ vJ
+            I = np.asarray(tree["I6"][j])
+            f[j] = I @ a[j] + (-_crm(v[j]).T) @ (I @ v[j])
+        for j in reversed(range(n)):
+            Q[k, j] = np.sum(f[j] * np.array(_AXIS_S[tree["axis"][j]]))
+            pa = tree["parent"][j]
+            if pa >= 0:
+                f[pa] = f[pa] + Xup[j].T @ f[j]
+    return Q

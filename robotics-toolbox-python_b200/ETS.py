@@ -462,12 +462,51 @@ class ETS:
             Jm = B.to_host(Jm)
         return Jm[0].reshape(self.n, 1) if single else Jm
 
+    _REPRESENTATIONS = {"rpy/xyz": 0, "rpy/zyx": 1, "eul": 2, "exp": 3}
+
+    def jacob0_analytical(self, q, representation: str = "rpy/xyz", tool=None, dtype=None):
+        """Analytical Jacobian in the base frame, (6,n) or (N,6,n): blkdiag(I, A^-1(Gamma)) jacob0, which maps joint
+        rates to the rates of the pose representation Gamma -- "rpy/xyz", "rpy/zyx", "eul" (ZYZ) or "exp"
+        (reference ETS.jacob0_analytical, ETS.py:1570-1626 -> spatialmath rotvelxform(R, inverse=True, full=True)).
+        Pose, Jacobian and the 3x3 rate transform are computed on the device in two launches."""
+        if representation not in self._REPRESENTATIONS:
+            raise ValueError(f"unknown representation {representation!r}; expecting one of {sorted(self._REPRESENTATIONS)}")
+        q2, single = self._qbatch(q)
+        dt = B.pick_dtype(q2, dtype)
+        host = not B.is_tensor(q2)
+        qd = B.to_device(q2, dt)
+        T, J = self.fkine_jacob0(qd, tool=tool, include_base=False, dtype=dt)
+        T, J = T.reshape(-1, 4, 4), J.reshape(-1, 6, self.n)
+        N = J.shape[0]
+        Ja = B.empty((N, 6, self.n), dt, like=J)
+        _lib.check(_lib.lib().b2k_jacob0_analytical(B.code(dt), self.n, B.ptr(T), B.ptr(J), N, self._REPRESENTATIONS[representation],
+                                                    B.ptr(Ja), B.stream_ptr(J)))
+        if host:
+            Ja = B.to_host(Ja)
+        return Ja[0] if single else Ja
+
     def jacob0_dot(self, q=None, qd=None, J0=None, representation=None, dtype=None):
         """Time derivative of the base-frame Jacobian, (6,n) or (N,6,n): sum_i hessian0[i] qd[i]
-        (reference Robot.jacob0_dot, Robot.py:964-1099, representation None; the analytical
-        representations differentiate numerically through spatialmath and are not accelerated)."""
+        (reference Robot.jacob0_dot, Robot.py:964-1099).  With a ``representation`` the reference differentiates
+        jacob0_analytical numerically (smb.numhess, Robot.py:1090-1092); here that is the central difference of
+        the analytical Jacobian along the joint velocity, two device evaluations."""
         if representation is not None:
-            raise NotImplementedError("only representation=None (geometric Jacobian) is accelerated")
+            if q is None or qd is None:
+                raise ValueError("q and qd must be supplied")
+            q2, single = self._qbatch(q)
+            dt = B.pick_dtype(q2, dtype)
+            host = not B.is_tensor(q2)
+            qt = B.to_device(q2, dt)
+            B.check_numeric(qd, "qd")
+            vt = B.to_device(qd, dt).reshape(-1, self.n)
+            if self._qwidth != self.n or qt.shape[1] != self.n:
+                raise ValueError("analytical jacob0_dot needs q rows of exactly n joints")
+            h = 1e-6 if dt == np.dtype(np.float64) else 1e-3
+            out = (self.jacob0_analytical(qt + h * vt, representation, dtype=dt)
+                   - self.jacob0_analytical(qt - h * vt, representation, dtype=dt)).reshape(-1, 6, self.n) / (2 * h)
+            if host:
+                out = B.to_host(out)
+            return out[0] if single else out
         if qd is None or (q is None and J0 is None):
             raise ValueError("qd and one of q or J0 must be supplied")
         if J0 is None:

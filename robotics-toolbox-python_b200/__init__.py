@@ -22,7 +22,7 @@ from .Robot import ERobot, Link, Robot  # noqa: F401
 from . import models  # noqa: F401
 from . import dist  # noqa: F401
 from . import trajectory  # noqa: F401
-from .trajectory import Trajectory, jtraj, lspb, mtraj, quintic, trapezoidal  # noqa: F401
+from .trajectory import Trajectory, ctraj, jtraj, lspb, mstraj, mtraj, quintic, trapezoidal  # noqa: F401
 from .p_servo import angle_axis, p_servo  # noqa: F401
 
 

@@ -46,6 +46,11 @@ _PROTOS = {
     "b2k_rne": (C.c_int, [vp, C.c_int, vp, vp, vp, i64, dp, dp, vp, vp]),
     "b2k_rne_codegen": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_char_p, i64, dp, C.c_int32, ip, ip]),
     "b2k_rne_spec_info": (C.c_int, [vp, C.c_int, C.c_int, dp, C.c_int, C.c_char_p, i64]),
+    "b2k_tree_create": (C.c_int, [C.c_int, ip, ip, ip, ip, dp, dp, C.POINTER(vp)]),
+    "b2k_tree_destroy": (C.c_int, [vp]),
+    "b2k_tree_rne": (C.c_int, [vp, C.c_int, vp, vp, vp, i64, dp, vp, vp]),
+    "b2k_tree_codegen": (C.c_int, [vp, C.c_int, C.c_char_p, i64, dp, C.c_int32, ip, ip]),
+    "b2k_tree_info": (C.c_int, [vp, C.c_int, dp, C.c_char_p, i64]),
     "b2k_rne_inertia": (C.c_int, [vp, C.c_int, vp, i64, vp, vp]),
     "b2k_rne_gravload": (C.c_int, [vp, C.c_int, vp, i64, dp, vp, vp]),
     "b2k_rne_itorque": (C.c_int, [vp, C.c_int, vp, vp, i64, vp, vp]),
@@ -58,6 +63,10 @@ _PROTOS = {
     "b2k_jacobm": (C.c_int, [C.c_int, C.c_int, vp, i64, C.c_uint32, vp, vp]),
     "b2k_angle_axis": (C.c_int, [C.c_int, vp, vp, i64, i64, vp, vp]),
     "b2k_p_servo": (C.c_int, [C.c_int, vp, vp, i64, i64, dp, C.c_double, vp, vp, vp]),
+    "b2k_jacob0_analytical": (C.c_int, [C.c_int, C.c_int, vp, vp, i64, C.c_int, vp, vp]),
+    "b2k_p_servo_rpy": (C.c_int, [C.c_int, vp, vp, i64, i64, dp, C.c_double, vp, vp, vp]),
+    "b2k_ctraj": (C.c_int, [C.c_int, dp, dp, vp, i64, vp, vp]),
+    "b2k_mstraj": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64), ip, dp, dp, dp, dp, i64, vp, vp]),
     "b2k_jtraj": (C.c_int, [C.c_int, C.c_int, dp, dp, dp, dp, i64, vp, C.c_double, vp, vp, vp, vp]),
     "b2k_mtraj": (C.c_int, [C.c_int, C.c_int, C.c_int, dp, dp, dp, dp, dp, i64, vp, C.c_double, vp, vp, vp, dp, vp]),
     "b2k_host_alloc": (C.c_int, [C.POINTER(vp), i64]),

@@ -356,14 +356,12 @@ std::vector<Sym> recursion(Gen &g, const std::vector<Link> &L, bool mdh, const I
             if (qdo.isc) {
                 const double c = qdo.c > 0 ? l.c_tcp : (qdo.c < 0 ? l.c_tcm : 0.0);
                 tq = g.fix(g.add(tq, Gen::cst(c)));
-            } else {
+            } else { // tq + Tc+ [qd > 0] + Tc- [qd < 0]: two FMAs against 0 / 1 masks, no branch
                 const std::string q = g.spell(qdo);
-                Opd p; p.isc = true; p.c = l.c_tcp;
-                Opd m; m.isc = true; m.c = l.c_tcm;
-                std::string e = g.spell(g.operand(tq)) + " + ((" + q + " > (real)0) ? " + (l.c_tcp != 0.0 ? g.spell(p) : "(real)0") +
-                                " : ((" + q + " < (real)0) ? " + (l.c_tcm != 0.0 ? g.spell(m) : "(real)0") + " : (real)0))";
+                std::string e = g.spell(g.operand(tq));
+                if (l.c_tcm != 0.0) { Opd m; m.isc = true; m.c = l.c_tcm; e = "fma(" + g.spell(m) + ", step_neg(" + q + "), " + e + ")"; g.n_fma++; }
+                if (l.c_tcp != 0.0) { Opd p; p.isc = true; p.c = l.c_tcp; e = "fma(" + g.spell(p) + ", step_pos(" + q + "), " + e + ")"; g.n_fma++; }
                 tq = g.emit(e);
-                g.n_add++;
             }
         }
         tau[j] = tq;
@@ -423,8 +421,8 @@ int b2k_rne_generate(const b2k_rne_s *r, const b2k_gen_opts &o, b2k_gen_out &out
     std::vector<std::string> tail;
     const char *sig = nullptr;
     if (o.mode == B2K_GEN_RNE) {
-        sig = "rne_row(const real *C, const real *grav, const real *fext, const real *st, const real *ct, const real *qd, "
-              "const real *qdd, real *out)";
+        sig = "rne_row(const real *C, const real *grav, const real *fext, const real *st, const real *ct, const real *qq, "
+              "const real *qd, const real *qdd, real *out)";
         in.qd = jvec("qd"); in.qdd = jvec("qdd");
         in.grav = gvec();
         if (o.has_fext) {
@@ -434,20 +432,20 @@ int b2k_rne_generate(const b2k_rne_s *r, const b2k_gen_opts &o, b2k_gen_out &out
         std::vector<Sym> tau = recursion(g, L, r->mdh != 0, in);
         for (int j = 0; j < N; j++) tail.push_back(assign(g, "out[" + std::to_string(j) + "]", tau[j]));
     } else if (o.mode == B2K_GEN_GRAVLOAD) { // rne(q, 0, 0, g)  Dynamics.py:912-915
-        sig = "rne_row(const real *C, const real *grav, const real *fext, const real *st, const real *ct, const real *in1, "
-              "const real *in2, real *out)";
+        sig = "rne_row(const real *C, const real *grav, const real *fext, const real *st, const real *ct, const real *qq, "
+              "const real *in1, const real *in2, real *out)";
         in.qd = zeros; in.qdd = zeros; in.grav = gvec();
         std::vector<Sym> tau = recursion(g, L, r->mdh != 0, in);
         for (int j = 0; j < N; j++) tail.push_back(assign(g, "out[" + std::to_string(j) + "]", tau[j]));
     } else if (o.mode == B2K_GEN_ITORQUE) { // rne(q, 0, qdd, g = 0)  Dynamics.py:1456-1459
-        sig = "rne_row(const real *C, const real *grav, const real *fext, const real *st, const real *ct, const real *in1, "
-              "const real *in2, real *out)";
+        sig = "rne_row(const real *C, const real *grav, const real *fext, const real *st, const real *ct, const real *qq, "
+              "const real *in1, const real *in2, real *out)";
         in.qd = zeros; in.qdd = jvec("in1");
         std::vector<Sym> tau = recursion(g, L, r->mdh != 0, in);
         for (int j = 0; j < N; j++) tail.push_back(assign(g, "out[" + std::to_string(j) + "]", tau[j]));
     } else if (o.mode == B2K_GEN_INERTIA) { // row i of M = rne(q, 0, e_i, g = 0)  Dynamics.py:752-758
-        sig = "rne_row(const real *C, const real *grav, const real *fext, const real *st, const real *ct, const real *in1, "
-              "const real *in2, real *out)";
+        sig = "rne_row(const real *C, const real *grav, const real *fext, const real *st, const real *ct, const real *qq, "
+              "const real *in1, const real *in2, real *out)";
         for (int i = 0; i < N; i++) {
             in.qd = zeros; in.qdd = zeros;
             in.qdd[i] = Gen::cst(1.0);
@@ -455,8 +453,8 @@ int b2k_rne_generate(const b2k_rne_s *r, const b2k_gen_opts &o, b2k_gen_out &out
             for (int k = 0; k < N; k++) tail.push_back(assign(g, "out[" + std::to_string(i * N + k) + "]", tau[k]));
         }
     } else if (o.mode == B2K_GEN_CORIOLIS) { // Dynamics.py:825-857 on the friction-free robot
-        sig = "rne_row(const real *C, const real *grav, const real *fext, const real *st, const real *ct, const real *in1, "
-              "const real *in2, real *out)";
+        sig = "rne_row(const real *C, const real *grav, const real *fext, const real *st, const real *ct, const real *qq, "
+              "const real *in1, const real *in2, real *out)";
         in.friction = false;
         std::vector<Sym> qd = jvec("in1");
         std::vector<std::vector<Sym>> Csq(N, std::vector<Sym>(N));
@@ -488,8 +486,8 @@ int b2k_rne_generate(const b2k_rne_s *r, const b2k_gen_opts &o, b2k_gen_out &out
     } else if (o.mode == B2K_GEN_ACCEL) {
         // tau0 = rne(q, qd, 0, g) with friction; M rows with unit accelerations, no gravity: out = [M (n*n) | torque - tau0 (n)]
         // (the kernel wrapper solves the n x n system; Dynamics.py:490-503)
-        sig = "rne_row(const real *C, const real *grav, const real *fext, const real *st, const real *ct, const real *in1, "
-              "const real *in2, real *out)";
+        sig = "rne_row(const real *C, const real *grav, const real *fext, const real *st, const real *ct, const real *qq, "
+              "const real *in1, const real *in2, real *out)";
         in.qd = jvec("in1"); in.qdd = zeros; in.grav = gvec();
         std::vector<Sym> tau0 = recursion(g, L, r->mdh != 0, in);
         std::vector<Sym> tq = jvec("in2");
@@ -506,6 +504,147 @@ int b2k_rne_generate(const b2k_rne_s *r, const b2k_gen_opts &o, b2k_gen_out &out
         return -1;
     }
     std::string src = std::string("__device__ __forceinline__ void ") + sig + "\n{\n";
+    for (const std::string &s : g.code) src += s + "\n";
+    for (const std::string &s : tail) src += s + "\n";
+    src += "}\n";
+    out.source = src;
+    out.consts = g.consts;
+    if (out.consts.empty()) out.consts.push_back(0.0);
+    out.n_mul = g.n_mul; out.n_fma = g.n_fma; out.n_add = g.n_add;
+    out.error.clear();
+    return 0;
+}
+
+// ------------------------------------------------------------------ rigid-body trees (Robot.rne)
+// Featherstone's recursion as the reference's Robot.rne runs it (Robot.py:1704-1903) with spatial vectors in
+// [linear; angular] order (spatialmath SpatialVelocity / SpatialForce): per joint group j with T_j = C_j J_j(q),
+//   v_j = X_j v_p + s_j qd_j            a_j = X_j a_p + s_j qdd_j + v_j x s_j qd_j      (root: a_p = -gravity)
+//   f_j = I_j a_j + v_j x* (I_j v_j)    tau_j = s_j . f_j      f_p += X_j^T f_j,        X_j = Ad(T_j^-1)
+// written out on 3-vectors and evaluated symbolically: constant rotations with 0 / +-1 entries become permutations,
+// zero inertia entries vanish, the root's velocities are one-component.  Reference quirks kept: the motion subspace
+// s_j ignores a joint's flip (ET.s, ET.py:592-608), the group inertia is the plain sum of SpatialInertia(m, r) of its
+// links without their rotational inertia, torques come out in group order.
+namespace {
+struct TreeOps {
+    Gen &g;
+    Vops v;
+    explicit TreeOps(Gen &gg) : g(gg), v(gg) {}
+    static double snap01(double x)
+    {
+        const double r = nearbyint(x);
+        return (fabs(x - r) < 4e-16 && fabs(r) <= 1.0) ? r : x;
+    }
+    V3 constR(const double *C, const V3 &u, bool transpose)
+    { // Rc u or Rc^T u, Rc = the rotation part of the 3x4 constant
+        V3 a = v.fix(u);
+        auto e = [&](int i, int j) { return Gen::cst(snap01(transpose ? C[j * 4 + i] : C[i * 4 + j])); };
+        auto row = [&](int i) { return g.sum({g.mul(e(i, 0), a.x), g.mul(e(i, 1), a.y), g.mul(e(i, 2), a.z)}); };
+        return {row(0), row(1), row(2)};
+    }
+    V3 jointR(int axis, const Sym &s, const Sym &c, const V3 &u, bool transpose)
+    {
+        if (axis > 2) return u; // prismatic: no rotation
+        V3 a = v.fix(u);
+        const Sym sx = transpose ? s : g.neg(s);
+        // rotation about axis k mixes the other two components (cyclic order)
+        Sym *comp[3] = {&a.x, &a.y, &a.z};
+        const int i = (axis + 1) % 3, j = (axis + 2) % 3;
+        V3 r = a;
+        Sym *out[3] = {&r.x, &r.y, &r.z};
+        *out[i] = g.sum({g.mul(c, *comp[i]), g.mul(sx, *comp[j])});
+        *out[j] = g.sum({g.mul(g.neg(sx), *comp[i]), g.mul(c, *comp[j])});
+        return r;
+    }
+    V3 mat3(const double *I6, int r0, int c0, const V3 &u)
+    { // 3x3 block (rows r0.., cols c0..) of the 6x6 constant times u
+        V3 a = v.fix(u);
+        auto row = [&](int i) {
+            return g.sum({g.mul(Gen::cst(I6[(r0 + i) * 6 + c0]), a.x), g.mul(Gen::cst(I6[(r0 + i) * 6 + c0 + 1]), a.y),
+                          g.mul(Gen::cst(I6[(r0 + i) * 6 + c0 + 2]), a.z)});
+        };
+        return {row(0), row(1), row(2)};
+    }
+};
+} // namespace
+
+int b2k_tree_generate(const b2k_tree_s *t, int grav_mask, b2k_gen_out &out)
+{
+    const int N = t->n;
+    Gen g;
+    TreeOps T(g);
+    Vops &v = T.v;
+    std::vector<Sym> st(N), ct(N), qq(N), qd(N), qdd(N);
+    for (int j = 0; j < N; j++) {
+        const std::string k = "[" + std::to_string(t->jindex[j]) + "]";
+        st[j] = g.var("st" + k); ct[j] = g.var("ct" + k); qq[j] = g.var("qq" + k);
+        qd[j] = g.var("qd" + k); qdd[j] = g.var("qdd" + k);
+        if (t->flip[j]) { st[j] = g.neg(st[j]); qq[j] = g.neg(qq[j]); } // eta = -q
+    }
+    V3 agrav; // a_grav = -gravity handed in as `grav` (the caller negates), linear part only
+    agrav.x = (grav_mask & 1) ? g.var("grav[0]") : Gen::zero();
+    agrav.y = (grav_mask & 2) ? g.var("grav[1]") : Gen::zero();
+    agrav.z = (grav_mask & 4) ? g.var("grav[2]") : Gen::zero();
+    std::vector<V3> w(N), vl(N), fl(N), fa(N), p(N);
+    std::vector<V3> aw(N), av(N);
+    auto unit = [&](int axis, const Sym &x) { // x * e_axis
+        V3 u = v.zero();
+        (axis % 3 == 0 ? u.x : (axis % 3 == 1 ? u.y : u.z)) = x;
+        return u;
+    };
+    for (int j = 0; j < N; j++) {
+        const double *C = t->C[j];
+        const int ax = t->axis[j];
+        const bool rev = ax < 3;
+        auto RT = [&](const V3 &u) { return T.jointR(ax, st[j], ct[j], T.constR(C, u, true), true); };
+        // p = pc + Rc (e_axis * eta) for a prismatic joint
+        const double pc[3] = {C[3], C[7], C[11]};
+        p[j] = v.cst(pc);
+        if (!rev) p[j] = v.fix(v.add(p[j], T.constR(C, unit(ax, qq[j]), false)));
+        const V3 vJw = rev ? unit(ax, qd[j]) : v.zero(), vJv = rev ? v.zero() : unit(ax, qd[j]);
+        const V3 aJw = rev ? unit(ax, qdd[j]) : v.zero(), aJv = rev ? v.zero() : unit(ax, qdd[j]);
+        const int pa = t->parent[j];
+        if (pa < 0) {
+            w[j] = vJw; vl[j] = vJv;
+            aw[j] = aJw;
+            av[j] = v.fix(v.add(RT(agrav), aJv));
+        } else {
+            w[j] = v.fix(v.add(RT(w[pa]), vJw));
+            vl[j] = v.fix(v.add(RT(v.cross_acc(w[pa], p[j], &vl[pa])), vJv));
+            const V3 wxJw = v.cross_acc(w[j], vJw);
+            aw[j] = v.fix(v.add(v.add(RT(aw[pa]), aJw), wxJw));
+            const V3 t1 = RT(v.cross_acc(aw[pa], p[j], &av[pa]));
+            const V3 t2 = v.cross_acc(w[j], vJv, &aJv);
+            const V3 t3 = v.cross_acc(vl[j], vJw, &t2);
+            av[j] = v.fix(v.add(t1, t3));
+        }
+        const double *I6 = t->I6[j];
+        const V3 hl = v.fix(v.add(T.mat3(I6, 0, 0, vl[j]), T.mat3(I6, 0, 3, w[j])));
+        const V3 ha = v.fix(v.add(T.mat3(I6, 3, 0, vl[j]), T.mat3(I6, 3, 3, w[j])));
+        const V3 il = v.add(T.mat3(I6, 0, 0, av[j]), T.mat3(I6, 0, 3, aw[j]));
+        const V3 ia = v.add(T.mat3(I6, 3, 0, av[j]), T.mat3(I6, 3, 3, aw[j]));
+        fl[j] = v.fix(v.cross_acc(w[j], hl, &il));
+        const V3 t4 = v.cross_acc(vl[j], hl, &ia);
+        fa[j] = v.fix(v.cross_acc(w[j], ha, &t4));
+    }
+    std::vector<std::string> tail;
+    for (int j = N - 1; j >= 0; j--) {
+        const int ax = t->axis[j];
+        const V3 &f = ax < 3 ? fa[j] : fl[j];
+        const Sym tq = ax % 3 == 0 ? f.x : (ax % 3 == 1 ? f.y : f.z);
+        tail.push_back(assign(g, "out[" + std::to_string(j) + "]", tq));
+        const int pa = t->parent[j];
+        if (pa >= 0) {
+            const double *C = t->C[j];
+            auto R = [&](const V3 &u) { return T.constR(C, T.jointR(ax, st[j], ct[j], u, false), false); };
+            const V3 Rf = v.fix(R(fl[j]));
+            fl[pa] = v.fix(v.add(fl[pa], Rf));
+            const V3 Rn = R(fa[j]);
+            const V3 pxf = v.cross_acc(p[j], Rf, &Rn);
+            fa[pa] = v.fix(v.add(fa[pa], pxf));
+        }
+    }
+    std::string src = "__device__ __forceinline__ void rne_row(const real *C, const real *grav, const real *fext, const real *st, "
+                      "const real *ct, const real *qq, const real *qd, const real *qdd, real *out)\n{\n";
     for (const std::string &s : g.code) src += s + "\n";
     for (const std::string &s : tail) src += s + "\n";
     src += "}\n";

@@ -21,6 +21,20 @@ struct b2k_gen_out {
     std::string error;
 };
 
+// A rigid-body tree in the form Robot.rne walks it (reference Robot.py:1704-1903): n joint groups in link order, group j
+// hangs off group parent[j] (-1: the base) through the constant transform C[j] (3x4 row-major; the static links of the
+// group and the constant part of the joint link folded) followed by ONE joint of kind axis[j] (B2K_RX..B2K_TZ, flip[j])
+// reading q[jindex[j]]; I6[j] is the 6x6 spatial inertia of the group in the joint link's frame, [linear; angular] order.
+#define B2K_TREE_MAX 16
+struct b2k_tree_s {
+    int n;
+    int parent[B2K_TREE_MAX], axis[B2K_TREE_MAX], flip[B2K_TREE_MAX], jindex[B2K_TREE_MAX];
+    double C[B2K_TREE_MAX][12];
+    double I6[B2K_TREE_MAX][36];
+    void *spec;
+};
+int b2k_tree_generate(const b2k_tree_s *t, int grav_mask, b2k_gen_out &out);
+
 // outputs of the generated function: RNE / GRAVLOAD / ITORQUE n values; INERTIA / CORIOLIS n*n; ACCEL n*n + n
 // (rows of M followed by torque - rne(q, qd, 0), the wrapper solves the system)
 int b2k_rne_generate(const b2k_rne_s *r, const b2k_gen_opts &o, b2k_gen_out &out);

@@ -17,6 +17,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <functional>
 #include <map>
 #include <mutex>
 #include <string>
@@ -37,7 +38,9 @@ typedef unsigned long long u64;
 struct TrigC { real two_over_pi, magic, pio2_hi, pio2_mid, pio2_lo, fast_limit; real s[6]; real c[6]; };
 struct SpecP { real C[NC]; real grav[3]; real fext[6]; real offset[NJ]; TrigC trig; };
 
-__device__ __forceinline__ real b2k_abs(real x) { return x < (real)0 ? -x : x; }
+// 1 where x > 0 (x < 0), else 0: compiles to a SET instruction, so the Coulomb term is two FMAs and no branch
+__device__ __forceinline__ real step_pos(real x) { return x > (real)0 ? (real)1 : (real)0; }
+__device__ __forceinline__ real step_neg(real x) { return x < (real)0 ? (real)1 : (real)0; }
 
 // sincos of the NJ joint angles as one interleaved batch: three-FMA Cody-Waite reduction by pi/2, fdlibm minimax
 // kernels on [-pi/4, pi/4], integer quadrant logic; every coefficient comes from the parameter bank (csrc/b2k_trig.cuh
@@ -56,21 +59,23 @@ __device__ __noinline__ SC sincos_slow(real x)
 __device__ __forceinline__ void sincos_batch(const real *x, const TrigC &t, real *s, real *c)
 {
 #if !REAL_IS_F64
-    {
-        bool all_small = true;
+    real amax = fabs(x[0]); // one comparison for the whole row (|x| is an operand modifier, max a single instruction)
 #pragma unroll
-        for (int j = 0; j < NJ; j++) all_small = all_small && (b2k_abs(x[j]) < 8.0f);
-        if (all_small) {
+    for (int j = 1; j < NJ; j++) amax = fmax(amax, fabs(x[j]));
+    {
+        if (amax < 8.0f) {
 #pragma unroll
             for (int j = 0; j < NJ; j++) { s[j] = __sinf(x[j]); c[j] = __cosf(x[j]); }
             return;
         }
     }
 #endif
-    bool all_fast = true;
+#if REAL_IS_F64
+    real amax = fabs(x[0]);
 #pragma unroll
-    for (int j = 0; j < NJ; j++) all_fast = all_fast && (b2k_abs(x[j]) < t.fast_limit);
-    if (!all_fast) { // rare: huge / non-finite angles somewhere in this row
+    for (int j = 1; j < NJ; j++) amax = fmax(amax, fabs(x[j]));
+#endif
+    if (!(amax < t.fast_limit)) { // rare: huge / non-finite angles somewhere in this row (NaN fails the test too)
 #pragma unroll
         for (int j = 0; j < NJ; j++) { const SC r = sincos_slow(x[j]); s[j] = r.s; c[j] = r.c; }
         return;
@@ -135,10 +140,13 @@ __device__ __forceinline__ void load_tile(real *s, const real *g, int lane)
         s[r * LDI + c] = g[i];
     }
 #else
-    const uint4 *gg = reinterpret_cast<const uint4 *>(g);
-    const unsigned sa = (unsigned)__cvta_generic_to_shared(s);
-    for (int u = lane; u < (32 * NJ * (int)sizeof(real)) / 16; u += 32)
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa + 16u * (unsigned)u), "l"(gg + u));
+    const uint4 *gg = reinterpret_cast<const uint4 *>(g) + lane;
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(s) + 16u * (unsigned)lane;
+    constexpr int UNITS = (32 * NJ * (int)sizeof(real)) / 16; // 16-byte units in the tile: trip count known at compile time
+#pragma unroll
+    for (int k = 0; k < (UNITS + 31) / 32; k++)
+        if (k * 32 + 32 <= UNITS || lane < UNITS - k * 32)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa + 512u * (unsigned)k), "l"(gg + 32 * k));
 #endif
 }
 
@@ -191,7 +199,7 @@ k_rne_spec(const __grid_constant__ SpecP P, const real *__restrict__ in0, const 
         }
         sincos_batch(th, P.trig, st, ct);
         real res[NRES];
-        rne_row(P.C, P.grav, P.fext, st, ct, a1, a2, res);
+        rne_row(P.C, P.grav, P.fext, st, ct, th, a1, a2, res);
 #if MODE == 5
         // accel: res = [M (NJ x NJ, row i = torques for a unit acceleration of joint i) | torque - rne(q, qd, 0)].
         // M is the joint-space inertia matrix (symmetric positive definite): LDL^T without pivoting, in registers.
@@ -342,13 +350,12 @@ int spec_setting()
 
 int gcd_i(int a, int b) { return b ? gcd_i(b, a % b) : a; }
 
-std::string build_source(const b2k_rne_s *r, int mode, int dtype, int grav_mask, int has_fext, Program &p, std::vector<std::string> &defs)
+typedef std::function<int(b2k_gen_out &)> GenFn; // runs the code generator for one (robot, operation, pattern)
+
+std::string build_source(const GenFn &gen, int n, int mode, int dtype, Program &p, std::vector<std::string> &defs)
 {
-    b2k_gen_opts o;
-    o.mode = mode; o.grav_mask = grav_mask; o.has_fext = has_fext;
     b2k_gen_out g;
-    if (b2k_rne_generate(r, o, g)) { p.why = g.error; return std::string(); }
-    const int n = r->n;
+    if (gen(g)) { p.why = g.error; return std::string(); }
     p.consts = g.consts;
     p.nc = (int)g.consts.size();
     p.n_mul = g.n_mul; p.n_fma = g.n_fma; p.n_add = g.n_add;
@@ -360,12 +367,15 @@ std::string build_source(const b2k_rne_s *r, int mode, int dtype, int grav_mask,
     const int padin = gcd_i(n * es / 4, es == 8 ? 32 : 32) > (es == 8 ? 4 : 2) ? 1 : 0;
     const int ldi = padin ? (n | 1) : n;
     const size_t in_bytes = ((size_t)32 * ldi * es + 15) & ~(size_t)15;
-    int tpw = (mode == B2K_GEN_CORIOLIS) ? 1 : 2; // tiles per warp (double-buffered inputs when > 1)
+    // tiles per warp (double-buffered inputs when > 1): measured no gain over one tile per warp on B200 -- the kernel is
+    // bound by instruction issue (2-cycle FP64 issue + integer / control), not by load latency -- so the default is 1
+    int tpw = 1;
     if (const char *e = getenv("B2K_RNE_SPEC_TPW")) tpw = atoi(e) > 0 ? atoi(e) : tpw;
     p.tpw = tpw;
     p.smem = 4 * ((tpw > 1 ? 2 : 1) * p.nin * in_bytes + (size_t)32 * p.nout * es);
     int minb = (int)((200 * 1024) / (p.smem + 1024));
-    const int want = mode == B2K_GEN_RNE || mode == B2K_GEN_GRAVLOAD || mode == B2K_GEN_ITORQUE ? (es == 8 ? 4 : 6) : (es == 8 ? 2 : 3);
+    // resident blocks to aim for (profiles/r02_rne_sweep.jsonl: fp64 96 registers / 5 blocks, fp32 72 registers / 6 blocks)
+    const int want = mode == B2K_GEN_RNE || mode == B2K_GEN_GRAVLOAD || mode == B2K_GEN_ITORQUE ? (es == 8 ? 5 : 6) : (es == 8 ? 2 : 3);
     if (minb > want) minb = want;
     if (minb < 1) minb = 1;
     if (const char *e = getenv("B2K_RNE_SPEC_MINB")) minb = atoi(e) > 0 ? atoi(e) : minb;
@@ -377,13 +387,13 @@ std::string build_source(const b2k_rne_s *r, int mode, int dtype, int grav_mask,
     return std::string(kPrologue) + g.source + kKernel;
 }
 
-void compile(const b2k_rne_s *r, const Key &key, Program &p)
+void compile(const GenFn &gen, int n, const Key &key, Program &p)
 {
-    const int mode = std::get<0>(key), dtype = std::get<1>(key);
+    const int mode = std::get<0>(key) % 100, dtype = std::get<1>(key);
     Nvrtc *N = nvrtc();
     if (!N->h) { p.why = N->why; return; }
     std::vector<std::string> defs;
-    const std::string src = build_source(r, mode, dtype, std::get<2>(key), std::get<3>(key), p, defs);
+    const std::string src = build_source(gen, n, mode, dtype, p, defs);
     if (src.empty()) return;
     std::vector<std::string> opts = {"--gpu-architecture=sm_100a", "--std=c++17"};
     if (getenv("B2K_RNE_SPEC_LINEINFO")) opts.push_back("-lineinfo");
@@ -410,7 +420,7 @@ void compile(const b2k_rne_s *r, const Key &key, Program &p)
     N->DestroyProgram(&prog);
     if (const char *dir = getenv("B2K_RNE_SPEC_DUMP")) { // for cuobjdump / offline inspection
         char name[512];
-        snprintf(name, sizeof(name), "%s/rne_spec_m%d_%s_n%d_g%d_f%d", dir, mode, dtype == B2K_F64 ? "f64" : "f32", r->n, std::get<2>(key), std::get<3>(key));
+        snprintf(name, sizeof(name), "%s/rne_spec_m%d_%s_n%d_g%d_f%d", dir, std::get<0>(key), dtype == B2K_F64 ? "f64" : "f32", n, std::get<2>(key), std::get<3>(key));
         if (FILE *f = fopen((std::string(name) + ".cubin").c_str(), "wb")) { fwrite(p.cubin.data(), 1, p.cubin.size(), f); fclose(f); }
         if (FILE *f = fopen((std::string(name) + ".cu").c_str(), "w")) {
             for (auto &d : defs) fprintf(f, "// %s\n", d.c_str());
@@ -421,19 +431,27 @@ void compile(const b2k_rne_s *r, const Key &key, Program &p)
     p.ok = true;
 }
 
-Program *get_program(const b2k_rne_s *r, const Key &key)
+Program *get_program(SpecCache *c, const GenFn &gen, int n, const Key &key)
 {
-    SpecCache *c = static_cast<SpecCache *>(r->spec);
     if (!c) return nullptr;
     std::lock_guard<std::mutex> lk(c->mu);
     auto it = c->progs.find(key);
     if (it == c->progs.end()) {
         Program &p = c->progs[key];
-        compile(r, key, p);
+        compile(gen, n, key, p);
         if (!p.ok && getenv("B2K_VERBOSE")) fprintf(stderr, "b2kin: RNE specialisation unavailable (%s); using the generic kernel\n", p.why.c_str());
         return &p;
     }
     return &it->second;
+}
+
+GenFn dh_gen(const b2k_rne_s *r, const Key &key)
+{
+    return [r, key](b2k_gen_out &g) {
+        b2k_gen_opts o;
+        o.mode = std::get<0>(key); o.grav_mask = std::get<2>(key); o.has_fext = std::get<3>(key);
+        return b2k_rne_generate(r, o, g);
+    };
 }
 
 int get_function(Program *p, CUfunction *out)
@@ -465,6 +483,47 @@ int get_function(Program *p, CUfunction *out)
 template <typename real>
 struct SpecParams { // byte image of the kernel's SpecP for NC constants (built in a buffer)
 };
+
+// Builds the kernel's parameter block SpecP { real C[NC]; real grav[3]; real fext[6]; real offset[NJ]; TrigC trig; } and
+// launches `ntiles` full tiles on `st`.
+int launch_tiles(Program *p, CUfunction fn, int n, int dtype, const double *offset, const void *in0, const void *in1, const void *in2,
+                 void *out, long long ntiles, const double *grav, const double *fext, cudaStream_t st)
+{
+    const int es = dtype == B2K_F64 ? 8 : 4;
+    const int nreal = p->nc + 3 + 6 + n + 18;
+    std::vector<unsigned char> pb((size_t)nreal * es);
+    auto put = [&](int idx, double v) {
+        if (es == 8) memcpy(&pb[(size_t)idx * 8], &v, 8);
+        else { float f = (float)v; memcpy(&pb[(size_t)idx * 4], &f, 4); }
+    };
+    int o = 0;
+    for (int k = 0; k < p->nc; k++) put(o++, p->consts[k]);
+    for (int k = 0; k < 3; k++) put(o++, grav ? grav[k] : 0.0);
+    for (int k = 0; k < 6; k++) put(o++, fext ? fext[k] : 0.0);
+    for (int j = 0; j < n; j++) put(o++, offset ? offset[j] : 0.0);
+    if (es == 8) {
+        TrigC<double> t;
+        b2k_fill_trig<double>(t);
+        memcpy(&pb[(size_t)o * 8], &t, sizeof(t));
+    } else {
+        TrigC<float> t;
+        b2k_fill_trig<float>(t);
+        memcpy(&pb[(size_t)o * 4], &t, sizeof(t));
+    }
+    long long nt = ntiles;
+    void *args[6] = {pb.data(), (void *)&in0, (void *)&in1, (void *)&in2, (void *)&out, (void *)&nt};
+    const long long per_block = 4LL * p->tpw;
+    const unsigned grid = (unsigned)((ntiles + per_block - 1) / per_block);
+    CUresult rc = driver()->LaunchKernel(fn, grid, 1, 1, 128, 1, 1, (unsigned)p->smem, (CUstream)st, args, nullptr);
+    if (rc != CUDA_SUCCESS) {
+        const char *es2 = nullptr;
+        driver()->GetErrorString(rc, &es2);
+        b2k_set_error("cuLaunchKernel(k_rne_spec): %s", es2 ? es2 : "?");
+        return B2K_ERR_CUDA;
+    }
+    b2k_count_launch();
+    return B2K_OK;
+}
 
 int grav_mask_of(const double *g)
 {
@@ -506,7 +565,7 @@ long long b2k_rne_spec_launch(const b2k_rne_s *r, int mode, int dtype, const voi
         for (int k = 0; k < 6; k++) has_fext |= (fext[k] != 0.0);
     const bool uses_grav = mode == B2K_GEN_RNE || mode == B2K_GEN_GRAVLOAD || mode == B2K_GEN_ACCEL;
     const Key key(mode, dtype, uses_grav ? grav_mask_of(grav) : 0, has_fext);
-    Program *p = get_program(r, key);
+    Program *p = get_program(static_cast<SpecCache *>(r->spec), dh_gen(r, key), r->n, key);
     if (!p || !p->ok) return refuse(p ? p->why : "no cache");
     CUfunction fn;
     {
@@ -514,40 +573,11 @@ long long b2k_rne_spec_launch(const b2k_rne_s *r, int mode, int dtype, const voi
         std::lock_guard<std::mutex> lk(c->mu);
         if (get_function(p, &fn)) return refuse(p->why);
     }
-    // parameter block: SpecP { real C[NC]; real grav[3]; real fext[6]; real offset[NJ]; TrigC trig; }
-    const int es = dtype == B2K_F64 ? 8 : 4;
-    const int nreal = p->nc + 3 + 6 + r->n + 18;
-    std::vector<unsigned char> pb((size_t)nreal * es);
-    auto put = [&](int idx, double v) {
-        if (es == 8) memcpy(&pb[(size_t)idx * 8], &v, 8);
-        else { float f = (float)v; memcpy(&pb[(size_t)idx * 4], &f, 4); }
-    };
-    int o = 0;
-    for (int k = 0; k < p->nc; k++) put(o++, p->consts[k]);
-    for (int k = 0; k < 3; k++) put(o++, (uses_grav && grav) ? grav[k] : 0.0);
-    for (int k = 0; k < 6; k++) put(o++, (has_fext && fext) ? fext[k] : 0.0);
-    for (int j = 0; j < r->n; j++) put(o++, r->L[j][5]);
-    if (es == 8) {
-        TrigC<double> t;
-        b2k_fill_trig<double>(t);
-        memcpy(&pb[(size_t)o * 8], &t, sizeof(t));
-    } else {
-        TrigC<float> t;
-        b2k_fill_trig<float>(t);
-        memcpy(&pb[(size_t)o * 4], &t, sizeof(t));
-    }
-    long long nt = ntiles;
-    void *args[6] = {pb.data(), (void *)&in0, (void *)&in1, (void *)&in2, (void *)&out, (void *)&nt};
-    const long long per_block = 4LL * p->tpw;
-    const unsigned grid = (unsigned)((ntiles + per_block - 1) / per_block);
-    CUresult rc = driver()->LaunchKernel(fn, grid, 1, 1, 128, 1, 1, (unsigned)p->smem, (CUstream)st, args, nullptr);
-    if (rc != CUDA_SUCCESS) {
-        const char *es2 = nullptr;
-        driver()->GetErrorString(rc, &es2);
-        b2k_set_error("cuLaunchKernel(k_rne_spec): %s", es2 ? es2 : "?");
-        return B2K_ERR_CUDA;
-    }
-    b2k_count_launch();
+    double offset[B2K_MAX_JOINTS];
+    for (int j = 0; j < r->n; j++) offset[j] = r->L[j][5];
+    const int lrc = launch_tiles(p, fn, r->n, dtype, offset, in0, in1, in2, out, ntiles, uses_grav ? grav : nullptr,
+                                 has_fext ? fext : nullptr, st);
+    if (lrc) return lrc;
     return ntiles * 32;
 }
 
@@ -584,7 +614,8 @@ extern "C" int b2k_rne_spec_info(b2k_rne_t r, int mode, int dtype, const double 
         if (pris) s = "generic (prismatic joint)";
         else {
             const bool uses_grav = mode == B2K_GEN_RNE || mode == B2K_GEN_GRAVLOAD || mode == B2K_GEN_ACCEL;
-            Program *p = get_program(r, Key(mode, dtype, uses_grav ? grav_mask_of(grav) : 0, has_fext));
+            const Key key(mode, dtype, uses_grav ? grav_mask_of(grav) : 0, has_fext);
+            Program *p = get_program(static_cast<SpecCache *>(r->spec), dh_gen(r, key), r->n, key);
             if (!p || !p->ok) s = std::string("generic (") + (p ? p->why : "no cache") + ")";
             else {
                 char t[256];
@@ -595,5 +626,127 @@ extern "C" int b2k_rne_spec_info(b2k_rne_t r, int mode, int dtype, const double 
         }
     }
     snprintf(buf, (size_t)cap, "%s", s.c_str());
+    return B2K_OK;
+}
+
+// ------------------------------------------------------------------ rigid-body trees: Robot.rne (reference Robot.py:1704-1903)
+// There is no pre-compiled kernel for an arbitrary tree: the recursion is always generated for the robot at hand
+// (b2k_tree_generate) and compiled with NVRTC at first use; without NVRTC / the driver API the call fails with an error.
+extern "C" int b2k_tree_create(int n, const int32_t *parent, const int32_t *axis, const int32_t *flip, const int32_t *jindex,
+                               const double *C, const double *I6, b2k_tree_t *out)
+{
+    const char *fn = "b2k_tree_create";
+    if (!out) { b2k_set_error("%s: out is NULL", fn); return B2K_ERR_INVALID; }
+    *out = nullptr;
+    if (n < 1 || n > B2K_TREE_MAX || !parent || !axis || !flip || !jindex || !C || !I6) {
+        b2k_set_error("%s: n = %d outside 1..%d or a NULL table", fn, n, B2K_TREE_MAX);
+        return B2K_ERR_INVALID;
+    }
+    bool seen[B2K_TREE_MAX] = {false};
+    for (int j = 0; j < n; j++) {
+        if (parent[j] < -1 || parent[j] >= j) { b2k_set_error("%s: parent[%d] = %d must precede the group (or be -1)", fn, j, parent[j]); return B2K_ERR_INVALID; }
+        if (axis[j] < 0 || axis[j] > 5) { b2k_set_error("%s: axis[%d] = %d is not B2K_RX..B2K_TZ", fn, j, axis[j]); return B2K_ERR_INVALID; }
+        if (jindex[j] < 0 || jindex[j] >= n || seen[jindex[j]]) { b2k_set_error("%s: the jindices must be a permutation of 0..n-1", fn); return B2K_ERR_INVALID; }
+        seen[jindex[j]] = true;
+    }
+    b2k_tree_s *t = (b2k_tree_s *)calloc(1, sizeof(b2k_tree_s));
+    if (!t) { b2k_set_error("%s: out of memory", fn); return B2K_ERR_ALLOC; }
+    t->n = n;
+    for (int j = 0; j < n; j++) {
+        t->parent[j] = parent[j]; t->axis[j] = axis[j]; t->flip[j] = flip[j] ? 1 : 0; t->jindex[j] = jindex[j];
+        memcpy(t->C[j], C + 12 * j, 12 * sizeof(double));
+        memcpy(t->I6[j], I6 + 36 * j, 36 * sizeof(double));
+    }
+    t->spec = new SpecCache();
+    *out = t;
+    return B2K_OK;
+}
+
+extern "C" int b2k_tree_destroy(b2k_tree_t t)
+{
+    if (t) delete static_cast<SpecCache *>(t->spec);
+    free(t);
+    return B2K_OK;
+}
+
+static Program *tree_program(b2k_tree_t t, int dtype, int gmask)
+{
+    const Key key(100 + B2K_GEN_RNE, dtype, gmask, 0);
+    return get_program(static_cast<SpecCache *>(t->spec), [t, gmask](b2k_gen_out &g) { return b2k_tree_generate(t, gmask, g); }, t->n, key);
+}
+
+extern "C" int b2k_tree_rne(b2k_tree_t t, int dtype, const void *q, const void *qd, const void *qdd, int64_t N, const double *grav,
+                            void *tau, void *stream)
+{
+    const char *fn = "b2k_tree_rne";
+    if (!t) { b2k_set_error("%s: tree handle is NULL", fn); return B2K_ERR_INVALID; }
+    if (dtype != B2K_F32 && dtype != B2K_F64) { b2k_set_error("%s: dtype must be B2K_F32 or B2K_F64", fn); return B2K_ERR_INVALID; }
+    if (N < 0 || (N > 0 && (!q || !qd || !qdd || !tau))) { b2k_set_error("%s: bad arguments", fn); return B2K_ERR_INVALID; }
+    if (!grav) { b2k_set_error("%s: grav is NULL (pass MINUS the robot's gravity: a_grav of Robot.rne)", fn); return B2K_ERR_INVALID; }
+    const uintptr_t al = (uintptr_t)q | (uintptr_t)qd | (uintptr_t)qdd | (uintptr_t)tau;
+    if (al & 15) { b2k_set_error("%s: arrays must be 16-byte aligned", fn); return B2K_ERR_INVALID; }
+    if (N == 0) return B2K_OK;
+    B2K_ON_DEVICE_OF(q);
+    Program *p = tree_program(t, dtype, grav_mask_of(grav));
+    if (!p || !p->ok) {
+        b2k_set_error("%s: the kernel for this robot could not be built (%s); Robot.rne has no pre-compiled kernel", fn, p ? p->why.c_str() : "no cache");
+        return B2K_ERR_INVALID;
+    }
+    CUfunction f;
+    {
+        SpecCache *c = static_cast<SpecCache *>(t->spec);
+        std::lock_guard<std::mutex> lk(c->mu);
+        if (get_function(p, &f)) { b2k_set_error("%s: %s", fn, p->why.c_str()); return B2K_ERR_CUDA; }
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int n = t->n;
+    const size_t es = dtype == B2K_F64 ? 8 : 4, rowb = (size_t)n * es;
+    const long long ntiles = N / 32, tail = N - ntiles * 32;
+    int rc = B2K_OK;
+    if (ntiles) rc = launch_tiles(p, f, n, dtype, nullptr, q, qd, qdd, tau, ntiles, grav, nullptr, st);
+    if (rc == B2K_OK && tail) { // ragged tail: one padded tile through stream-ordered scratch
+        b2k_keep_mempool();
+        char *scr = nullptr;
+        B2K_CUDA(cudaMallocAsync((void **)&scr, 4 * 32 * rowb, st));
+        cudaMemsetAsync(scr, 0, 3 * 32 * rowb, st);
+        const size_t off = (size_t)ntiles * 32 * rowb;
+        const void *src[3] = {q, qd, qdd};
+        for (int i = 0; i < 3; i++) cudaMemcpyAsync(scr + i * 32 * rowb, (const char *)src[i] + off, tail * rowb, cudaMemcpyDeviceToDevice, st);
+        rc = launch_tiles(p, f, n, dtype, nullptr, scr, scr + 32 * rowb, scr + 2 * 32 * rowb, scr + 3 * 32 * rowb, 1, grav, nullptr, st);
+        cudaMemcpyAsync((char *)tau + off, scr + 3 * 32 * rowb, tail * rowb, cudaMemcpyDeviceToDevice, st);
+        cudaFreeAsync(scr, st);
+        cudaError_t e = cudaGetLastError();
+        if (rc == B2K_OK && e != cudaSuccess) rc = b2k_cuda_fail(e, "tail tile of b2k_tree_rne");
+    }
+    return rc;
+}
+
+extern "C" int b2k_tree_codegen(b2k_tree_t t, int grav_mask, char *src, int64_t src_cap, double *consts, int32_t consts_cap,
+                                int32_t *n_consts, int32_t *counts)
+{
+    if (!t) { b2k_set_error("b2k_tree_codegen: tree handle is NULL"); return B2K_ERR_INVALID; }
+    b2k_gen_out g;
+    if (b2k_tree_generate(t, grav_mask, g)) { b2k_set_error("b2k_tree_codegen: %s", g.error.c_str()); return B2K_ERR_INVALID; }
+    if (n_consts) *n_consts = (int32_t)g.consts.size();
+    if (counts) { counts[0] = g.n_mul; counts[1] = g.n_fma; counts[2] = g.n_add; }
+    if (src) {
+        if ((int64_t)g.source.size() + 1 > src_cap) { b2k_set_error("b2k_tree_codegen: source needs %zu bytes", g.source.size() + 1); return B2K_ERR_INVALID; }
+        memcpy(src, g.source.c_str(), g.source.size() + 1);
+    }
+    if (consts) {
+        if ((int32_t)g.consts.size() > consts_cap) { b2k_set_error("b2k_tree_codegen: %zu constants", g.consts.size()); return B2K_ERR_INVALID; }
+        memcpy(consts, g.consts.data(), g.consts.size() * sizeof(double));
+    }
+    return B2K_OK;
+}
+
+extern "C" int b2k_tree_info(b2k_tree_t t, int dtype, const double *grav, char *buf, int64_t cap)
+{
+    if (!t || !buf || cap < 1) { b2k_set_error("b2k_tree_info: bad arguments"); return B2K_ERR_INVALID; }
+    Program *p = tree_program(t, dtype, grav_mask_of(grav));
+    if (!p || !p->ok) snprintf(buf, (size_t)cap, "unavailable (%s)", p ? p->why.c_str() : "no cache");
+    else
+        snprintf(buf, (size_t)cap, "k_rne_spec<%s,tree n=%d>: %d mul + %d fma + %d add per row, %d constants, %d regs, %zu B smem/block",
+                 dtype == B2K_F64 ? "double" : "float", t->n, p->n_mul, p->n_fma, p->n_add, p->nc, p->regs, p->smem);
     return B2K_OK;
 }

@@ -1,8 +1,10 @@
 """Batched pose error and position-based servo (reference tools/p_servo.py).
 
 ``angle_axis(T, Td)`` is the batched ``fknm.Angle_Axis`` (fknm.cpp:112-162); ``p_servo`` is
-tools/p_servo.py:46-106 for ``method="angle-axis"``.  The default ``method="rpy"`` of the reference
-goes through spatialmath's ``tr2rpy``, which is not part of the reference tree: it is not accelerated.
+tools/p_servo.py:46-106 for both of its methods: "angle-axis" (error in the base frame) and the reference's
+default "rpy" (error in the end-effector frame, e = [t(Te^-1 Tep); tr2rpy(Te^-1 Tep, order="zyx")]).  ``tr2rpy``
+belongs to spatialmath, which is not part of the reference tree: its zyx convention (R = Rz(yaw) Ry(pitch) Rx(roll),
+result (roll, pitch, yaw), roll := 0 at the pitch = +-pi/2 singularity) is restated in csrc/b2k_pose.cu.
 """
 from __future__ import annotations
 
@@ -49,19 +51,19 @@ def angle_axis(T, Td, dtype=None):
     return e[0] if single else e
 
 
-def p_servo(wTe, wTep, gain=1.0, threshold=0.1, method="angle-axis", dtype=None):
+def p_servo(wTe, wTep, gain=1.0, threshold=0.1, method="rpy", dtype=None):
     """End-effector velocity that drives wTe towards wTep, and the `arrived` flag(s)
     (reference tools/p_servo.py:46-106).  Returns (v, arrived): (6,), bool for one pose pair;
     (N,6), (N,) bool for a batch."""
-    if method == "rpy":
-        raise NotImplementedError("method='rpy' needs spatialmath's tr2rpy (outside the reference tree); "
-                                  "use method='angle-axis'")
+    if method not in ("rpy", "angle-axis"):
+        raise ValueError("method must be 'rpy' or 'angle-axis'")
     a, b, N, stride, dt, host, single = _poses(wTe, wTep, dtype)
     g = np.full(6, float(gain)) if np.isscalar(gain) else np.ascontiguousarray(np.asarray(gain, dtype=np.float64).reshape(6))
     v = B.empty((N, 6), dt, like=a)
     arrived = B.empty_i32((N,), like=a)
-    _lib.check(_lib.lib().b2k_p_servo(B.code(dt), B.ptr(a), B.ptr(b), N, stride, _lib.dptr(g), float(threshold),
-                                      B.ptr(v), B.ptr(arrived), B.stream_ptr(a)))
+    fn = _lib.lib().b2k_p_servo_rpy if method == "rpy" else _lib.lib().b2k_p_servo
+    _lib.check(fn(B.code(dt), B.ptr(a), B.ptr(b), N, stride, _lib.dptr(g), float(threshold), B.ptr(v), B.ptr(arrived),
+                  B.stream_ptr(a)))
     if host:
         v, arrived = B.to_host(v), B.to_host(arrived).astype(bool)
     else:

@@ -11,7 +11,7 @@ cap() { # name, kernel regex, --only filter, skip
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:$2 -s ${4:-2} -c 1 -f -o gpurun_out/prof_$1 python scripts/kernel_bench.py --steps 2 --warmup 2 --only "$3" > gpurun_out/ncu_$1.log 2>&1; echo "ncu $1 rc=$?"
 }
 for w in $WHAT; do case $w in
-tests) echo "== pytest -m gpu"; timeout 1500 python -m pytest tests -m gpu -x -q ${PYTEST_K:+-k "$PYTEST_K"} > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -12 gpurun_out/pytest_gpu.log;;
+tests) echo "== pytest -m gpu"; timeout 1500 python -m pytest tests -m gpu -q ${PYTEST_K:+-k "$PYTEST_K"} > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -12 gpurun_out/pytest_gpu.log;;
 smoke) timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?"; tail -3 gpurun_out/smoke.log;;
 bench) echo "== bench"; timeout 900 python bench.py ${BENCH_ARGS:-} > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"; cat gpurun_out/bench.json; tail -5 gpurun_out/bench.err;;
 ref) echo "== bench reference arm"; timeout 900 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; cat gpurun_out/bench_ref.json; tail -3 gpurun_out/bench_ref.err;;

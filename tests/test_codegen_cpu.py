@@ -23,14 +23,16 @@ HARNESS = r"""
 #define __forceinline__ inline
 typedef double real;
 using std::fma;
+static inline real step_pos(real x) { return x > 0 ? 1.0 : 0.0; }
+static inline real step_neg(real x) { return x < 0 ? 1.0 : 0.0; }
 %s
 extern "C" void eval(const double *Cst, const double *grav, const double *fext, const double *offset, int n, int nout,
                      const double *q, const double *a1, const double *a2, long N, double *out)
 {
     for (long i = 0; i < N; i++) {
-        double st[16], ct[16], z[16] = {0};
-        for (int j = 0; j < n; j++) { st[j] = std::sin(q[i * n + j] + offset[j]); ct[j] = std::cos(q[i * n + j] + offset[j]); }
-        rne_row(Cst, grav, fext, st, ct, a1 ? a1 + i * n : z, a2 ? a2 + i * n : z, out + i * nout);
+        double st[16], ct[16], th[16], z[16] = {0};
+        for (int j = 0; j < n; j++) { th[j] = q[i * n + j] + offset[j]; st[j] = std::sin(th[j]); ct[j] = std::cos(th[j]); }
+        rne_row(Cst, grav, fext, st, ct, th, a1 ? a1 + i * n : z, a2 ? a2 + i * n : z, out + i * nout);
     }
 }
 """
@@ -186,3 +188,119 @@ def test_generated_kernels_compile_for_sm_100a_through_the_library():
                 rtb._lib.check(lib.b2k_rne_spec_info(h, mode, dt, rtb._lib.dptr(g), 0, buf, 4096))
                 assert buf.value.startswith(b"k_rne_spec<"), buf.value[:600]
         lib.b2k_rne_destroy(h)
+
+
+# ------------------------------------------------------------------ rigid-body trees (Robot.rne)
+TREE_HARNESS = r"""
+#include <cmath>
+#define __device__
+#define __forceinline__ inline
+typedef double real;
+using std::fma;
+%s
+extern "C" void eval(const double *Cst, const double *grav, int n, const double *q, const double *qd, const double *qdd, long N,
+                     double *out)
+{
+    double fext[6] = {0};
+    for (long i = 0; i < N; i++) {
+        double st[16], ct[16];
+        for (int j = 0; j < n; j++) { st[j] = std::sin(q[i * n + j]); ct[j] = std::cos(q[i * n + j]); }
+        rne_row(Cst, grav, fext, st, ct, q + i * n, qd + i * n, qdd + i * n, out + i * n);
+    }
+}
+"""
+
+
+def tree_handle(tree):
+    n = len(tree["parent"])
+    i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)  # noqa: E731
+    Cm = np.ascontiguousarray(np.asarray(tree["C"], dtype=np.float64)[:, :3, :].reshape(n, 12))
+    I6 = np.ascontiguousarray(np.asarray(tree["I6"], dtype=np.float64).reshape(n, 36))
+    h = C.c_void_p()
+    ip = rtb._lib.ip
+    keep = [i32(tree[k]) for k in ("parent", "axis", "flip", "jindex")]
+    rtb._lib.check(rtb._lib.lib().b2k_tree_create(n, *(k.ctypes.data_as(ip) for k in keep), rtb._lib.dptr(Cm), rtb._lib.dptr(I6), C.byref(h)))
+    return h
+
+
+def tree_host_fn(tmp_path, tag, h, grav_mask):
+    lib = rtb._lib.lib()
+    src = C.create_string_buffer(1 << 21)
+    consts = np.zeros(8192)
+    nc = C.c_int32()
+    counts = (C.c_int32 * 3)()
+    rtb._lib.check(lib.b2k_tree_codegen(h, grav_mask, src, len(src), rtb._lib.dptr(consts), 8192, C.byref(nc), counts))
+    cpp, so = tmp_path / f"{tag}.cpp", tmp_path / f"{tag}.so"
+    cpp.write_text(TREE_HARNESS % src.value.decode())
+    subprocess.check_call(["g++", "-O1", "-ffp-contract=off", "-shared", "-fPIC", str(cpp), "-o", str(so)])
+    L = C.CDLL(str(so))
+    dp = C.POINTER(C.c_double)
+    L.eval.argtypes = [dp, dp, C.c_int, dp, dp, dp, C.c_long, dp]
+    cst = consts[:nc.value].copy()
+
+    def run(grav, q, qd, qdd):
+        a = [np.ascontiguousarray(x, dtype=np.float64) for x in (cst, grav, q, qd, qdd)]
+        out = np.zeros_like(a[2])
+        L.eval(a[0].ctypes.data_as(dp), a[1].ctypes.data_as(dp), a[2].shape[1], a[2].ctypes.data_as(dp), a[3].ctypes.data_as(dp),
+               a[4].ctypes.data_as(dp), a[2].shape[0], out.ctypes.data_as(dp))
+        return out
+
+    return run, tuple(counts)
+
+
+def random_tree(rng, n, branched=True):
+    parent = [-1] + [int(rng.integers(0, j)) if branched else j - 1 for j in range(1, n)]
+    Cs = []
+    for _ in range(n):
+        if rng.random() < 0.5:  # axis-aligned constant (URDF style: rpy multiples of pi/2) or a general one
+            R = ch.trotz(rng.choice([0, np.pi / 2, -np.pi / 2, np.pi])) @ ch.trotx(rng.choice([0, np.pi / 2, -np.pi / 2]))
+        else:
+            R = ch.trotz(rng.uniform(-3, 3)) @ ch.troty(rng.uniform(-1, 1)) @ ch.trotx(rng.uniform(-3, 3))
+        T = R.copy()
+        T[:3, 3] = rng.uniform(-0.4, 0.4, 3) * rng.integers(0, 2, 3)
+        Cs.append(T)
+    I6 = [orc.spatial_inertia(rng.uniform(0.2, 3), rng.uniform(-0.2, 0.2, 3) * rng.integers(0, 2, 3))
+          + (orc.spatial_inertia(rng.uniform(0.1, 1), rng.uniform(-0.2, 0.2, 3)) if rng.random() < 0.3 else 0) for _ in range(n)]
+    return dict(parent=parent, axis=[int(a) for a in rng.integers(0, 6, n)], flip=[int(f) for f in rng.integers(0, 2, n)],
+                jindex=list(range(n)), C=Cs, I6=I6)
+
+
+def test_generated_tree_recursion_equals_featherstone_oracle(tmp_path):
+    """Robot.rne for rigid-body trees: the generated row function against the numpy restatement of the reference's
+    spatial-vector recursion (which reproduces the reference's own KATs, tests/test_ERobot.py:100-154: checked here too)."""
+    pi = np.pi
+    spong = dict(parent=[-1, 0], axis=[1, 1], flip=[0, 0], jindex=[0, 1], C=[np.eye(4), ch.transl(1, 0, 0)],
+                 I6=[orc.spatial_inertia(1, [0.5, 0, 0])] * 2)
+    h = tree_handle(spong)
+    f, cnt = tree_host_fn(tmp_path, "spong", h, 4)
+    z = np.zeros((1, 2))
+    g = np.array([0, 0, 9.81])  # a_grav = -gravity
+    np.testing.assert_allclose(f(g, z, z, z) / 9.81, [[-2, -0.5]], atol=1e-12)
+    np.testing.assert_allclose(f(g, [[0.0, -pi / 2]], z, z) / 9.81, [[-1.5, 0]], atol=1e-12)
+    np.testing.assert_allclose(f(g, [[-pi / 2, pi / 2]], z, z) / 9.81, [[-0.5, -0.5]], atol=1e-12)
+    f0, _ = tree_host_fn(tmp_path, "spong0", h, 0)
+    q = np.array([[0, -pi / 2]])
+    hh = -0.5 * np.sin(q[0, 1])
+    np.testing.assert_allclose(f0(np.zeros(3), q, [[1.0, 1.0]], z), [np.r_[3, -1] * hh], atol=1e-12)
+    d11, d12 = 1.5 + np.cos(q[0, 1]), 0.25 + 0.5 * np.cos(q[0, 1])
+    np.testing.assert_allclose(f0(np.zeros(3), q, z, [[1.0, 1.0]]), [[d11 + d12, d12 + 0.25]], atol=1e-12)
+    rtb._lib.lib().b2k_tree_destroy(h)
+    rng = np.random.default_rng(77)
+    for k, (n, branched) in enumerate([(1, False), (3, False), (6, True), (9, True), (16, True)]):
+        tree = random_tree(rng, n, branched)
+        h = tree_handle(tree)
+        N = 60
+        q, qd, qdd = rng.uniform(-3, 3, (N, n)), rng.normal(size=(N, n)), rng.normal(size=(N, n))
+        for gm, grav in ((7, np.array([0.5, -1.0, -9.81])), (4, np.array([0, 0, -9.81])), (0, np.zeros(3))):
+            f, cnt = tree_host_fn(tmp_path, f"t{k}_{gm}", h, gm)
+            np.testing.assert_allclose(f(-grav, q, qd, qdd), orc.tree_rne(tree, q, qd, qdd, grav), rtol=1e-9, atol=1e-9,
+                                       err_msg=f"tree {k} n={n} gmask={gm}")
+        rtb._lib.lib().b2k_tree_destroy(h)
+    # validation
+    lib = rtb._lib.lib()
+    bad = dict(spong, parent=[0, -1])
+    with pytest.raises(ValueError, match="precede"):
+        tree_handle(bad)
+    with pytest.raises(ValueError, match="permutation"):
+        tree_handle(dict(spong, jindex=[0, 0]))
+    assert lib.b2k_tree_rne(None, 1, None, None, None, 0, None, None, None) == -1

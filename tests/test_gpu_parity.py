@@ -298,8 +298,8 @@ def test_hessian_and_manipulability():
     Q6 = np.random.default_rng(6).uniform(-3, 3, (50, 6))
     J6 = host(ur.jacob0(dev(Q6)))
     np.testing.assert_allclose(host(ur.manipulability(dev(Q6))), [orc.yoshikawa(Jk) for Jk in J6], rtol=1e-9, atol=1e-12)
-    with pytest.raises(NotImplementedError):
-        e.manipulability(q1, method="minsingular")
+    with pytest.raises(ValueError):
+        e.manipulability(q1, method="asada")
     # manipulability Jacobian: reference test literal (tests/test_ERobot.py:28-52: q as array, list, (1,n), (n,1), J=)
     kat = KAT["panda_jacobm"]
     pe = rtb.models.Panda().ets()
@@ -343,13 +343,13 @@ def test_fixture_ik_fp64_explicit_q0():
     for tag, method, k in (("chan1", "chan", 1.0), ("chan01", "chan", 0.1), ("sugi", "sugihara", 1e-4)):
         q, s, it, sr, E = (host(x) for x in e.ik_LM(Tep, q0=q0, slimit=1, joint_limits=False, k=k, method=method))
         same = (s == z[tag + "_success"]) & (it == z[tag + "_it"]) & (sr == z[tag + "_search"])
-        assert same.mean() >= 0.98, f"{tag}: {same.mean():.3f} of rows reproduce the reference's counters"
+        assert same.all(), f"{tag}: rows {np.nonzero(~same)[0]} do not reproduce the reference's counters"
         ok = same & (s == 1)
         np.testing.assert_allclose(q[ok], z[tag + "_q"][ok], atol=1e-7)
         np.testing.assert_allclose(E[ok], z[tag + "_E"][ok], atol=1e-11)
     # fmod wrap + joint-limit rejection (ik.cpp:50-52)
     q, s, it, sr, E = (host(x) for x in e.ik_LM(Tep, q0=q0, slimit=1, joint_limits=True, k=1.0))
-    assert ((s == z["jl_success"]) & (it == z["jl_it"])).mean() >= 0.98
+    assert ((s == z["jl_success"]) & (it == z["jl_it"])).all()
     # masked (position-only) solve
     q, s, it, sr, E = (host(x) for x in e.ik_LM(Tep, q0=q0, slimit=1, joint_limits=False, mask=z["mask"], k=1.0))
     assert (s == z["mask_success"]).mean() >= 0.95
@@ -830,18 +830,18 @@ def test_angle_axis_and_p_servo():
     far = np.abs(z["e"]).max(axis=1) < 3.0  # away from the angle = pi discontinuity, where fp32 rounding picks a branch
     np.testing.assert_allclose(e32[far], z["e"][far], rtol=2e-3, atol=2e-3)
     gain = np.array([1, 2, 3, 0.5, 0.25, 4.0])
-    v, arrived = rtb.p_servo(z["Te"], z["Tep"], gain=gain, threshold=0.4)
+    v, arrived = rtb.p_servo(z["Te"], z["Tep"], gain=gain, threshold=0.4, method="angle-axis")
     np.testing.assert_allclose(v, z["e"] * gain, rtol=1e-10, atol=1e-12)
     assert (arrived == (np.abs(z["e"]).sum(axis=1) < 0.4)).all()
-    v1, a1 = rtb.p_servo(z["Te"][0], z["Tep"][0], gain=2.0)
+    v1, a1 = rtb.p_servo(z["Te"][0], z["Tep"][0], gain=2.0, method="angle-axis")
     assert v1.shape == (6,) and a1 is True
     panda = rtb.models.Panda()
     Q = dev(np.random.default_rng(1).uniform(-2, 2, (4096, 7)))
     T = panda.ets().eval(Q)
-    v, arr = rtb.p_servo(T, T[7], gain=1.5)  # servo every pose of the batch towards one target, all on the device
+    v, arr = rtb.p_servo(T, T[7], gain=1.5, method="angle-axis")  # servo every pose of the batch towards one target, all on the device
     assert v.is_cuda and v.shape == (4096, 6) and bool(arr[7]) and float(v[7].abs().max()) == 0.0
-    with pytest.raises(NotImplementedError):
-        rtb.p_servo(z["Te"][0], z["Tep"][0], method="rpy")
+    with pytest.raises(ValueError):
+        rtb.p_servo(z["Te"][0], z["Tep"][0], method="quaternion")
 
 
 def test_c_program_through_the_c_abi(tmp_path):

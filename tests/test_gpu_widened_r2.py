@@ -48,3 +48,117 @@ def test_manipulability_minsingular_and_invcondition():
     np.testing.assert_allclose(got32, orc.manip_svd(J[1:], kind="minsingular"), rtol=2e-3, atol=2e-5)
     with pytest.raises(ValueError):
         panda.manipulability(Q[1], method="asada")
+
+
+def test_jacob0_analytical_all_representations():
+    """ETS.jacob0_analytical (ETS.py:1570-1626) for rpy/xyz, rpy/zyx, eul, exp against the oracle's restatement of
+    rotvelxform, and -- independently of any restatement -- against the finite-difference derivative of the
+    representation of the pose the product itself computes."""
+    rng = np.random.default_rng(21)
+    panda = rtb.models.Panda()
+    e = panda.ets()
+    C = orc.Chain(e.describe())
+    Q = rng.uniform(-2, 2, (400, 7))
+    T, J = C.fkine(Q), C.jacob0(Q)
+    for rep in ("rpy/xyz", "rpy/zyx", "eul", "exp"):
+        Ja = host(e.jacob0_analytical(dev(Q), representation=rep))
+        want = orc.jacob0_analytical(T, J, rep)
+        ok = np.abs(want).max(axis=(1, 2)) < 1e4  # rows next to the representation's singularity: 1/cos(pitch) etc. blow up
+        np.testing.assert_allclose(Ja[ok], want[ok], rtol=1e-8, atol=1e-9, err_msg=rep)
+        one = e.jacob0_analytical(Q[3], representation=rep)
+        assert isinstance(one, np.ndarray) and one.shape == (6, 7)
+        np.testing.assert_allclose(one, want[3], rtol=1e-8, atol=1e-9)
+    # finite differences through the product's own FK
+    h = 1e-6
+    Ja = host(e.jacob0_analytical(dev(Q[:50]), representation="rpy/zyx"))
+    for j in (0, 3, 6):
+        dq = np.zeros(7); dq[j] = h
+        gp = np.stack([orc.tr2rpy(t, "zyx") for t in host(e.eval(dev(Q[:50] + dq)))])
+        gm = np.stack([orc.tr2rpy(t, "zyx") for t in host(e.eval(dev(Q[:50] - dq)))])
+        d = (gp - gm + np.pi) % (2 * np.pi) - np.pi
+        good = np.abs(d).max(axis=1) < 1e-3
+        np.testing.assert_allclose(Ja[:50][good][:, 3:, j], d[good] / (2 * h), rtol=1e-4, atol=1e-5)
+    with pytest.raises(ValueError):
+        e.jacob0_analytical(Q[0], representation="quaternion")
+    # analytical jacob0_dot: the reference differentiates jacob0_analytical numerically (Robot.py:1090-1092)
+    qd = rng.normal(size=(50, 7))
+    Jd = host(e.jacob0_dot(dev(Q[:50]), dev(qd), representation="rpy/xyz"))
+    hh = 1e-5
+    num = (orc.jacob0_analytical(C.fkine(Q[:50] + hh * qd), C.jacob0(Q[:50] + hh * qd), "rpy/xyz")
+           - orc.jacob0_analytical(C.fkine(Q[:50] - hh * qd), C.jacob0(Q[:50] - hh * qd), "rpy/xyz")) / (2 * hh)
+    ok = np.abs(num).max(axis=(1, 2)) < 1e3
+    np.testing.assert_allclose(Jd[ok], num[ok], rtol=1e-4, atol=1e-4)
+
+
+def test_p_servo_rpy_method():
+    """tools/p_servo.py:80-106 with the reference's default method='rpy' (error in the end-effector frame)."""
+    rng = np.random.default_rng(22)
+    C = orc.Chain(ch.panda_ets())
+    Te, Tep = C.fkine(rng.uniform(-2, 2, (300, 7))), C.fkine(rng.uniform(-2, 2, (300, 7)))
+    gain = np.array([1, 2, 3, 0.5, 0.25, 4.0])
+    v, arrived = rtb.p_servo(Te, Tep, gain=gain, threshold=2.5)  # default method is rpy, as in the reference
+    wv, wa = orc.p_servo_rpy(Te, Tep, gain, 2.5)
+    np.testing.assert_allclose(v, wv, rtol=1e-10, atol=1e-11)
+    assert (arrived == wa).all() and 0 < arrived.sum() < 300
+    v1, a1 = rtb.p_servo(Te[0], Te[0], gain=2.0)
+    assert v1.shape == (6,) and a1 is True and np.abs(v1).max() < 1e-12
+    vd, ad = rtb.p_servo(dev(Te), dev(Tep[5]), gain=1.5, method="rpy")
+    wv, wa = orc.p_servo_rpy(Te, Tep[5], 1.5, 0.1)
+    np.testing.assert_allclose(host(vd), wv, rtol=1e-10, atol=1e-11)
+    v32, _ = rtb.p_servo(Te.astype(np.float32), Tep.astype(np.float32), gain=1.0)
+    far = np.abs(np.abs(orc.p_servo_rpy(Te, Tep, 1.0, 0.1)[0][:, 3:]) - np.pi).min(axis=1) > 0.05  # away from the +-pi wrap
+    np.testing.assert_allclose(v32[far], orc.p_servo_rpy(Te, Tep, 1.0, 0.1)[0][far], rtol=2e-3, atol=2e-3)
+
+
+def test_ctraj_feeds_ik_on_the_device():
+    """tools.trajectory.ctraj (trajectory.py:782-841): the pose batch is produced in HBM and consumed there by ik_LM."""
+    rng = np.random.default_rng(23)
+    panda = rtb.models.Panda().ets()
+    C = orc.Chain(panda.describe())
+    qa, qb = rng.uniform(-1.5, 1.5, 7), rng.uniform(-1.5, 1.5, 7)
+    T0, T1 = C.fkine(qa)[0], C.fkine(qb)[0]
+    s = np.r_[rng.uniform(0, 1, 300), 0.0, 1.0, -0.2, 1.3]
+    P = rtb.ctraj(T0, T1, s=s)
+    np.testing.assert_allclose(P.A, orc.ctraj_poses(T0, T1, s), rtol=1e-10, atol=1e-12)
+    for n in (2, 25, 100):  # ctraj(T0, T1, n): trapezoidal path fraction
+        Pn = rtb.ctraj(T0, T1, n)
+        sn = orc.trapezoidal(0, 1, n)[1]
+        np.testing.assert_allclose(Pn.A, orc.ctraj_poses(T0, T1, sn), rtol=1e-9, atol=1e-11)
+    t = np.linspace(0, 4, 33)
+    np.testing.assert_allclose(rtb.ctraj(T0, T1, t).A, orc.ctraj_poses(T0, T1, orc.trapezoidal(0, 1, t / t.max())[1]), rtol=1e-9, atol=1e-11)
+    # opposite-hemisphere quaternions take the shorter arc; identical orientations interpolate the translation only
+    T2 = T0.copy(); T2[:3, 3] += [0.1, -0.2, 0.3]
+    np.testing.assert_allclose(rtb.ctraj(T0, T2, s=[0.25]).A[:3, :3], T0[:3, :3], atol=1e-12)
+    Td = rtb.ctraj(T0, T1, 200, device=True)
+    assert Td.is_cuda and Td.shape == (200, 4, 4)
+    q, ok, it, sr, E = panda.ik_LM(Td, q0=dev(qa), joint_limits=False, k=0.1)
+    assert bool(ok.all())
+    np.testing.assert_allclose(C.fkine(host(q)), host(Td), atol=5e-3)
+    with pytest.raises(TypeError):
+        rtb.ctraj(T0, T1)
+
+
+def test_mstraj_sample_table():
+    """tools.trajectory.mstraj (trajectory.py:852-1152): plan on the host, samples on the device; against the numpy
+    restatement of the reference loop, both timing modes, initial / final velocities, scalar and per-segment tacc."""
+    via = np.array([[0.0, 0.0, 0.2], [1.0, 0.5, -0.4], [1.0, 2.0, 0.0], [-0.5, 2.0, 0.9], [0.3, -1.0, 0.9]])
+    cases = [dict(dt=0.1, tacc=0.4, qdmax=[1.0, 0.8, 0.5]), dict(dt=0.05, tacc=0.2, qdmax=1.5),
+             dict(dt=0.1, tacc=0.0, qdmax=[1.0, 0.8, 0.5]), dict(dt=0.2, tacc=0.5, tsegment=[2.0, 3.0, 2.5, 4.0]),
+             dict(dt=0.1, tacc=[0.2, 0.4, 0.6, 0.3], qdmax=2.0, qd0=[0.1, 0.0, -0.1], qdf=[0.0, 0.2, 0.0]),
+             dict(dt=0.1, tacc=0.3, qdmax=1.0, q0=[0.5, 0.5, 0.5])]
+    for kw in cases:
+        tr = rtb.mstraj(via, **kw)
+        t, q, arrive = orc.mstraj(via, **kw)
+        assert tr.q.shape == q.shape, (kw, tr.q.shape, q.shape)
+        np.testing.assert_allclose(tr.q, q, rtol=1e-10, atol=1e-12, err_msg=str(kw))
+        np.testing.assert_allclose(tr.t, t, atol=1e-12)
+        np.testing.assert_allclose(tr.arrive, arrive, atol=1e-12)
+        assert len(tr.info) == (len(via) if "q0" in kw else len(via) - 1) + 1
+    trd = rtb.mstraj(via, dt=0.1, tacc=0.4, qdmax=[1.0, 0.8, 0.5], device=True)
+    assert trd.q.is_cuda
+    tr32 = rtb.mstraj(via, dt=0.1, tacc=0.4, qdmax=[1.0, 0.8, 0.5], dtype=np.float32)
+    np.testing.assert_allclose(tr32.q, orc.mstraj(via, dt=0.1, tacc=0.4, qdmax=[1.0, 0.8, 0.5])[1], rtol=1e-5, atol=1e-6)
+    with pytest.raises(ValueError):
+        rtb.mstraj(via, dt=0.1, tacc=0.2, qdmax=1.0, tsegment=[1, 1, 1, 1])
+    with pytest.raises(ValueError):
+        rtb.mstraj(via, dt=0.1, tacc=0.2)

@@ -303,3 +303,59 @@ def test_quintic_trapezoidal_restatements():
         orc.trapezoidal(1, 2, 11, 0.01)
     with pytest.raises(ValueError):
         orc.trapezoidal(1, 2, 11, 1.0)
+
+
+def test_pose_representation_restatements_are_self_consistent():
+    """tr2rpy / tr2eul / trlog / rotvelxform come from spatialmath (not under the reference tree): the oracle's
+    restatements are pinned by identities instead -- round trips through the defining products, and the analytical
+    Jacobian being the derivative of the representation along the chain."""
+    from oracle import chains as ch
+
+    rng = np.random.default_rng(3)
+    rx, ry, rz = (lambda a: ch.trotx(a)[:3, :3]), (lambda a: ch.troty(a)[:3, :3]), (lambda a: ch.trotz(a)[:3, :3])
+    for _ in range(50):
+        r, p, y = rng.uniform(-3, 3), rng.uniform(-1.5, 1.5), rng.uniform(-3, 3)
+        np.testing.assert_allclose(orc.tr2rpy(rz(y) @ ry(p) @ rx(r), "zyx"), [r, p, y], atol=1e-12)
+        np.testing.assert_allclose(orc.tr2rpy(rx(y) @ ry(p) @ rz(r), "xyz"), [r, p, y], atol=1e-12)
+        ph, th, ps = rng.uniform(-3, 3), rng.uniform(0.05, 3.0), rng.uniform(-3, 3)
+        np.testing.assert_allclose(orc.tr2eul(rz(ph) @ ry(th) @ rz(ps)), [ph, th, ps], atol=1e-12)
+    # gimbal lock: roll := 0 and the product is still reproduced
+    for p in (np.pi / 2, -np.pi / 2):
+        R = rz(0.3) @ ry(p) @ rx(0.7)
+        g = orc.tr2rpy(R, "zyx")
+        assert g[0] == 0
+        np.testing.assert_allclose(rz(g[2]) @ ry(g[1]) @ rx(g[0]), R, atol=1e-12)
+    C = orc.Chain(ch.panda_ets())
+    Q = rng.uniform(-2, 2, (20, 7))
+    T, J = C.fkine(Q), C.jacob0(Q)
+    h = 1e-6
+    for rep in ("rpy/xyz", "rpy/zyx", "eul", "exp"):
+        Ja = orc.jacob0_analytical(T, J, rep)
+        np.testing.assert_array_equal(Ja[:, :3], J[:, :3])
+        for k in range(len(Q)):
+            for j in range(7):
+                dq = np.zeros(7); dq[j] = h
+                gp = orc.r2x(C.fkine(Q[k] + dq)[0, :3, :3], rep)
+                gm = orc.r2x(C.fkine(Q[k] - dq)[0, :3, :3], rep)
+                d = gp - gm
+                if rep != "exp":
+                    d = (d + np.pi) % (2 * np.pi) - np.pi
+                if np.abs(d).max() < 1e-3:  # skip samples that straddle a branch cut of the representation
+                    np.testing.assert_allclose(Ja[k, 3:, j], d / (2 * h), rtol=2e-5, atol=2e-6, err_msg=f"{rep} row {k} joint {j}")
+    # Cartesian interpolation: end points, linear translation, constant angular rate along the shorter arc
+    T0, T1 = T[0], T[1]
+    s = np.linspace(0, 1, 11)
+    P = orc.ctraj_poses(T0, T1, s)
+    np.testing.assert_allclose(P[0], T0, atol=1e-12)
+    np.testing.assert_allclose(P[-1], T1, atol=1e-12)
+    np.testing.assert_allclose(P[:, :3, 3], T0[:3, 3] + s[:, None] * (T1[:3, 3] - T0[:3, 3]), atol=1e-12)
+    ang = np.array([np.linalg.norm(orc.trlog(T0[:3, :3].T @ p[:3, :3])) for p in P])
+    np.testing.assert_allclose(ang, s * ang[-1], atol=1e-10)
+    assert ang[-1] <= np.pi + 1e-12
+    # mstraj: passes through the neighbourhood of the via points, starts at q0, ends at the last via point, dt grid
+    via = np.array([[0.0, 0.0], [1.0, 0.5], [1.0, 2.0], [-0.5, 2.0]])
+    t, q, arrive = orc.mstraj(via, dt=0.1, tacc=0.4, qdmax=[1.0, 0.8])
+    np.testing.assert_allclose(np.diff(t), 0.1)
+    np.testing.assert_allclose(q[-1], via[-1], atol=1e-12)
+    assert np.abs(q[0] - via[0]).max() < 0.1 and (np.diff(arrive) > 0).all()
+    assert (np.abs(np.diff(q, axis=0)).max(axis=0) / 0.1 <= 1.25 * np.array([1.0, 0.8])).all()  # blends overshoot the cruise speed a little
