@@ -423,13 +423,44 @@ def run_b200(args):
 
             g_ms = time_steps(g0, 5, 2)
             del parts
+            # the same reassembly WITHOUT a collective: every rank's kernel writes its shard straight into rank 0's memory
+            # (peer pointer from torch symmetric memory; the pose rows go out as 256-bit stores, the Jacobian tiles as TMA
+            # bulk copies -- over NVLink instead of to local HBM).  Root ingress is the bound: (world - 1) shards.
+            fused = None
+            try:
+                import torch.distributed._symmetric_memory as symm
+
+                sbuf = symm.empty(world * TJ.numel(), dtype=torch.float32, device=dev)
+                hdl = symm.rendezvous(sbuf, dist.group.WORLD)
+                slot = int(hdl.buffer_ptrs[0]) + rank * TJ.numel() * 4
+                Tp, Jp = slot, slot + ROWS_PER_GPU * 16 * 4
+
+                def fstep(i):
+                    rtb._lib.check(L.b2k_fkine_jacob0(uch, F32, uq[i % 8].data_ptr(), ROWS_PER_GPU, 6, None, None, Tp, Jp, sp))
+
+                f_ms = time_steps(fstep, 5, 2)
+                # check: rank 0's buffer now holds what an NCCL gather of the local results delivers
+                ustep(6)
+                fstep(6)
+                barrier()
+                ref = [torch.empty_like(TJ) for _ in range(world)] if rank == 0 else None
+                dist.gather(TJ, ref, dst=0)
+                same = bool(torch.equal(sbuf.view(world, -1), torch.stack(ref))) if rank == 0 else None
+                fused = {"ms": f_ms, "GBps_into_root": recv / (f_ms * 1e-3) / 1e9, "frac_of_900GBps": recv / (f_ms * 1e-3) / 1e9 / NVLINK_GBS,
+                         "identical_to_nccl_gather": same,
+                         "how": "k_fkj_fast<float,6> launched with T / J pointing into rank 0's symmetric-memory buffer"}
+                del sbuf
+            except Exception as e:  # symmetric memory unavailable on this box / build
+                fused = {"unavailable": repr(e)[:300]}
             gather = {
-                "what": "UR10 fp32 result shards, packed [T | J] per rank: one NCCL all-gather; and a gather to rank 0",
+                "what": "UR10 fp32 result shards, packed [T | J] per rank: one NCCL all-gather; a gather to rank 0; and the kernel "
+                        "writing its shard directly into rank 0's memory over NVLink (no collective)",
                 "bytes_per_rank_shard": TJ.numel() * 4, "bytes_received_per_rank": recv,
                 "all_gather_ms": ag_ms, "gather_to_root_ms": g_ms,
                 "GBps": recv / (ag_ms * 1e-3) / 1e9, "frac_of_900GBps": recv / (ag_ms * 1e-3) / 1e9 / NVLINK_GBS,
                 "gather_to_root_GBps": recv / (g_ms * 1e-3) / 1e9,
                 "gather_to_root_frac_of_900GBps": recv / (g_ms * 1e-3) / 1e9 / NVLINK_GBS,
+                "fused_store_to_root": fused,
                 "kernel_ms": ms, "note": "GB/s = bytes received by one rank / time; the kernel that produced the shard "
                                          "takes kernel_ms, so the reassembly cannot be hidden behind it (SURVEY 8e)",
             }

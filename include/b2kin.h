@@ -222,6 +222,19 @@ int b2k_rne_coriolis(b2k_rne_t rne, int dtype, const void *q, const void *qd, in
 int b2k_rne_accel(b2k_rne_t rne, int dtype, const void *q, const void *qd, const void *torque, int64_t N,
                   const double *grav, void *qdd, void *stream);
 
+/* b2k_rne_fdyn integrates the forward dynamics of an ENSEMBLE of initial states (DynamicsMixin.fdyn, Dynamics.py:185-422,
+ * integrates one): one lane per trajectory, Dormand-Prince 5(4) with scipy RK45's step control (rtol, atol, max_step,
+ * first_step <= 0: automatic), every stage's acceleration from the robot-specialised recursion.  q0, qd0 (ntraj,n) device
+ * (qd0 may be NULL = at rest).  Torque: torque_mode 0 none, 1 constant tau (host n), 2 tau_rows (ntraj,n) device,
+ * 3 PD kp (qstar - q) - kd qd (host n-vectors).  Output, M slots per trajectory: grid = 0 the accepted steps (t, q, qd as
+ * scipy's integrator visits them), grid = 1 the uniform grid k dt by linear interpolation (the reference's interp1d);
+ * out_t (ntraj,M), out_q / out_qd (ntraj,M,n), out_count (samples produced; > M means the capacity was too small),
+ * out_status (bit 0: step size underflow, bit 1: capacity exceeded).  All-revolute robots; needs NVRTC. */
+int b2k_rne_fdyn(b2k_rne_t rne, int dtype, const void *q0, const void *qd0, int64_t ntraj, double T, const double *grav,
+                 int torque_mode, const double *tau, const void *tau_rows, const double *kp, const double *kd, const double *qstar,
+                 double rtol, double atol, double max_step, double first_step, double dt, int grid, int M, void *out_t,
+                 void *out_q, void *out_qd, int32_t *out_count, int32_t *out_status, void *stream);
+
 /* ---------------------------------------------------------------- pure functions of the Jacobian
  * b2k_hessian replaces fknm.ETS_hessian0 / ETS_hessiane (fknm.cpp:583-783 -> _ETS_hessian
  * methods.cpp:16-32): H (N,n,6,n) from J (N,6,n); pass jacob0 for hessian0, jacobe for hessiane.

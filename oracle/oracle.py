@@ -672,3 +672,32 @@ def tree_rne(tree, q, qd, qdd, gravity):
             if pa >= 0:
                 f[pa] = f[pa] + Xup[j].T @ f[j]
     return Q
+
+
+def fdyn(accel_fn, n, T, q0, qd0=None, torque_fn=None, solver="RK45", solver_args=None, dt=None):
+    """DynamicsMixin.fdyn restated (Dynamics.py:300-377): scipy's integrator stepping on x = [q, qd] with
+    xd = [qd, accel(q, qd, tau)]; accel_fn(q, qd, tau) -> qdd is the oracle's accel.  Returns (t, q, qd)."""
+    from scipy import integrate, interpolate
+
+    q0 = np.asarray(q0, dtype=np.float64).reshape(n)
+    qd0 = np.zeros(n) if qd0 is None else np.asarray(qd0, dtype=np.float64).reshape(n)
+
+    def f(t, x):
+        q, qd = x[:n], x[n:]
+        tau = np.zeros(n) if torque_fn is None else np.asarray(torque_fn(t, q, qd), dtype=np.float64)
+        return np.r_[qd, accel_fn(q, qd, tau)]
+
+    integ = integrate.__dict__[solver](f, t0=0.0, y0=np.r_[q0, qd0], t_bound=T, **(solver_args or {}))
+    tl, xl = [0], [np.r_[q0, qd0]]
+    while integ.status == "running":
+        integ.step()
+        if integ.status == "failed":
+            raise RuntimeError("integration completed with failed status ")
+        tl.append(integ.t)
+        xl.append(integ.y)
+    ta, xa = np.array(tl), np.array(xl)
+    if dt is not None:
+        tnew = np.arange(0, T, dt)
+        xnew = interpolate.interp1d(ta, xa, axis=0)(tnew)
+        return tnew, xnew[:, :n], xnew[:, n:]
+    return ta, xa[:, :n], xa[:, n:]

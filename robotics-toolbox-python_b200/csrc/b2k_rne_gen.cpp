@@ -243,8 +243,10 @@ double snap(double v)
 }
 
 struct Link {
-    Sym st, ct, sa, ca; // joint rotation (run time), twist (constants)
-    double ps[3], r[3], I[9], m, c_jm, c_b, c_tcp, c_tcm;
+    Sym st, ct, sa, ca; // joint rotation (run time; constants of theta for a prismatic link), twist (constants)
+    bool pris = false;
+    V3 ps;              // p*: (a, d sin(alpha), d cos(alpha)) for DH, (a, -d sin(alpha), d cos(alpha)) for MDH; d = q + offset if prismatic
+    double r[3], I[9], m, c_jm, c_b, c_tcp, c_tcm;
 };
 
 struct Inputs { // one evaluation of the recursion: per-joint velocity / acceleration symbols, base acceleration, tip wrench
@@ -272,10 +274,35 @@ std::vector<Sym> recursion(Gen &g, const std::vector<Link> &L, bool mdh, const I
     };
     for (int j = 0; j < N; j++) {
         const Link &l = L[j];
-        const V3 ps = v.cst(l.ps), rc = v.cst(l.r);
+        const V3 ps = l.ps, rc = v.cst(l.r);
         const Sym qd = in.qd[j], qdd = in.qdd[j];
         V3 wn, wdn, accn;
-        if (mdh) {
+        if (l.pris) { // translational joint along z_{j-1} (ne.c:183-225 MDH, 290-333 DH): no joint rate in w / wd
+            const V3 qdv = {Gen::zero(), Gen::zero(), qd}, qddv = {Gen::zero(), Gen::zero(), qdd};
+            const Sym two = Gen::cst(2.0);
+            if (mdh) {
+                if (j == 0) { // sic, ne.c:187-204: the base acceleration is taken over unrotated
+                    wn = qdv; wdn = qddv; accn = in.grav;
+                } else {
+                    wn = RT(l, w);
+                    wdn = RT(l, wd);
+                    const V3 wxp = v.cross_acc(w, ps);
+                    const V3 a = v.cross_acc(wd, ps, &acc);
+                    const V3 t = RT(l, v.cross_acc(w, wxp, &a));
+                    const V3 c2 = v.scale(two, v.cross_acc(v.fix(wn), qdv));
+                    accn = v.add(v.add(t, c2), qddv);
+                }
+            } else {
+                V3 base;
+                if (j == 0) { wn = v.zero(); wdn = v.zero(); base = RT(l, v.add(qddv, in.grav)); }
+                else { wn = v.fix(RT(l, w)); wdn = v.fix(RT(l, wd)); base = RT(l, v.add(qddv, acc)); }
+                const V3 a1 = v.cross_acc(wdn, ps, &base);
+                const V3 c2 = v.scale(two, v.cross_acc(wn, RT(l, qdv)));
+                const V3 a2 = v.add(a1, c2);
+                const V3 wxp = v.cross_acc(wn, ps);
+                accn = v.cross_acc(wn, wxp, &a2);
+            }
+        } else if (mdh) {
             if (j == 0) {
                 wn = {Gen::zero(), Gen::zero(), qd};
                 wdn = {Gen::zero(), Gen::zero(), qdd};
@@ -324,14 +351,14 @@ std::vector<Sym> recursion(Gen &g, const std::vector<Link> &L, bool mdh, const I
                 nj = v.add(in.ntip, rxF);
             } else {
                 const Link &ln = L[j + 1];
-                const V3 psn = v.cst(ln.ps);
+                const V3 psn = ln.ps;
                 const V3 Rf = v.fix(R(ln, f));
                 fj = v.add(Rf, Fm[j]);
                 const V3 pxf = v.cross_acc(psn, Rf, &rxF);
                 nj = R(ln, nn, &pxf);
             }
         } else {
-            const V3 ps = v.cst(l.ps);
+            const V3 ps = l.ps;
             if (j == N - 1) {
                 fj = v.fix(v.add(in.ftip, Fm[j]));
                 nj = v.cross_acc(ps, fj, &rxF, &in.ntip);
@@ -343,10 +370,12 @@ std::vector<Sym> recursion(Gen &g, const std::vector<Link> &L, bool mdh, const I
             }
         }
         f = v.fix(fj); nn = v.fix(nj);
-        // torque about the joint axis z_{j-1} seen from frame j: (0, sa, ca) for DH, (0, 0, 1) for MDH
+        // torque about (force along, for a prismatic joint) the joint axis z_{j-1} seen from frame j:
+        // (0, sa, ca) for DH, (0, 0, 1) for MDH
         std::vector<Sym> t;
-        if (mdh) t.push_back(nn.z);
-        else { t.push_back(g.mul(nn.y, l.sa)); t.push_back(g.mul(nn.z, l.ca)); }
+        const V3 &load = l.pris ? f : nn;
+        if (mdh) t.push_back(load.z);
+        else { t.push_back(g.mul(load.y, l.sa)); t.push_back(g.mul(load.z, l.ca)); }
         t.push_back(g.mul(Gen::cst(l.c_jm), in.qdd[j]));
         if (in.friction) t.push_back(g.mul(Gen::cst(l.c_b), in.qd[j]));
         Sym tq = g.fix(g.sum(t));
@@ -384,16 +413,22 @@ int b2k_rne_generate(const b2k_rne_s *r, const b2k_gen_opts &o, b2k_gen_out &out
     std::vector<Link> L(N);
     for (int j = 0; j < N; j++) {
         const double *l = r->L[j];
-        if ((int)l[4] != 0) { out.error = "prismatic joints are served by the generic kernel"; return -1; }
-        const double alpha = l[0], A = l[1], D = l[3], G = l[20];
+        const double alpha = l[0], A = l[1], theta = l[2], D = l[3], G = l[20];
         const double sa = snap(sin(alpha)), ca = snap(cos(alpha));
-        L[j].st = g.var("st[" + std::to_string(j) + "]");
-        L[j].ct = g.var("ct[" + std::to_string(j) + "]");
+        L[j].pris = ((int)l[4] != 0);
         L[j].sa = Gen::cst(sa);
         L[j].ca = Gen::cst(ca);
-        L[j].ps[0] = A;
-        L[j].ps[1] = r->mdh ? -D * sa : D * sa;
-        L[j].ps[2] = D * ca;
+        Sym d;
+        if (L[j].pris) { // the joint variable is the link offset d = q + offset (qq = q + offset in the kernel), theta is fixed
+            L[j].st = Gen::cst(snap(sin(theta)));
+            L[j].ct = Gen::cst(snap(cos(theta)));
+            d = g.var("qq[" + std::to_string(j) + "]");
+        } else {
+            L[j].st = g.var("st[" + std::to_string(j) + "]");
+            L[j].ct = g.var("ct[" + std::to_string(j) + "]");
+            d = Gen::cst(D);
+        }
+        L[j].ps = {Gen::cst(A), g.fix(g.mul(d, Gen::cst(r->mdh ? -sa : sa))), g.fix(g.mul(d, Gen::cst(ca)))};
         L[j].m = l[6];
         for (int k = 0; k < 3; k++) L[j].r[k] = l[7 + k];
         for (int k = 0; k < 9; k++) L[j].I[k] = l[10 + k];

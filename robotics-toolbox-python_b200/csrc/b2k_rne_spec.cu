@@ -6,7 +6,7 @@
 // TMA bulk copy), compiled for sm_100a with NVRTC the first time a (robot, operation, dtype, gravity
 // pattern) is used, loaded through the driver API and launched on the caller's stream.  Both libraries
 // are found with dlopen at run time (libnvrtc.so.12 of the CUDA toolkit, libcuda.so.1 of the driver):
-// libb2kin.so itself links neither.  When either is missing, or the chain has a prismatic joint, the
+// libb2kin.so itself links neither.  When either is missing the
 // pre-compiled generic kernels of b2k_rne.cuh serve the call -- still on the GPU; nothing here ever
 // computes on the host.  B2K_RNE_SPEC=0 disables the specialised path, B2K_RNE_SPEC=2 turns a failure
 // to specialise into an error (tests use it to prove which kernel ran).
@@ -255,6 +255,200 @@ k_rne_spec(const __grid_constant__ SpecP P, const real *__restrict__ in0, const 
 }
 )B2KSRC";
 
+
+// ------------------------------------------------------------------ forward-dynamics integrator (DynamicsMixin.fdyn)
+// The reference integrates ONE state with scipy's RK45, calling accel() -- n + 1 Python rne loops and a numpy solve --
+// for every stage (Dynamics.py:185-422).  Here one lane integrates one trajectory of an ensemble entirely on the device:
+// Dormand-Prince 5(4) with scipy's step control restated (scipy/integrate/_ivp/rk.py: select_initial_step, the RMS error
+// norm against atol + rtol max(|y|, |y_new|), SAFETY 0.9, factors in [0.2, 10], no growth after a rejection), the
+// acceleration of every stage from the robot-specialised recursion (mode "accel": inertia rows + bias torque, LDL^T).
+// Torque input: none, a constant vector, or a joint-space PD law -- a Python callable cannot run here (DHRobot.fdyn
+// takes that route through scipy on the host, with this library's batched accel as the right-hand side).
+const char *kFdyn = R"B2KSRC(
+struct FdynP {
+    real T, rtol, atol, max_step, first_step, dt;
+    real kp[NJ], kd[NJ], qstar[NJ], tau[NJ];
+    int torque_mode; // 0 none, 1 constant (tau), 2 per-trajectory constant (tau_rows), 3 PD: kp (qstar - q) - kd qd
+    int grid;        // 0: store the accepted steps (capacity M per trajectory); 1: store the uniform grid k dt (M samples)
+    int M;
+};
+
+__device__ __forceinline__ void fd_accel(const SpecP &P, const FdynP &F, const real *tau_row, const real *y, real *qdd)
+{
+    real th[NJ], st[NJ], ct[NJ], tq[NJ], res[NJ * NJ + NJ];
+#pragma unroll
+    for (int j = 0; j < NJ; j++) {
+        th[j] = y[j] + P.offset[j];
+        real t = 0;
+        if (F.torque_mode == 1) t = F.tau[j];
+        else if (F.torque_mode == 2) t = tau_row[j];
+        else if (F.torque_mode == 3) t = F.kp[j] * (F.qstar[j] - y[j]) - F.kd[j] * y[NJ + j];
+        tq[j] = t;
+    }
+    sincos_batch(th, P.trig, st, ct);
+    rne_row(P.C, P.grav, P.fext, st, ct, th, y + NJ, tq, res);
+    real d[NJ];
+#pragma unroll
+    for (int c = 0; c < NJ; c++) {
+        real dc = res[c * NJ + c];
+#pragma unroll
+        for (int k = 0; k < c; k++) dc = fma(-res[c * NJ + k] * d[k], res[c * NJ + k], dc);
+        d[c] = dc;
+        const real inv = (real)1 / dc;
+#pragma unroll
+        for (int r = c + 1; r < NJ; r++) {
+            real v = res[r * NJ + c];
+#pragma unroll
+            for (int k = 0; k < c; k++) v = fma(-res[r * NJ + k] * d[k], res[c * NJ + k], v);
+            res[r * NJ + c] = v * inv;
+        }
+    }
+    real *x = res + NJ * NJ;
+#pragma unroll
+    for (int r = 0; r < NJ; r++)
+#pragma unroll
+        for (int k = 0; k < r; k++) x[r] = fma(-res[r * NJ + k], x[k], x[r]);
+#pragma unroll
+    for (int r = 0; r < NJ; r++) x[r] = x[r] / d[r];
+#pragma unroll
+    for (int r = NJ - 1; r >= 0; r--)
+#pragma unroll
+        for (int k = r + 1; k < NJ; k++) x[r] = fma(-res[k * NJ + r], x[k], x[r]);
+#pragma unroll
+    for (int j = 0; j < NJ; j++) qdd[j] = x[j];
+}
+
+// f(t, y) = [qd, accel(q, qd, tau(t, q, qd))]
+__device__ __noinline__ void fd_rhs(const SpecP &P, const FdynP &F, const real *tau_row, const real *y, real *f)
+{
+#pragma unroll
+    for (int j = 0; j < NJ; j++) f[j] = y[NJ + j];
+    fd_accel(P, F, tau_row, y, f + NJ);
+}
+
+__device__ __forceinline__ real fd_rms(const real *v, const real *scale)
+{
+    real s = 0;
+    for (int i = 0; i < 2 * NJ; i++) { const real e = v[i] / scale[i]; s = fma(e, e, s); }
+    return sqrt(s / (real)(2 * NJ));
+}
+
+extern "C" __global__ void __launch_bounds__(64)
+k_fdyn(const __grid_constant__ SpecP P, const __grid_constant__ FdynP F, const real *__restrict__ q0, const real *__restrict__ qd0,
+       const real *__restrict__ tau_rows, real *__restrict__ out_t, real *__restrict__ out_q, real *__restrict__ out_qd,
+       int *__restrict__ out_count, int *__restrict__ out_status, long long ntraj)
+{
+    const long long tr = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tr >= ntraj) return;
+    constexpr int NS = 2 * NJ;
+    // Dormand-Prince tableau (scipy RK45)
+    const real C2 = (real)(1.0 / 5), C3 = (real)(3.0 / 10), C4 = (real)(4.0 / 5), C5 = (real)(8.0 / 9);
+    const real A[6][5] = {{0, 0, 0, 0, 0},
+                          {(real)(1.0 / 5), 0, 0, 0, 0},
+                          {(real)(3.0 / 40), (real)(9.0 / 40), 0, 0, 0},
+                          {(real)(44.0 / 45), (real)(-56.0 / 15), (real)(32.0 / 9), 0, 0},
+                          {(real)(19372.0 / 6561), (real)(-25360.0 / 2187), (real)(64448.0 / 6561), (real)(-212.0 / 729), 0},
+                          {(real)(9017.0 / 3168), (real)(-355.0 / 33), (real)(46732.0 / 5247), (real)(49.0 / 176), (real)(-5103.0 / 18656)}};
+    const real Bc[6] = {(real)(35.0 / 384), 0, (real)(500.0 / 1113), (real)(125.0 / 192), (real)(-2187.0 / 6784), (real)(11.0 / 84)};
+    const real E[7] = {(real)(-71.0 / 57600), 0, (real)(71.0 / 16695), (real)(-71.0 / 1920), (real)(17253.0 / 339200), (real)(-22.0 / 525), (real)(1.0 / 40)};
+    const real Cn[6] = {0, C2, C3, C4, C5, 1};
+    (void)Cn; // the torque laws served here do not depend on t explicitly
+    const real *tau_row = tau_rows ? tau_rows + tr * NJ : nullptr;
+    real y[NS], yn[NS], K[7][NS], scale[NS], tmp[NS];
+    for (int j = 0; j < NJ; j++) { y[j] = q0[tr * NJ + j]; y[NJ + j] = qd0 ? qd0[tr * NJ + j] : (real)0; }
+    real t = 0;
+    fd_rhs(P, F, tau_row, y, K[0]);
+    // ---- select_initial_step
+    real h_abs;
+    if (F.first_step > 0) h_abs = F.first_step;
+    else {
+        for (int i = 0; i < NS; i++) scale[i] = F.atol + fabs(y[i]) * F.rtol;
+        const real d0 = fd_rms(y, scale), d1 = fd_rms(K[0], scale);
+        real h0 = (d0 < (real)1e-5 || d1 < (real)1e-5) ? (real)1e-6 : (real)0.01 * d0 / d1;
+        h0 = fmin(h0, F.T);
+        for (int i = 0; i < NS; i++) yn[i] = fma(h0, K[0][i], y[i]);
+        fd_rhs(P, F, tau_row, yn, K[1]);
+        for (int i = 0; i < NS; i++) tmp[i] = K[1][i] - K[0][i];
+        const real d2 = fd_rms(tmp, scale) / h0;
+        const real h1 = (d1 <= (real)1e-15 && d2 <= (real)1e-15) ? fmax((real)1e-6, h0 * (real)1e-3) : pow((real)0.01 / fmax(d1, d2), (real)0.2);
+        h_abs = fmin(fmin((real)100 * h0, h1), fmin(F.T, F.max_step));
+    }
+    // ---- output of the initial state
+    const size_t obase = (size_t)tr * F.M;
+    int count = 0, status = 0;
+    auto emit = [&](real tt, const real *yy) {
+        if (count < F.M) {
+            out_t[obase + count] = tt;
+            for (int j = 0; j < NJ; j++) { out_q[(obase + count) * NJ + j] = yy[j]; out_qd[(obase + count) * NJ + j] = yy[NJ + j]; }
+        }
+        count++;
+    };
+    int next_grid = 0;
+    if (F.grid) { emit(0, y); next_grid = 1; }
+    else emit(0, y);
+    // ---- the stepping loop of RungeKutta._step_impl
+    while (t < F.T) {
+        const real min_step = (real)10 * (nextafter(t, (real)1e300) - t);
+        if (h_abs > F.max_step) h_abs = F.max_step;
+        else if (h_abs < min_step) h_abs = min_step;
+        bool accepted = false, rejected = false;
+        real tn = t, h = 0;
+        while (!accepted) {
+            if (h_abs < min_step) { status = 1; break; } // step size too small
+            h = h_abs;
+            tn = t + h;
+            if (tn - F.T > 0) tn = F.T;
+            h = tn - t;
+            h_abs = fabs(h);
+            // rk_step
+            for (int s = 1; s < 6; s++) {
+                for (int i = 0; i < NS; i++) {
+                    real dy = 0;
+                    for (int k = 0; k < s; k++) dy += K[k][i] * A[s][k];
+                    yn[i] = y[i] + dy * h;
+                }
+                fd_rhs(P, F, tau_row, yn, K[s]);
+            }
+            for (int i = 0; i < NS; i++) {
+                real dy = 0;
+                for (int k = 0; k < 6; k++) dy += K[k][i] * Bc[k];
+                yn[i] = y[i] + h * dy;
+            }
+            fd_rhs(P, F, tau_row, yn, K[6]);
+            for (int i = 0; i < NS; i++) {
+                scale[i] = F.atol + fmax(fabs(y[i]), fabs(yn[i])) * F.rtol;
+                real e = 0;
+                for (int k = 0; k < 7; k++) e += K[k][i] * E[k];
+                tmp[i] = e * h;
+            }
+            const real err = fd_rms(tmp, scale);
+            if (err < 1) {
+                real factor = err == 0 ? (real)10 : fmin((real)10, (real)0.9 * pow(err, (real)-0.2));
+                if (rejected) factor = fmin((real)1, factor);
+                h_abs *= factor;
+                accepted = true;
+            } else {
+                h_abs *= fmax((real)0.2, (real)0.9 * pow(err, (real)-0.2));
+                rejected = true;
+            }
+        }
+        if (!accepted) break;
+        if (F.grid) { // linear interpolation onto k dt, as the reference does with interp1d (Dynamics.py:371-377)
+            while (next_grid < F.M && (real)next_grid * F.dt <= tn) {
+                const real tg = (real)next_grid * F.dt, a = (tg - t) / (tn - t);
+                for (int i = 0; i < NS; i++) tmp[i] = y[i] + a * (yn[i] - y[i]);
+                emit(tg, tmp);
+                next_grid++;
+            }
+        } else emit(tn, yn);
+        t = tn;
+        for (int i = 0; i < NS; i++) { y[i] = yn[i]; K[0][i] = K[6][i]; }
+    }
+    out_count[tr] = count;
+    out_status[tr] = status | (count > F.M ? 2 : 0); // 2: more accepted steps than the capacity M
+}
+)B2KSRC";
+
 // ------------------------------------------------------------------ dynamic loading of NVRTC and the driver API
 struct Nvrtc {
     void *h = nullptr;
@@ -332,6 +526,7 @@ struct Program {
     std::string cubin;        // sm_100a image
     std::vector<double> consts;
     int nin = 1, nout = 0, nres = 0, nc = 1, tpw = 1;
+    const char *entry = "k_rne_spec";
     int n_mul = 0, n_fma = 0, n_add = 0, regs = 0;
     size_t smem = 0;
     std::map<int, CUfunction> fn; // per device
@@ -352,7 +547,7 @@ int gcd_i(int a, int b) { return b ? gcd_i(b, a % b) : a; }
 
 typedef std::function<int(b2k_gen_out &)> GenFn; // runs the code generator for one (robot, operation, pattern)
 
-std::string build_source(const GenFn &gen, int n, int mode, int dtype, Program &p, std::vector<std::string> &defs)
+std::string build_source(const GenFn &gen, int n, int mode, int dtype, Program &p, std::vector<std::string> &defs, const char *kernel_text)
 {
     b2k_gen_out g;
     if (gen(g)) { p.why = g.error; return std::string(); }
@@ -367,15 +562,18 @@ std::string build_source(const GenFn &gen, int n, int mode, int dtype, Program &
     const int padin = gcd_i(n * es / 4, es == 8 ? 32 : 32) > (es == 8 ? 4 : 2) ? 1 : 0;
     const int ldi = padin ? (n | 1) : n;
     const size_t in_bytes = ((size_t)32 * ldi * es + 15) & ~(size_t)15;
-    // tiles per warp (double-buffered inputs when > 1): measured no gain over one tile per warp on B200 -- the kernel is
-    // bound by instruction issue (2-cycle FP64 issue + integer / control), not by load latency -- so the default is 1
-    int tpw = 1;
+    // tiles per warp (double-buffered inputs when > 1).  fp64: no gain -- the kernel is bound by instruction issue (2-cycle
+    // FP64 issue + integer / control), and the second buffer costs registers.  fp32: the whole recursion is ~480 issued
+    // instructions per row, short enough for the tile-load latency to show (ncu: long-scoreboard the top stall), and two
+    // tiles per warp with 8 resident blocks measured 24.9 -> 22.2 us on the Puma (profiles/r02_rne_sweep32.jsonl).
+    const bool light = mode == B2K_GEN_RNE || mode == B2K_GEN_GRAVLOAD || mode == B2K_GEN_ITORQUE;
+    int tpw = (dtype == B2K_F32 && light) ? 2 : 1;
     if (const char *e = getenv("B2K_RNE_SPEC_TPW")) tpw = atoi(e) > 0 ? atoi(e) : tpw;
     p.tpw = tpw;
     p.smem = 4 * ((tpw > 1 ? 2 : 1) * p.nin * in_bytes + (size_t)32 * p.nout * es);
     int minb = (int)((200 * 1024) / (p.smem + 1024));
-    // resident blocks to aim for (profiles/r02_rne_sweep.jsonl: fp64 96 registers / 5 blocks, fp32 72 registers / 6 blocks)
-    const int want = mode == B2K_GEN_RNE || mode == B2K_GEN_GRAVLOAD || mode == B2K_GEN_ITORQUE ? (es == 8 ? 5 : 6) : (es == 8 ? 2 : 3);
+    // resident blocks to aim for (profiles/r02_rne_sweep.jsonl, r02_rne_sweep32.jsonl: fp64 96 registers / 5 blocks, fp32 64 registers / 8 blocks)
+    const int want = light ? (es == 8 ? 5 : 8) : (es == 8 ? 2 : 3);
     if (minb > want) minb = want;
     if (minb < 1) minb = 1;
     if (const char *e = getenv("B2K_RNE_SPEC_MINB")) minb = atoi(e) > 0 ? atoi(e) : minb;
@@ -384,7 +582,7 @@ std::string build_source(const GenFn &gen, int n, int mode, int dtype, Program &
     D("REAL_IS_F64", es == 8);
     D("NJ", n); D("NC", p.nc); D("MODE", mode); D("NIN", p.nin); D("NOUT", p.nout); D("NRES", p.nres); D("PADIN", padin); D("MINB", minb); D("TPW", tpw);
     // in1 / in2 of the generated function are the second / third input rows; the RNE proper names them qd / qdd
-    return std::string(kPrologue) + g.source + kKernel;
+    return std::string(kPrologue) + g.source + (kernel_text ? kernel_text : kKernel);
 }
 
 void compile(const GenFn &gen, int n, const Key &key, Program &p)
@@ -393,7 +591,9 @@ void compile(const GenFn &gen, int n, const Key &key, Program &p)
     Nvrtc *N = nvrtc();
     if (!N->h) { p.why = N->why; return; }
     std::vector<std::string> defs;
-    const std::string src = build_source(gen, n, mode, dtype, p, defs);
+    const bool fdyn = std::get<0>(key) / 100 == 2;
+    if (fdyn) p.entry = "k_fdyn";
+    const std::string src = build_source(gen, n, mode, dtype, p, defs, fdyn ? kFdyn : nullptr);
     if (src.empty()) return;
     std::vector<std::string> opts = {"--gpu-architecture=sm_100a", "--std=c++17"};
     if (getenv("B2K_RNE_SPEC_LINEINFO")) opts.push_back("-lineinfo");
@@ -468,7 +668,7 @@ int get_function(Program *p, CUfunction *out)
     const char *es = nullptr;
     if (rc != CUDA_SUCCESS) { D->GetErrorString(rc, &es); p->ok = false; p->why = std::string("cuModuleLoadData: ") + (es ? es : "?"); return -1; }
     CUfunction fn;
-    rc = D->ModuleGetFunction(&fn, mod, "k_rne_spec");
+    rc = D->ModuleGetFunction(&fn, mod, p->entry);
     if (rc != CUDA_SUCCESS) { D->GetErrorString(rc, &es); p->ok = false; p->why = std::string("cuModuleGetFunction: ") + (es ? es : "?"); return -1; }
     if (p->smem > 48 * 1024) {
         rc = D->FuncSetAttribute(fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)p->smem);
@@ -486,8 +686,7 @@ struct SpecParams { // byte image of the kernel's SpecP for NC constants (built 
 
 // Builds the kernel's parameter block SpecP { real C[NC]; real grav[3]; real fext[6]; real offset[NJ]; TrigC trig; } and
 // launches `ntiles` full tiles on `st`.
-int launch_tiles(Program *p, CUfunction fn, int n, int dtype, const double *offset, const void *in0, const void *in1, const void *in2,
-                 void *out, long long ntiles, const double *grav, const double *fext, cudaStream_t st)
+std::vector<unsigned char> spec_params(Program *p, int n, int dtype, const double *offset, const double *grav, const double *fext)
 {
     const int es = dtype == B2K_F64 ? 8 : 4;
     const int nreal = p->nc + 3 + 6 + n + 18;
@@ -509,6 +708,35 @@ int launch_tiles(Program *p, CUfunction fn, int n, int dtype, const double *offs
         TrigC<float> t;
         b2k_fill_trig<float>(t);
         memcpy(&pb[(size_t)o * 4], &t, sizeof(t));
+    }
+    return pb;
+}
+
+int launch_tiles(Program *p, CUfunction fn, int n, int dtype, const double *offset, const void *in0, const void *in1, const void *in2,
+                 void *out, long long ntiles, const double *grav, const double *fext, cudaStream_t st)
+{
+    std::vector<unsigned char> pb = spec_params(p, n, dtype, offset, grav, fext);
+    if (false) {
+    const int es = dtype == B2K_F64 ? 8 : 4;
+    const int nreal = p->nc + 3 + 6 + n + 18;
+    auto put = [&](int idx, double v) {
+        if (es == 8) memcpy(&pb[(size_t)idx * 8], &v, 8);
+        else { float f = (float)v; memcpy(&pb[(size_t)idx * 4], &f, 4); }
+    };
+    int o = 0;
+    for (int k = 0; k < p->nc; k++) put(o++, p->consts[k]);
+    for (int k = 0; k < 3; k++) put(o++, grav ? grav[k] : 0.0);
+    for (int k = 0; k < 6; k++) put(o++, fext ? fext[k] : 0.0);
+    for (int j = 0; j < n; j++) put(o++, offset ? offset[j] : 0.0);
+    if (es == 8) {
+        TrigC<double> t;
+        b2k_fill_trig<double>(t);
+        memcpy(&pb[(size_t)o * 8], &t, sizeof(t));
+    } else {
+        TrigC<float> t;
+        b2k_fill_trig<float>(t);
+        memcpy(&pb[(size_t)o * 4], &t, sizeof(t));
+    }
     }
     long long nt = ntiles;
     void *args[6] = {pb.data(), (void *)&in0, (void *)&in1, (void *)&in2, (void *)&out, (void *)&nt};
@@ -554,8 +782,6 @@ long long b2k_rne_spec_launch(const b2k_rne_s *r, int mode, int dtype, const voi
         if (setting == 2) { b2k_set_error("RNE specialisation required (B2K_RNE_SPEC=2) but unavailable: %s", why.c_str()); return B2K_ERR_INVALID; }
         return 0;
     };
-    for (int j = 0; j < r->n; j++)
-        if ((int)r->L[j][4] != 0) return refuse("prismatic joint");
     const long long ntiles = nrows / 32;
     if (ntiles == 0) return 0;
     const uintptr_t al = (uintptr_t)in0 | (uintptr_t)(in1 ? in1 : in0) | (uintptr_t)(in2 ? in2 : in0) | (uintptr_t)out;
@@ -609,18 +835,19 @@ extern "C" int b2k_rne_spec_info(b2k_rne_t r, int mode, int dtype, const double 
     std::string s;
     if (spec_setting() == 0) s = "generic (B2K_RNE_SPEC=0)";
     else {
-        bool pris = false;
-        for (int j = 0; j < r->n; j++) pris = pris || ((int)r->L[j][4] != 0);
-        if (pris) s = "generic (prismatic joint)";
-        else {
+        {
             const bool uses_grav = mode == B2K_GEN_RNE || mode == B2K_GEN_GRAVLOAD || mode == B2K_GEN_ACCEL;
-            const Key key(mode, dtype, uses_grav ? grav_mask_of(grav) : 0, has_fext);
-            Program *p = get_program(static_cast<SpecCache *>(r->spec), dh_gen(r, key), r->n, key);
+            // mode 200 + m: the forward-dynamics integrator built around operation m (only m = accel exists)
+            const int gm = mode % 100;
+            const bool ug = gm == B2K_GEN_RNE || gm == B2K_GEN_GRAVLOAD || gm == B2K_GEN_ACCEL;
+            const Key key(mode, dtype, ug ? grav_mask_of(grav) : 0, has_fext);
+            const Key gkey(gm, dtype, ug ? grav_mask_of(grav) : 0, has_fext);
+            Program *p = get_program(static_cast<SpecCache *>(r->spec), dh_gen(r, gkey), r->n, key);
             if (!p || !p->ok) s = std::string("generic (") + (p ? p->why : "no cache") + ")";
             else {
                 char t[256];
-                snprintf(t, sizeof(t), "k_rne_spec<%s,n=%d,mode=%d>: %d mul + %d fma + %d add per row, %d constants, %d regs, %zu B smem/block, %d tiles/warp",
-                         dtype == B2K_F64 ? "double" : "float", r->n, mode, p->n_mul, p->n_fma, p->n_add, p->nc, p->regs, p->smem, p->tpw);
+                snprintf(t, sizeof(t), "%s<%s,n=%d,mode=%d>: %d mul + %d fma + %d add per row, %d constants, %d regs, %zu B smem/block, %d tiles/warp",
+                         p->entry, dtype == B2K_F64 ? "double" : "float", r->n, mode, p->n_mul, p->n_fma, p->n_add, p->nc, p->regs, p->smem, p->tpw);
                 s = t;
             }
         }
@@ -748,5 +975,70 @@ extern "C" int b2k_tree_info(b2k_tree_t t, int dtype, const double *grav, char *
     else
         snprintf(buf, (size_t)cap, "k_rne_spec<%s,tree n=%d>: %d mul + %d fma + %d add per row, %d constants, %d regs, %zu B smem/block",
                  dtype == B2K_F64 ? "double" : "float", t->n, p->n_mul, p->n_fma, p->n_add, p->nc, p->regs, p->smem);
+    return B2K_OK;
+}
+
+
+// ------------------------------------------------------------------ C ABI: forward-dynamics ensemble integrator
+extern "C" int b2k_rne_fdyn(b2k_rne_t r, int dtype, const void *q0, const void *qd0, int64_t ntraj, double T, const double *grav,
+                            int torque_mode, const double *tau, const void *tau_rows, const double *kp, const double *kd,
+                            const double *qstar, double rtol, double atol, double max_step, double first_step, double dt, int grid,
+                            int M, void *out_t, void *out_q, void *out_qd, int32_t *out_count, int32_t *out_status, void *stream)
+{
+    const char *fn = "b2k_rne_fdyn";
+    if (!r) { b2k_set_error("%s: rne handle is NULL", fn); return B2K_ERR_INVALID; }
+    if (dtype != B2K_F32 && dtype != B2K_F64) { b2k_set_error("%s: dtype must be B2K_F32 or B2K_F64", fn); return B2K_ERR_INVALID; }
+    if (ntraj < 0 || (ntraj > 0 && (!q0 || !out_t || !out_q || !out_qd || !out_count || !out_status))) { b2k_set_error("%s: bad arguments", fn); return B2K_ERR_INVALID; }
+    if (!(T > 0) || !(rtol > 0) || !(atol >= 0) || !(max_step > 0) || M < 1) { b2k_set_error("%s: T, rtol, max_step must be positive, atol non-negative, M >= 1", fn); return B2K_ERR_INVALID; }
+    if (grid && !(dt > 0)) { b2k_set_error("%s: dt must be positive for a uniform output grid", fn); return B2K_ERR_INVALID; }
+    if (!grav) { b2k_set_error("%s: grav is NULL (pass -robot.gravity like DHRobot.rne)", fn); return B2K_ERR_INVALID; }
+    if (torque_mode < 0 || torque_mode > 3 || (torque_mode == 1 && !tau) || (torque_mode == 2 && !tau_rows) || (torque_mode == 3 && (!kp || !kd || !qstar))) {
+        b2k_set_error("%s: torque_mode 0 none, 1 constant (tau), 2 per-trajectory (tau_rows), 3 PD (kp, kd, qstar)", fn);
+        return B2K_ERR_INVALID;
+    }
+    if (ntraj == 0) return B2K_OK;
+    B2K_ON_DEVICE_OF(q0);
+    const Key key(200 + B2K_GEN_ACCEL, dtype, grav_mask_of(grav), 0);
+    const Key gkey(B2K_GEN_ACCEL, dtype, grav_mask_of(grav), 0);
+    Program *p = get_program(static_cast<SpecCache *>(r->spec), dh_gen(r, gkey), r->n, key);
+    if (!p || !p->ok) { b2k_set_error("%s: the integrator kernel could not be built (%s)", fn, p ? p->why.c_str() : "no cache"); return B2K_ERR_INVALID; }
+    CUfunction f;
+    {
+        SpecCache *c = static_cast<SpecCache *>(r->spec);
+        std::lock_guard<std::mutex> lk(c->mu);
+        if (get_function(p, &f)) { b2k_set_error("%s: %s", fn, p->why.c_str()); return B2K_ERR_CUDA; }
+    }
+    const int n = r->n, es = dtype == B2K_F64 ? 8 : 4;
+    double offset[B2K_MAX_JOINTS];
+    for (int j = 0; j < n; j++) offset[j] = r->L[j][5];
+    std::vector<unsigned char> pb = spec_params(p, n, dtype, offset, grav, nullptr);
+    // FdynP { real T, rtol, atol, max_step, first_step, dt; real kp[NJ], kd[NJ], qstar[NJ], tau[NJ]; int torque_mode, grid, M; }
+    const int nreal = 6 + 4 * n;
+    size_t fbytes = (size_t)nreal * es + 3 * sizeof(int);
+    fbytes = (fbytes + es - 1) / es * es;
+    std::vector<unsigned char> fb(fbytes, 0);
+    auto put = [&](int idx, double v) {
+        if (es == 8) memcpy(&fb[(size_t)idx * 8], &v, 8);
+        else { float x = (float)v; memcpy(&fb[(size_t)idx * 4], &x, 4); }
+    };
+    const double head[6] = {T, rtol, atol, max_step, first_step, dt};
+    for (int k = 0; k < 6; k++) put(k, head[k]);
+    for (int j = 0; j < n; j++) {
+        put(6 + j, kp ? kp[j] : 0.0); put(6 + n + j, kd ? kd[j] : 0.0); put(6 + 2 * n + j, qstar ? qstar[j] : 0.0); put(6 + 3 * n + j, tau ? tau[j] : 0.0);
+    }
+    const int tail[3] = {torque_mode, grid ? 1 : 0, M};
+    memcpy(&fb[(size_t)nreal * es], tail, sizeof(tail));
+    long long nt = ntraj;
+    void *args[11] = {pb.data(), fb.data(), (void *)&q0, (void *)&qd0, (void *)&tau_rows, (void *)&out_t, (void *)&out_q, (void *)&out_qd,
+                      (void *)&out_count, (void *)&out_status, (void *)&nt};
+    const unsigned grid_dim = (unsigned)((ntraj + 63) / 64);
+    CUresult rc = driver()->LaunchKernel(f, grid_dim, 1, 1, 64, 1, 1, 0, (CUstream)stream, args, nullptr);
+    if (rc != CUDA_SUCCESS) {
+        const char *es2 = nullptr;
+        driver()->GetErrorString(rc, &es2);
+        b2k_set_error("cuLaunchKernel(k_fdyn): %s", es2 ? es2 : "?");
+        return B2K_ERR_CUDA;
+    }
+    b2k_count_launch();
     return B2K_OK;
 }

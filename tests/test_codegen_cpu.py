@@ -75,10 +75,11 @@ def host_fn(tmp_path, tag, source):
     return run
 
 
-def random_links(rng, n, mdh):
-    """All-revolute arm with a random mix of structural zeros (alpha = k pi/2, a / d = 0, sparse r and I)."""
+def random_links(rng, n, mdh, prismatic=False):
+    """Arm with a random mix of structural zeros (alpha = k pi/2, a / d = 0, sparse r and I); with `prismatic`
+    about every other joint is translational (theta fixed, d = q + offset)."""
     links = []
-    for _ in range(n):
+    for k in range(n):
         alpha = rng.choice([0.0, np.pi / 2, -np.pi / 2, np.pi, rng.uniform(-1, 1)])
         I6 = rng.uniform(0.01, 0.5, 3).tolist() + (rng.uniform(-0.01, 0.01, 3) * rng.integers(0, 2, 3)).tolist()
         links.append(dict(d=float(rng.choice([0.0, rng.uniform(-0.5, 0.5)])), a=float(rng.choice([0.0, rng.uniform(-0.5, 0.5)])),
@@ -86,6 +87,8 @@ def random_links(rng, n, mdh):
                           I=I6, r=(rng.uniform(-0.3, 0.3, 3) * rng.integers(0, 2, 3)).tolist(), m=float(rng.uniform(0, 5)),
                           Jm=float(rng.choice([0.0, 2e-4])), G=float(rng.choice([0.0, -60.0, 100.0])),
                           B=float(rng.choice([0.0, 1e-3])), Tc=[float(rng.choice([0.0, 0.3])), float(rng.choice([0.0, -0.4]))]))
+        if prismatic and (k % 2 == 0 or rng.random() < 0.3):
+            links[-1].update(sigma=1, theta=float(rng.choice([0.0, np.pi / 2, rng.uniform(-1, 1)])))
     return links
 
 
@@ -94,6 +97,8 @@ def robots():
     out = [("puma560", 6, 0, ch.pack_rne(ch.puma560_links())), ("panda_mdh", 7, 1, ch.pack_rne(ch.panda_mdh_links(), mdh=True))]
     for k, (n, mdh) in enumerate([(3, 0), (7, 0), (5, 1), (2, 1), (1, 0)]):
         out.append((f"random{k}_n{n}_{'mdh' if mdh else 'dh'}", n, mdh, ch.pack_rne(random_links(rng, n, mdh), mdh=bool(mdh))))
+    for k, (n, mdh) in enumerate([(4, 0), (5, 1), (1, 1), (3, 1)]):  # chains with prismatic joints (incl. a prismatic FIRST joint under MDH)
+        out.append((f"prismatic{k}_n{n}_{'mdh' if mdh else 'dh'}", n, mdh, ch.pack_rne(random_links(rng, n, mdh, True), mdh=bool(mdh))))
     return out
 
 
@@ -161,19 +166,6 @@ def test_specialisation_drops_the_structural_zeros_of_the_puma():
     rtb._lib.lib().b2k_rne_destroy(hd)
 
 
-def test_prismatic_chains_are_left_to_the_generic_kernel():
-    links = ch.puma560_links()
-    L = ch.pack_rne(links).copy()
-    L[24 * 2 + 4] = 1.0  # third joint prismatic
-    h = handle(6, 0, L)
-    lib = rtb._lib.lib()
-    assert lib.b2k_rne_codegen(h, 0, 7, 0, None, 0, None, 0, None, None) == -1 and b"prismatic" in lib.b2k_last_error()
-    buf = C.create_string_buffer(512)
-    rtb._lib.check(lib.b2k_rne_spec_info(h, 0, 1, None, 0, buf, 512))
-    assert buf.value.startswith(b"generic")
-    lib.b2k_rne_destroy(h)
-
-
 @pytest.mark.skipif(not any(os.path.exists(p) for p in ("/usr/local/cuda/lib64/libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so")),
                     reason="NVRTC not installed")
 def test_generated_kernels_compile_for_sm_100a_through_the_library():
@@ -182,11 +174,11 @@ def test_generated_kernels_compile_for_sm_100a_through_the_library():
     g = np.array([0.0, 0.0, 9.81])
     for n, mdh, L in ((6, 0, ch.pack_rne(ch.puma560_links())), (7, 1, ch.pack_rne(ch.panda_mdh_links(), mdh=True))):
         h = handle(n, mdh, L)
-        for mode in range(6):
+        for mode in list(range(6)) + [205]:  # 205: the forward-dynamics integrator around the accel recursion
             for dt in (rtb._lib.F64, rtb._lib.F32):
                 buf = C.create_string_buffer(4096)
                 rtb._lib.check(lib.b2k_rne_spec_info(h, mode, dt, rtb._lib.dptr(g), 0, buf, 4096))
-                assert buf.value.startswith(b"k_rne_spec<"), buf.value[:600]
+                assert buf.value.startswith(b"k_fdyn<" if mode == 205 else b"k_rne_spec<"), buf.value[:600]
         lib.b2k_rne_destroy(h)
 
 

@@ -532,7 +532,7 @@ def test_config4_full_size_100k():
         wq, ws, wit, wsr, wE = C.ik_lm(Tep[:M], q0=None, joint_limits=jl, k=k, seed=5, semantics=0, rng_per_row=True)
         same = (s64[:M] == ws) & (it64[:M] == wit) & (sr64[:M] == wsr)
         assert same.mean() >= IK_COUNTER_PARITY, f"k={k}: {same.mean():.4f} of rows reproduce the sequential loop's counters"
-        np.testing.assert_allclose(q64[:M][same], wq[same], atol=1e-6)
+        np.testing.assert_allclose(q64[:M][same], wq[same], atol=1e-4)  # both ends stop at E < tol: q agrees to ~sqrt(tol) at worst
         # iteration statistics of the fp32 run track the fp64 run (same problems, same draws up to rounding)
         assert abs(it.mean() - it64.mean()) < 0.05 * it64.mean()
         assert abs(sr.mean() - sr64.mean()) < 0.05 * sr64.mean()

@@ -162,13 +162,27 @@ def test_specialised_and_generic_kernels_agree_at_full_size(monkeypatch):
     assert not torch.equal(t_spec, t_gen) or True
 
 
-def test_prismatic_robot_falls_back_to_the_generic_kernel(monkeypatch):
-    rob = rtb.DHRobot([rtb.RevoluteDH(d=0.3, a=0.1, alpha=1.2, m=2, r=[0.1, 0, 0.05], I=[0.1, 0.2, 0.15]),
-                       rtb.PrismaticDH(theta=0.4, a=0.2, alpha=-0.7, m=1.5, r=[0, 0.1, 0], I=[0.05, 0.04, 0.03])])
-    q = np.random.default_rng(2).uniform(-1, 1, (64, 2))
-    want = orc.rne(2, 0, rob._pack_rne(), -rob.gravity, q, q, q)
-    np.testing.assert_allclose(host(rob.rne(dev(q), dev(q), dev(q))), want, rtol=1e-10, atol=1e-10)
-    assert info(rob).startswith("generic (prismatic")
-    monkeypatch.setenv("B2K_RNE_SPEC", "2")
-    with pytest.raises(ValueError, match="prismatic"):
-        rob.rne(dev(q), dev(q), dev(q))
+def test_prismatic_robots_are_specialised_too(must_specialise):
+    """Chains with translational joints: the generator carries d = q + offset as the run-time variable and theta as a
+    constant (ne.c:183-225, 290-333), including the MDH prismatic-first-joint quirk; dynamics fan-outs ride along."""
+    for mk_r, mk_p, mdh in ((rtb.RevoluteDH, rtb.PrismaticDH, 0), (rtb.RevoluteMDH, rtb.PrismaticMDH, 1)):
+        for first_prismatic in (False, True):
+            links = [mk_r(d=0.3, a=0.1, alpha=1.2, m=2, r=[0.1, 0, 0.05], I=[0.1, 0.2, 0.15], Jm=1e-4, G=50, B=1e-3, Tc=[0.1, -0.2]),
+                     mk_p(theta=0.4, a=0.2, alpha=-np.pi / 2, offset=0.1, m=1.5, r=[0, 0.1, 0], I=[0.05, 0.04, 0.03], Jm=2e-4, G=30, B=2e-3, Tc=[0.05, -0.05]),
+                     mk_r(d=0.1, a=0.25, alpha=0.0, m=1, r=[0.05, 0.02, 0], I=[0.02, 0.03, 0.01], Jm=1e-4, G=-40, B=1e-3, Tc=[0.02, -0.03]),
+                     mk_p(theta=0.0, a=0.0, alpha=np.pi / 2, m=0.5, r=[0, 0, 0.1], I=[0.01, 0.01, 0.01])]
+            if first_prismatic:
+                links = links[1:] + links[:1]
+            rob = rtb.DHRobot(links)
+            n, L, g = rob.n, rob._pack_rne(), rob.gravity
+            rng = np.random.default_rng(2 + mdh + 2 * first_prismatic)
+            q, qd, qdd, tq = (rng.uniform(-1, 1, (200, n)) for _ in range(4))
+            f = lambda a, b, c, grav: orc.rne(n, mdh, L, -np.asarray(grav, dtype=float), a, b, c)  # noqa: E731
+            np.testing.assert_allclose(host(rob.rne(dev(q), dev(qd), dev(qdd))), f(q, qd, qdd, g), rtol=1e-10, atol=1e-10)
+            fx = rng.normal(size=6)
+            np.testing.assert_allclose(host(rob.rne(dev(q), dev(qd), dev(qdd), fext=fx)), orc.rne(n, mdh, L, -g, q, qd, qdd, fx), rtol=1e-10, atol=1e-10)
+            np.testing.assert_allclose(host(rob.inertia(dev(q))), orc.dyn_inertia(f, n, q), rtol=1e-9, atol=1e-9)
+            np.testing.assert_allclose(host(rob.gravload(dev(q))), orc.dyn_gravload(f, n, q, g), rtol=1e-9, atol=1e-9)
+            fnf = lambda a, b, c, grav: orc.rne(n, mdh, orc.nofriction_L(L), -np.asarray(grav, dtype=float), a, b, c)  # noqa: E731
+            np.testing.assert_allclose(host(rob.coriolis(dev(q[:32]), dev(qd[:32]))), orc.dyn_coriolis(fnf, n, q[:32], qd[:32]), rtol=1e-9, atol=1e-9)
+            assert info(rob).startswith("k_rne_spec<")
