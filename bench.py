@@ -428,6 +428,8 @@ def run_b200(args):
             # bulk copies -- over NVLink instead of to local HBM).  Root ingress is the bound: (world - 1) shards.
             fused = None
             try:
+                if args.no_fused_gather:
+                    raise RuntimeError("disabled by --no-fused-gather")
                 import torch.distributed._symmetric_memory as symm
 
                 sbuf = symm.empty(world * TJ.numel(), dtype=torch.float32, device=dev)
@@ -621,6 +623,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--headline-only", action="store_true", help="skip the secondary configs and the gather")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-fused-gather", action="store_true", help="skip the symmetric-memory store-to-root experiment (N>1)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

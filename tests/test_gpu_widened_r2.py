@@ -115,7 +115,8 @@ def test_ctraj_feeds_ik_on_the_device():
     rng = np.random.default_rng(23)
     panda = rtb.models.Panda().ets()
     C = orc.Chain(panda.describe())
-    qa, qb = rng.uniform(-1.5, 1.5, 7), rng.uniform(-1.5, 1.5, 7)
+    qa = rng.uniform(-1.5, 1.5, 7)
+    qb = qa + rng.uniform(-0.4, 0.4, 7)  # a short move: the straight Cartesian line stays inside the workspace
     T0, T1 = C.fkine(qa)[0], C.fkine(qb)[0]
     s = np.r_[rng.uniform(0, 1, 300), 0.0, 1.0, -0.2, 1.3]
     P = rtb.ctraj(T0, T1, s=s)
@@ -132,8 +133,8 @@ def test_ctraj_feeds_ik_on_the_device():
     Td = rtb.ctraj(T0, T1, 200, device=True)
     assert Td.is_cuda and Td.shape == (200, 4, 4)
     q, ok, it, sr, E = panda.ik_LM(Td, q0=dev(qa), joint_limits=False, k=0.1)
-    okh = host(ok).astype(bool)  # a straight Cartesian line between two reachable poses may leave the workspace: most, not all, solve
-    assert okh[0] and okh[-1] and okh.mean() > 0.8
+    okh = host(ok).astype(bool)
+    assert okh.all()
     np.testing.assert_allclose(C.fkine(host(q))[okh], host(Td)[okh], atol=5e-3)
     with pytest.raises(TypeError):
         rtb.ctraj(T0, T1)
