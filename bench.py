@@ -370,9 +370,10 @@ def run_b200(args):
     headline_parity = parity_fkj(ets, "panda_fkj", make_q(4242, PARITY_ROWS, 7), np.float64, 1e-10, 1e-12)
 
     # ================================================================ the other BASELINE configs
-    def roof(bytes_per_row, rows, ms, bound="hbm", note=None):
+    def roof(bytes_per_row, rows, ms, bound="hbm", note=None, traffic_key=None):
         a = bytes_per_row * rows / (ms * 1e-3) / 1e9
         r = {"bound": bound, "achieved": a, "peak": peak, "unit": "GB/s", "frac": a / peak,
+             "traffic": load_traffic(traffic_key) if traffic_key else None,
              "algorithmic_bytes_per_launch": bytes_per_row * rows}
         if note:
             r["note"] = note
@@ -495,7 +496,7 @@ def run_b200(args):
             "baseline_config": "configs[2]: Puma560 DHRobot rne (q, qd, qdd) batch 1M fp64",
             "ms": ms, "value": ROWS_PER_GPU / (ms * 1e-3), "unit": "rows/s", "rows": ROWS_PER_GPU, "dtype": "f64",
             "steps": KS, "kernel": rtb.rne_kernel_name(puma) if hasattr(rtb, "rne_kernel_name") else "k_rne<double,6,DH,allrev>",
-            "roofline": roof(24 * 8, ROWS_PER_GPU, ms, note="FP64-pipe co-limited: see DESIGN 3.4"),
+            "roofline": roof(24 * 8, ROWS_PER_GPU, ms, note="issue-bound (2-cycle FP64 issue + integer / control): DESIGN 3.4", traffic_key="rne_puma_f64_1M"),
             "cpu_baseline": cpu["configs"].get("rne_puma_f64_1M") if cpu else None, "parity": par,
         }
         del rb, tau
@@ -542,7 +543,8 @@ def run_b200(args):
                 "ms": ms, "value": IK_ROWS / (ms * 1e-3), "unit": "solves/s", "rows": IK_ROWS, "dtype": "f32", "steps": 5,
                 "kernel": "k_ik_lm + k_ik_restarts", "launches_per_step": ik_launches,
                 "roofline": roof((16 + 7 + 4) * 4, IK_ROWS, ms, bound="latency",
-                                 note="serial LM iterations per target: latency / issue bound, HBM fraction reported for completeness"),
+                                 note="serial LM iterations per target: latency / issue bound, HBM fraction reported for completeness",
+                                 traffic_key="ik_lm_panda_f32_100k_chan0.1" if name.endswith("chan0.1") else None),
                 "cpu_baseline": cpu["configs"].get(name) if cpu else None, "parity": par,
             }
         del qstar, Tep64, Tep32
