@@ -252,3 +252,47 @@ def test_sub_chain_ets_start_end():
     nt.assert_allclose(fwd.eval(Q) @ back.eval(Q), np.broadcast_to(np.eye(4), (64, 4, 4)), rtol=0, atol=1e-12)
     e = rtb.ET.Rz(jindex=2) * rtb.ET.tx(1) * rtb.ET.Rx(jindex=3, flip=True) * rtb.ET.tx(1)  # docstring example of ETS.inv
     nt.assert_allclose(e.eval(Q[:, :4]) @ e.inv().eval(Q[:, :4]), np.broadcast_to(np.eye(4), (64, 4, 4)), rtol=0, atol=1e-12)
+
+
+def test_trajectory_ctraj_and_mstraj_reference_unit_tests():
+    """reference tests/test_trajectory.py:175-204 (test_ctraj) and 592-664 (test_mstraj), replayed through the mirror."""
+    import json
+
+    from oracle import chains as ch
+
+    T0, T1 = ch.transl(1, 2, 3), ch.transl(-1, -2, -3)
+    T = rtb.ctraj(T0, T1, 3)
+    assert len(T) == 3
+    np.testing.assert_array_almost_equal(T[0].A, T0)
+    np.testing.assert_array_almost_equal(T[2].A, T1)
+    np.testing.assert_array_almost_equal(T[1].A, np.eye(4))
+    T = rtb.ctraj(T0, T1, [1, 0, 0.5])
+    assert len(T) == 3
+    np.testing.assert_array_almost_equal(T[0].A, T1)
+    np.testing.assert_array_almost_equal(T[1].A, T0)
+    np.testing.assert_array_almost_equal(T[2].A, np.eye(4))
+    T0, T1 = ch.trotx(-np.pi / 2), ch.trotx(np.pi / 2)
+    T = rtb.ctraj(T0, T1, 3)
+    np.testing.assert_array_almost_equal(T[0].A, T0)
+    np.testing.assert_array_almost_equal(T[2].A, T1)
+    np.testing.assert_array_almost_equal(T[1].A, np.eye(4))
+    with pytest.raises(TypeError):
+        rtb.ctraj(T0, T1, "hello")
+
+    K = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_kats.json")))["mstraj"]
+    via = np.array(K["via"])
+    out = rtb.mstraj(via, dt=1, tacc=1, qdmax=[2, 1], q0=[4, 1])
+    np.testing.assert_array_almost_equal(out.q, np.array(K["qdmax_case"]["q"]), decimal=4)
+    out = rtb.mstraj(via, dt=1, tacc=1, tsegment=[2, 1, 3, 4], q0=[4, 1])
+    np.testing.assert_array_almost_equal(out.q, np.array(K["tsegment_case"]["q"]), decimal=4)
+    out = rtb.mstraj(via, dt=1, tacc=1, tsegment=[1, 2, 3, 4], q0=via[0, :])
+    assert out.t.shape[0] == out.q.shape[0]
+    assert isinstance(out.info, list) and len(out.info) == via.shape[0] + 1
+    rtb.mstraj(via, dt=1, tacc=1, qdmax=[2, 1])
+    rtb.mstraj(via, dt=1, tacc=1, qdmax=2)
+    for kw in (dict(qdmax=[2, 1], q0=[1, 2, 3]), dict(qdmax=[2, 1], tsegment=[1, 2, 3, 4]), dict(), dict(tsegment=[3, 4]),
+               dict(qdmax=[2, 1, 3]), dict(qdmax=[2, 1], qd0=[1, 2, 3], q0=[1, 2]), dict(qdmax=[2, 1], qdf=[1, 2, 3], q0=[1, 2])):
+        with pytest.raises(ValueError):
+            rtb.mstraj(via, dt=1, tacc=1, **kw)
+    with pytest.raises(ValueError):
+        rtb.mstraj(via, dt=1, tacc=[1, 2, 3, 4, 5], qdmax=[2, 1])

@@ -359,3 +359,24 @@ def test_pose_representation_restatements_are_self_consistent():
     np.testing.assert_allclose(q[-1], via[-1], atol=1e-12)
     assert np.abs(q[0] - via[0]).max() < 0.1 and (np.diff(arrive) > 0).all()
     assert (np.abs(np.diff(q, axis=0)).max(axis=0) / 0.1 <= 1.25 * np.array([1.0, 0.8])).all()  # blends overshoot the cruise speed a little
+
+
+def test_trajectory_restatements_reproduce_the_reference_kats():
+    """mstraj / ctraj literals of the reference's own tests (tests/test_trajectory.py:175-204, 592-631)."""
+    import json
+    import os
+
+    K = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_kats.json")))["mstraj"]
+    via = np.array(K["via"])
+    c = K["qdmax_case"]
+    np.testing.assert_array_almost_equal(orc.mstraj(via, dt=c["dt"], tacc=c["tacc"], qdmax=c["qdmax"], q0=c["q0"])[1], np.array(c["q"]), decimal=4)
+    c = K["tsegment_case"]
+    np.testing.assert_array_almost_equal(orc.mstraj(via, dt=c["dt"], tacc=c["tacc"], tsegment=c["tsegment"], q0=c["q0"])[1], np.array(c["q"]), decimal=4)
+    from oracle import chains as ch
+
+    s3 = orc.trapezoidal(0, 1, 3)[1]
+    for T0, T1 in ((ch.transl(1, 2, 3), ch.transl(-1, -2, -3)), (ch.trotx(-np.pi / 2), ch.trotx(np.pi / 2))):
+        P = orc.ctraj_poses(T0, T1, s3)
+        np.testing.assert_array_almost_equal(P[0], T0)
+        np.testing.assert_array_almost_equal(P[2], T1)
+        np.testing.assert_array_almost_equal(P[1], np.eye(4))
