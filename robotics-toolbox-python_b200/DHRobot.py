@@ -147,6 +147,10 @@ class DHRobot:
     def jacob0_dot(self, q=None, qd=None, J0=None, representation=None, **kwargs):
         return self.ets().jacob0_dot(q, qd, J0=J0, representation=representation, **kwargs)
 
+    def jacob0_analytical(self, q, representation="rpy/xyz", **kwargs):
+        """reference DHRobot.jacob0_analytical (DHRobot.py:1200-1262) -> rotvelxform(R, inverse=True) @ jacob0"""
+        return self.ets().jacob0_analytical(q, representation=representation, **kwargs)
+
     def ikine_LM(self, Tep, q0=None, ilimit=30, slimit=100, tol=1e-6, joint_limits=False, mask=None, seed=None,
                  **kwargs):
         """reference DHRobot.ikine_LM 2454-2474 (note joint_limits defaults to False here)."""

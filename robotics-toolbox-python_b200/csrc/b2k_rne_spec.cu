@@ -466,6 +466,7 @@ struct Driver {
     void *h = nullptr;
     CUresult (*ModuleLoadData)(CUmodule *, const void *);
     CUresult (*ModuleGetFunction)(CUfunction *, CUmodule, const char *);
+    CUresult (*ModuleUnload)(CUmodule);
     CUresult (*LaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, CUstream, void **, void **);
     CUresult (*FuncSetAttribute)(CUfunction, CUfunction_attribute, int);
     CUresult (*FuncGetAttribute)(int *, CUfunction_attribute, CUfunction);
@@ -511,7 +512,7 @@ Driver *driver()
     std::call_once(once, [] {
         D.h = dlopen("libcuda.so.1", RTLD_NOW | RTLD_LOCAL);
         if (!D.h) { D.why = "libcuda.so.1 not found"; return; }
-        bool ok = sym(D.h, "cuModuleLoadData", D.ModuleLoadData, D.why) && sym(D.h, "cuModuleGetFunction", D.ModuleGetFunction, D.why) &&
+        bool ok = sym(D.h, "cuModuleLoadData", D.ModuleLoadData, D.why) && sym(D.h, "cuModuleGetFunction", D.ModuleGetFunction, D.why) && sym(D.h, "cuModuleUnload", D.ModuleUnload, D.why) &&
                   sym(D.h, "cuLaunchKernel", D.LaunchKernel, D.why) && sym(D.h, "cuFuncSetAttribute", D.FuncSetAttribute, D.why) &&
                   sym(D.h, "cuFuncGetAttribute", D.FuncGetAttribute, D.why) && sym(D.h, "cuGetErrorString", D.GetErrorString, D.why);
         if (!ok) { dlclose(D.h); D.h = nullptr; }
@@ -530,12 +531,22 @@ struct Program {
     int n_mul = 0, n_fma = 0, n_add = 0, regs = 0;
     size_t smem = 0;
     std::map<int, CUfunction> fn; // per device
+    std::vector<CUmodule> modules; // loaded images, unloaded with the robot handle
 };
 typedef std::tuple<int, int, int, int> Key; // mode, dtype, grav_mask, has_fext
 struct SpecCache {
     std::mutex mu;
     std::map<Key, Program> progs;
+    ~SpecCache();
 };
+
+SpecCache::~SpecCache()
+{ // release the loaded images (best effort: the context may already be gone at interpreter shutdown)
+    Driver *D = driver();
+    if (!D->h) return;
+    for (auto &kv : progs)
+        for (CUmodule m : kv.second.modules) D->ModuleUnload(m);
+}
 
 int spec_setting()
 { // read at every call so a process can switch (tests run both paths)
@@ -676,6 +687,7 @@ int get_function(Program *p, CUfunction *out)
     }
     D->FuncGetAttribute(&p->regs, CU_FUNC_ATTRIBUTE_NUM_REGS, fn);
     p->fn[dev] = fn;
+    p->modules.push_back(mod);
     *out = fn;
     return 0;
 }

@@ -154,6 +154,56 @@ if want("dyn_"):
                                                      "kernel": rtb.rne_kernel_info(puma, name.split("_")[1], np.float64)})
     os.environ["B2K_RNE_SPEC"] = "1"
 
+# Robot.rne on a rigid-body tree (generated Featherstone recursion): the Puma560 assembled as an ETS robot from its DH table
+if want("tree_"):
+    ET, ETS, Link = rtb.ET, rtb.ETS, rtb.Link
+    links, prev = [], ETS()
+    for j, l in enumerate(puma.links):
+        post = ETS()
+        for kind, v in (("tz", l.d), ("tx", l.a), ("Rx", l.alpha)):
+            if v != 0:
+                post = post * getattr(ET, kind)(v)
+        Tp = np.eye(4)
+        for et in post:
+            Tp = Tp @ et.A()
+        links.append(Link(prev * ET.Rz(), name=f"l{j}", parent=links[-1] if links else None, m=l.m, r=Tp[:3, :3] @ l.r + Tp[:3, 3]))
+        prev = post
+    links.append(Link(prev, name="tool", parent=links[-1]))
+    trob = rtb.Robot(links)
+    for dt in (np.float64, np.float32):
+        tag = "f64" if dt == np.float64 else "f32"
+        if not want(f"tree_rne_puma_{tag}"):
+            continue
+        es = np.dtype(dt).itemsize
+        bufs = [tuple(torch.from_numpy(a.astype(dt)).to(dev) for a in (rng.uniform(-3, 3, (N, 6)), rng.normal(size=(N, 6)), rng.normal(size=(N, 6)))) for _ in range(3)]
+        tau = torch.empty((N, 6), dtype=tdt[dt], device=dev)
+        h = trob._tree_handle()
+        L = rtb._lib.lib()
+        st = torch.cuda.current_stream().cuda_stream
+        code = rtb._lib.F64 if dt == np.float64 else rtb._lib.F32
+        ag = np.ascontiguousarray(-trob.gravity)
+        report(f"tree_rne_puma_{tag}", timeit(lambda i: L.b2k_tree_rne(h, code, bufs[i][0].data_ptr(), bufs[i][1].data_ptr(), bufs[i][2].data_ptr(), N, rtb._lib.dptr(ag), tau.data_ptr(), st), 3), N, 24 * es,
+               {"kernel": trob.rne_kernel_info(dt)})
+        del bufs, tau
+
+# forward-dynamics ensemble: friction-free Puma falling from qn for 0.5 s, rtol 1e-6, one lane per trajectory
+if want("fdyn_"):
+    nf = puma.nofriction()
+    for B_ in (1024, 16384):
+        if not want(f"fdyn_puma_f64_ens{B_}"):
+            continue
+        Q0 = torch.from_numpy(nf.qn + rng.uniform(-0.3, 0.3, (B_, 6))).to(dev)
+        nf.fdyn(0.05, Q0[:64], dt=0.01)  # builds the kernel
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = nf.fdyn(0.5, Q0, solver_args=dict(rtol=1e-6, atol=1e-9), dt=0.01)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        print(json.dumps({"case": f"fdyn_puma_f64_ens{B_}", "trajectories": B_, "T": 0.5, "rtol": 1e-6, "ms": round(ms, 3),
+                          "trajectory_seconds_per_s": B_ * 0.5 / (ms * 1e-3), "grid_samples": int(out.q.shape[1])}), flush=True)
+
 # IK (config 4): reachable targets, chan
 if want("ik_"):
     panda = rtb.models.Panda().ets()
