@@ -12,7 +12,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libb2kin.so")
+# B2K_LIB points the binding at another build of the same library (kernel experiments: scripts/ik_occ.sh)
+LIB_PATH = os.environ.get("B2K_LIB") or os.path.join(_HERE, "lib", "libb2kin.so")
 
 F32, F64 = 0, 1
 MAX_JOINTS = 10

@@ -250,7 +250,9 @@ __device__ __forceinline__ void je_col_pri(const Pose<real> &U, real sg, real *c
 //     Straight-line code: no switches (the compiler if-converts small uniform switches into
 //     select chains, ncu profiles/r01_fkj_v2.md), all n sincos evaluated as one interleaved batch.
 //   0 generic: any axis / flip / constant, runtime (uniform) switches.
-template <typename real, int N, bool WJ, int PROF, typename GetQ>
+//   TRIG = 1 (the IK loop, whose iterates leave [-pi, pi] in some lanes of most warps): fp32 angles are reduced once
+//   and go to the special-function unit whatever their size, so a warp never runs two sincos paths back to back.
+template <typename real, int N, bool WJ, int PROF, int TRIG = 0, typename GetQ>
 __device__ __forceinline__ void chain_forward(const ChainP<real, N> &P, GetQ getq, Pose<real> &T,
                                               real (*zj)[3], real (*pj)[3])
 {
@@ -258,7 +260,8 @@ __device__ __forceinline__ void chain_forward(const ChainP<real, N> &P, GetQ get
         real eta[N], sn[N], cs[N];
 #pragma unroll
         for (int j = 0; j < N; j++) eta[j] = getq(j, P.jidx[j]);
-        b2k_sincos_batch<real, N>(eta, P.trig, sn, cs);
+        if constexpr (TRIG == 1 && sizeof(real) == 4) b2k_sincos_batch_reduced<N>(eta, sn, cs);
+        else b2k_sincos_batch<real, N>(eta, P.trig, sn, cs);
         pose_from_const(T, P.A[0]);
 #pragma unroll
         for (int j = 0; j < N; j++) {

@@ -18,6 +18,7 @@
 #pragma once
 
 #include "b2k_fkj.cuh"
+#include <type_traits>
 
 template <typename real, int N>
 struct IkP {
@@ -37,10 +38,13 @@ __device__ __forceinline__ unsigned long long b2k_mix64(unsigned long long x)
     return x ^ (x >> 31);
 }
 
-// uniform in [0,1): 53 random bits for fp64, the top 24 of the same word for fp32
+// uniform in [0,1): 53 random bits for fp64, the top 24 of the same word for fp32.
+// Deliberately NOT inlined: a draw is ~60 instructions of 64-bit integer arithmetic per joint and happens once per
+// search, but it used to be expanded at every place a problem can start or restart -- 5 000 of the 10 700
+// instructions of k_ik_lm<float,7> -- and the LM evaluation (the only hot code) had to jump around it.
 template <typename real>
-__device__ __forceinline__ real b2k_rand_u01(unsigned long long seed, unsigned long long row, unsigned search,
-                                             unsigned joint)
+__device__ __noinline__ real b2k_rand_u01(unsigned long long seed, unsigned long long row, unsigned search,
+                                          unsigned joint)
 {
     unsigned long long h = b2k_mix64(seed ^ (0x5851F42D4C957F2DULL * (row + 1)));
     h = b2k_mix64(h + (((unsigned long long)search << 32) | (unsigned long long)joint));
@@ -54,9 +58,29 @@ template <> __device__ __forceinline__ float b2k_sqrt<float>(float x) { return s
 template <typename real> __device__ __forceinline__ real b2k_atan2(real y, real x);
 template <> __device__ __forceinline__ double b2k_atan2<double>(double y, double x) { return atan2(y, x); }
 template <> __device__ __forceinline__ float b2k_atan2<float>(float y, float x) { return atan2f(y, x); }
-template <typename real> __device__ __forceinline__ real b2k_fmod(real y, real x);
-template <> __device__ __forceinline__ double b2k_fmod<double>(double y, double x) { return fmod(y, x); }
-template <> __device__ __forceinline__ float b2k_fmod<float>(float y, float x) { return fmodf(y, x); }
+// fmod runs once per joint when a search converges; out of line for the same reason as the draws (1 700 instructions)
+static __device__ __noinline__ double b2k_fmod_out_of_line(double y, double x) { return fmod(y, x); }
+static __device__ __noinline__ float b2k_fmod_out_of_line(float y, float x) { return fmodf(y, x); }
+template <typename real> __device__ __forceinline__ real b2k_fmod(real y, real x) { return b2k_fmod_out_of_line(y, x); }
+// 1 / sqrt(d) of a Cholesky pivot.  fp64 keeps the IEEE square root and division (the counters of the compiled
+// reference are reproduced bit for bit on its fixtures); fp32 has no such contract (outcome tests, 1e-4
+// bar) and takes the special-function unit's rsqrt: 1 instruction on the serial chain of the factorisation
+// instead of ~20 with two slow-path branches.
+template <typename real> __device__ __forceinline__ real b2k_rsqrt_pivot(real d);
+template <> __device__ __forceinline__ double b2k_rsqrt_pivot<double>(double d) { return 1.0 / sqrt(d); }
+template <> __device__ __forceinline__ float b2k_rsqrt_pivot<float>(float d) { return rsqrtf(d); }
+
+// compile-time loop: the body receives std::integral_constant<int, I>, so every index into a register array is a
+// constant expression.  (#pragma unroll left the triangular loops of the factorisation as run-time loops for two of
+// the columns, which put the whole packed matrix in local memory: 22 LDL + 14 STL per evaluation on the serial chain.)
+template <int B, int E, typename F>
+__device__ __forceinline__ void b2k_static_for(F &&f)
+{
+    if constexpr (B < E) {
+        f(std::integral_constant<int, B>());
+        b2k_static_for<B + 1, E>(f);
+    }
+}
 
 // restart sample, _rand_q ik.cpp:288-299: qlim_l + (U(-1,1) + 1) * range/2
 template <typename real, int N>
@@ -85,7 +109,14 @@ __device__ __forceinline__ void ik_angle_axis(const Pose<real> &Te, const real *
         for (int j = 0; j < 3; j++)
             R[i][j] = Tp[i * 4 + 0] * Te.c0[j] + Tp[i * 4 + 1] * Te.c1[j] + Tp[i * 4 + 2] * Te.c2[j];
     real lx = R[2][1] - R[1][2], ly = R[0][2] - R[2][0], lz = R[1][0] - R[0][1];
-    real ln = b2k_sqrt<real>(lx * lx + ly * ly + lz * lz);
+    const real l2 = lx * lx + ly * ly + lz * lz;
+    real ln, inv_ln = 0;
+    if constexpr (sizeof(real) == 4) { // fp32: |l| and 1/|l| from one rsqrt (no IEEE sqrt + three divisions on the chain)
+        inv_ln = rsqrtf(fmaxf(l2, 1e-30f));
+        ln = l2 * inv_ln;
+    } else {
+        ln = b2k_sqrt<real>(l2);
+    }
     real tr = R[0][0] + R[1][1] + R[2][2];
     if (ln < (real)1e-6) {
         if (tr > 0) {
@@ -98,9 +129,14 @@ __device__ __forceinline__ void ik_angle_axis(const Pose<real> &Te, const real *
         }
     } else {
         real ang = b2k_atan2<real>(ln, tr - 1);
-        e[3] = ang * lx / ln;
-        e[4] = ang * ly / ln;
-        e[5] = ang * lz / ln;
+        if constexpr (sizeof(real) == 4) {
+            const real sc = ang * inv_ln;
+            e[3] = sc * lx; e[4] = sc * ly; e[5] = sc * lz;
+        } else { // the reference's order of operations (ik.cpp:283-285)
+            e[3] = ang * lx / ln;
+            e[4] = ang * ly / ln;
+            e[5] = ang * lz / ln;
+        }
     }
 }
 
@@ -110,38 +146,34 @@ template <typename real, int N>
 __device__ __forceinline__ bool ik_chol_solve(real *A, real *b)
 {
     bool ok = true;
-#pragma unroll
-    for (int j = 0; j < N; j++) {
-        real d = A[j * (j + 1) / 2 + j];
-#pragma unroll
-        for (int k = 0; k < j; k++) d -= A[j * (j + 1) / 2 + k] * A[j * (j + 1) / 2 + k];
+    b2k_static_for<0, N>([&](auto jc) {
+        constexpr int j = decltype(jc)::value, rj = j * (j + 1) / 2;
+        real d = A[rj + j];
+        b2k_static_for<0, j>([&](auto kc) { constexpr int k = decltype(kc)::value; d -= A[rj + k] * A[rj + k]; });
         ok = ok && (d > 0) && isfinite(d);
-        real inv = (real)1 / b2k_sqrt<real>(d);
-        A[j * (j + 1) / 2 + j] = inv; // store 1/L_jj
-#pragma unroll
-        for (int i = j + 1; i < N; i++) {
-            real s = A[i * (i + 1) / 2 + j];
-#pragma unroll
-            for (int k = 0; k < j; k++) s -= A[i * (i + 1) / 2 + k] * A[j * (j + 1) / 2 + k];
-            A[i * (i + 1) / 2 + j] = s * inv;
-        }
-    }
+        const real inv = b2k_rsqrt_pivot<real>(d);
+        A[rj + j] = inv; // store 1/L_jj
+        b2k_static_for<j + 1, N>([&](auto ic) {
+            constexpr int i = decltype(ic)::value, ri = i * (i + 1) / 2;
+            real s = A[ri + j];
+            b2k_static_for<0, j>([&](auto kc) { constexpr int k = decltype(kc)::value; s -= A[ri + k] * A[rj + k]; });
+            A[ri + j] = s * inv;
+        });
+    });
     // forward L y = b
-#pragma unroll
-    for (int i = 0; i < N; i++) {
+    b2k_static_for<0, N>([&](auto ic) {
+        constexpr int i = decltype(ic)::value, ri = i * (i + 1) / 2;
         real s = b[i];
-#pragma unroll
-        for (int k = 0; k < i; k++) s -= A[i * (i + 1) / 2 + k] * b[k];
-        b[i] = s * A[i * (i + 1) / 2 + i];
-    }
+        b2k_static_for<0, i>([&](auto kc) { constexpr int k = decltype(kc)::value; s -= A[ri + k] * b[k]; });
+        b[i] = s * A[ri + i];
+    });
     // backward L^T x = y
-#pragma unroll
-    for (int i = N - 1; i >= 0; i--) {
+    b2k_static_for<0, N>([&](auto ic) {
+        constexpr int i = N - 1 - decltype(ic)::value;
         real s = b[i];
-#pragma unroll
-        for (int k = i + 1; k < N; k++) s -= A[k * (k + 1) / 2 + i] * b[k];
+        b2k_static_for<i + 1, N>([&](auto kc) { constexpr int k = decltype(kc)::value; s -= A[k * (k + 1) / 2 + i] * b[k]; });
         b[i] = s * A[i * (i + 1) / 2 + i];
-    }
+    });
     return ok;
 }
 
@@ -216,7 +248,7 @@ __device__ __forceinline__ bool ik_eval(const ChainP<real, N> &P, const IkP<real
     Pose<real> Te;
     real zj[N][3], pj[N][3], e[6];
     // jindex is dense 0..n-1 here (checked on the host, like the reference's C++ loop assumes)
-    chain_forward<real, N, true, PROF>(P, [&](int j, int) { return q[j]; }, Te, zj, pj);
+    chain_forward<real, N, true, PROF, 1>(P, [&](int j, int) { return q[j]; }, Te, zj, pj);
     ik_angle_axis<real>(Te, Tp, e);
     real E = 0;
     if (K.unit_w) {
@@ -306,8 +338,16 @@ __device__ __forceinline__ bool ik_wrap_and_check(const IkP<real, N> &K, real *q
 // iteration the lane is at, so the lanes of a warp never leave the common code.  With
 // two_phase != 0 a lane does only the FIRST search of a problem; a problem whose first search
 // fails is appended to the hard list (with its iteration contribution) for k_ik_restarts.
+// Resident blocks per SM asked of ptxas: with the normal equations and the Jacobian in registers the fp32 kernels
+// fit 128 registers (4 blocks) without spilling, the fp64 ones need ~250 (2 blocks).  -DB2K_IK_MINB=n overrides both
+// (DESIGN 3.5 has the sweep: 4 / 5 / 6 blocks measure the same, 8 spills and is 10 % slower).
+#ifdef B2K_IK_MINB
+template <typename real> constexpr int ik_min_blocks() { return B2K_IK_MINB; }
+#else
+template <typename real> constexpr int ik_min_blocks() { return sizeof(real) == 4 ? 4 : 2; }
+#endif
 template <typename real, int N, int PROF, int STEP = 0>
-__global__ void __launch_bounds__(B2K_THREADS)
+__global__ void __launch_bounds__(B2K_THREADS, ik_min_blocks<real>())
 k_ik_lm(const __grid_constant__ ChainP<real, N> P, const __grid_constant__ IkP<real, N> K,
         const real *__restrict__ Tep, const real *__restrict__ q0, long long nprob, real *__restrict__ q_out,
         int *__restrict__ success, int *__restrict__ iterations, int *__restrict__ searches,
@@ -327,8 +367,12 @@ k_ik_lm(const __grid_constant__ ChainP<real, N> P, const __grid_constant__ IkP<r
     real q[N], Tp[12], E = 0;
     int it = 0, search = 0, iter = 0; // search is 0-based here; reported 1-based (cpp: ik.cpp:39-69, python: IK.py:299-348)
     int evals = 0;                    // evaluations of the current problem in this launch
-    bool active = pos < nwork;
-    long long idx = active ? (in_list ? (long long)in_list[pos] : pos) : 0;
+    long long idx = 0;
+    // A lane asks for its next problem by setting `fetch`; the fetch itself (target load, first q) is expanded ONCE, at
+    // the top of the loop, instead of at each of the nine places a problem can end -- the loop body is the LM
+    // evaluation plus ~200 instructions of bookkeeping, and stays inside the instruction caches.
+    bool fetch = true;
+    pos -= stride;
 
     auto begin_problem = [&]() {
         const real *t = Tep + idx * 16;
@@ -336,10 +380,10 @@ k_ik_lm(const __grid_constant__ ChainP<real, N> P, const __grid_constant__ IkP<r
         for (int k = 0; k < 12; k++) Tp[k] = t[k];
         const unsigned long long row = K.rng_per_row ? (unsigned long long)idx : 0ULL;
         evals = 0;
+        E = 0; it = 0; search = 0;
         if (in_list) { // resume a parked first search
 #pragma unroll
             for (int i = 0; i < N; i++) q[i] = q_out[idx * N + i];
-            E = 0; it = 0; search = 0;
             iter = iterations[idx];
             return;
         }
@@ -349,17 +393,9 @@ k_ik_lm(const __grid_constant__ ChainP<real, N> P, const __grid_constant__ IkP<r
         } else {
             ik_rand_q<real, N>(K, row, 0u, q);
         }
-        E = 0; it = 0; search = 0;
         iter = cpp ? 1 : 0; // the C++ loop's first search starts counting at 1 (ik.cpp:39), later ones at 0 (ik.cpp:67)
     };
-    auto next_problem = [&]() {
-        pos += stride;
-        active = pos < nwork;
-        if (active) {
-            idx = in_list ? (long long)in_list[pos] : pos;
-            begin_problem();
-        }
-    };
+    auto next_problem = [&]() { fetch = true; };
     // park the running first search when this launch's evaluation budget for it is used up
     auto maybe_yield = [&]() {
         if (iter_cap > 0 && ++evals >= iter_cap) {
@@ -384,8 +420,8 @@ k_ik_lm(const __grid_constant__ ChainP<real, N> P, const __grid_constant__ IkP<r
         it += iter; iter = 0; search++;
         const unsigned long long row = K.rng_per_row ? (unsigned long long)idx : 0ULL;
         if (search >= K.slimit) {
-            if (cpp) { ik_rand_q<real, N>(K, row, (unsigned)search, q); finish(0, it, K.slimit + 1); } // ik.cpp:66-69 then exit
-            else finish(0, it, K.slimit);                                                               // IK.py:360-367
+            if (cpp) ik_rand_q<real, N>(K, row, (unsigned)search, q); // ik.cpp:66-69: a fresh draw is what remains in q
+            finish(0, it, cpp ? K.slimit + 1 : K.slimit);              // python: IK.py:360-367
             return;
         }
         if (two_phase) {
@@ -396,14 +432,22 @@ k_ik_lm(const __grid_constant__ ChainP<real, N> P, const __grid_constant__ IkP<r
         }
         ik_rand_q<real, N>(K, row, (unsigned)search, q);
     };
-    if (active) begin_problem();
 
-    while (active) {
+    while (true) {
+        if (fetch) {
+            pos += stride;
+            if (pos >= nwork) break;
+            idx = in_list ? (long long)in_list[pos] : pos;
+            begin_problem();
+            fetch = false;
+        }
         real g[N], Ecur;
+        // one call site for both loop orders (the evaluation is ~600 instructions; two inlined copies only cost
+        // instruction-cache misses): the C++ order skips the step when the test before it has already passed
+        const bool ok = ik_eval<real, N, PROF, STEP>(P, K, Tp, q, Ecur, g, cpp);
+        E = Ecur;
         if (cpp) {
             // test before stepping (ik.cpp:44-58)
-            const bool ok = ik_eval<real, N, PROF, STEP>(P, K, Tp, q, Ecur, g, true);
-            E = Ecur;
             if (Ecur < K.tol) {
                 const bool inlim = ik_wrap_and_check<real, N>(K, q);
                 if (!K.reject_jl || inlim) finish(1, it + iter, search + 1);
@@ -419,8 +463,6 @@ k_ik_lm(const __grid_constant__ ChainP<real, N> P, const __grid_constant__ IkP<r
             else maybe_yield();
         } else {
             // count the step, apply it, then test the PRE-step E (IK.py:314-348)
-            const bool ok = ik_eval<real, N, PROF, STEP>(P, K, Tp, q, Ecur, g, false);
-            E = Ecur;
             iter++;
             if (!ok) { search_failed(); continue; } // numpy LinAlgError: abandon the search (IK.py:321-324)
 #pragma unroll
@@ -446,7 +488,7 @@ k_ik_lm(const __grid_constant__ ChainP<real, N> P, const __grid_constant__ IkP<r
 // the sequential loop reports, but the latency of a problem needing k restarts drops from
 // k x ilimit LM iterations to ceil(k / G) x ilimit.
 template <typename real, int N, int PROF, int G, int STEP = 0>
-__global__ void __launch_bounds__(B2K_THREADS)
+__global__ void __launch_bounds__(B2K_THREADS, ik_min_blocks<real>())
 k_ik_restarts(const __grid_constant__ ChainP<real, N> P, const __grid_constant__ IkP<real, N> K,
               const real *__restrict__ Tep, real *__restrict__ q_out, int *__restrict__ success,
               int *__restrict__ iterations, int *__restrict__ searches, real *__restrict__ residual,
@@ -489,9 +531,9 @@ k_ik_restarts(const __grid_constant__ ChainP<real, N> P, const __grid_constant__
             while (__any_sync(FULL, going)) {
                 if (going) {
                     real g[N], Ecur;
+                    const bool ok = ik_eval<real, N, PROF, STEP>(P, K, Tp, q, Ecur, g, cpp);
+                    E = Ecur;
                     if (cpp) {
-                        const bool ok = ik_eval<real, N, PROF, STEP>(P, K, Tp, q, Ecur, g, true);
-                        E = Ecur;
                         if (Ecur < K.tol) {
                             const bool inlim = ik_wrap_and_check<real, N>(K, q);
                             won = !K.reject_jl || inlim;
@@ -505,8 +547,6 @@ k_ik_restarts(const __grid_constant__ ChainP<real, N> P, const __grid_constant__
                             if (!ok || iters > K.ilimit) going = false;
                         }
                     } else {
-                        const bool ok = ik_eval<real, N, PROF, STEP>(P, K, Tp, q, Ecur, g, false);
-                        E = Ecur;
                         iters++;
                         if (!ok) going = false;
                         else {

@@ -101,6 +101,24 @@ __device__ __forceinline__ void b2k_sincos(float x, const TrigC<float> &t, float
 // N independent sincos evaluated stage by stage: every coefficient is fetched once and used N
 // times, and the N dependency chains interleave (instruction-level parallelism for a kernel that
 // runs only ~4 warps per scheduler).
+// fp32, any finite angle, no data-dependent path: r = x - 2 pi rint(x / 2 pi) by a two-term Cody-Waite product, then
+// sin.approx / cos.approx on |r| <= pi (absolute error 2^-21.4 there; the reduction adds ~|x| 2^-24 relative to a
+// period, i.e. nothing below |x| ~ 1e3 and an angle that is itself only known to an ulp beyond).  7 instructions
+// per joint.  Used by the IK loop, where a diverging iterate in one lane must not send the whole warp through the
+// polynomial path as well as the fast one.
+template <int N>
+__device__ __forceinline__ void b2k_sincos_batch_reduced(const float *x, float *s, float *c)
+{
+#pragma unroll
+    for (int j = 0; j < N; j++) {
+        const float k = rintf(x[j] * 0.15915494309189535f);
+        float r = fmaf(-k, 6.2831854820251465f, x[j]);
+        r = fmaf(-k, -1.7484555e-7f, r);
+        s[j] = __sinf(r);
+        c[j] = __cosf(r);
+    }
+}
+
 template <typename real, int N>
 __device__ __forceinline__ void b2k_sincos_batch(const real *x, const TrigC<real> &t, real *s, real *c)
 {
