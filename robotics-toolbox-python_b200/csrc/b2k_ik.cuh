@@ -339,12 +339,12 @@ __device__ __forceinline__ bool ik_wrap_and_check(const IkP<real, N> &K, real *q
 // two_phase != 0 a lane does only the FIRST search of a problem; a problem whose first search
 // fails is appended to the hard list (with its iteration contribution) for k_ik_restarts.
 // Resident blocks per SM asked of ptxas: with the normal equations and the Jacobian in registers the fp32 kernels
-// fit 128 registers (4 blocks) without spilling, the fp64 ones need ~250 (2 blocks).  -DB2K_IK_MINB=n overrides both
+// fit 128 registers (4 blocks) without spilling; the fp64 ones would take ~250 (2 blocks) and run 1-4 % faster held to 168 (3 blocks, ~150 B of spills; profiles/r02_ik_seg_sweep.jsonl).  -DB2K_IK_MINB=n overrides both
 // (DESIGN 3.5 has the sweep: 4 / 5 / 6 blocks measure the same, 8 spills and is 10 % slower).
 #ifdef B2K_IK_MINB
 template <typename real> constexpr int ik_min_blocks() { return B2K_IK_MINB; }
 #else
-template <typename real> constexpr int ik_min_blocks() { return sizeof(real) == 4 ? 4 : 2; }
+template <typename real> constexpr int ik_min_blocks() { return sizeof(real) == 4 ? 4 : 3; }
 #endif
 template <typename real, int N, int PROF, int STEP = 0>
 __global__ void __launch_bounds__(B2K_THREADS, ik_min_blocks<real>())
