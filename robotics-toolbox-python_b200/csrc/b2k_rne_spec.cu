@@ -42,33 +42,6 @@ struct SpecP { real C[NC]; real grav[3]; real fext[6]; real offset[NJ]; TrigC tr
 __device__ __forceinline__ real step_pos(real x) { return x > (real)0 ? (real)1 : (real)0; }
 __device__ __forceinline__ real step_neg(real x) { return x < (real)0 ? (real)1 : (real)0; }
 
-// The generated recursion is written over `rowt` values and `creal` constants.  PAIR = 0: both are `real`.
-// PAIR = 1 (fp32): a lane carries TWO rows in the halves of a 64-bit register pair, and Blackwell issues fma / mul /
-// add on such pairs as one instruction (PTX fma.rn.f32x2 -> SASS FFMA2, with the per-operand negation and a
-// scalar-broadcast form for the constants, so `-a * C[k]` is still one issue slot).  The fp32 recursion is bound by
-// instruction issue, so halving the arithmetic instructions per row is what moves it.
-#if PAIR
-struct rowt {
-    u64 v;
-    __device__ __forceinline__ rowt() {}
-    __device__ __forceinline__ rowt(float lo, float hi) { asm("mov.b64 %0, {%1, %2};" : "=l"(v) : "f"(lo), "f"(hi)); }
-    __device__ __forceinline__ rowt(float c) { asm("mov.b64 %0, {%1, %1};" : "=l"(v) : "f"(c)); } // same value for both rows
-    __device__ __forceinline__ float lo() const { float a, b; asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); return a; }
-    __device__ __forceinline__ float hi() const { float a, b; asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); return b; }
-};
-typedef float creal;
-__device__ __forceinline__ rowt operator-(rowt a) { return rowt(-a.lo(), -a.hi()); } // ptxas folds this into the operand modifier
-__device__ __forceinline__ rowt operator*(rowt a, rowt b) { rowt r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
-__device__ __forceinline__ rowt operator+(rowt a, rowt b) { rowt r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
-__device__ __forceinline__ rowt operator-(rowt a, rowt b) { return a + (-b); }
-__device__ __forceinline__ rowt fma(rowt a, rowt b, rowt c) { rowt r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v)); return r; }
-__device__ __forceinline__ rowt step_pos(rowt x) { return rowt(step_pos(x.lo()), step_pos(x.hi())); }
-__device__ __forceinline__ rowt step_neg(rowt x) { return rowt(step_neg(x.lo()), step_neg(x.hi())); }
-#else
-typedef real rowt;
-typedef real creal;
-#endif
-
 // sincos of the NJ joint angles as one interleaved batch: three-FMA Cody-Waite reduction by pi/2, fdlibm minimax
 // kernels on [-pi/4, pi/4], integer quadrant logic; every coefficient comes from the parameter bank (csrc/b2k_trig.cuh
 // is the same code; measured <= 1.6 ulp).  fp32 rows with every |angle| < 8 take the special-function unit.
@@ -153,24 +126,23 @@ __device__ __forceinline__ void sincos_batch(const real *x, const TrigC &t, real
 
 const char *kKernel = R"B2KSRC(
 #define LDI (PADIN ? (NJ | 1) : NJ)                  /* smem row stride of the input tiles, in reals */
-#define ROWS (PAIR ? 64 : 32)                        /* rows per tile: one per lane, or two (fp32 pairs) */
-#define IN_BYTES ((ROWS * LDI * (int)sizeof(real) + 15) & ~15)
-#define OUT_BYTES (ROWS * NOUT * (int)sizeof(real))
-#define NBUF ((TPW > 1 || PERSIST) ? 2 : 1)          /* input buffers per warp */
+#define IN_BYTES ((32 * LDI * (int)sizeof(real) + 15) & ~15)
+#define OUT_BYTES (32 * NOUT * (int)sizeof(real))
+#define NBUF (TPW > 1 ? 2 : 1)                        /* input buffers per warp */
 #define WARP_BYTES (NBUF * NIN * IN_BYTES + OUT_BYTES)
 
 __device__ __forceinline__ void load_tile(real *s, const real *g, int lane)
 {
 #if PADIN
     // padded rows: the exact image would make the one-row-per-lane reads collide on the shared-memory banks
-    for (int i = lane; i < ROWS * NJ; i += 32) {
+    for (int i = lane; i < 32 * NJ; i += 32) {
         const int r = i / NJ, c = i - r * NJ;
         s[r * LDI + c] = g[i];
     }
 #else
     const uint4 *gg = reinterpret_cast<const uint4 *>(g) + lane;
     const unsigned sa = (unsigned)__cvta_generic_to_shared(s) + 16u * (unsigned)lane;
-    constexpr int UNITS = (ROWS * NJ * (int)sizeof(real)) / 16; // 16-byte units in the tile: trip count known at compile time
+    constexpr int UNITS = (32 * NJ * (int)sizeof(real)) / 16; // 16-byte units in the tile: trip count known at compile time
 #pragma unroll
     for (int k = 0; k < (UNITS + 31) / 32; k++)
         if (k * 32 + 32 <= UNITS || lane < UNITS - k * 32)
@@ -188,21 +160,13 @@ k_rne_spec(const __grid_constant__ SpecP P, const real *__restrict__ in0, const 
 {
     extern __shared__ __align__(16) unsigned char smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#if PERSIST
-    // persistent form: the grid fills the machine once and a warp strides over the tiles (adjacent warps take adjacent
-    // tiles), always with the next tile's loads in flight -- no block turnover between tiles, no wave quantisation
-    const long long tstride = (long long)gridDim.x * 4;
-    const long long tile0 = (long long)blockIdx.x * 4 + warp;
-#else
-    const long long tstride = 1;
     const long long tile0 = ((long long)blockIdx.x * 4 + warp) * TPW;
-#endif
     if (tile0 >= ntiles) return;
     unsigned char *wb = smem + (size_t)warp * WARP_BYTES;
     real *so = reinterpret_cast<real *>(wb + NBUF * NIN * IN_BYTES);
     auto load = [&](long long tile, int buf) {
         unsigned char *b = wb + (size_t)buf * NIN * IN_BYTES;
-        const size_t row0 = (size_t)tile * ROWS;
+        const size_t row0 = (size_t)tile * 32;
         load_tile(reinterpret_cast<real *>(b), in0 + row0 * NJ, lane);
         if (NIN >= 2) load_tile(reinterpret_cast<real *>(b + IN_BYTES), in1 + row0 * NJ, lane);
         if (NIN >= 3) load_tile(reinterpret_cast<real *>(b + 2 * IN_BYTES), in2 + row0 * NJ, lane);
@@ -212,11 +176,11 @@ k_rne_spec(const __grid_constant__ SpecP P, const real *__restrict__ in0, const 
     };
     load(tile0, 0);
 #pragma unroll 1
-    for (int t = 0; PERSIST || t < TPW; t++) {
-        const long long tile = tile0 + t * tstride;
+    for (int t = 0; t < TPW; t++) {
+        const long long tile = tile0 + t;
         if (tile >= ntiles) break;
-        const bool more = (PERSIST || t + 1 < TPW) && (tile + tstride < ntiles);
-        if (more) load(tile + tstride, (t + 1) & (NBUF - 1));
+        const bool more = (t + 1 < TPW) && (tile + 1 < ntiles);
+        if (more) load(tile + 1, (t + 1) & (NBUF - 1));
 #if !PADIN
         if (more) asm volatile("cp.async.wait_group 1;\n" ::: "memory");
         else asm volatile("cp.async.wait_group 0;\n" ::: "memory");
@@ -226,26 +190,6 @@ k_rne_spec(const __grid_constant__ SpecP P, const real *__restrict__ in0, const 
         const real *s0 = reinterpret_cast<const real *>(b);
         const real *s1 = reinterpret_cast<const real *>(b + IN_BYTES);
         const real *s2 = reinterpret_cast<const real *>(b + 2 * IN_BYTES);
-#if PAIR
-        // rows `lane` and `lane + 32` of the 64-row tile travel together; the sincos are per row (special-function unit)
-        rowt th[NJ], st[NJ], ct[NJ], a1[NJ], a2[NJ];
-        {
-            real tl[NJ], tu[NJ], sl[NJ], su[NJ], cl[NJ], cu[NJ];
-#pragma unroll
-            for (int j = 0; j < NJ; j++) {
-                tl[j] = s0[lane * LDI + j] + P.offset[j];
-                tu[j] = s0[(lane + 32) * LDI + j] + P.offset[j];
-                a1[j] = NIN >= 2 ? rowt(s1[lane * LDI + j], s1[(lane + 32) * LDI + j]) : rowt(0.0f);
-                a2[j] = NIN >= 3 ? rowt(s2[lane * LDI + j], s2[(lane + 32) * LDI + j]) : rowt(0.0f);
-            }
-            sincos_batch(tl, P.trig, sl, cl);
-            sincos_batch(tu, P.trig, su, cu);
-#pragma unroll
-            for (int j = 0; j < NJ; j++) { th[j] = rowt(tl[j], tu[j]); st[j] = rowt(sl[j], su[j]); ct[j] = rowt(cl[j], cu[j]); }
-        }
-        rowt res[NRES];
-        rne_row(P.C, P.grav, P.fext, st, ct, th, a1, a2, res);
-#else
         real th[NJ], st[NJ], ct[NJ], a1[NJ], a2[NJ];
 #pragma unroll
         for (int j = 0; j < NJ; j++) {
@@ -256,7 +200,6 @@ k_rne_spec(const __grid_constant__ SpecP P, const real *__restrict__ in0, const 
         sincos_batch(th, P.trig, st, ct);
         real res[NRES];
         rne_row(P.C, P.grav, P.fext, st, ct, th, a1, a2, res);
-#endif
 #if MODE == 5
         // accel: res = [M (NJ x NJ, row i = torques for a unit acceleration of joint i) | torque - rne(q, qd, 0)].
         // M is the joint-space inertia matrix (symmetric positive definite): LDL^T without pivoting, in registers.
@@ -289,26 +232,21 @@ k_rne_spec(const __grid_constant__ SpecP P, const real *__restrict__ in0, const 
             for (int k = r + 1; k < NJ; k++) y[r] = fma(-res[k * NJ + r], y[k], y[r]);
         const real *o = y;
 #else
-        const rowt *o = res;
+        const real *o = res;
 #endif
         // the previous tile's bulk copy must have finished READING the stage before it is overwritten
         if (t > 0) {
             if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
             __syncwarp();
         }
-#if PAIR
-#pragma unroll
-        for (int k = 0; k < NOUT; k++) { so[lane * NOUT + k] = o[k].lo(); so[(lane + 32) * NOUT + k] = o[k].hi(); }
-#else
 #pragma unroll
         for (int k = 0; k < NOUT; k++) so[lane * NOUT + k] = o[k];
-#endif
         // the staged tile is the exact image of the output block: one TMA bulk copy (shared -> global) by lane 0
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
         if (lane == 0) {
             const unsigned ss = (unsigned)__cvta_generic_to_shared(so);
-            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(out + (size_t)tile * ROWS * NOUT), "r"(ss),
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(out + (size_t)tile * 32 * NOUT), "r"(ss),
                          "r"((unsigned)OUT_BYTES) : "memory");
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
@@ -589,9 +527,6 @@ struct Program {
     std::string cubin;        // sm_100a image
     std::vector<double> consts;
     int nin = 1, nout = 0, nres = 0, nc = 1, tpw = 1;
-    int rows = 32;            // rows per tile: 32, or 64 when a lane carries two fp32 rows (PAIR)
-    bool persist = false;     // grid sized to the machine, warps stride over the tiles
-    int minb = 1;             // resident blocks per SM the kernel was compiled for
     const char *entry = "k_rne_spec";
     int n_mul = 0, n_fma = 0, n_add = 0, regs = 0;
     size_t smem = 0;
@@ -637,45 +572,33 @@ std::string build_source(const GenFn &gen, int n, int mode, int dtype, Program &
     // one-row-per-lane reads of an exact-image tile: conflict degree gcd(row words, banks served per wavefront)
     const int padin = gcd_i(n * es / 4, es == 8 ? 32 : 32) > (es == 8 ? 4 : 2) ? 1 : 0;
     const int ldi = padin ? (n | 1) : n;
-    // fp32: two rows per lane as f32x2 pairs (kPrologue).  Not for accel / fdyn (their LDL^T solve is written on scalars).
-    bool pair = es == 4 && mode != B2K_GEN_ACCEL && !kernel_text && !padin;
-    if (const char *e = getenv("B2K_RNE_SPEC_PAIR")) pair = pair && atoi(e) != 0;
-    p.rows = pair ? 64 : 32;
-    const size_t in_bytes = ((size_t)p.rows * ldi * es + 15) & ~(size_t)15;
+    const size_t in_bytes = ((size_t)32 * ldi * es + 15) & ~(size_t)15;
     // tiles per warp (double-buffered inputs when > 1).  fp64: no gain -- the kernel is bound by instruction issue (2-cycle
     // FP64 issue + integer / control), and the second buffer costs registers.  fp32: the whole recursion is ~480 issued
     // instructions per row, short enough for the tile-load latency to show (ncu: long-scoreboard the top stall), and two
     // tiles per warp with 8 resident blocks measured 24.9 -> 22.2 us on the Puma (profiles/r02_rne_sweep32.jsonl).
+    // Tried and dropped (commit b8738be, profiles/r02_rne_pair_sweep.jsonl, r02_rne_persist_sweep.jsonl): two fp32 rows per
+    // lane as f32x2 pairs (FFMA2 / FMUL2: 35 % fewer issued instructions, same time -- an FFMA2 still holds the FP32
+    // pipe for two cycles and the kernel is not bound by issue at this size) and a persistent grid-stride loop with
+    // double-buffered tiles (fp32 equal, fp64 slower: the second buffer's registers spill).  At 1M rows the one-shot
+    // kernel pays 4-6 us of fill / drain per launch; at 4M rows it streams at 0.82 (fp64) / 0.91 (fp32) of HBM.
     const bool light = mode == B2K_GEN_RNE || mode == B2K_GEN_GRAVLOAD || mode == B2K_GEN_ITORQUE;
-    int tpw = (dtype == B2K_F32 && light && !pair) ? 2 : 1;
+    int tpw = (dtype == B2K_F32 && light) ? 2 : 1;
     if (const char *e = getenv("B2K_RNE_SPEC_TPW")) tpw = atoi(e) > 0 ? atoi(e) : tpw;
-    bool persist = false;
-    if (const char *e = getenv("B2K_RNE_SPEC_PERSIST")) persist = atoi(e) != 0;
-    if (kernel_text) persist = false;
-    p.persist = persist;
-    p.tpw = persist ? 0 : tpw;
-    p.smem = 4 * (((tpw > 1 || persist) ? 2 : 1) * p.nin * in_bytes + (size_t)p.rows * p.nout * es);
+    p.tpw = tpw;
+    p.smem = 4 * ((tpw > 1 ? 2 : 1) * p.nin * in_bytes + (size_t)32 * p.nout * es);
     int minb = (int)((200 * 1024) / (p.smem + 1024));
     // resident blocks to aim for (profiles/r02_rne_sweep.jsonl, r02_rne_sweep32.jsonl: fp64 96 registers / 5 blocks, fp32 64 registers / 8 blocks)
-    const int want = pair ? (light ? 4 : 2) : light ? (es == 8 ? 5 : 8) : (es == 8 ? 2 : 3);
+    const int want = light ? (es == 8 ? 5 : 8) : (es == 8 ? 2 : 3);
     if (minb > want) minb = want;
     if (minb < 1) minb = 1;
     if (const char *e = getenv("B2K_RNE_SPEC_MINB")) minb = atoi(e) > 0 ? atoi(e) : minb;
     auto D = [&](const char *k, long long v) { defs.push_back(std::string("-D") + k + "=" + std::to_string(v)); };
     defs.push_back(std::string("-DREAL=") + (es == 8 ? "double" : "float"));
     D("REAL_IS_F64", es == 8);
-    D("NJ", n); D("NC", p.nc); D("MODE", mode); D("NIN", p.nin); D("NOUT", p.nout); D("NRES", p.nres); D("PADIN", padin); D("MINB", minb); D("TPW", tpw); D("PAIR", pair); D("PERSIST", persist);
-    p.minb = minb;
+    D("NJ", n); D("NC", p.nc); D("MODE", mode); D("NIN", p.nin); D("NOUT", p.nout); D("NRES", p.nres); D("PADIN", padin); D("MINB", minb); D("TPW", tpw);
     // in1 / in2 of the generated function are the second / third input rows; the RNE proper names them qd / qdd
-    std::string body = g.source;
-    if (pair) { // the recursion's values become row pairs, its constants stay scalars (see rowt / creal in kPrologue)
-        const std::string from = "const real *C, const real *grav, const real *fext", to = "const creal *C, const creal *grav, const creal *fext";
-        const size_t at = body.find(from);
-        if (at == std::string::npos) { p.why = "generated signature not recognised"; return std::string(); }
-        body.replace(at, from.size(), to);
-        body = "#define real rowt\n" + body + "#undef real\n";
-    }
-    return std::string(kPrologue) + body + (kernel_text ? kernel_text : kKernel);
+    return std::string(kPrologue) + g.source + (kernel_text ? kernel_text : kKernel);
 }
 
 void compile(const GenFn &gen, int n, const Key &key, Program &p)
@@ -812,13 +735,8 @@ int launch_tiles(Program *p, CUfunction fn, int n, int dtype, const double *offs
     std::vector<unsigned char> pb = spec_params(p, n, dtype, offset, grav, fext);
     long long nt = ntiles;
     void *args[6] = {pb.data(), (void *)&in0, (void *)&in1, (void *)&in2, (void *)&out, (void *)&nt};
-    const long long per_block = 4LL * (p->persist ? 1 : p->tpw);
-    long long blocks = (ntiles + per_block - 1) / per_block;
-    if (p->persist) { // one resident generation of blocks
-        const long long fill = (long long)b2k_num_sms() * p->minb;
-        if (blocks > fill) blocks = fill;
-    }
-    const unsigned grid = (unsigned)blocks;
+    const long long per_block = 4LL * p->tpw;
+    const unsigned grid = (unsigned)((ntiles + per_block - 1) / per_block);
     CUresult rc = driver()->LaunchKernel(fn, grid, 1, 1, 128, 1, 1, (unsigned)p->smem, (CUstream)st, args, nullptr);
     if (rc != CUDA_SUCCESS) {
         const char *es2 = nullptr;
@@ -859,7 +777,8 @@ long long b2k_rne_spec_launch(const b2k_rne_s *r, int mode, int dtype, const voi
         if (setting == 2) { b2k_set_error("RNE specialisation required (B2K_RNE_SPEC=2) but unavailable: %s", why.c_str()); return B2K_ERR_INVALID; }
         return 0;
     };
-    if (nrows < 32) return 0;
+    const long long ntiles = nrows / 32;
+    if (ntiles == 0) return 0;
     const uintptr_t al = (uintptr_t)in0 | (uintptr_t)(in1 ? in1 : in0) | (uintptr_t)(in2 ? in2 : in0) | (uintptr_t)out;
     if (al & 15) return refuse("arrays are not 16-byte aligned");
     int has_fext = 0;
@@ -875,14 +794,12 @@ long long b2k_rne_spec_launch(const b2k_rne_s *r, int mode, int dtype, const voi
         std::lock_guard<std::mutex> lk(c->mu);
         if (get_function(p, &fn)) return refuse(p->why);
     }
-    const long long ntiles = nrows / p->rows; // the rows beyond the last full tile go to the generic kernel
-    if (ntiles == 0) return 0;
     double offset[B2K_MAX_JOINTS];
     for (int j = 0; j < r->n; j++) offset[j] = r->L[j][5];
     const int lrc = launch_tiles(p, fn, r->n, dtype, offset, in0, in1, in2, out, ntiles, uses_grav ? grav : nullptr,
                                  has_fext ? fext : nullptr, st);
     if (lrc) return lrc;
-    return ntiles * p->rows;
+    return ntiles * 32;
 }
 
 // ------------------------------------------------------------------ C ABI: introspection (tests, bench, DESIGN numbers)
@@ -914,7 +831,6 @@ extern "C" int b2k_rne_spec_info(b2k_rne_t r, int mode, int dtype, const double 
     if (spec_setting() == 0) s = "generic (B2K_RNE_SPEC=0)";
     else {
         {
-            const bool uses_grav = mode == B2K_GEN_RNE || mode == B2K_GEN_GRAVLOAD || mode == B2K_GEN_ACCEL;
             // mode 200 + m: the forward-dynamics integrator built around operation m (only m = accel exists)
             const int gm = mode % 100;
             const bool ug = gm == B2K_GEN_RNE || gm == B2K_GEN_GRAVLOAD || gm == B2K_GEN_ACCEL;
@@ -924,8 +840,8 @@ extern "C" int b2k_rne_spec_info(b2k_rne_t r, int mode, int dtype, const double 
             if (!p || !p->ok) s = std::string("generic (") + (p ? p->why : "no cache") + ")";
             else {
                 char t[256];
-                snprintf(t, sizeof(t), "%s<%s,n=%d,mode=%d>: %d mul + %d fma + %d add per row, %d constants, %d regs, %zu B smem/block, %d tiles/warp, %d rows/tile",
-                         p->entry, dtype == B2K_F64 ? "double" : "float", r->n, mode, p->n_mul, p->n_fma, p->n_add, p->nc, p->regs, p->smem, p->tpw, p->rows);
+                snprintf(t, sizeof(t), "%s<%s,n=%d,mode=%d>: %d mul + %d fma + %d add per row, %d constants, %d regs, %zu B smem/block, %d tiles/warp",
+                         p->entry, dtype == B2K_F64 ? "double" : "float", r->n, mode, p->n_mul, p->n_fma, p->n_add, p->nc, p->regs, p->smem, p->tpw);
                 s = t;
             }
         }
@@ -1006,19 +922,19 @@ extern "C" int b2k_tree_rne(b2k_tree_t t, int dtype, const void *q, const void *
     cudaStream_t st = (cudaStream_t)stream;
     const int n = t->n;
     const size_t es = dtype == B2K_F64 ? 8 : 4, rowb = (size_t)n * es;
-    const long long R = p->rows, ntiles = N / R, tail = N - ntiles * R;
+    const long long ntiles = N / 32, tail = N - ntiles * 32;
     int rc = B2K_OK;
     if (ntiles) rc = launch_tiles(p, f, n, dtype, nullptr, q, qd, qdd, tau, ntiles, grav, nullptr, st);
     if (rc == B2K_OK && tail) { // ragged tail: one padded tile through stream-ordered scratch
         b2k_keep_mempool();
         char *scr = nullptr;
-        B2K_CUDA(cudaMallocAsync((void **)&scr, 4 * R * rowb, st));
-        cudaMemsetAsync(scr, 0, 3 * R * rowb, st);
-        const size_t off = (size_t)ntiles * R * rowb;
+        B2K_CUDA(cudaMallocAsync((void **)&scr, 4 * 32 * rowb, st));
+        cudaMemsetAsync(scr, 0, 3 * 32 * rowb, st);
+        const size_t off = (size_t)ntiles * 32 * rowb;
         const void *src[3] = {q, qd, qdd};
-        for (int i = 0; i < 3; i++) cudaMemcpyAsync(scr + i * R * rowb, (const char *)src[i] + off, tail * rowb, cudaMemcpyDeviceToDevice, st);
-        rc = launch_tiles(p, f, n, dtype, nullptr, scr, scr + R * rowb, scr + 2 * R * rowb, scr + 3 * R * rowb, 1, grav, nullptr, st);
-        cudaMemcpyAsync((char *)tau + off, scr + 3 * R * rowb, tail * rowb, cudaMemcpyDeviceToDevice, st);
+        for (int i = 0; i < 3; i++) cudaMemcpyAsync(scr + i * 32 * rowb, (const char *)src[i] + off, tail * rowb, cudaMemcpyDeviceToDevice, st);
+        rc = launch_tiles(p, f, n, dtype, nullptr, scr, scr + 32 * rowb, scr + 2 * 32 * rowb, scr + 3 * 32 * rowb, 1, grav, nullptr, st);
+        cudaMemcpyAsync((char *)tau + off, scr + 3 * 32 * rowb, tail * rowb, cudaMemcpyDeviceToDevice, st);
         cudaFreeAsync(scr, st);
         cudaError_t e = cudaGetLastError();
         if (rc == B2K_OK && e != cudaSuccess) rc = b2k_cuda_fail(e, "tail tile of b2k_tree_rne");
