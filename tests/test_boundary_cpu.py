@@ -407,3 +407,38 @@ def test_dh_kinematic_setters_invalidate_the_chain_and_the_rne_table():
 def test_numa_helpers_are_safe_without_a_gpu():
     assert rtb.dist._parse_cpulist("0-2,5,7-8\n") == {0, 1, 2, 5, 7, 8}
     assert rtb.dist.bind_to_gpu_numa(0) in (None,) or isinstance(rtb.dist.bind_to_gpu_numa(0), dict)
+
+
+def test_ik_kernels_keep_the_normal_equations_in_registers():
+    """Guards the round-2 finding: `#pragma unroll` once left two columns of the Cholesky as run-time loops,
+    which put the whole packed matrix in local memory (144 B stack frame, 22 LDL + 14 STL per evaluation, no spill
+    warning).  The resource table of the shipped fp32 Panda / UR10 / Puma kernels must show no stack frame and at most
+    128 registers (4 resident blocks); the fp64 ones are held to 168 registers (3 blocks)."""
+    import shutil
+
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    out = subprocess.run([cuobjdump, "--dump-resource-usage", rtb._lib.LIB_PATH], capture_output=True, text=True).stdout
+    usage = {}
+    name = None
+    for line in out.splitlines():
+        m = re.search(r"Function (\S+?):", line)
+        if m:
+            name = m.group(1)
+            continue
+        m = re.search(r"REG:(\d+) STACK:(\d+)", line)
+        if m and name:
+            usage[name] = (int(m.group(1)), int(m.group(2)))
+            name = None
+    seen = 0
+    for fn, (reg, stack) in usage.items():
+        m = re.match(r"_Z(?:7k_ik_lm|13k_ik_restarts)I([fd])Li([67])ELi1E", fn)  # DH-like profile, n = 6 / 7 (LM and NR / GN)
+        if not m:
+            continue
+        seen += 1
+        if m.group(1) == "f":
+            assert reg <= 128 and stack == 0, (fn, reg, stack)
+        else:
+            assert reg <= 168, (fn, reg, stack)
+    assert seen >= 24, f"only {seen} IK kernels recognised in the resource table"
