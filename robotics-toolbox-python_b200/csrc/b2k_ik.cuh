@@ -562,7 +562,8 @@ k_ik_restarts(const __grid_constant__ ChainP<real, N> P, const __grid_constant__
                 }
             }
             // group reduction: lowest successful search wins; iteration contributions of the searches before it add up
-            const unsigned wins = (__ballot_sync(FULL, won) >> gbase) & ((1u << G) - 1u);
+            const unsigned gmask = G >= 32 ? 0xffffffffu : ((1u << (G & 31)) - 1u);
+            const unsigned wins = (__ballot_sync(FULL, won) >> gbase) & gmask;
             const int wsub = wins ? (__ffs(wins) - 1) : G;
             int pre = 0, all = 0; // sum of iters over subs < wsub / over the whole batch
 #pragma unroll
@@ -640,11 +641,15 @@ int ik_launch_n(const b2k_chain_s *c, const real *Tep, long long nprob, const re
     int *scratch = nullptr;
     if (two_phase) {
         b2k_keep_mempool(); // do not hand the pool's memory back to the OS at every synchronisation
-        B2K_CUDA(cudaMallocAsync((void **)&scratch, sizeof(int) * (size_t)(2 * nprob + 2), st));
-        B2K_CUDA(cudaMemsetAsync(scratch, 0, 2 * sizeof(int), st));
+        B2K_CUDA(cudaMallocAsync((void **)&scratch, sizeof(int) * (size_t)(2 * nprob + 4), st));
+        B2K_CUDA(cudaMemsetAsync(scratch, 0, 4 * sizeof(int), st)); // one counter per list: no memset between the launches
     }
-    int *hard_count = scratch, *cont_count = scratch ? scratch + 1 : nullptr;
-    int *hard_idx = scratch ? scratch + 2 : nullptr, *cont_idx = scratch ? scratch + 2 + nprob : nullptr;
+    // lists: hard (first search failed; phase A -> restart round one), parked (segment one -> two of the first search),
+    // cont (round one -> two), third (round two -> three).  Two index buffers serve all four: the parked list is
+    // consumed before round one writes `cont` into the same buffer, and the hard list before round two writes `third`.
+    int *hard_count = scratch, *park_count = scratch ? scratch + 1 : nullptr, *cont_count = scratch ? scratch + 2 : nullptr;
+    int *third_count = scratch ? scratch + 3 : nullptr;
+    int *hard_idx = scratch ? scratch + 4 : nullptr, *cont_idx = scratch ? scratch + 4 + nprob : nullptr;
     auto launch_a = [&](auto kern) -> int {
         int per_sm = b2k_blocks_per_sm((const void *)kern, B2K_THREADS, 0);
         if (per_sm < 1) return per_sm < 0 ? per_sm : (b2k_set_error("ik kernel does not fit on an SM"), B2K_ERR_INVALID);
@@ -655,12 +660,12 @@ int ik_launch_n(const b2k_chain_s *c, const real *Tep, long long nprob, const re
         const bool seg = mode == 2 && ilimit > IK_SEG1 + 2;
         kern<<<(unsigned)grid, B2K_THREADS, 0, st>>>(P, K, Tep, q0, nprob, q_out, success, iterations, searches, residual,
                                                      two_phase ? 1 : 0, hard_idx, hard_count, seg ? IK_SEG1 : 0, nullptr,
-                                                     nullptr, cont_idx, cont_count);
+                                                     nullptr, cont_idx, park_count);
         b2k_count_launch();
         B2K_CUDA(cudaGetLastError());
         if (seg) { // second segment: the parked problems, re-packed (the list length is only known on the device)
             kern<<<(unsigned)grid, B2K_THREADS, 0, st>>>(P, K, Tep, q0, nprob, q_out, success, iterations, searches,
-                                                         residual, 1, hard_idx, hard_count, 0, cont_idx, cont_count, nullptr,
+                                                         residual, 1, hard_idx, hard_count, 0, cont_idx, park_count, nullptr,
                                                          nullptr);
             b2k_count_launch();
             B2K_CUDA(cudaGetLastError());
@@ -684,13 +689,22 @@ int ik_launch_n(const b2k_chain_s *c, const real *Tep, long long nprob, const re
     };
     int rc = c->dh_like ? launch_a(k_ik_lm<real, N, 1, STEP>) : launch_a(k_ik_lm<real, N, 0, STEP>);
     if (rc == B2K_OK && two_phase) {
-        static const int rounds_env = getenv("B2K_IK_ROUNDS") ? atoi(getenv("B2K_IK_ROUNDS")) : 2; // 1: single G = 8 round
-        constexpr int G1 = 4;
+        // B2K_IK_ROUNDS: 1 = a single round of 8-lane groups; 2 = 4 lanes for searches 1-4, then 8 lanes to the end;
+        // 3 (default) = 4 lanes, ONE batch of 8 lanes (searches 5-12), then whole warps (32 searches per batch) for the
+        // handful of problems still unsolved -- a protocol whose hardest problem needs 50 (or all 100) searches otherwise
+        // runs 6 (12) serial batches of 30 evaluations for a few dozen problems.
+        static const int rounds_env = getenv("B2K_IK_ROUNDS") ? atoi(getenv("B2K_IK_ROUNDS")) : 3;
+        constexpr int G1 = 4, G3 = 32;
         if (rounds_env >= 2 && slimit > 1 + G1) {
-            B2K_CUDA(cudaMemsetAsync(cont_count, 0, sizeof(int), st)); // the parked-problem list of phase A is free again
             rc = c->dh_like ? launch_b(k_ik_restarts<real, N, 1, G1, STEP>, G1, hard_idx, hard_count, 1, 1, cont_idx, cont_count)
                             : launch_b(k_ik_restarts<real, N, 0, G1, STEP>, G1, hard_idx, hard_count, 1, 1, cont_idx, cont_count);
-            if (rc == B2K_OK)
+            if (rc == B2K_OK && rounds_env >= 3 && slimit > 1 + G1 + G) {
+                rc = c->dh_like ? launch_b(k_ik_restarts<real, N, 1, G, STEP>, G, cont_idx, cont_count, 1 + G1, 1, hard_idx, third_count)
+                                : launch_b(k_ik_restarts<real, N, 0, G, STEP>, G, cont_idx, cont_count, 1 + G1, 1, hard_idx, third_count);
+                if (rc == B2K_OK)
+                    rc = c->dh_like ? launch_b(k_ik_restarts<real, N, 1, G3, STEP>, G3, hard_idx, third_count, 1 + G1 + G, 0x7fffffff, nullptr, nullptr)
+                                    : launch_b(k_ik_restarts<real, N, 0, G3, STEP>, G3, hard_idx, third_count, 1 + G1 + G, 0x7fffffff, nullptr, nullptr);
+            } else if (rc == B2K_OK)
                 rc = c->dh_like ? launch_b(k_ik_restarts<real, N, 1, G, STEP>, G, cont_idx, cont_count, 1 + G1, 0x7fffffff, nullptr, nullptr)
                                 : launch_b(k_ik_restarts<real, N, 0, G, STEP>, G, cont_idx, cont_count, 1 + G1, 0x7fffffff, nullptr, nullptr);
         } else {
