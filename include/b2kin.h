@@ -200,9 +200,27 @@ int b2k_tree_create(int n, const int32_t *parent, const int32_t *axis, const int
 int b2k_tree_destroy(b2k_tree_t tree);
 int b2k_tree_rne(b2k_tree_t tree, int dtype, const void *q, const void *qd, const void *qdd, int64_t N, const double *grav,
                  void *tau, void *stream);
-int b2k_tree_codegen(b2k_tree_t tree, int grav_mask, char *src, int64_t src_cap, double *consts, int32_t consts_cap,
+/* The operations DynamicsMixin derives from rne (Dynamics.py: inertia 752-758, gravload 912-915, itorque 1456-1459,
+ * coriolis 825-857, accel 490-503) for a tree robot -- in the reference n to n(n+1)/2 + 1 Python rne loops per row, here
+ * one generated kernel per operation (the same recursion over symbolic unit / zero inputs, like the DH entry points below).
+ *   op B2K_DYN_INERTIA  in0 = q                      out (N,n,n)  row i = rne(q, 0, e_i, gravity 0)
+ *      B2K_DYN_GRAVLOAD in0 = q                      out (N,n)    rne(q, 0, 0)                          uses grav
+ *      B2K_DYN_ITORQUE  in0 = q, in1 = qdd           out (N,n)    rne(q, 0, qdd, gravity 0)
+ *      B2K_DYN_CORIOLIS in0 = q, in1 = qd            out (N,n,n)  the reference's combination rule
+ *      B2K_DYN_ACCEL    in0 = q, in1 = qd, in2 = tau out (N,n)    M(q)^-1 (tau - rne(q, qd, 0))         uses grav
+ * (B2K_DYN_RNE = b2k_tree_rne).  e_i and the input columns are in q order, the torque columns in group order, exactly as
+ * the reference's calls produce them.  b2k_tree_codegen / b2k_tree_info take the same op codes. */
+#define B2K_DYN_RNE 0
+#define B2K_DYN_INERTIA 1
+#define B2K_DYN_GRAVLOAD 2
+#define B2K_DYN_ITORQUE 3
+#define B2K_DYN_CORIOLIS 4
+#define B2K_DYN_ACCEL 5
+int b2k_tree_dyn(b2k_tree_t tree, int op, int dtype, const void *in0, const void *in1, const void *in2, int64_t N,
+                 const double *grav, void *out, void *stream);
+int b2k_tree_codegen(b2k_tree_t tree, int op, int grav_mask, char *src, int64_t src_cap, double *consts, int32_t consts_cap,
                      int32_t *n_consts, int32_t *counts);
-int b2k_tree_info(b2k_tree_t tree, int dtype, const double *grav, char *buf, int64_t cap);
+int b2k_tree_info(b2k_tree_t tree, int op, int dtype, const double *grav, char *buf, int64_t cap);
 
 /* ---------------------------------------------------------------- dynamics built on the recursion
  * The reference's DynamicsMixin (robot/Dynamics.py) obtains these by looping frne calls in
@@ -231,6 +249,11 @@ int b2k_rne_accel(b2k_rne_t rne, int dtype, const void *q, const void *qd, const
  * out_t (ntraj,M), out_q / out_qd (ntraj,M,n), out_count (samples produced; > M means the capacity was too small),
  * out_status (bit 0: step size underflow, bit 1: capacity exceeded).  All-revolute robots; needs NVRTC. */
 int b2k_rne_fdyn(b2k_rne_t rne, int dtype, const void *q0, const void *qd0, int64_t ntraj, double T, const double *grav,
+                 int torque_mode, const double *tau, const void *tau_rows, const double *kp, const double *kd, const double *qstar,
+                 double rtol, double atol, double max_step, double first_step, double dt, int grid, int M, void *out_t,
+                 void *out_q, void *out_qd, int32_t *out_count, int32_t *out_status, void *stream);
+/* the same integrator around the accel recursion of a rigid-body tree (Robot.fdyn); grav = MINUS the robot's gravity */
+int b2k_tree_fdyn(b2k_tree_t tree, int dtype, const void *q0, const void *qd0, int64_t ntraj, double T, const double *grav,
                  int torque_mode, const double *tau, const void *tau_rows, const double *kp, const double *kd, const double *qstar,
                  double rtol, double atol, double max_step, double first_step, double dt, int grid, int M, void *out_t,
                  void *out_q, void *out_qd, int32_t *out_count, int32_t *out_status, void *stream);

@@ -452,12 +452,81 @@ class Robot:
             tau = B.to_host(tau)
         return tau[0] if single else tau
 
-    def rne_kernel_info(self, dtype=np.float64, gravity=None) -> str:
+    _DYN_OPS = {"rne": 0, "inertia": 1, "gravload": 2, "itorque": 3, "coriolis": 4, "accel": 5}
+
+    def rne_kernel_info(self, dtype=np.float64, gravity=None, op="rne") -> str:
         g = self._gravity if gravity is None else np.asarray(gravity, dtype=np.float64).reshape(3)
         ag = np.ascontiguousarray(-g)
         buf = C.create_string_buffer(2048)
-        _lib.check(_lib.lib().b2k_tree_info(self._tree_handle(), B.code(np.dtype(dtype)), _lib.dptr(ag), buf, 2048))
+        _lib.check(_lib.lib().b2k_tree_info(self._tree_handle(), self._DYN_OPS[op], B.code(np.dtype(dtype)), _lib.dptr(ag), buf, 2048))
         return buf.value.decode()
+
+    # ---- dynamics built on the recursion (reference DynamicsMixin, Dynamics.py, which BaseRobot inherits: each method
+    #      there is a Python loop of self.rne calls; here one generated kernel per operation, b2k_tree_dyn)
+    def _tree_dyn(self, op, ins, names, out_tail, gravity=None, dtype=None):
+        for x, nm in zip(ins, names):
+            B.check_numeric(x, nm)
+        n = self.n
+        dt = B.pick_dtype(ins[0], dtype)
+        host = not B.is_tensor(ins[0])
+        single = (ins[0].dim() if B.is_tensor(ins[0]) else np.ndim(ins[0])) == 1
+        dev = []
+        for x, nm in zip(ins, names):
+            t = B.to_device(x, dt)
+            t = t.reshape(1, -1) if t.dim() == 1 else t
+            if t.dim() != 2 or t.shape[1] != n:
+                raise ValueError(f"{nm} must have shape ({n},) or (N,{n}); got {tuple(t.shape)}")
+            dev.append(t.contiguous())
+        N = dev[0].shape[0]
+        if any(t.shape[0] != N for t in dev):
+            raise ValueError(", ".join(names) + " must have the same number of rows")
+        g = self._gravity if gravity is None else np.asarray(gravity, dtype=np.float64).reshape(3)
+        ag = np.ascontiguousarray(-g)
+        out = B.empty((N,) + tuple(out_tail), dt, like=dev[0])
+        ptrs = [B.ptr(t) for t in dev] + [None] * (3 - len(dev))
+        _lib.check(_lib.lib().b2k_tree_dyn(self._tree_handle(), self._DYN_OPS[op], B.code(dt), ptrs[0], ptrs[1], ptrs[2], N,
+                                           _lib.dptr(ag), B.ptr(out), B.stream_ptr(dev[0])))
+        if host:
+            out = B.to_host(out)
+        return out[0] if single else out
+
+    def inertia(self, q, dtype=None):
+        """Joint-space inertia matrix M(q), (n,n) or (N,n,n) (Dynamics.py:700-758: n rne calls per row there)."""
+        return self._tree_dyn("inertia", (q,), ("q",), (self.n, self.n), dtype=dtype)
+
+    def gravload(self, q, gravity=None, dtype=None):
+        """Gravity torque rne(q, 0, 0) (Dynamics.py:861-915)."""
+        return self._tree_dyn("gravload", (q,), ("q",), (self.n,), gravity=gravity, dtype=dtype)
+
+    def itorque(self, q, qdd, dtype=None):
+        """Inertia torque M(q) qdd = rne(q, 0, qdd) without gravity (Dynamics.py:1418-1459)."""
+        return self._tree_dyn("itorque", (q, qdd), ("q", "qdd"), (self.n,), dtype=dtype)
+
+    def coriolis(self, q, qd, dtype=None):
+        """Coriolis / centripetal matrix C(q, qd), (n,n) or (N,n,n) (Dynamics.py:760-857: n(n+1)/2 rne calls per row)."""
+        return self._tree_dyn("coriolis", (q, qd), ("q", "qd"), (self.n, self.n), dtype=dtype)
+
+    def accel(self, q, qd, torque, gravity=None, dtype=None):
+        """Forward dynamics qdd = M(q)^-1 (torque - rne(q, qd, 0)) (Dynamics.py:424-503: n + 1 rne calls and a numpy
+        solve per row there)."""
+        return self._tree_dyn("accel", (q, qd, torque), ("q", "qd", "torque"), (self.n,), gravity=gravity, dtype=dtype)
+
+    def fdyn(self, T, q0, Q=None, Q_args=None, qd0=None, solver="RK45", solver_args=None, dt=None, progress=False, gravity=None,
+             max_steps: int = 4096, dtype=None):
+        """Integrate the forward dynamics of the tree robot over [0, T] (DynamicsMixin.fdyn, Dynamics.py:185-422, inherited
+        by the reference's Robot through BaseRobot).  Arguments, torque laws, ensemble form ((B,n) initial states, one lane
+        per trajectory) and return values as ``DHRobot.fdyn``; the right-hand side is this robot's generated ``accel``
+        recursion (b2k_tree_fdyn)."""
+        from ._fdyn import fdyn as _fdyn
+
+        def kernel_gravity(gravity):
+            g = self._gravity if gravity is None else np.asarray(gravity, dtype=np.float64).reshape(3)
+            return -g  # a_grav = -gravity (Robot.py:1785-1788)
+
+        callable_q = callable(Q)
+        return _fdyn(self, None if callable_q else _lib.lib().b2k_tree_fdyn, None if callable_q else self._tree_handle(), kernel_gravity,
+                     T, q0, Q=Q, Q_args=Q_args, qd0=qd0, solver=solver, solver_args=solver_args, dt=dt, gravity=gravity,
+                     max_steps=max_steps, dtype=dtype)
 
     # ---- model ingestion
     @classmethod

@@ -49,11 +49,14 @@ _PROTOS = {
     "b2k_rne_spec_info": (C.c_int, [vp, C.c_int, C.c_int, dp, C.c_int, C.c_char_p, i64]),
     "b2k_rne_fdyn": (C.c_int, [vp, C.c_int, vp, vp, i64, C.c_double, dp, C.c_int, dp, vp, dp, dp, dp, C.c_double, C.c_double,
                                C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp]),
+    "b2k_tree_fdyn": (C.c_int, [vp, C.c_int, vp, vp, i64, C.c_double, dp, C.c_int, dp, vp, dp, dp, dp, C.c_double, C.c_double,
+                               C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp]),
     "b2k_tree_create": (C.c_int, [C.c_int, ip, ip, ip, ip, dp, dp, C.POINTER(vp)]),
     "b2k_tree_destroy": (C.c_int, [vp]),
     "b2k_tree_rne": (C.c_int, [vp, C.c_int, vp, vp, vp, i64, dp, vp, vp]),
-    "b2k_tree_codegen": (C.c_int, [vp, C.c_int, C.c_char_p, i64, dp, C.c_int32, ip, ip]),
-    "b2k_tree_info": (C.c_int, [vp, C.c_int, dp, C.c_char_p, i64]),
+    "b2k_tree_dyn": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, vp, i64, dp, vp, vp]),
+    "b2k_tree_codegen": (C.c_int, [vp, C.c_int, C.c_int, C.c_char_p, i64, dp, C.c_int32, ip, ip]),
+    "b2k_tree_info": (C.c_int, [vp, C.c_int, C.c_int, dp, C.c_char_p, i64]),
     "b2k_rne_inertia": (C.c_int, [vp, C.c_int, vp, i64, vp, vp]),
     "b2k_rne_gravload": (C.c_int, [vp, C.c_int, vp, i64, dp, vp, vp]),
     "b2k_rne_itorque": (C.c_int, [vp, C.c_int, vp, vp, i64, vp, vp]),

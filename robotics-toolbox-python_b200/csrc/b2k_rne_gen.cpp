@@ -19,6 +19,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <functional>
 #include <map>
 #include <string>
 #include <vector>
@@ -404,6 +405,114 @@ std::string assign(Gen &g, const std::string &lhs, const Sym &s)
     return "    " + lhs + " = " + g.spell(g.operand(s)) + ";";
 }
 
+// The operations of DynamicsMixin as evaluations of ONE recursion over symbolic inputs (`rec`: per-joint velocity and
+// acceleration symbols in q order, base acceleration, tip wrench -> joint torques): shared by the DH recursion and the
+// spatial-vector recursion of rigid-body trees.  Fills the statements that store the result (`tail`) and the signature.
+typedef std::function<std::vector<Sym>(const Inputs &)> RecFn;
+int assemble(Gen &g, int N, const b2k_gen_opts &o, const RecFn &rec, std::vector<std::string> &tail, const char *&sig, std::string &err)
+{
+    auto jvec = [&](const char *name) {
+        std::vector<Sym> s(N);
+        for (int j = 0; j < N; j++) s[j] = g.var(std::string(name) + "[" + std::to_string(j) + "]");
+        return s;
+    };
+    auto gvec = [&]() {
+        V3 v;
+        v.x = (o.grav_mask & 1) ? g.var("grav[0]") : Gen::zero();
+        v.y = (o.grav_mask & 2) ? g.var("grav[1]") : Gen::zero();
+        v.z = (o.grav_mask & 4) ? g.var("grav[2]") : Gen::zero();
+        return v;
+    };
+    const std::vector<Sym> zeros(N, Gen::zero());
+    Vops vo(g);
+    Inputs in;
+    in.grav = vo.zero(); in.ftip = vo.zero(); in.ntip = vo.zero();
+    if (o.mode == B2K_GEN_RNE) {
+        sig = "rne_row(const real *C, const real *grav, const real *fext, const real *st, const real *ct, const real *qq, "
+              "const real *qd, const real *qdd, real *out)";
+        in.qd = jvec("qd"); in.qdd = jvec("qdd");
+        in.grav = gvec();
+        if (o.has_fext) {
+            in.ftip = {g.var("fext[0]"), g.var("fext[1]"), g.var("fext[2]")};
+            in.ntip = {g.var("fext[3]"), g.var("fext[4]"), g.var("fext[5]")};
+        }
+        std::vector<Sym> tau = rec(in);
+        for (int j = 0; j < N; j++) tail.push_back(assign(g, "out[" + std::to_string(j) + "]", tau[j]));
+    } else if (o.mode == B2K_GEN_GRAVLOAD) { // rne(q, 0, 0, g)  Dynamics.py:912-915
+        sig = "rne_row(const real *C, const real *grav, const real *fext, const real *st, const real *ct, const real *qq, "
+              "const real *in1, const real *in2, real *out)";
+        in.qd = zeros; in.qdd = zeros; in.grav = gvec();
+        std::vector<Sym> tau = rec(in);
+        for (int j = 0; j < N; j++) tail.push_back(assign(g, "out[" + std::to_string(j) + "]", tau[j]));
+    } else if (o.mode == B2K_GEN_ITORQUE) { // rne(q, 0, qdd, g = 0)  Dynamics.py:1456-1459
+        sig = "rne_row(const real *C, const real *grav, const real *fext, const real *st, const real *ct, const real *qq, "
+              "const real *in1, const real *in2, real *out)";
+        in.qd = zeros; in.qdd = jvec("in1");
+        std::vector<Sym> tau = rec(in);
+        for (int j = 0; j < N; j++) tail.push_back(assign(g, "out[" + std::to_string(j) + "]", tau[j]));
+    } else if (o.mode == B2K_GEN_INERTIA) { // row i of M = rne(q, 0, e_i, g = 0)  Dynamics.py:752-758
+        sig = "rne_row(const real *C, const real *grav, const real *fext, const real *st, const real *ct, const real *qq, "
+              "const real *in1, const real *in2, real *out)";
+        for (int i = 0; i < N; i++) {
+            in.qd = zeros; in.qdd = zeros;
+            in.qdd[i] = Gen::cst(1.0);
+            std::vector<Sym> tau = rec(in);
+            for (int k = 0; k < N; k++) tail.push_back(assign(g, "out[" + std::to_string(i * N + k) + "]", tau[k]));
+        }
+    } else if (o.mode == B2K_GEN_CORIOLIS) { // Dynamics.py:825-857 on the friction-free robot
+        sig = "rne_row(const real *C, const real *grav, const real *fext, const real *st, const real *ct, const real *qq, "
+              "const real *in1, const real *in2, real *out)";
+        in.friction = false;
+        std::vector<Sym> qd = jvec("in1");
+        std::vector<std::vector<Sym>> Csq(N, std::vector<Sym>(N));
+        std::vector<std::vector<std::vector<Sym>>> terms(N, std::vector<std::vector<Sym>>(N));
+        for (int i = 0; i < N; i++) { // centripetal: joint i alone at unit speed
+            in.qd = zeros; in.qdd = zeros;
+            in.qd[i] = Gen::cst(1.0);
+            std::vector<Sym> tau = rec(in);
+            for (int k = 0; k < N; k++) Csq[k][i] = g.fix(tau[k]);
+        }
+        const Sym half = Gen::cst(0.5);
+        for (int i = 0; i < N; i++)
+            for (int j = i + 1; j < N; j++) { // Coriolis: joints i and j at unit speed
+                in.qd = zeros; in.qdd = zeros;
+                in.qd[i] = Gen::cst(1.0); in.qd[j] = Gen::cst(1.0);
+                std::vector<Sym> tau = rec(in);
+                for (int k = 0; k < N; k++) {
+                    const Sym t = g.fix(g.sum({tau[k], g.neg(Csq[k][j]), g.neg(Csq[k][i])}));
+                    const Sym th = g.fix(g.mul(half, t));
+                    terms[k][j].push_back(g.mul(th, qd[i]));
+                    terms[k][i].push_back(g.mul(th, qd[j]));
+                }
+            }
+        for (int k = 0; k < N; k++)
+            for (int i = 0; i < N; i++) {
+                terms[k][i].push_back(g.mul(Csq[k][i], qd[i]));
+                tail.push_back(assign(g, "out[" + std::to_string(k * N + i) + "]", g.sum(terms[k][i])));
+            }
+    } else if (o.mode == B2K_GEN_ACCEL) {
+        // tau0 = rne(q, qd, 0, g) with friction; M rows with unit accelerations, no gravity: out = [M (n*n) | torque - tau0 (n)]
+        // (the kernel wrapper solves the n x n system; Dynamics.py:490-503)
+        sig = "rne_row(const real *C, const real *grav, const real *fext, const real *st, const real *ct, const real *qq, "
+              "const real *in1, const real *in2, real *out)";
+        in.qd = jvec("in1"); in.qdd = zeros; in.grav = gvec();
+        std::vector<Sym> tau0 = rec(in);
+        std::vector<Sym> tq = jvec("in2");
+        for (int k = 0; k < N; k++) tail.push_back(assign(g, "out[" + std::to_string(N * N + k) + "]", g.sub(tq[k], tau0[k])));
+        in.grav = vo.zero();
+        for (int i = 0; i < N; i++) {
+            in.qd = zeros; in.qdd = zeros;
+            in.qdd[i] = Gen::cst(1.0);
+            std::vector<Sym> tau = rec(in);
+            for (int k = 0; k < N; k++) tail.push_back(assign(g, "out[" + std::to_string(i * N + k) + "]", tau[k]));
+        }
+    } else {
+        err = "unknown generator mode";
+        return -1;
+    }
+    return 0;
+}
+
 } // namespace
 
 int b2k_rne_generate(const b2k_rne_s *r, const b2k_gen_opts &o, b2k_gen_out &out)
@@ -437,107 +546,9 @@ int b2k_rne_generate(const b2k_rne_s *r, const b2k_gen_opts &o, b2k_gen_out &out
         L[j].c_tcp = fabs(G) * l[22];
         L[j].c_tcm = fabs(G) * l[23];
     }
-    auto jvec = [&](const char *name) {
-        std::vector<Sym> s(N);
-        for (int j = 0; j < N; j++) s[j] = g.var(std::string(name) + "[" + std::to_string(j) + "]");
-        return s;
-    };
-    auto gvec = [&]() {
-        V3 v;
-        v.x = (o.grav_mask & 1) ? g.var("grav[0]") : Gen::zero();
-        v.y = (o.grav_mask & 2) ? g.var("grav[1]") : Gen::zero();
-        v.z = (o.grav_mask & 4) ? g.var("grav[2]") : Gen::zero();
-        return v;
-    };
-    const std::vector<Sym> zeros(N, Gen::zero());
-    Vops vo(g);
-    Inputs in;
-    in.grav = vo.zero(); in.ftip = vo.zero(); in.ntip = vo.zero();
     std::vector<std::string> tail;
     const char *sig = nullptr;
-    if (o.mode == B2K_GEN_RNE) {
-        sig = "rne_row(const real *C, const real *grav, const real *fext, const real *st, const real *ct, const real *qq, "
-              "const real *qd, const real *qdd, real *out)";
-        in.qd = jvec("qd"); in.qdd = jvec("qdd");
-        in.grav = gvec();
-        if (o.has_fext) {
-            in.ftip = {g.var("fext[0]"), g.var("fext[1]"), g.var("fext[2]")};
-            in.ntip = {g.var("fext[3]"), g.var("fext[4]"), g.var("fext[5]")};
-        }
-        std::vector<Sym> tau = recursion(g, L, r->mdh != 0, in);
-        for (int j = 0; j < N; j++) tail.push_back(assign(g, "out[" + std::to_string(j) + "]", tau[j]));
-    } else if (o.mode == B2K_GEN_GRAVLOAD) { // rne(q, 0, 0, g)  Dynamics.py:912-915
-        sig = "rne_row(const real *C, const real *grav, const real *fext, const real *st, const real *ct, const real *qq, "
-              "const real *in1, const real *in2, real *out)";
-        in.qd = zeros; in.qdd = zeros; in.grav = gvec();
-        std::vector<Sym> tau = recursion(g, L, r->mdh != 0, in);
-        for (int j = 0; j < N; j++) tail.push_back(assign(g, "out[" + std::to_string(j) + "]", tau[j]));
-    } else if (o.mode == B2K_GEN_ITORQUE) { // rne(q, 0, qdd, g = 0)  Dynamics.py:1456-1459
-        sig = "rne_row(const real *C, const real *grav, const real *fext, const real *st, const real *ct, const real *qq, "
-              "const real *in1, const real *in2, real *out)";
-        in.qd = zeros; in.qdd = jvec("in1");
-        std::vector<Sym> tau = recursion(g, L, r->mdh != 0, in);
-        for (int j = 0; j < N; j++) tail.push_back(assign(g, "out[" + std::to_string(j) + "]", tau[j]));
-    } else if (o.mode == B2K_GEN_INERTIA) { // row i of M = rne(q, 0, e_i, g = 0)  Dynamics.py:752-758
-        sig = "rne_row(const real *C, const real *grav, const real *fext, const real *st, const real *ct, const real *qq, "
-              "const real *in1, const real *in2, real *out)";
-        for (int i = 0; i < N; i++) {
-            in.qd = zeros; in.qdd = zeros;
-            in.qdd[i] = Gen::cst(1.0);
-            std::vector<Sym> tau = recursion(g, L, r->mdh != 0, in);
-            for (int k = 0; k < N; k++) tail.push_back(assign(g, "out[" + std::to_string(i * N + k) + "]", tau[k]));
-        }
-    } else if (o.mode == B2K_GEN_CORIOLIS) { // Dynamics.py:825-857 on the friction-free robot
-        sig = "rne_row(const real *C, const real *grav, const real *fext, const real *st, const real *ct, const real *qq, "
-              "const real *in1, const real *in2, real *out)";
-        in.friction = false;
-        std::vector<Sym> qd = jvec("in1");
-        std::vector<std::vector<Sym>> Csq(N, std::vector<Sym>(N));
-        std::vector<std::vector<std::vector<Sym>>> terms(N, std::vector<std::vector<Sym>>(N));
-        for (int i = 0; i < N; i++) { // centripetal: joint i alone at unit speed
-            in.qd = zeros; in.qdd = zeros;
-            in.qd[i] = Gen::cst(1.0);
-            std::vector<Sym> tau = recursion(g, L, r->mdh != 0, in);
-            for (int k = 0; k < N; k++) Csq[k][i] = g.fix(tau[k]);
-        }
-        const Sym half = Gen::cst(0.5);
-        for (int i = 0; i < N; i++)
-            for (int j = i + 1; j < N; j++) { // Coriolis: joints i and j at unit speed
-                in.qd = zeros; in.qdd = zeros;
-                in.qd[i] = Gen::cst(1.0); in.qd[j] = Gen::cst(1.0);
-                std::vector<Sym> tau = recursion(g, L, r->mdh != 0, in);
-                for (int k = 0; k < N; k++) {
-                    const Sym t = g.fix(g.sum({tau[k], g.neg(Csq[k][j]), g.neg(Csq[k][i])}));
-                    const Sym th = g.fix(g.mul(half, t));
-                    terms[k][j].push_back(g.mul(th, qd[i]));
-                    terms[k][i].push_back(g.mul(th, qd[j]));
-                }
-            }
-        for (int k = 0; k < N; k++)
-            for (int i = 0; i < N; i++) {
-                terms[k][i].push_back(g.mul(Csq[k][i], qd[i]));
-                tail.push_back(assign(g, "out[" + std::to_string(k * N + i) + "]", g.sum(terms[k][i])));
-            }
-    } else if (o.mode == B2K_GEN_ACCEL) {
-        // tau0 = rne(q, qd, 0, g) with friction; M rows with unit accelerations, no gravity: out = [M (n*n) | torque - tau0 (n)]
-        // (the kernel wrapper solves the n x n system; Dynamics.py:490-503)
-        sig = "rne_row(const real *C, const real *grav, const real *fext, const real *st, const real *ct, const real *qq, "
-              "const real *in1, const real *in2, real *out)";
-        in.qd = jvec("in1"); in.qdd = zeros; in.grav = gvec();
-        std::vector<Sym> tau0 = recursion(g, L, r->mdh != 0, in);
-        std::vector<Sym> tq = jvec("in2");
-        for (int k = 0; k < N; k++) tail.push_back(assign(g, "out[" + std::to_string(N * N + k) + "]", g.sub(tq[k], tau0[k])));
-        in.grav = vo.zero();
-        for (int i = 0; i < N; i++) {
-            in.qd = zeros; in.qdd = zeros;
-            in.qdd[i] = Gen::cst(1.0);
-            std::vector<Sym> tau = recursion(g, L, r->mdh != 0, in);
-            for (int k = 0; k < N; k++) tail.push_back(assign(g, "out[" + std::to_string(i * N + k) + "]", tau[k]));
-        }
-    } else {
-        out.error = "unknown generator mode";
-        return -1;
-    }
+    if (assemble(g, N, o, [&](const Inputs &in) { return recursion(g, L, r->mdh != 0, in); }, tail, sig, out.error)) return -1;
     std::string src = std::string("__device__ __forceinline__ void ") + sig + "\n{\n";
     for (const std::string &s : g.code) src += s + "\n";
     for (const std::string &s : tail) src += s + "\n";
@@ -602,84 +613,89 @@ struct TreeOps {
 };
 } // namespace
 
-int b2k_tree_generate(const b2k_tree_s *t, int grav_mask, b2k_gen_out &out)
+int b2k_tree_generate(const b2k_tree_s *t, const b2k_gen_opts &o, b2k_gen_out &out)
 {
     const int N = t->n;
     Gen g;
     TreeOps T(g);
     Vops &v = T.v;
-    std::vector<Sym> st(N), ct(N), qq(N), qd(N), qdd(N);
+    std::vector<Sym> st(N), ct(N), qq(N);
     for (int j = 0; j < N; j++) {
         const std::string k = "[" + std::to_string(t->jindex[j]) + "]";
         st[j] = g.var("st" + k); ct[j] = g.var("ct" + k); qq[j] = g.var("qq" + k);
-        qd[j] = g.var("qd" + k); qdd[j] = g.var("qdd" + k);
         if (t->flip[j]) { st[j] = g.neg(st[j]); qq[j] = g.neg(qq[j]); } // eta = -q
     }
-    V3 agrav; // a_grav = -gravity handed in as `grav` (the caller negates), linear part only
-    agrav.x = (grav_mask & 1) ? g.var("grav[0]") : Gen::zero();
-    agrav.y = (grav_mask & 2) ? g.var("grav[1]") : Gen::zero();
-    agrav.z = (grav_mask & 4) ? g.var("grav[2]") : Gen::zero();
-    std::vector<V3> w(N), vl(N), fl(N), fa(N), p(N);
-    std::vector<V3> aw(N), av(N);
     auto unit = [&](int axis, const Sym &x) { // x * e_axis
         V3 u = v.zero();
         (axis % 3 == 0 ? u.x : (axis % 3 == 1 ? u.y : u.z)) = x;
         return u;
     };
-    for (int j = 0; j < N; j++) {
-        const double *C = t->C[j];
-        const int ax = t->axis[j];
-        const bool rev = ax < 3;
-        auto RT = [&](const V3 &u) { return T.jointR(ax, st[j], ct[j], T.constR(C, u, true), true); };
-        // p = pc + Rc (e_axis * eta) for a prismatic joint
-        const double pc[3] = {C[3], C[7], C[11]};
-        p[j] = v.cst(pc);
-        if (!rev) p[j] = v.fix(v.add(p[j], T.constR(C, unit(ax, qq[j]), false)));
-        const V3 vJw = rev ? unit(ax, qd[j]) : v.zero(), vJv = rev ? v.zero() : unit(ax, qd[j]);
-        const V3 aJw = rev ? unit(ax, qdd[j]) : v.zero(), aJv = rev ? v.zero() : unit(ax, qdd[j]);
-        const int pa = t->parent[j];
-        if (pa < 0) {
-            w[j] = vJw; vl[j] = vJv;
-            aw[j] = aJw;
-            av[j] = v.fix(v.add(RT(agrav), aJv));
-        } else {
-            w[j] = v.fix(v.add(RT(w[pa]), vJw));
-            vl[j] = v.fix(v.add(RT(v.cross_acc(w[pa], p[j], &vl[pa])), vJv));
-            const V3 wxJw = v.cross_acc(w[j], vJw);
-            aw[j] = v.fix(v.add(v.add(RT(aw[pa]), aJw), wxJw));
-            const V3 t1 = RT(v.cross_acc(aw[pa], p[j], &av[pa]));
-            const V3 t2 = v.cross_acc(w[j], vJv, &aJv);
-            const V3 t3 = v.cross_acc(vl[j], vJw, &t2);
-            av[j] = v.fix(v.add(t1, t3));
-        }
-        const double *I6 = t->I6[j];
-        const V3 hl = v.fix(v.add(T.mat3(I6, 0, 0, vl[j]), T.mat3(I6, 0, 3, w[j])));
-        const V3 ha = v.fix(v.add(T.mat3(I6, 3, 0, vl[j]), T.mat3(I6, 3, 3, w[j])));
-        const V3 il = v.add(T.mat3(I6, 0, 0, av[j]), T.mat3(I6, 0, 3, aw[j]));
-        const V3 ia = v.add(T.mat3(I6, 3, 0, av[j]), T.mat3(I6, 3, 3, aw[j]));
-        fl[j] = v.fix(v.cross_acc(w[j], hl, &il));
-        const V3 t4 = v.cross_acc(vl[j], hl, &ia);
-        fa[j] = v.fix(v.cross_acc(w[j], ha, &t4));
-    }
-    std::vector<std::string> tail;
-    for (int j = N - 1; j >= 0; j--) {
-        const int ax = t->axis[j];
-        const V3 &f = ax < 3 ? fa[j] : fl[j];
-        const Sym tq = ax % 3 == 0 ? f.x : (ax % 3 == 1 ? f.y : f.z);
-        tail.push_back(assign(g, "out[" + std::to_string(j) + "]", tq));
-        const int pa = t->parent[j];
-        if (pa >= 0) {
+    // one evaluation of the recursion: in.qd / in.qdd are indexed like q (jindex), the torques come out in group order
+    // (Robot.py:1890-1899); in.grav is a_grav = MINUS the gravity vector (the caller negates), linear part only
+    auto rec = [&](const Inputs &in) {
+        const V3 &agrav = in.grav;
+        std::vector<V3> w(N), vl(N), fl(N), fa(N), p(N);
+        std::vector<V3> aw(N), av(N);
+        for (int j = 0; j < N; j++) {
             const double *C = t->C[j];
-            auto R = [&](const V3 &u) { return T.constR(C, T.jointR(ax, st[j], ct[j], u, false), false); };
-            const V3 Rf = v.fix(R(fl[j]));
-            fl[pa] = v.fix(v.add(fl[pa], Rf));
-            const V3 Rn = R(fa[j]);
-            const V3 pxf = v.cross_acc(p[j], Rf, &Rn);
-            fa[pa] = v.fix(v.add(fa[pa], pxf));
+            const int ax = t->axis[j];
+            const bool rev = ax < 3;
+            const Sym &qdj = in.qd[t->jindex[j]], &qddj = in.qdd[t->jindex[j]];
+            auto RT = [&](const V3 &u) { return T.jointR(ax, st[j], ct[j], T.constR(C, u, true), true); };
+            // p = pc + Rc (e_axis * eta) for a prismatic joint
+            const double pc[3] = {C[3], C[7], C[11]};
+            p[j] = v.cst(pc);
+            if (!rev) p[j] = v.fix(v.add(p[j], T.constR(C, unit(ax, qq[j]), false)));
+            const V3 vJw = rev ? unit(ax, qdj) : v.zero(), vJv = rev ? v.zero() : unit(ax, qdj);
+            const V3 aJw = rev ? unit(ax, qddj) : v.zero(), aJv = rev ? v.zero() : unit(ax, qddj);
+            const int pa = t->parent[j];
+            if (pa < 0) {
+                w[j] = vJw; vl[j] = vJv;
+                aw[j] = aJw;
+                av[j] = v.fix(v.add(RT(agrav), aJv));
+            } else {
+                w[j] = v.fix(v.add(RT(w[pa]), vJw));
+                vl[j] = v.fix(v.add(RT(v.cross_acc(w[pa], p[j], &vl[pa])), vJv));
+                const V3 wxJw = v.cross_acc(w[j], vJw);
+                aw[j] = v.fix(v.add(v.add(RT(aw[pa]), aJw), wxJw));
+                const V3 t1 = RT(v.cross_acc(aw[pa], p[j], &av[pa]));
+                const V3 t2 = v.cross_acc(w[j], vJv, &aJv);
+                const V3 t3 = v.cross_acc(vl[j], vJw, &t2);
+                av[j] = v.fix(v.add(t1, t3));
+            }
+            const double *I6 = t->I6[j];
+            const V3 hl = v.fix(v.add(T.mat3(I6, 0, 0, vl[j]), T.mat3(I6, 0, 3, w[j])));
+            const V3 ha = v.fix(v.add(T.mat3(I6, 3, 0, vl[j]), T.mat3(I6, 3, 3, w[j])));
+            const V3 il = v.add(T.mat3(I6, 0, 0, av[j]), T.mat3(I6, 0, 3, aw[j]));
+            const V3 ia = v.add(T.mat3(I6, 3, 0, av[j]), T.mat3(I6, 3, 3, aw[j]));
+            fl[j] = v.fix(v.cross_acc(w[j], hl, &il));
+            const V3 t4 = v.cross_acc(vl[j], hl, &ia);
+            fa[j] = v.fix(v.cross_acc(w[j], ha, &t4));
         }
-    }
-    std::string src = "__device__ __forceinline__ void rne_row(const real *C, const real *grav, const real *fext, const real *st, "
-                      "const real *ct, const real *qq, const real *qd, const real *qdd, real *out)\n{\n";
+        std::vector<Sym> tau(N);
+        for (int j = N - 1; j >= 0; j--) {
+            const int ax = t->axis[j];
+            const V3 &f = ax < 3 ? fa[j] : fl[j];
+            tau[j] = g.fix(ax % 3 == 0 ? f.x : (ax % 3 == 1 ? f.y : f.z));
+            const int pa = t->parent[j];
+            if (pa >= 0) {
+                const double *C = t->C[j];
+                auto R = [&](const V3 &u) { return T.constR(C, T.jointR(ax, st[j], ct[j], u, false), false); };
+                const V3 Rf = v.fix(R(fl[j]));
+                fl[pa] = v.fix(v.add(fl[pa], Rf));
+                const V3 Rn = R(fa[j]);
+                const V3 pxf = v.cross_acc(p[j], Rf, &Rn);
+                fa[pa] = v.fix(v.add(fa[pa], pxf));
+            }
+        }
+        return tau;
+    };
+    std::vector<std::string> tail;
+    const char *sig = nullptr;
+    b2k_gen_opts oo = o;
+    oo.has_fext = 0; // Robot.rne has no tip wrench
+    if (assemble(g, N, oo, rec, tail, sig, out.error)) return -1;
+    std::string src = std::string("__device__ __forceinline__ void ") + sig + "\n{\n";
     for (const std::string &s : g.code) src += s + "\n";
     for (const std::string &s : tail) src += s + "\n";
     src += "}\n";

@@ -33,7 +33,7 @@ struct b2k_tree_s {
     double I6[B2K_TREE_MAX][36];
     void *spec;
 };
-int b2k_tree_generate(const b2k_tree_s *t, int grav_mask, b2k_gen_out &out);
+int b2k_tree_generate(const b2k_tree_s *t, const b2k_gen_opts &o, b2k_gen_out &out);
 
 // outputs of the generated function: RNE / GRAVLOAD / ITORQUE n values; INERTIA / CORIOLIS n*n; ACCEL n*n + n
 // (rows of M followed by torque - rne(q, qd, 0), the wrapper solves the system)

@@ -587,6 +587,7 @@ std::string build_source(const GenFn &gen, int n, int mode, int dtype, Program &
     if (const char *e = getenv("B2K_RNE_SPEC_TPW")) tpw = atoi(e) > 0 ? atoi(e) : tpw;
     p.tpw = tpw;
     p.smem = 4 * ((tpw > 1 ? 2 : 1) * p.nin * in_bytes + (size_t)32 * p.nout * es);
+    if (p.smem > 220 * 1024) { p.why = "a tile of this operation does not fit the shared memory of an SM (" + std::to_string(p.smem) + " B)"; return std::string(); }
     int minb = (int)((200 * 1024) / (p.smem + 1024));
     // resident blocks to aim for (profiles/r02_rne_sweep.jsonl, r02_rne_sweep32.jsonl: fp64 96 registers / 5 blocks, fp32 64 registers / 8 blocks)
     const int want = light ? (es == 8 ? 5 : 8) : (es == 8 ? 2 : 3);
@@ -890,25 +891,35 @@ extern "C" int b2k_tree_destroy(b2k_tree_t t)
     return B2K_OK;
 }
 
-static Program *tree_program(b2k_tree_t t, int dtype, int gmask)
+static Program *tree_program(b2k_tree_t t, int mode, int dtype, int gmask)
 {
-    const Key key(100 + B2K_GEN_RNE, dtype, gmask, 0);
-    return get_program(static_cast<SpecCache *>(t->spec), [t, gmask](b2k_gen_out &g) { return b2k_tree_generate(t, gmask, g); }, t->n, key);
+    const Key key(100 + mode, dtype, gmask, 0);
+    return get_program(static_cast<SpecCache *>(t->spec), [t, mode, gmask](b2k_gen_out &g) {
+        b2k_gen_opts o;
+        o.mode = mode; o.grav_mask = gmask; o.has_fext = 0;
+        return b2k_tree_generate(t, o, g);
+    }, t->n, key);
 }
 
-extern "C" int b2k_tree_rne(b2k_tree_t t, int dtype, const void *q, const void *qd, const void *qdd, int64_t N, const double *grav,
-                            void *tau, void *stream)
+static bool mode_uses_gravity(int mode) { return mode == B2K_GEN_RNE || mode == B2K_GEN_GRAVLOAD || mode == B2K_GEN_ACCEL; }
+
+// Robot.rne (mode 0) and the operations DynamicsMixin builds on it (modes 1-5: inertia, gravload, itorque, coriolis, accel)
+// for a rigid-body tree: the generated kernel on the full tiles, one padded tile for the ragged tail.
+static int tree_run(const char *fn, b2k_tree_t t, int mode, int dtype, const void *in0, const void *in1, const void *in2, int64_t N,
+                    const double *grav, void *out, void *stream)
 {
-    const char *fn = "b2k_tree_rne";
     if (!t) { b2k_set_error("%s: tree handle is NULL", fn); return B2K_ERR_INVALID; }
+    if (mode < B2K_GEN_RNE || mode > B2K_GEN_ACCEL) { b2k_set_error("%s: operation %d is not one of B2K_DYN_*", fn, mode); return B2K_ERR_INVALID; }
     if (dtype != B2K_F32 && dtype != B2K_F64) { b2k_set_error("%s: dtype must be B2K_F32 or B2K_F64", fn); return B2K_ERR_INVALID; }
-    if (N < 0 || (N > 0 && (!q || !qd || !qdd || !tau))) { b2k_set_error("%s: bad arguments", fn); return B2K_ERR_INVALID; }
-    if (!grav) { b2k_set_error("%s: grav is NULL (pass MINUS the robot's gravity: a_grav of Robot.rne)", fn); return B2K_ERR_INVALID; }
-    const uintptr_t al = (uintptr_t)q | (uintptr_t)qd | (uintptr_t)qdd | (uintptr_t)tau;
+    const int nin = (mode == B2K_GEN_RNE || mode == B2K_GEN_ACCEL) ? 3 : ((mode == B2K_GEN_ITORQUE || mode == B2K_GEN_CORIOLIS) ? 2 : 1);
+    if (N < 0 || (N > 0 && (!in0 || (nin >= 2 && !in1) || (nin >= 3 && !in2) || !out))) { b2k_set_error("%s: bad arguments", fn); return B2K_ERR_INVALID; }
+    const bool ug = mode_uses_gravity(mode);
+    if (ug && !grav) { b2k_set_error("%s: grav is NULL (pass MINUS the robot's gravity: a_grav of Robot.rne)", fn); return B2K_ERR_INVALID; }
+    const uintptr_t al = (uintptr_t)in0 | (uintptr_t)(nin >= 2 ? in1 : in0) | (uintptr_t)(nin >= 3 ? in2 : in0) | (uintptr_t)out;
     if (al & 15) { b2k_set_error("%s: arrays must be 16-byte aligned", fn); return B2K_ERR_INVALID; }
     if (N == 0) return B2K_OK;
-    B2K_ON_DEVICE_OF(q);
-    Program *p = tree_program(t, dtype, grav_mask_of(grav));
+    B2K_ON_DEVICE_OF(in0);
+    Program *p = tree_program(t, mode, dtype, ug ? grav_mask_of(grav) : 0);
     if (!p || !p->ok) {
         b2k_set_error("%s: the kernel for this robot could not be built (%s); Robot.rne has no pre-compiled kernel", fn, p ? p->why.c_str() : "no cache");
         return B2K_ERR_INVALID;
@@ -921,33 +932,49 @@ extern "C" int b2k_tree_rne(b2k_tree_t t, int dtype, const void *q, const void *
     }
     cudaStream_t st = (cudaStream_t)stream;
     const int n = t->n;
-    const size_t es = dtype == B2K_F64 ? 8 : 4, rowb = (size_t)n * es;
+    const size_t es = dtype == B2K_F64 ? 8 : 4, rowb = (size_t)n * es, orowb = (size_t)p->nout * es;
     const long long ntiles = N / 32, tail = N - ntiles * 32;
+    const double *gv = ug ? grav : nullptr;
     int rc = B2K_OK;
-    if (ntiles) rc = launch_tiles(p, f, n, dtype, nullptr, q, qd, qdd, tau, ntiles, grav, nullptr, st);
+    if (ntiles) rc = launch_tiles(p, f, n, dtype, nullptr, in0, in1, in2, out, ntiles, gv, nullptr, st);
     if (rc == B2K_OK && tail) { // ragged tail: one padded tile through stream-ordered scratch
         b2k_keep_mempool();
         char *scr = nullptr;
-        B2K_CUDA(cudaMallocAsync((void **)&scr, 4 * 32 * rowb, st));
+        B2K_CUDA(cudaMallocAsync((void **)&scr, 3 * 32 * rowb + 32 * orowb, st));
         cudaMemsetAsync(scr, 0, 3 * 32 * rowb, st);
         const size_t off = (size_t)ntiles * 32 * rowb;
-        const void *src[3] = {q, qd, qdd};
-        for (int i = 0; i < 3; i++) cudaMemcpyAsync(scr + i * 32 * rowb, (const char *)src[i] + off, tail * rowb, cudaMemcpyDeviceToDevice, st);
-        rc = launch_tiles(p, f, n, dtype, nullptr, scr, scr + 32 * rowb, scr + 2 * 32 * rowb, scr + 3 * 32 * rowb, 1, grav, nullptr, st);
-        cudaMemcpyAsync((char *)tau + off, scr + 3 * 32 * rowb, tail * rowb, cudaMemcpyDeviceToDevice, st);
+        const void *src[3] = {in0, in1, in2};
+        for (int i = 0; i < nin; i++) cudaMemcpyAsync(scr + i * 32 * rowb, (const char *)src[i] + off, tail * rowb, cudaMemcpyDeviceToDevice, st);
+        char *so = scr + 3 * 32 * rowb;
+        rc = launch_tiles(p, f, n, dtype, nullptr, scr, scr + 32 * rowb, scr + 2 * 32 * rowb, so, 1, gv, nullptr, st);
+        cudaMemcpyAsync((char *)out + (size_t)ntiles * 32 * orowb, so, tail * orowb, cudaMemcpyDeviceToDevice, st);
         cudaFreeAsync(scr, st);
         cudaError_t e = cudaGetLastError();
-        if (rc == B2K_OK && e != cudaSuccess) rc = b2k_cuda_fail(e, "tail tile of b2k_tree_rne");
+        if (rc == B2K_OK && e != cudaSuccess) rc = b2k_cuda_fail(e, "tail tile of a tree kernel");
     }
     return rc;
 }
 
-extern "C" int b2k_tree_codegen(b2k_tree_t t, int grav_mask, char *src, int64_t src_cap, double *consts, int32_t consts_cap,
+extern "C" int b2k_tree_rne(b2k_tree_t t, int dtype, const void *q, const void *qd, const void *qdd, int64_t N, const double *grav,
+                            void *tau, void *stream)
+{
+    return tree_run("b2k_tree_rne", t, B2K_GEN_RNE, dtype, q, qd, qdd, N, grav, tau, stream);
+}
+
+extern "C" int b2k_tree_dyn(b2k_tree_t t, int op, int dtype, const void *in0, const void *in1, const void *in2, int64_t N,
+                            const double *grav, void *out, void *stream)
+{
+    return tree_run("b2k_tree_dyn", t, op, dtype, in0, in1, in2, N, grav, out, stream);
+}
+
+extern "C" int b2k_tree_codegen(b2k_tree_t t, int op, int grav_mask, char *src, int64_t src_cap, double *consts, int32_t consts_cap,
                                 int32_t *n_consts, int32_t *counts)
 {
     if (!t) { b2k_set_error("b2k_tree_codegen: tree handle is NULL"); return B2K_ERR_INVALID; }
     b2k_gen_out g;
-    if (b2k_tree_generate(t, grav_mask, g)) { b2k_set_error("b2k_tree_codegen: %s", g.error.c_str()); return B2K_ERR_INVALID; }
+    b2k_gen_opts o;
+    o.mode = op; o.grav_mask = grav_mask; o.has_fext = 0;
+    if (b2k_tree_generate(t, o, g)) { b2k_set_error("b2k_tree_codegen: %s", g.error.c_str()); return B2K_ERR_INVALID; }
     if (n_consts) *n_consts = (int32_t)g.consts.size();
     if (counts) { counts[0] = g.n_mul; counts[1] = g.n_fma; counts[2] = g.n_add; }
     if (src) {
@@ -961,26 +988,29 @@ extern "C" int b2k_tree_codegen(b2k_tree_t t, int grav_mask, char *src, int64_t 
     return B2K_OK;
 }
 
-extern "C" int b2k_tree_info(b2k_tree_t t, int dtype, const double *grav, char *buf, int64_t cap)
+extern "C" int b2k_tree_info(b2k_tree_t t, int op, int dtype, const double *grav, char *buf, int64_t cap)
 {
     if (!t || !buf || cap < 1) { b2k_set_error("b2k_tree_info: bad arguments"); return B2K_ERR_INVALID; }
-    Program *p = tree_program(t, dtype, grav_mask_of(grav));
+    if (op < B2K_GEN_RNE || op > B2K_GEN_ACCEL) { b2k_set_error("b2k_tree_info: operation %d is not one of B2K_DYN_*", op); return B2K_ERR_INVALID; }
+    Program *p = tree_program(t, op, dtype, mode_uses_gravity(op) ? grav_mask_of(grav) : 0);
     if (!p || !p->ok) snprintf(buf, (size_t)cap, "unavailable (%s)", p ? p->why.c_str() : "no cache");
-    else
+    else if (op == B2K_GEN_RNE)
         snprintf(buf, (size_t)cap, "k_rne_spec<%s,tree n=%d>: %d mul + %d fma + %d add per row, %d constants, %d regs, %zu B smem/block",
                  dtype == B2K_F64 ? "double" : "float", t->n, p->n_mul, p->n_fma, p->n_add, p->nc, p->regs, p->smem);
+    else
+        snprintf(buf, (size_t)cap, "k_rne_spec<%s,tree n=%d,mode=%d>: %d mul + %d fma + %d add per row, %d constants, %d regs, %zu B smem/block",
+                 dtype == B2K_F64 ? "double" : "float", t->n, op, p->n_mul, p->n_fma, p->n_add, p->nc, p->regs, p->smem);
     return B2K_OK;
 }
 
 
 // ------------------------------------------------------------------ C ABI: forward-dynamics ensemble integrator
-extern "C" int b2k_rne_fdyn(b2k_rne_t r, int dtype, const void *q0, const void *qd0, int64_t ntraj, double T, const double *grav,
+static int fdyn_run(const char *fn, SpecCache *cache, const GenFn &gen, int n, const double *offset, int dtype, const void *q0, const void *qd0, int64_t ntraj, double T, const double *grav,
                             int torque_mode, const double *tau, const void *tau_rows, const double *kp, const double *kd,
                             const double *qstar, double rtol, double atol, double max_step, double first_step, double dt, int grid,
                             int M, void *out_t, void *out_q, void *out_qd, int32_t *out_count, int32_t *out_status, void *stream)
 {
-    const char *fn = "b2k_rne_fdyn";
-    if (!r) { b2k_set_error("%s: rne handle is NULL", fn); return B2K_ERR_INVALID; }
+    if (!cache) { b2k_set_error("%s: robot handle is NULL", fn); return B2K_ERR_INVALID; }
     if (dtype != B2K_F32 && dtype != B2K_F64) { b2k_set_error("%s: dtype must be B2K_F32 or B2K_F64", fn); return B2K_ERR_INVALID; }
     if (ntraj < 0 || (ntraj > 0 && (!q0 || !out_t || !out_q || !out_qd || !out_count || !out_status))) { b2k_set_error("%s: bad arguments", fn); return B2K_ERR_INVALID; }
     if (!(T > 0) || !(rtol > 0) || !(atol >= 0) || !(max_step > 0) || M < 1) { b2k_set_error("%s: T, rtol, max_step must be positive, atol non-negative, M >= 1", fn); return B2K_ERR_INVALID; }
@@ -993,18 +1023,14 @@ extern "C" int b2k_rne_fdyn(b2k_rne_t r, int dtype, const void *q0, const void *
     if (ntraj == 0) return B2K_OK;
     B2K_ON_DEVICE_OF(q0);
     const Key key(200 + B2K_GEN_ACCEL, dtype, grav_mask_of(grav), 0);
-    const Key gkey(B2K_GEN_ACCEL, dtype, grav_mask_of(grav), 0);
-    Program *p = get_program(static_cast<SpecCache *>(r->spec), dh_gen(r, gkey), r->n, key);
+    Program *p = get_program(cache, gen, n, key);
     if (!p || !p->ok) { b2k_set_error("%s: the integrator kernel could not be built (%s)", fn, p ? p->why.c_str() : "no cache"); return B2K_ERR_INVALID; }
     CUfunction f;
     {
-        SpecCache *c = static_cast<SpecCache *>(r->spec);
-        std::lock_guard<std::mutex> lk(c->mu);
+        std::lock_guard<std::mutex> lk(cache->mu);
         if (get_function(p, &f)) { b2k_set_error("%s: %s", fn, p->why.c_str()); return B2K_ERR_CUDA; }
     }
-    const int n = r->n, es = dtype == B2K_F64 ? 8 : 4;
-    double offset[B2K_MAX_JOINTS];
-    for (int j = 0; j < n; j++) offset[j] = r->L[j][5];
+    const int es = dtype == B2K_F64 ? 8 : 4;
     std::vector<unsigned char> pb = spec_params(p, n, dtype, offset, grav, nullptr);
     // FdynP { real T, rtol, atol, max_step, first_step, dt; real kp[NJ], kd[NJ], qstar[NJ], tau[NJ]; int torque_mode, grid, M; }
     const int nreal = 6 + 4 * n;
@@ -1035,4 +1061,37 @@ extern "C" int b2k_rne_fdyn(b2k_rne_t r, int dtype, const void *q0, const void *
     }
     b2k_count_launch();
     return B2K_OK;
+}
+
+extern "C" int b2k_rne_fdyn(b2k_rne_t r, int dtype, const void *q0, const void *qd0, int64_t ntraj, double T, const double *grav,
+                            int torque_mode, const double *tau, const void *tau_rows, const double *kp, const double *kd,
+                            const double *qstar, double rtol, double atol, double max_step, double first_step, double dt, int grid,
+                            int M, void *out_t, void *out_q, void *out_qd, int32_t *out_count, int32_t *out_status, void *stream)
+{
+    if (!r) { b2k_set_error("b2k_rne_fdyn: rne handle is NULL"); return B2K_ERR_INVALID; }
+    double offset[B2K_MAX_JOINTS];
+    for (int j = 0; j < r->n; j++) offset[j] = r->L[j][5];
+    const Key gkey(B2K_GEN_ACCEL, dtype, grav_mask_of(grav), 0);
+    return fdyn_run("b2k_rne_fdyn", static_cast<SpecCache *>(r->spec), dh_gen(r, gkey), r->n, offset, dtype, q0, qd0, ntraj, T, grav,
+                    torque_mode, tau, tau_rows, kp, kd, qstar, rtol, atol, max_step, first_step, dt, grid, M, out_t, out_q, out_qd,
+                    out_count, out_status, stream);
+}
+
+// The same integrator around the accel recursion of a rigid-body tree (Robot.fdyn: DynamicsMixin.fdyn calls self.accel,
+// which for a tree robot is n + 1 Python Robot.rne loops per stage in the reference).
+extern "C" int b2k_tree_fdyn(b2k_tree_t t, int dtype, const void *q0, const void *qd0, int64_t ntraj, double T, const double *grav,
+                             int torque_mode, const double *tau, const void *tau_rows, const double *kp, const double *kd,
+                             const double *qstar, double rtol, double atol, double max_step, double first_step, double dt, int grid,
+                             int M, void *out_t, void *out_q, void *out_qd, int32_t *out_count, int32_t *out_status, void *stream)
+{
+    if (!t) { b2k_set_error("b2k_tree_fdyn: tree handle is NULL"); return B2K_ERR_INVALID; }
+    const int gmask = grav_mask_of(grav);
+    GenFn gen = [t, gmask](b2k_gen_out &g) {
+        b2k_gen_opts o;
+        o.mode = B2K_GEN_ACCEL; o.grav_mask = gmask; o.has_fext = 0;
+        return b2k_tree_generate(t, o, g);
+    };
+    return fdyn_run("b2k_tree_fdyn", static_cast<SpecCache *>(t->spec), gen, t->n, nullptr, dtype, q0, qd0, ntraj, T, grav, torque_mode,
+                    tau, tau_rows, kp, kd, qstar, rtol, atol, max_step, first_step, dt, grid, M, out_t, out_q, out_qd, out_count,
+                    out_status, stream);
 }

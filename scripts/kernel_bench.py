@@ -184,6 +184,17 @@ if want("tree_"):
         ag = np.ascontiguousarray(-trob.gravity)
         report(f"tree_rne_puma_{tag}", timeit(lambda i: L.b2k_tree_rne(h, code, bufs[i][0].data_ptr(), bufs[i][1].data_ptr(), bufs[i][2].data_ptr(), N, rtb._lib.dptr(ag), tau.data_ptr(), st), 3), N, 24 * es,
                {"kernel": trob.rne_kernel_info(dt)})
+        if dt == np.float64:  # the DynamicsMixin operations of the same tree robot, 250k rows (like the dyn_ block)
+            Nd = 250_000
+            for op, nin, nout, recs in (("inertia", 1, 36, 6), ("coriolis", 2, 36, 21), ("accel", 3, 6, 7)):
+                if not want(f"tree_{op}_puma_f64"):
+                    continue
+                out = torch.empty((Nd, nout), dtype=tdt[dt], device=dev)
+                ptr = [bufs[0][i].data_ptr() if i < nin else None for i in range(3)]
+                opc = trob._DYN_OPS[op]
+                report(f"tree_{op}_puma_f64", timeit(lambda i: L.b2k_tree_dyn(h, opc, code, ptr[0], ptr[1], ptr[2], Nd, rtb._lib.dptr(ag), out.data_ptr(), st), 3),
+                       Nd, (6 * nin + nout) * es, {"recursions_per_row": recs, "kernel": trob.rne_kernel_info(dt, op=op)})
+                del out
         del bufs, tau
 
 # forward-dynamics ensemble: friction-free Puma falling from qn for 0.5 s, rtol 1e-6, one lane per trajectory

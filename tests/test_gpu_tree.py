@@ -147,3 +147,103 @@ def test_urdf_robot_dynamics_and_kinematics_on_the_device():
     np.testing.assert_allclose(e.eval(dev(q)).cpu().numpy(), C.fkine(q), rtol=1e-10, atol=1e-12)
     J = rob.jacob0(dev(q), end="r_skew")
     np.testing.assert_allclose(J.cpu().numpy(), orc.Chain(rob.ets(end="r_skew").describe()).jacob0(q), rtol=1e-10, atol=1e-12)
+
+
+def _oracle_rne_fn(tree):
+    return lambda a, b, c, g: orc.tree_rne(tree, np.atleast_2d(a), np.atleast_2d(b), np.atleast_2d(c), g)
+
+
+@pytest.mark.parametrize("case", ["urdf", "random7", "puma_ets"])
+def test_tree_robot_dynamics_operations_against_the_reference_loops(case):
+    """Robot.inertia / gravload / itorque / coriolis / accel (DynamicsMixin on a tree robot: Python loops of self.rne in
+    the reference, Dynamics.py:424-503, 700-915, 1418-1459) -- one generated kernel each, against the loops restated in
+    oracle.dyn_* over the spatial-vector oracle.  fp64 to 1e-9, fp32 to its bar, host and device inputs, ragged batch."""
+    rng = np.random.default_rng({"urdf": 21, "random7": 22, "puma_ets": 23}[case])
+    if case == "urdf":
+        rob = Robot.URDF(os.path.join(URDF_DIR, "two_arm.urdf"))
+    elif case == "random7":
+        rob = random_robot(rng, 7, True)
+    else:
+        dh = ch.puma560_links()
+        links, prev = [], ETS()
+        for j, l in enumerate(dh):
+            post = ETS()
+            for kind, v in (("tz", l["d"]), ("tx", l["a"]), ("Rx", l["alpha"])):
+                if v != 0:
+                    post = post * getattr(ET, kind)(v)
+            Tpost = np.eye(4)
+            for et in post:
+                Tpost = Tpost @ et.A()
+            r_in = Tpost[:3, :3] @ np.asarray(l["r"], dtype=float) + Tpost[:3, 3]
+            links.append(Link(prev * ET.Rz(), name=f"l{j}", parent=links[-1] if links else None, m=l["m"] + 0.5, r=r_in + 0.05))
+            prev = post
+        rob = Robot(links)
+    n = rob.n
+    tree = rob.tree_description()
+    f = _oracle_rne_fn(tree)
+    N = 77  # two full tiles and a ragged tail
+    q, qd, x = rng.uniform(-3, 3, (N, n)), rng.normal(size=(N, n)), rng.normal(size=(N, n))
+    grav = [0.4, -0.3, -9.81]
+    tol = dict(rtol=1e-9, atol=1e-9)
+    M = orc.dyn_inertia(f, n, q)
+    np.testing.assert_allclose(rob.inertia(dev(q)).cpu().numpy(), M, **tol)
+    np.testing.assert_allclose(rob.gravload(dev(q)).cpu().numpy(), orc.dyn_gravload(f, n, q, rob.gravity), **tol)
+    np.testing.assert_allclose(rob.gravload(dev(q), gravity=grav).cpu().numpy(), orc.dyn_gravload(f, n, q, np.asarray(grav)), **tol)
+    np.testing.assert_allclose(rob.itorque(dev(q), dev(x)).cpu().numpy(), orc.dyn_itorque(f, n, q, x), **tol)
+    np.testing.assert_allclose(rob.coriolis(dev(q), dev(qd)).cpu().numpy(), orc.dyn_coriolis(f, n, q, qd), **tol)
+    # consistency the reference's formulas imply: M qdd = itorque, tau = M qdd + C qd + g
+    np.testing.assert_allclose(np.einsum("kij,ki->kj", M, x), orc.dyn_itorque(f, n, q, x), rtol=1e-9, atol=1e-9)
+    if np.linalg.cond(M).max() < 1e6:
+        want = orc.dyn_accel(f, n, q, qd, x, np.asarray(grav))
+        np.testing.assert_allclose(rob.accel(dev(q), dev(qd), dev(x), gravity=grav).cpu().numpy(), want, rtol=1e-6, atol=1e-7)
+        got32 = rob.accel(q.astype(np.float32), qd.astype(np.float32), x.astype(np.float32), gravity=grav)
+        assert got32.dtype == np.float32
+        np.testing.assert_allclose(got32, want, rtol=5e-2, atol=5e-3 * max(1.0, np.abs(want).max()))
+    else:
+        assert case != "puma_ets", "the Puma-derived tree must have a regular inertia matrix"
+    # numpy in -> numpy out, single state, fp32
+    one = rob.inertia(q[0])
+    assert isinstance(one, np.ndarray) and one.shape == (n, n)
+    np.testing.assert_allclose(one, M[0], **tol)
+    M32 = rob.inertia(q.astype(np.float32))
+    assert M32.dtype == np.float32
+    np.testing.assert_allclose(M32, M, rtol=2e-3, atol=2e-3 * max(1.0, np.abs(M).max()))
+    assert rob.rne_kernel_info(op="coriolis").startswith(f"k_rne_spec<double,tree n={n},mode=4>")
+    with pytest.raises(ValueError):
+        rob.coriolis(q, qd[:-1])
+
+
+def test_tree_robot_fdyn_follows_scipy_rk45_on_the_oracle():
+    """Robot.fdyn (DynamicsMixin.fdyn through BaseRobot): the device-resident Dormand-Prince integrator around the tree's
+    generated accel recursion takes the steps scipy's RK45 takes on the oracle's accel (the reference's procedure)."""
+    rob = Robot.URDF(os.path.join(URDF_DIR, "two_arm.urdf"))
+    n = rob.n
+    tree = rob.tree_description()
+    f = _oracle_rne_fn(tree)
+    rng = np.random.default_rng(31)
+    q0 = rng.uniform(-0.5, 0.5, n)
+    M0 = orc.dyn_inertia(f, n, q0)
+    if np.linalg.cond(M0).max() > 1e6:  # point-mass links on their own axes: not integrable, in the reference either
+        rob = random_robot(np.random.default_rng(4), 5, True)
+        n, tree = rob.n, rob.tree_description()
+        f = _oracle_rne_fn(tree)
+        q0 = rng.uniform(-0.5, 0.5, n)
+        assert np.linalg.cond(orc.dyn_inertia(f, n, q0)).max() < 1e6
+    acc = lambda q, qd, tau: orc.dyn_accel(f, n, q, qd, tau, rob.gravity)[0]  # noqa: E731
+    sa = dict(rtol=1e-6, atol=1e-9)
+    tg = rob.fdyn(0.25, q0, solver_args=sa)
+    t, q, qd = orc.fdyn(acc, n, 0.25, q0, solver_args=sa)
+    assert tg.t.shape == t.shape, (tg.t.shape, t.shape)
+    np.testing.assert_allclose(tg.t, t, rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(tg.q, q, rtol=1e-6, atol=1e-8)
+    np.testing.assert_allclose(tg.qd, qd, rtol=1e-5, atol=1e-7)
+    tau = rng.normal(size=n)
+    tg = rob.fdyn(0.2, q0, Q=tau, solver_args=sa, dt=0.02)
+    t, q, qd = orc.fdyn(acc, n, 0.2, q0, torque_fn=lambda t, q, qd: tau, solver_args=sa, dt=0.02)
+    np.testing.assert_allclose(tg.q, q, rtol=1e-6, atol=1e-8)
+    Q0 = q0 + rng.uniform(-0.2, 0.2, (64, n))
+    ens = rob.fdyn(0.2, dev(Q0), solver_args=sa, dt=0.02)
+    assert ens.q.is_cuda and ens.q.shape == (64, 10, n)
+    for i in (0, 63):
+        t, q, qd = orc.fdyn(acc, n, 0.2, Q0[i], solver_args=sa, dt=0.02)
+        np.testing.assert_allclose(ens.q[i].cpu().numpy(), q, rtol=1e-6, atol=1e-8)
