@@ -397,6 +397,13 @@ class Robot:
         return desc
 
     def _tree_handle(self):
+        # the kernels are generated from the links' masses and centres of mass: a changed parameter (link.m = ..., or an
+        # in-place edit of link.r) must not keep serving the old program
+        sig = np.concatenate([np.r_[l.m, np.asarray(l.r, dtype=np.float64).reshape(3)] for l in self.links]).tobytes()
+        if self._tree is not None and sig != getattr(self, "_tree_sig", None):
+            _lib.lib().b2k_tree_destroy(self._tree)
+            self._tree = None
+        self._tree_sig = sig
         if self._tree is None:
             d = self.tree_description()
             n = len(d["parent"])

@@ -185,3 +185,24 @@ def test_reference_descriptions_load_and_agree_with_the_dh_models():
     assert abs(np.linalg.norm(tail[:3, 3]) - 0.1034) < 1e-3 or np.linalg.norm(tail[:3, 3]) < 0.2
     puma = Robot.URDF(os.path.join(REF_XACRO, "puma560_description/urdf/puma560_robot.urdf.xacro"))
     assert puma.n == 6
+
+
+def test_changed_link_parameters_rebuild_the_tree_program():
+    """Robot.rne's kernels are generated from the link masses / centres of mass; editing them after the first call must
+    rebuild the handle (the DH classes track this with dirty flags, reference DHRobot.py:1326-1361)."""
+    import ctypes as C
+
+    l1 = rtb.Link(rtb.ETS(rtb.ET.Ry()), m=1, r=[0.5, 0, 0], name="l1")
+    l2 = rtb.Link(rtb.ETS(rtb.ET.tx(1)) * rtb.ET.Ry(), m=1, r=[0.5, 0, 0], parent=l1, name="l2")
+    rob = rtb.Robot([l1, l2])
+    info0 = rob.rne_kernel_info()
+    h0 = rob._tree_handle()
+    assert rob._tree_handle() is h0
+    l2.m = 3.0
+    h1 = rob._tree_handle()
+    assert h1 is not h0
+    l2.r[1] = 0.25  # in-place edit of the centre of mass
+    h2 = rob._tree_handle()
+    assert h2 is not h1
+    assert rob.rne_kernel_info() != info0  # an off-axis centre of mass adds terms to the generated recursion
+    assert isinstance(h2, C.c_void_p)
