@@ -41,6 +41,7 @@ class DHRobot:
         self._rne_ob = None
         self._dynchanged = False
         self._ets_cache = None
+        self._prefix_cache = None
         self._configs = {}
 
     # ---- structure
@@ -60,6 +61,7 @@ class DHRobot:
     def base(self, T):
         self._base = np.eye(4) if T is None else _mat44(T, "base")
         self._ets_cache = None
+        self._prefix_cache = None
 
     @property
     def tool(self) -> SE3:
@@ -69,6 +71,7 @@ class DHRobot:
     def tool(self, T):
         self._tool = np.eye(4) if T is None else _mat44(T, "tool")
         self._ets_cache = None
+        self._prefix_cache = None
 
     @property
     def gravity(self) -> np.ndarray:
@@ -117,6 +120,14 @@ class DHRobot:
 
     def eval(self, q, **kwargs):
         return self.ets().eval(q, **kwargs)
+
+    def fkine_all(self, q, old=True, dtype=None):
+        """Link frame poses {0} .. {n}: base, base A1, base A1 A2, ... (reference DHRobot.fkine_all, DHRobot.py:1018-1064;
+        the tool does not enter, joint offsets do).  (n+1,4,4) for one q, (N,n+1,4,4) for a batch."""
+        if self._prefix_cache is None:
+            self._prefix_cache = [ETS.from_links([l.ets for l in self.links[:k + 1]]) for k in range(self.n)]
+        base = None if np.array_equal(self._base, np.eye(4)) else self._base
+        return ETS.eval_frames(self._prefix_cache, q, base=base, dtype=dtype)
 
     def jacobe(self, q, **kwargs):
         """Jacobian in the end-effector frame (reference DHRobot.jacobe 1066-1140)."""
@@ -190,6 +201,7 @@ class DHRobot:
         """A link's DH parameter changed: the cached ETS (and with it the compiled chain handle) and the
         packed RNE table are both stale (reference DHLink.py:448-563 @_listen_dyn on theta/d/a/alpha/sigma/mdh)."""
         self._ets_cache = None
+        self._prefix_cache = None
         self._dynchanged = True
 
     def dynchanged(self, what=None):

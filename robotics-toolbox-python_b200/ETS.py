@@ -282,6 +282,44 @@ class ETS:
                                B.ptr(T), B.stream_ptr(qd)))
         return T[0] if single else T
 
+    @staticmethod
+    def eval_frames(chains, q, base=None, dtype=None):
+        """Poses of several frames of one robot for the same q batch: ``chains[k]`` is the ETS from the robot's base to
+        frame k + 1, frame 0 is the base itself.  Returns (K+1,4,4) for one configuration, (N,K+1,4,4) for a batch (a
+        device tensor for device input -- a view of frame-major memory, every kernel writes its frame contiguously --,
+        numpy for host input).  One FK launch per frame over the full q rows (each chain reads the joints it needs):
+        the building block of ``fkine_all`` (reference Robot.fkine_all, Robot.py:638-700; DHRobot.fkine_all 1018-1064)."""
+        if not chains:
+            raise ValueError("no frames requested")
+        jointed = [e for e in chains if e.n > 0]
+        if not jointed:
+            raise ValueError("none of the frames depends on a joint")
+        widest = max(jointed, key=lambda e: int(max(e.jindices)))
+        q2, single = widest._qbatch(q)
+        dt = B.pick_dtype(q2, dtype)
+        host = not B.is_tensor(q2)
+        qd = B.to_device(q2, dt).contiguous()
+        N = qd.shape[0]
+        base = _mat44(base, "base")
+        frames = B.empty((len(chains) + 1, N, 4, 4), dt, like=qd)
+        t = B.require_cuda()
+        b0 = np.eye(4) if base is None else base
+        frames[0] = t.as_tensor(b0, dtype=frames.dtype, device=frames.device)
+        L = _lib.lib()
+        for k, e in enumerate(chains):
+            if e.n == 0:  # a static frame (a link before the first joint): base times the constant transforms
+                Tc = b0.copy()
+                for et in e:
+                    Tc = Tc @ et.A()
+                frames[k + 1] = t.as_tensor(Tc, dtype=frames.dtype, device=frames.device)
+                continue
+            _lib.check(L.b2k_fkine(e._chain, B.code(dt), B.ptr(qd), N, qd.shape[1], _lib.dptr(base), None, B.ptr(frames[k + 1]),
+                                   B.stream_ptr(qd)))
+        out = frames.permute(1, 0, 2, 3)
+        if host:
+            out = np.ascontiguousarray(B.to_host(out.contiguous()))
+        return out[0] if single else out
+
     def fkine(self, q, base=None, tool=None, include_base: bool = True, dtype=None) -> SE3:
         """Forward kinematics as an SE3 container (reference ETS.fkine, ETS.py:951-1019); one
         batched container instead of N Python objects."""

@@ -305,6 +305,13 @@ class Robot:
     def eval(self, q, end=None, start=None, tool=None, include_base: bool = True, **kw):
         return self.ets(start, end).eval(q, base=self._base_arg(), tool=self._tool_arg(tool), include_base=include_base, **kw)
 
+    def fkine_all(self, q, dtype=None):
+        """Pose of every link frame (reference Robot.fkine_all, Robot.py:638-700): frame 0 is the base transform, frame i
+        the pose of the link whose number is i (its position in ``robot.links`` + 1).  (L+1,4,4) for one q,
+        (N,L+1,4,4) for a batch; tool transforms do not enter, as in the reference."""
+        chains = [self.ets(end=l) for l in self.links]
+        return ETS.eval_frames(chains, q, base=self._base_arg(), dtype=dtype)
+
     # RobotKinematics.py:158 / 219: the Jacobians do NOT see the base
     def jacob0(self, q, end=None, start=None, tool=None, **kw):
         return self.ets(start, end).jacob0(q, tool=self._tool_arg(tool), **kw)

@@ -226,3 +226,71 @@ def test_fdyn_device_integrator_follows_scipy_rk45():
         puma.fdyn(0.5, q0, solver_args=dict(rtol=1e-10, atol=1e-12), max_steps=8)
     with pytest.raises(ValueError):
         puma.fdyn(0.1, q0, solver="Radau")
+
+
+def test_fkine_all_reference_literals_and_dh_link_products():
+    """DHRobot.fkine_all (DHRobot.py:1018-1064): the literal frames of the reference's own test (tests/test_DHRobot.py:
+    638-710, DH Panda at q = 1..7, 4 decimals) and, for batches, the running product base * A1 ... Ak of the DH link
+    transforms restated independently in oracle/chains.py."""
+    panda = rtb.models.DH.Panda()
+    q = np.arange(1.0, 8.0)
+    T = panda.fkine_all(q)
+    assert T.shape == (8, 4, 4)
+    lit = {
+        0: np.eye(4),
+        1: [[0.5403, -0.8415, 0, 0], [0.8415, 0.5403, 0, 0], [0, 0, 1, 0.333], [0, 0, 0, 1]],
+        2: [[-0.2248, -0.4913, -0.8415, 0], [-0.3502, -0.7651, 0.5403, 0], [-0.9093, 0.4161, 0, 0.333], [0, 0, 0, 1]],
+        3: [[0.1038, 0.8648, 0.4913, 0.1552], [0.4229, -0.4855, 0.7651, 0.2418], [0.9002, 0.1283, -0.4161, 0.2015], [0, 0, 0, 1]],
+        4: [[-0.4397, -0.2425, -0.8648, 0.1638], [-0.8555, -0.1801, 0.4855, 0.2767], [-0.2735, 0.9533, -0.1283, 0.2758], [0, 0, 0, 1]],
+        5: [[-0.9540, -0.1763, -0.2425, 0.107], [0.2229, -0.9581, -0.1801, 0.2781], [-0.2006, -0.2258, 0.9533, 0.6644], [0, 0, 0, 1]],
+        6: [[-0.8482, -0.4994, 0.1763, 0.107], [0.2643, -0.1106, 0.9581, 0.2781], [-0.4590, 0.8593, 0.2258, 0.6644], [0, 0, 0, 1]],
+        7: [[-0.5236, 0.6902, 0.4994, 0.08575], [0.8287, 0.5487, 0.1106, 0.3132], [-0.1977, 0.4718, -0.8593, 0.5321], [0, 0, 0, 1]],
+    }
+    for k, want in lit.items():
+        np.testing.assert_array_almost_equal(T[k], np.asarray(want, dtype=float), decimal=4)
+    rng = np.random.default_rng(12)
+    for robot, links, mdh in ((panda, ch.panda_mdh_links(), True), (rtb.models.Puma560(), ch.puma560_links(), False)):
+        n = robot.n
+        Q = rng.uniform(-np.pi, np.pi, (257, n))
+        base = ch.transl(0.1, -0.2, 0.3) @ ch.trotz(0.4)
+        robot.base = base
+        got = robot.fkine_all(dev(Q))
+        assert got.is_cuda and tuple(got.shape) == (257, n + 1, 4, 4)
+        got = got.cpu().numpy()
+        for i in (0, 100, 256):
+            Tk = base.copy()
+            np.testing.assert_allclose(got[i, 0], Tk, atol=1e-14)
+            for k in range(n):
+                Tk = Tk @ ch.dh_A(links[k], Q[i, k], mdh=mdh)
+                np.testing.assert_allclose(got[i, k + 1], Tk, rtol=1e-10, atol=1e-12)
+        # the last frame is fkine without the tool
+        np.testing.assert_allclose(got[:, n], robot.eval(dev(Q)).cpu().numpy() @ np.linalg.inv(robot.tool.A), rtol=1e-10, atol=1e-12)
+        host = robot.fkine_all(Q[:5].astype(np.float32))
+        assert isinstance(host, np.ndarray) and host.dtype == np.float32 and host.shape == (5, n + 1, 4, 4)
+        np.testing.assert_allclose(host, got[:5], rtol=1e-4, atol=1e-5)
+        robot.base = None
+
+
+def test_fkine_all_of_a_branched_urdf_robot():
+    """Robot.fkine_all (Robot.py:638-700): frame i = pose of link number i, every branch, static links included; each
+    frame against the product of link.A(q) from the base link down (the reference's recursion)."""
+    import os
+
+    rob = rtb.Robot.URDF(os.path.join(os.path.dirname(__file__), "golden", "urdf", "two_arm.urdf"))
+    rng = np.random.default_rng(13)
+    Q = rng.uniform(-1.5, 1.5, (65, rob.n))
+    got = rob.fkine_all(dev(Q)).cpu().numpy()
+    assert got.shape == (65, len(rob.links) + 1, 4, 4)
+    for i in (0, 64):
+        np.testing.assert_allclose(got[i, 0], np.eye(4), atol=1e-15)
+        for k, link in enumerate(rob.links):
+            T, l, chain = np.eye(4), link, []
+            while l is not None:
+                chain.append(l)
+                l = l.parent
+            for l in reversed(chain):
+                T = T @ l.A(Q[i, l.jindex] if l.isjoint else 0.0)
+            np.testing.assert_allclose(got[i, k + 1], T, rtol=1e-10, atol=1e-12, err_msg=link.name)
+    one = rob.fkine_all(Q[0])
+    assert one.shape == (len(rob.links) + 1, 4, 4)
+    np.testing.assert_allclose(one, got[0], rtol=1e-12, atol=1e-13)
