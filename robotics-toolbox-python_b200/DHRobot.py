@@ -171,6 +171,15 @@ class DHRobot:
     def ik_LM(self, Tep, **kwargs):
         return self.ets().ik_LM(Tep, **kwargs)
 
+    def jtraj(self, T1, T2, t, device=None, **kwargs):
+        """Joint-space trajectory between two end-effector poses (reference Robot.jtraj, Robot.py:917-961): both poses go
+        through ``ikine_LM`` (``kwargs`` to the solver), the quintic ``jtraj`` joins the solutions; ``device=True`` leaves
+        the (N,n) samples in HBM for ``rne`` / ``eval``."""
+        from .trajectory import jtraj as _jtraj
+
+        q1, q2 = self.ikine_LM(T1, **kwargs), self.ikine_LM(T2, **kwargs)
+        return _jtraj(q1.q, q2.q, t, device=device)
+
     def ik_NR(self, Tep, **kwargs):
         return self.ets().ik_NR(Tep, **kwargs)
 

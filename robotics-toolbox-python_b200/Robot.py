@@ -348,6 +348,15 @@ class Robot:
     def ikine_LM(self, Tep, end=None, start=None, **kw):
         return self.ets(start, end).ikine_LM(Tep, **kw)
 
+    def jtraj(self, T1, T2, t, device=None, **kwargs):
+        """Joint-space trajectory between two end-effector poses (reference Robot.jtraj, Robot.py:917-961): both poses go
+        through ``ikine_LM`` (``kwargs`` to the solver), the quintic ``jtraj`` joins the solutions; ``device=True`` leaves
+        the (N,n) samples in HBM for ``rne`` / ``eval``."""
+        from .trajectory import jtraj as _jtraj
+
+        q1, q2 = self.ikine_LM(T1, **kwargs), self.ikine_LM(T2, **kwargs)
+        return _jtraj(q1.q, q2.q, t, device=device)
+
     # reference RobotKinematics.py:748-1027 (ik_NR, ik_GN), 1228-1525 (ikine_NR, ikine_GN)
     def ik_NR(self, Tep, end=None, start=None, **kw):
         return self.ets(start, end).ik_NR(Tep, **kw)

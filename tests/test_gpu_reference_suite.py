@@ -296,3 +296,23 @@ def test_trajectory_ctraj_and_mstraj_reference_unit_tests():
             rtb.mstraj(via, dt=1, tacc=1, **kw)
     with pytest.raises(ValueError):
         rtb.mstraj(via, dt=1, tacc=[1, 2, 3, 4, 5], qdmax=[2, 1])
+
+
+def test_robot_jtraj_between_poses():
+    """Robot.jtraj (Robot.py:917-961): IK at both ends, quintic in between -- the end points of the trajectory reach the
+    two poses, the interior is the quintic of tools/trajectory.jtraj (checked elsewhere), for the ETS and the DH class."""
+    from oracle import oracle as orc
+
+    for robot in (rtb.models.Panda(), rtb.models.Puma560()):
+        C = orc.Chain(robot.ets().describe())
+        qa, qb = (np.r_[0.1, -0.4, 0.2, -1.9, 0.1, 1.6, 0.5][:robot.n], np.r_[0.6, 0.1, -0.3, -1.4, 0.4, 1.2, -0.2][:robot.n])
+        T1, T2 = C.fkine(qa[None])[0], C.fkine(qb[None])[0]
+        tg = robot.jtraj(T1, T2, 50, seed=3)
+        assert tg.q.shape == (50, robot.n)
+        np.testing.assert_allclose(C.fkine(tg.q[:1])[0], T1, atol=5e-3)
+        np.testing.assert_allclose(C.fkine(tg.q[-1:])[0], T2, atol=5e-3)
+        np.testing.assert_allclose(tg.qd[0], 0, atol=1e-12)
+        np.testing.assert_allclose(tg.qd[-1], 0, atol=1e-9)
+        dv = robot.jtraj(T1, T2, 50, device=True, seed=3)
+        assert dv.q.is_cuda
+        np.testing.assert_allclose(dv.q.cpu().numpy(), tg.q, atol=1e-9)
