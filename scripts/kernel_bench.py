@@ -215,6 +215,42 @@ if want("fdyn_"):
         print(json.dumps({"case": f"fdyn_puma_f64_ens{B_}", "trajectories": B_, "T": 0.5, "rtol": 1e-6, "ms": round(ms, 3),
                           "trajectory_seconds_per_s": B_ * 0.5 / (ms * 1e-3), "grid_samples": int(out.q.shape[1])}), flush=True)
 
+# The widened rows through the public API -- the call a user makes, Python dispatch included (tens of
+# microseconds per call, visible only on the shortest ones).  Bytes per row = what the operation must read and write.
+if want("extra_"):
+    NX = args.rows
+    rngx = np.random.default_rng(4)
+    pe = rtb.models.Panda().ets()
+    Qx = torch.from_numpy(rngx.uniform(-2.5, 2.5, (NX, 7))).to(dev)
+    QDx = torch.from_numpy(rngx.normal(size=(NX, 7))).to(dev)
+    Jx = pe.jacob0(Qx)
+    Tx = pe.eval(Qx)
+    Ty = pe.eval(torch.roll(Qx, 1, 0))
+    cases = [
+        ("extra_hessian0_from_J_f64", lambda i: pe.hessian0(J0=Jx), (42 + 294) * 8),
+        ("extra_yoshikawa_from_J_f64", lambda i: pe.manipulability(J=Jx), (42 + 1) * 8),
+        ("extra_minsingular_from_J_f64", lambda i: pe.manipulability(J=Jx, method="minsingular"), (42 + 1) * 8),
+        ("extra_jacobm_from_J_f64", lambda i: pe.jacobm(J=Jx), (42 + 7) * 8),
+        ("extra_jacob0_dot_f64", lambda i: pe.jacob0_dot(qd=QDx, J0=Jx), (42 + 7 + 42) * 8),
+        ("extra_jacob0_analytical_rpy_f64", lambda i: pe.jacob0_analytical(Qx), (7 + 42) * 8),
+        ("extra_angle_axis_f64", lambda i: rtb.angle_axis(Tx, Ty), (32 + 6) * 8),
+        ("extra_p_servo_rpy_f64", lambda i: rtb.p_servo(Tx, Ty), (32 + 6) * 8 + 1),
+        ("extra_jtraj_f64", lambda i: rtb.jtraj(np.zeros(7), np.ones(7), NX, device=True), 21 * 8),
+        ("extra_mtraj_trapezoidal_f64", lambda i: rtb.mtraj(rtb.trapezoidal, np.zeros(7), np.ones(7), NX, device=True), 21 * 8),
+        ("extra_ctraj_f64", lambda i: rtb.ctraj(Tx[0].cpu().numpy(), Tx[1].cpu().numpy(), NX, device=True), 16 * 8),
+        ("extra_fkine_all_panda_f64", lambda i: PD.fkine_all(Qx), (7 + 8 * 16) * 8),
+    ]
+    PD = rtb.models.DH.Panda()
+    for name, fn, bpr in cases:
+        if not want(name):
+            continue
+        try:
+            ms = timeit(fn, 1)
+            report(name, ms, NX, bpr, {"api": "public Python call on device-resident inputs"})
+        except Exception as e:  # keep the table going
+            print(json.dumps({"case": name, "error": f"{type(e).__name__}: {e}"[:300]}), flush=True)
+    del Qx, QDx, Jx, Tx, Ty
+
 # IK (config 4): reachable targets, chan
 if want("ik_"):
     panda = rtb.models.Panda().ets()
