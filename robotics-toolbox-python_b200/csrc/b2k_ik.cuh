@@ -143,8 +143,8 @@ __device__ __forceinline__ void ik_angle_axis(const Pose<real> &Te, const real *
 // In-place Cholesky solve of the packed-lower SPD system A x = b (A: N(N+1)/2 entries, row-wise
 // lower triangle).  Returns false on a non-positive / non-finite pivot.
 template <typename real, int N>
-__device__ __forceinline__ bool ik_chol_solve(real *A, real *b)
-{
+__device__ __forceinline__ bool ik_chol_factor(real *A)
+{ // in place: A <- L (row-wise packed lower triangle) with 1 / L_jj on the diagonal; false on a non-positive pivot
     bool ok = true;
     b2k_static_for<0, N>([&](auto jc) {
         constexpr int j = decltype(jc)::value, rj = j * (j + 1) / 2;
@@ -160,6 +160,12 @@ __device__ __forceinline__ bool ik_chol_solve(real *A, real *b)
             A[ri + j] = s * inv;
         });
     });
+    return ok;
+}
+
+template <typename real, int N>
+__device__ __forceinline__ void ik_chol_subst(const real *A, real *b)
+{ // b <- (L L^T)^-1 b for the factor ik_chol_factor left in A
     // forward L y = b
     b2k_static_for<0, N>([&](auto ic) {
         constexpr int i = decltype(ic)::value, ri = i * (i + 1) / 2;
@@ -174,6 +180,13 @@ __device__ __forceinline__ bool ik_chol_solve(real *A, real *b)
         b2k_static_for<i + 1, N>([&](auto kc) { constexpr int k = decltype(kc)::value; s -= A[k * (k + 1) / 2 + i] * b[k]; });
         b[i] = s * A[i * (i + 1) / 2 + i];
     });
+}
+
+template <typename real, int N>
+__device__ __forceinline__ bool ik_chol_solve(real *A, real *b)
+{
+    const bool ok = ik_chol_factor<real, N>(A);
+    ik_chol_subst<real, N>(A, b);
     return ok;
 }
 
