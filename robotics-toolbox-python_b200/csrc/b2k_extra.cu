@@ -37,6 +37,90 @@ __global__ void __launch_bounds__(256) k_hessian(const real *__restrict__ J, lon
     }
 }
 
+// ---- lane-per-row kernels over Jacobian rows: 64-thread blocks, each warp stages its tile of 32 rows (6N reals each)
+// through shared memory so that the global loads / stores are coalesced, and a lane then owns one row in registers.
+// (Reading the rows straight from global memory -- 32 lanes x a 6N-real stride per load instruction -- measured
+// 0.14-0.2 of the HBM rate on 1M Panda rows; profiles/r02_kernels_extra.jsonl.)
+#define B2K_XT 64 /* threads per block of the staged kernels: 2 warps x 32 x 60 doubles = 30 KB at n = 10 */
+template <typename real>
+__device__ __forceinline__ void xt_copy(real *dst, const real *src, int count, int lane)
+{
+    for (int e = lane; e < count; e += 32) dst[e] = src[e];
+}
+
+// Yoshikawa measure with all six axes selected and n > 6 (the Gram matrix J J^T is 6 x 6 SPD): m = prod L_jj.
+template <typename real, int N>
+__global__ void __launch_bounds__(B2K_XT) k_yoshikawa_all(const real *__restrict__ J, long long nrows, real *__restrict__ m)
+{
+    __shared__ real tile[B2K_XT / 32][32 * 6 * N];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long row0 = ((long long)blockIdx.x * (B2K_XT / 32) + warp) * 32;
+    if (row0 >= nrows) return;
+    const int rows = (int)(nrows - row0 < 32 ? nrows - row0 : 32);
+    xt_copy(tile[warp], J + row0 * (6 * N), rows * 6 * N, lane);
+    __syncwarp();
+    if (lane >= rows) return;
+    const real *j = tile[warp] + lane * (6 * N);
+    real A[21];
+#pragma unroll
+    for (int a = 0; a < 6; a++)
+#pragma unroll
+        for (int b = 0; b <= a; b++) {
+            real s = 0;
+#pragma unroll
+            for (int k = 0; k < N; k++) s = fma(j[a * N + k], j[b * N + k], s);
+            A[a * (a + 1) / 2 + b] = s;
+        }
+    const bool ok = ik_chol_factor<real, 6>(A);
+    real p = 1;
+#pragma unroll
+    for (int a = 0; a < 6; a++) p *= A[a * (a + 1) / 2 + a]; // 1 / L_aa
+    m[row0 + lane] = ok ? (real)1 / p : (real)0; // a rank-deficient J: det(J J^T) = 0 up to rounding
+}
+
+// Jd = sum_i H[i] qd[i]  (Robot.jacob0_dot, Robot.py:964-1099: np.tensordot(H, qd, (0, 0))) without materialising H:
+// Jd[r, b] = sum_a qd[a] * H[a, r, b], H from J as in k_hessian (methods.cpp:16-32).  One lane per row, J and qd in
+// registers, the tile doubling as the output stage.  (The first version was a warp per row over shared memory:
+// 0.57 ms for 1M Panda rows, 0.19 of HBM.)
+template <typename real, int N>
+__global__ void __launch_bounds__(B2K_XT) k_jacob_dot_lane(const real *__restrict__ J, const real *__restrict__ qd, long long nrows,
+                                                           real *__restrict__ Jd)
+{
+    __shared__ real tile[B2K_XT / 32][32 * 6 * N];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long row0 = ((long long)blockIdx.x * (B2K_XT / 32) + warp) * 32;
+    if (row0 >= nrows) return;
+    const int rows = (int)(nrows - row0 < 32 ? nrows - row0 : 32);
+    real *t = tile[warp];
+    xt_copy(t, J + row0 * (6 * N), rows * 6 * N, lane);
+    __syncwarp();
+    real j[6 * N], v[N];
+    const int lr = lane < rows ? lane : 0;
+#pragma unroll
+    for (int e = 0; e < 6 * N; e++) j[e] = t[lr * (6 * N) + e];
+#pragma unroll
+    for (int a = 0; a < N; a++) v[a] = qd[(row0 + lr) * N + a];
+    __syncwarp(); // every lane has its row: the tile becomes the output stage
+#pragma unroll
+    for (int r = 0; r < 6; r++) {
+        const int c = r % 3, c1 = (c + 1) % 3, c2 = (c + 2) % 3, wrow = r < 3 ? 0 : 3;
+#pragma unroll
+        for (int b = 0; b < N; b++) {
+            real acc = 0;
+#pragma unroll
+            for (int a = 0; a < N; a++) {
+                if (b >= a || r < 3) {
+                    const int lo = b >= a ? a : b, hi = b >= a ? b : a;
+                    acc = fma(v[a], fma(j[(3 + c1) * N + lo], j[(wrow + c2) * N + hi], -(j[(3 + c2) * N + lo] * j[(wrow + c1) * N + hi])), acc);
+                }
+            }
+            if (lane < rows) t[lane * (6 * N) + r * N + b] = acc;
+        }
+    }
+    __syncwarp();
+    xt_copy(Jd + row0 * (6 * N), t, rows * 6 * N, lane);
+}
+
 // m = sqrt(|det(Ja Ja^T)|) with Ja = the selected rows of J (|det Ja| when Ja is square), ETS.py:1780-1787
 template <typename real, int N>
 __global__ void __launch_bounds__(128) k_yoshikawa(const real *__restrict__ J, long long nrows, unsigned axes_mask,
@@ -78,38 +162,6 @@ __global__ void __launch_bounds__(128) k_yoshikawa(const real *__restrict__ J, l
     m[row] = square ? fabs(det) : sqrt(fabs(det));
 }
 
-// Jd = sum_i H[i] qd[i]  (Robot.jacob0_dot, Robot.py:964-1099: np.tensordot(H, qd, (0, 0))) without
-// materialising H: Jd[r, b] = sum_a qd[a] * H[a, r, b].  Same mapping as k_hessian (warp per row).
-template <typename real, int N>
-__global__ void __launch_bounds__(256) k_jacob_dot(const real *__restrict__ J, const real *__restrict__ qd, long long nrows,
-                                                   real *__restrict__ Jd)
-{
-    __shared__ real sJ[8][6 * N + N];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const long long wstride = (long long)gridDim.x * 8;
-    for (long long row = (long long)blockIdx.x * 8 + warp; row < nrows; row += wstride) {
-        for (int e = lane; e < 6 * N; e += 32) sJ[warp][e] = J[row * (6 * N) + e];
-        for (int e = lane; e < N; e += 32) sJ[warp][6 * N + e] = qd[row * N + e];
-        __syncwarp();
-        const real *j = sJ[warp], *v = sJ[warp] + 6 * N;
-        for (int e = lane; e < 6 * N; e += 32) {
-            const int r = e / N, b = e % N;
-            const int c = r % 3, c1 = (c + 1) % 3, c2 = (c + 2) % 3, wrow = r < 3 ? 0 : 3;
-            real acc = 0;
-            for (int a = 0; a < N; a++) {
-                if (b >= a || r < 3) {
-                    const int lo = b >= a ? a : b, hi = b >= a ? b : a;
-                    const real u1 = j[(3 + c1) * N + lo], u2 = j[(3 + c2) * N + lo];
-                    const real w1 = j[(wrow + c1) * N + hi], w2 = j[(wrow + c2) * N + hi];
-                    acc += v[a] * (u1 * w2 - u2 * w1);
-                }
-            }
-            Jd[row * (6 * N) + e] = acc;
-        }
-        __syncwarp();
-    }
-}
-
 // Manipulability Jacobian dm/dq (ETS.jacobm ETS.py:1628-1685, Robot.jacobm Robot.py:1124-1232):
 //   Jm[i] = m * sum_{a,b} (Ja Ha_i^T)[a,b] * inv(Ja Ja^T)[a,b],  Ja / Ha = the selected Cartesian rows, m = Yoshikawa.
 // One lane per row; the na x na Gram matrix is inverted by Gauss-Jordan with partial pivoting (its determinant
@@ -122,14 +174,20 @@ __global__ void __launch_bounds__(256) k_jacob_dot(const real *__restrict__ J, c
 // row instead of ~14 000.  Measured, 1M Panda rows fp64: 4.19 ms with the general kernel below (na read at run time,
 // Gauss-Jordan with pivoting, every array in local memory).
 template <typename real, int N>
-__global__ void __launch_bounds__(128) k_jacobm_all(const real *__restrict__ J, long long nrows, real *__restrict__ Jm)
+__global__ void __launch_bounds__(B2K_XT) k_jacobm_all(const real *__restrict__ J, long long nrows, real *__restrict__ Jm)
 {
-    const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (row >= nrows) return;
-    const real *jr = J + row * (6 * N);
+    __shared__ real tile[B2K_XT / 32][32 * 6 * N];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long row0 = ((long long)blockIdx.x * (B2K_XT / 32) + warp) * 32;
+    if (row0 >= nrows) return;
+    const int rows = (int)(nrows - row0 < 32 ? nrows - row0 : 32);
+    xt_copy(tile[warp], J + row0 * (6 * N), rows * 6 * N, lane);
+    __syncwarp();
+    if (lane >= rows) return;
+    const long long row = row0 + lane;
     real j[6 * N];
 #pragma unroll
-    for (int e = 0; e < 6 * N; e++) j[e] = jr[e];
+    for (int e = 0; e < 6 * N; e++) j[e] = tile[warp][lane * (6 * N) + e];
     real A[21];
 #pragma unroll
     for (int a = 0; a < 6; a++)
@@ -306,12 +364,14 @@ static int extra_launch(int what, int n, const void *J, long long N, unsigned ax
             const long long cap = (long long)b2k_num_sms() * 16;                                                      \
             if (blocks > cap) blocks = cap;                                                                           \
             if (what == 0) k_hessian<real, NN><<<(unsigned)blocks, 256, 0, st>>>((const real *)J, N, (real *)out);    \
-            else k_jacob_dot<real, NN><<<(unsigned)blocks, 256, 0, st>>>((const real *)J, (const real *)aux, N, (real *)out); \
+            else k_jacob_dot_lane<real, NN><<<(unsigned)((N + B2K_XT - 1) / B2K_XT), B2K_XT, 0, st>>>((const real *)J, (const real *)aux, N, (real *)out); \
         } else if (what == 3) {                                                                                       \
-            if (axes_mask == 63u && NN >= 6) k_jacobm_all<real, NN><<<(unsigned)((N + 127) / 128), 128, 0, st>>>((const real *)J, N, (real *)out); \
+            if (axes_mask == 63u && NN >= 6) k_jacobm_all<real, NN><<<(unsigned)((N + B2K_XT - 1) / B2K_XT), B2K_XT, 0, st>>>((const real *)J, N, (real *)out); \
             else k_jacobm<real, NN><<<(unsigned)((N + 127) / 128), 128, 0, st>>>((const real *)J, N, axes_mask, (real *)out); \
         } else if (what == 4 || what == 5) {                                                                          \
             k_singular<real, NN><<<(unsigned)((N + 127) / 128), 128, 0, st>>>((const real *)J, N, axes_mask, what - 4, (real *)out); \
+        } else if (axes_mask == 63u && NN > 6) {                                                                      \
+            k_yoshikawa_all<real, NN><<<(unsigned)((N + B2K_XT - 1) / B2K_XT), B2K_XT, 0, st>>>((const real *)J, N, (real *)out); \
         } else {                                                                                                      \
             k_yoshikawa<real, NN><<<(unsigned)((N + 127) / 128), 128, 0, st>>>((const real *)J, N, axes_mask, (real *)out); \
         }                                                                                                             \

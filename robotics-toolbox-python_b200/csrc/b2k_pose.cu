@@ -125,30 +125,41 @@ __device__ __forceinline__ void rotvel_inverse(int rep, const real g[3], real A[
     }
 }
 
+// One lane per row; the warp stages its 32 Jacobian rows through shared memory (coalesced both ways) and converts them
+// in place: the translational rows pass through, the rotational ones are multiplied by A^-1(Gamma(R)).
 template <typename real>
-__global__ void __launch_bounds__(128) k_janalytical(const real *__restrict__ T, const real *__restrict__ J, long long nrows, int n,
-                                                     int rep, real *__restrict__ Ja)
+__global__ void __launch_bounds__(64) k_janalytical(const real *__restrict__ T, const real *__restrict__ J, long long nrows, int n,
+                                                    int rep, real *__restrict__ Ja)
 {
-    const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (row >= nrows) return;
-    const real *t = T + row * 16;
-    real R[3][3], g[3], A[3][3];
-    for (int i = 0; i < 3; i++)
-        for (int j = 0; j < 3; j++) R[i][j] = t[i * 4 + j];
-    if (rep == REP_RPY_ZYX) rot_to_rpy_zyx<real>(R, g);
-    else if (rep == REP_RPY_XYZ) rot_to_rpy_xyz<real>(R, g);
-    else if (rep == REP_EUL) rot_to_eul<real>(R, g);
-    else rot_to_exp<real>(R, g);
-    rotvel_inverse<real>(rep, g, A);
-    const real *j = J + row * 6 * n;
-    real *o = Ja + row * 6 * n;
-    for (int c = 0; c < n; c++) {
-        const real w0 = j[3 * n + c], w1 = j[4 * n + c], w2 = j[5 * n + c];
-        o[0 * n + c] = j[0 * n + c];
-        o[1 * n + c] = j[1 * n + c];
-        o[2 * n + c] = j[2 * n + c];
-        for (int i = 0; i < 3; i++) o[(3 + i) * n + c] = A[i][0] * w0 + A[i][1] * w1 + A[i][2] * w2;
+    __shared__ real tile[2][32 * 6 * B2K_MAX_JOINTS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long row0 = ((long long)blockIdx.x * 2 + warp) * 32;
+    if (row0 >= nrows) return;
+    const int rows = (int)(nrows - row0 < 32 ? nrows - row0 : 32), w = 6 * n;
+    real *tl = tile[warp];
+    for (int e = lane; e < rows * w; e += 32) tl[e] = J[row0 * w + e];
+    __syncwarp();
+    if (lane < rows) {
+        const real *t = T + (row0 + lane) * 16;
+        real R[3][3], g[3], A[3][3];
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+#pragma unroll
+            for (int j = 0; j < 3; j++) R[i][j] = t[i * 4 + j];
+        if (rep == REP_RPY_ZYX) rot_to_rpy_zyx<real>(R, g);
+        else if (rep == REP_RPY_XYZ) rot_to_rpy_xyz<real>(R, g);
+        else if (rep == REP_EUL) rot_to_eul<real>(R, g);
+        else rot_to_exp<real>(R, g);
+        rotvel_inverse<real>(rep, g, A);
+        real *j = tl + lane * w;
+        for (int c = 0; c < n; c++) {
+            const real w0 = j[3 * n + c], w1 = j[4 * n + c], w2 = j[5 * n + c];
+#pragma unroll
+            for (int i = 0; i < 3; i++) j[(3 + i) * n + c] = A[i][0] * w0 + A[i][1] * w1 + A[i][2] * w2;
+        }
     }
+    __syncwarp();
+    for (int e = lane; e < rows * w; e += 32) Ja[row0 * w + e] = tl[e];
 }
 
 // e = [Re^T (tp - te); rpy_zyx(Re^T Rep)], v = gain .* e, arrived = sum |e| < threshold
@@ -282,9 +293,9 @@ extern "C" int b2k_jacob0_analytical(int dtype, int n, const void *T, const void
     if (N == 0) return B2K_OK;
     B2K_ON_DEVICE_OF(J);
     cudaStream_t st = (cudaStream_t)stream;
-    const unsigned blocks = (unsigned)((N + 127) / 128);
-    if (dtype == B2K_F64) k_janalytical<double><<<blocks, 128, 0, st>>>((const double *)T, (const double *)J, N, n, representation, (double *)Ja);
-    else k_janalytical<float><<<blocks, 128, 0, st>>>((const float *)T, (const float *)J, N, n, representation, (float *)Ja);
+    const unsigned blocks = (unsigned)((N + 63) / 64);
+    if (dtype == B2K_F64) k_janalytical<double><<<blocks, 64, 0, st>>>((const double *)T, (const double *)J, N, n, representation, (double *)Ja);
+    else k_janalytical<float><<<blocks, 64, 0, st>>>((const float *)T, (const float *)J, N, n, representation, (float *)Ja);
     b2k_count_launch();
     B2K_CUDA(cudaGetLastError());
     return B2K_OK;
