@@ -6,35 +6,32 @@
 #include "b2k_ik.cuh" // ik_angle_axis
 
 // H[a, 0:3, b] = Jw_a x Jv_b, H[a, 3:6, b] = Jw_a x Jw_b for b >= a; mirrored translational block and a zero
-// rotational block for b < a (methods.cpp:18-31).  One warp per row: the 6n values of J are staged in shared
-// memory, the 6 n^2 outputs of the row are produced by consecutive lanes -> fully coalesced stores.
+// rotational block for b < a (methods.cpp:18-31).
 template <typename real, int N>
 __global__ void __launch_bounds__(256) k_hessian(const real *__restrict__ J, long long nrows, real *__restrict__ H)
 {
-    __shared__ real sJ[8][6 * N];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const long long wstride = (long long)gridDim.x * 8;
-    for (long long row = (long long)blockIdx.x * 8 + warp; row < nrows; row += wstride) {
-        for (int e = lane; e < 6 * N; e += 32) sJ[warp][e] = J[row * (6 * N) + e];
-        __syncwarp();
-        const real *j = sJ[warp];
-        real *out = H + row * (6 * N * N);
-        for (int e = lane; e < 6 * N * N; e += 32) {
-            const int a = e / (6 * N), r = (e / N) % 6, b = e % N;
-            real v = 0;
-            if (b >= a || r < 3) {
-                // u x w, component c: u = Jw of the lower-numbered joint, w = Jv (r < 3) or Jw (r >= 3) of the other
-                const int lo = b >= a ? a : b, hi = b >= a ? b : a;
-                const int c = r % 3, c1 = (c + 1) % 3, c2 = (c + 2) % 3;
-                const int wrow = r < 3 ? 0 : 3;
-                const real u1 = j[(3 + c1) * N + lo], u2 = j[(3 + c2) * N + lo];
-                const real w1 = j[(wrow + c1) * N + hi], w2 = j[(wrow + c2) * N + hi];
-                v = u1 * w2 - u2 * w1;
-            }
-            out[e] = v;
-        }
-        __syncwarp();
+    // One thread per OUTPUT element: H is 6 n^2 reals per row (2.35 KB for the Panda) against 6 n of input, so the
+    // kernel is a store stream; consecutive threads write consecutive addresses, and the four J values an element
+    // needs come through L1 (a warp's 32 elements belong to one or two rows).  The first version gave a warp one row at
+    // a time through shared memory -- load, barrier, ten strided passes, barrier -- and reached 0.49 of HBM.
+    constexpr int W = 6 * N * N;
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nrows * W) return;
+    const long long row = e / W;
+    const int rem = (int)(e - row * W);
+    const int a = rem / (6 * N), r = (rem / N) % 6, b = rem % N;
+    real v = 0;
+    if (b >= a || r < 3) {
+        // u x w, component c: u = Jw of the lower-numbered joint, w = Jv (r < 3) or Jw (r >= 3) of the other
+        const real *j = J + row * (6 * N);
+        const int lo = b >= a ? a : b, hi = b >= a ? b : a;
+        const int c = r % 3, c1 = (c + 1) % 3, c2 = (c + 2) % 3;
+        const int wrow = r < 3 ? 0 : 3;
+        const real u1 = __ldg(j + (3 + c1) * N + lo), u2 = __ldg(j + (3 + c2) * N + lo);
+        const real w1 = __ldg(j + (wrow + c1) * N + hi), w2 = __ldg(j + (wrow + c2) * N + hi);
+        v = u1 * w2 - u2 * w1;
     }
+    H[e] = v;
 }
 
 // ---- lane-per-row kernels over Jacobian rows: 64-thread blocks, each warp stages its tile of 32 rows (6N reals each)
@@ -414,10 +411,7 @@ static int extra_launch(int what, int n, const void *J, long long N, unsigned ax
 #define B2K_CASE(NN)                                                                                                  \
     case NN:                                                                                                          \
         if (what == 0 || what == 2) {                                                                                 \
-            long long blocks = (N + 7) / 8;                                                                           \
-            const long long cap = (long long)b2k_num_sms() * 16;                                                      \
-            if (blocks > cap) blocks = cap;                                                                           \
-            if (what == 0) k_hessian<real, NN><<<(unsigned)blocks, 256, 0, st>>>((const real *)J, N, (real *)out);    \
+            if (what == 0) k_hessian<real, NN><<<(unsigned)((N * 6 * NN * NN + 255) / 256), 256, 0, st>>>((const real *)J, N, (real *)out); \
             else k_jacob_dot_lane<real, NN><<<(unsigned)((N + B2K_XT - 1) / B2K_XT), B2K_XT, 0, st>>>((const real *)J, (const real *)aux, N, (real *)out); \
         } else if (what == 3) {                                                                                       \
             if (axes_mask == 63u && NN >= 6) k_jacobm_all<real, NN><<<(unsigned)((N + 127) / 128), 128, 0, st>>>((const real *)J, N, (real *)out); \
