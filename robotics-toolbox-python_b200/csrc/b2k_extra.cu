@@ -6,32 +6,36 @@
 #include "b2k_ik.cuh" // ik_angle_axis
 
 // H[a, 0:3, b] = Jw_a x Jv_b, H[a, 3:6, b] = Jw_a x Jw_b for b >= a; mirrored translational block and a zero
-// rotational block for b < a (methods.cpp:18-31).
+// rotational block for b < a (methods.cpp:18-31).  One warp per row: the 6n values of J are staged in shared
+// memory, the 6 n^2 outputs of the row are produced by consecutive lanes -> fully coalesced stores.  (One thread per
+// output element with the J values through L1 was tried: 1.21 ms against 0.84 ms for 1M Panda rows.)
 template <typename real, int N>
 __global__ void __launch_bounds__(256) k_hessian(const real *__restrict__ J, long long nrows, real *__restrict__ H)
 {
-    // One thread per OUTPUT element: H is 6 n^2 reals per row (2.35 KB for the Panda) against 6 n of input, so the
-    // kernel is a store stream; consecutive threads write consecutive addresses, and the four J values an element
-    // needs come through L1 (a warp's 32 elements belong to one or two rows).  The first version gave a warp one row at
-    // a time through shared memory -- load, barrier, ten strided passes, barrier -- and reached 0.49 of HBM.
-    constexpr int W = 6 * N * N;
-    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= nrows * W) return;
-    const long long row = e / W;
-    const int rem = (int)(e - row * W);
-    const int a = rem / (6 * N), r = (rem / N) % 6, b = rem % N;
-    real v = 0;
-    if (b >= a || r < 3) {
-        // u x w, component c: u = Jw of the lower-numbered joint, w = Jv (r < 3) or Jw (r >= 3) of the other
-        const real *j = J + row * (6 * N);
-        const int lo = b >= a ? a : b, hi = b >= a ? b : a;
-        const int c = r % 3, c1 = (c + 1) % 3, c2 = (c + 2) % 3;
-        const int wrow = r < 3 ? 0 : 3;
-        const real u1 = __ldg(j + (3 + c1) * N + lo), u2 = __ldg(j + (3 + c2) * N + lo);
-        const real w1 = __ldg(j + (wrow + c1) * N + hi), w2 = __ldg(j + (wrow + c2) * N + hi);
-        v = u1 * w2 - u2 * w1;
+    __shared__ real sJ[8][6 * N];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long wstride = (long long)gridDim.x * 8;
+    for (long long row = (long long)blockIdx.x * 8 + warp; row < nrows; row += wstride) {
+        for (int e = lane; e < 6 * N; e += 32) sJ[warp][e] = J[row * (6 * N) + e];
+        __syncwarp();
+        const real *j = sJ[warp];
+        real *out = H + row * (6 * N * N);
+        for (int e = lane; e < 6 * N * N; e += 32) {
+            const int a = e / (6 * N), r = (e / N) % 6, b = e % N;
+            real v = 0;
+            if (b >= a || r < 3) {
+                // u x w, component c: u = Jw of the lower-numbered joint, w = Jv (r < 3) or Jw (r >= 3) of the other
+                const int lo = b >= a ? a : b, hi = b >= a ? b : a;
+                const int c = r % 3, c1 = (c + 1) % 3, c2 = (c + 2) % 3;
+                const int wrow = r < 3 ? 0 : 3;
+                const real u1 = j[(3 + c1) * N + lo], u2 = j[(3 + c2) * N + lo];
+                const real w1 = j[(wrow + c1) * N + hi], w2 = j[(wrow + c2) * N + hi];
+                v = u1 * w2 - u2 * w1;
+            }
+            out[e] = v;
+        }
+        __syncwarp();
     }
-    H[e] = v;
 }
 
 // ---- lane-per-row kernels over Jacobian rows: 64-thread blocks, each warp stages its tile of 32 rows (6N reals each)
@@ -411,7 +415,10 @@ static int extra_launch(int what, int n, const void *J, long long N, unsigned ax
 #define B2K_CASE(NN)                                                                                                  \
     case NN:                                                                                                          \
         if (what == 0 || what == 2) {                                                                                 \
-            if (what == 0) k_hessian<real, NN><<<(unsigned)((N * 6 * NN * NN + 255) / 256), 256, 0, st>>>((const real *)J, N, (real *)out); \
+            long long blocks = (N + 7) / 8;                                                                           \
+            const long long cap = (long long)b2k_num_sms() * 16;                                                      \
+            if (blocks > cap) blocks = cap;                                                                           \
+            if (what == 0) k_hessian<real, NN><<<(unsigned)blocks, 256, 0, st>>>((const real *)J, N, (real *)out);    \
             else k_jacob_dot_lane<real, NN><<<(unsigned)((N + B2K_XT - 1) / B2K_XT), B2K_XT, 0, st>>>((const real *)J, (const real *)aux, N, (real *)out); \
         } else if (what == 3) {                                                                                       \
             if (axes_mask == 63u && NN >= 6) k_jacobm_all<real, NN><<<(unsigned)((N + 127) / 128), 128, 0, st>>>((const real *)J, N, (real *)out); \
@@ -567,7 +574,21 @@ extern "C" int b2k_jtraj(int dtype, int n, const double *q0, const double *qf, c
 // Batched fknm.Angle_Axis (fknm.cpp:112-162 -> _angle_axis ik.cpp:241-286) and tools/p_servo.py:46-106 with
 // method="angle-axis": e = angle_axis(Te, Tep), v = gain .* e, arrived = sum|e| < threshold.
 // Lane per row; tep_stride = 0 broadcasts one target to every row.
-template <typename real>
+template <typename real> __device__ __forceinline__ void load12(const real *p, real *o);
+template <> __device__ __forceinline__ void load12<double>(const double *p, double *o)
+{
+    const double2 *v = reinterpret_cast<const double2 *>(p);
+#pragma unroll
+    for (int k = 0; k < 6; k++) { const double2 x = __ldg(v + k); o[2 * k] = x.x; o[2 * k + 1] = x.y; }
+}
+template <> __device__ __forceinline__ void load12<float>(const float *p, float *o)
+{
+    const float4 *v = reinterpret_cast<const float4 *>(p);
+#pragma unroll
+    for (int k = 0; k < 3; k++) { const float4 x = __ldg(v + k); o[4 * k] = x.x; o[4 * k + 1] = x.y; o[4 * k + 2] = x.z; o[4 * k + 3] = x.w; }
+}
+
+template <typename real, bool VEC>
 __global__ void __launch_bounds__(256) k_pose_error(const real *__restrict__ Te, const real *__restrict__ Tep,
                                                     long long tep_stride, long long nrows, real g0, real g1, real g2,
                                                     real g3, real g4, real g5, real threshold, real *__restrict__ out,
@@ -575,12 +596,18 @@ __global__ void __launch_bounds__(256) k_pose_error(const real *__restrict__ Te,
 {
     const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= nrows) return;
-    const real *a = Te + row * 16, *b = Tep + row * tep_stride;
-    Pose<real> T;
-    pose_from_const<real>(T, a);
-    real Tp[12], e[6];
+    // the three used rows of each 4x4 matrix as 16-byte vector loads where both arrays are 16-byte aligned (the launcher
+    // looks; any torch allocation is): a third of the load instructions of the scalar form
+    real ar[12], Tp[12], e[6];
+    if (VEC) {
+        load12<real>(Te + row * 16, ar);
+        load12<real>(Tep + row * tep_stride, Tp);
+    } else {
 #pragma unroll
-    for (int k = 0; k < 12; k++) Tp[k] = b[k];
+        for (int k = 0; k < 12; k++) { ar[k] = Te[row * 16 + k]; Tp[k] = Tep[row * tep_stride + k]; }
+    }
+    Pose<real> T;
+    pose_from_const<real>(T, ar);
     ik_angle_axis<real>(T, Tp, e);
     const real g[6] = {g0, g1, g2, g3, g4, g5};
     real sum = 0;
@@ -604,13 +631,13 @@ static int pose_error_launch(const char *fn, int dtype, const void *Te, const vo
     for (int k = 0; k < 6; k++) g[k] = gain ? gain[k] : 1.0;
     cudaStream_t st = (cudaStream_t)stream;
     const unsigned blocks = (unsigned)((N + 255) / 256);
-    if (dtype == B2K_F64)
-        k_pose_error<double><<<blocks, 256, 0, st>>>((const double *)Te, (const double *)Tep, tep_stride, N, g[0], g[1], g[2],
-                                                     g[3], g[4], g[5], threshold, (double *)out, arrived);
-    else
-        k_pose_error<float><<<blocks, 256, 0, st>>>((const float *)Te, (const float *)Tep, tep_stride, N, (float)g[0],
-                                                    (float)g[1], (float)g[2], (float)g[3], (float)g[4], (float)g[5],
-                                                    (float)threshold, (float *)out, arrived);
+    const bool vec = (((uintptr_t)Te | (uintptr_t)Tep) & 15) == 0;
+#define B2K_PE(REAL, V)                                                                                                        \
+    k_pose_error<REAL, V><<<blocks, 256, 0, st>>>((const REAL *)Te, (const REAL *)Tep, tep_stride, N, (REAL)g[0], (REAL)g[1], \
+                                                  (REAL)g[2], (REAL)g[3], (REAL)g[4], (REAL)g[5], (REAL)threshold, (REAL *)out, arrived)
+    if (dtype == B2K_F64) { if (vec) B2K_PE(double, true); else B2K_PE(double, false); }
+    else { if (vec) B2K_PE(float, true); else B2K_PE(float, false); }
+#undef B2K_PE
     b2k_count_launch();
     B2K_CUDA(cudaGetLastError());
     return B2K_OK;
