@@ -6,33 +6,73 @@
 #include "b2k_ik.cuh" // ik_angle_axis
 
 // H[a, 0:3, b] = Jw_a x Jv_b, H[a, 3:6, b] = Jw_a x Jw_b for b >= a; mirrored translational block and a zero
-// rotational block for b < a (methods.cpp:18-31).  One warp per row: the 6n values of J are staged in shared
-// memory, the 6 n^2 outputs of the row are produced by consecutive lanes -> fully coalesced stores.  (One thread per
-// output element with the J values through L1 was tried: 1.21 ms against 0.84 ms for 1M Panda rows.)
+// rotational block for b < a (methods.cpp:18-31).  A store stream: 6 n^2 outputs per row against 6 n inputs.
+// One warp per row; the 6n values of J sit in shared memory (slot 6n holds a zero) and lane l produces the output pairs
+// l, l + 32, ... of the row.  Which four J entries an output needs depends only on its position in the row, i.e. on
+// (lane, iteration): the shared-memory offsets are worked out ONCE per thread and kept in registers, so a row costs
+// 8 LDS + 4 flops + one vector store per pair and no index arithmetic (the previous form decoded (a, r, b) and
+// branched per element: ~40 instructions per output, issue-bound at 0.84 ms for 1M Panda rows; one thread per output
+// element with J through L1 was slower still, 1.21 ms).  The next row's J values are fetched while this one is written.
+template <typename real> struct Pair2;
+template <> struct Pair2<double> { typedef double2 type; };
+template <> struct Pair2<float> { typedef float2 type; };
+
 template <typename real, int N>
-__global__ void __launch_bounds__(256) k_hessian(const real *__restrict__ J, long long nrows, real *__restrict__ H)
+__global__ void __launch_bounds__(256) k_hessian(const real *__restrict__ J, long long nrows, real *__restrict__ H, int vec_ok)
 {
-    __shared__ real sJ[8][6 * N];
+    constexpr int E = 6 * N, PAIRS = 3 * N * N, IT = (PAIRS + 31) / 32, LD = (E + 31) / 32;
+    typedef typename Pair2<real>::type real2;
+    __shared__ real sJ[8][E + 2];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    real *j = sJ[warp];
+    if (lane == 0) j[E] = 0;
+
+    // per-thread table: shared-memory slots of (u1, u2, w1, w2) for both elements of each of this lane's pairs
+    unsigned short ix[IT][2][4];
+#pragma unroll
+    for (int i = 0; i < IT; i++)
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            const int e = 2 * (lane + 32 * i) + k;
+            const int a = e / E, r = (e / N) % 6, b = e % N;
+            const bool live = e < 6 * N * N && (b >= a || r < 3);
+            // u x w, component c: u = Jw of the lower-numbered joint, w = Jv (r < 3) or Jw (r >= 3) of the other
+            const int lo = b >= a ? a : b, hi = b >= a ? b : a;
+            const int c = r % 3, c1 = (c + 1) % 3, c2 = (c + 2) % 3, wrow = r < 3 ? 0 : 3;
+            ix[i][k][0] = live ? (3 + c1) * N + lo : E;
+            ix[i][k][1] = live ? (3 + c2) * N + lo : E;
+            ix[i][k][2] = live ? (wrow + c1) * N + hi : E;
+            ix[i][k][3] = live ? (wrow + c2) * N + hi : E;
+        }
+
     const long long wstride = (long long)gridDim.x * 8;
-    for (long long row = (long long)blockIdx.x * 8 + warp; row < nrows; row += wstride) {
-        for (int e = lane; e < 6 * N; e += 32) sJ[warp][e] = J[row * (6 * N) + e];
+    long long row = (long long)blockIdx.x * 8 + warp;
+    real nx[LD];
+#pragma unroll
+    for (int t = 0; t < LD; t++) nx[t] = (row < nrows && lane + 32 * t < E) ? J[row * E + lane + 32 * t] : (real)0;
+    for (; row < nrows; row += wstride) {
+#pragma unroll
+        for (int t = 0; t < LD; t++)
+            if (lane + 32 * t < E) j[lane + 32 * t] = nx[t];
         __syncwarp();
-        const real *j = sJ[warp];
+        const long long nrow = row + wstride;
+#pragma unroll
+        for (int t = 0; t < LD; t++)
+            if (nrow < nrows && lane + 32 * t < E) nx[t] = J[nrow * E + lane + 32 * t];
         real *out = H + row * (6 * N * N);
-        for (int e = lane; e < 6 * N * N; e += 32) {
-            const int a = e / (6 * N), r = (e / N) % 6, b = e % N;
-            real v = 0;
-            if (b >= a || r < 3) {
-                // u x w, component c: u = Jw of the lower-numbered joint, w = Jv (r < 3) or Jw (r >= 3) of the other
-                const int lo = b >= a ? a : b, hi = b >= a ? b : a;
-                const int c = r % 3, c1 = (c + 1) % 3, c2 = (c + 2) % 3;
-                const int wrow = r < 3 ? 0 : 3;
-                const real u1 = j[(3 + c1) * N + lo], u2 = j[(3 + c2) * N + lo];
-                const real w1 = j[(wrow + c1) * N + hi], w2 = j[(wrow + c2) * N + hi];
-                v = u1 * w2 - u2 * w1;
+#pragma unroll
+        for (int i = 0; i < IT; i++) {
+            const int p = lane + 32 * i;
+            const real v0 = j[ix[i][0][0]] * j[ix[i][0][3]] - j[ix[i][0][1]] * j[ix[i][0][2]];
+            const real v1 = j[ix[i][1][0]] * j[ix[i][1][3]] - j[ix[i][1][1]] * j[ix[i][1][2]];
+            if (i < IT - 1 || p < PAIRS) {
+                if (vec_ok) {
+                    real2 v; v.x = v0; v.y = v1;
+                    reinterpret_cast<real2 *>(out)[p] = v;
+                } else {
+                    out[2 * p] = v0; out[2 * p + 1] = v1;
+                }
             }
-            out[e] = v;
         }
         __syncwarp();
     }
@@ -416,9 +456,11 @@ static int extra_launch(int what, int n, const void *J, long long N, unsigned ax
     case NN:                                                                                                          \
         if (what == 0 || what == 2) {                                                                                 \
             long long blocks = (N + 7) / 8;                                                                           \
-            const long long cap = (long long)b2k_num_sms() * 16;                                                      \
+            /* k_hessian: 4 resident blocks per SM (64 registers x 256 threads); one wave, so that the per-thread  */ \
+            /* index table is set up once per ~200 rows                                                             */ \
+            const long long cap = (long long)b2k_num_sms() * (what == 0 ? 4 : 16);                                    \
             if (blocks > cap) blocks = cap;                                                                           \
-            if (what == 0) k_hessian<real, NN><<<(unsigned)blocks, 256, 0, st>>>((const real *)J, N, (real *)out);    \
+            if (what == 0) k_hessian<real, NN><<<(unsigned)blocks, 256, 0, st>>>((const real *)J, N, (real *)out, (int)(((uintptr_t)out & (2 * sizeof(real) - 1)) == 0)); \
             else k_jacob_dot_lane<real, NN><<<(unsigned)((N + B2K_XT - 1) / B2K_XT), B2K_XT, 0, st>>>((const real *)J, (const real *)aux, N, (real *)out); \
         } else if (what == 3) {                                                                                       \
             if (axes_mask == 63u && NN >= 6) k_jacobm_all<real, NN><<<(unsigned)((N + 127) / 128), 128, 0, st>>>((const real *)J, N, (real *)out); \

@@ -294,3 +294,42 @@ def test_fkine_all_of_a_branched_urdf_robot():
     one = rob.fkine_all(Q[0])
     assert one.shape == (len(rob.links) + 1, 4, 4)
     np.testing.assert_allclose(one, got[0], rtol=1e-12, atol=1e-13)
+
+
+def _hessian_batch(J):
+    """methods.cpp:16-32 over a batch: J (N,6,n) -> H (N,n,6,n); the oracle's loop (oracle.hessian) vectorised over rows."""
+    N, _, n = J.shape
+    H = np.zeros((N, n, 6, n))
+    for a in range(n):
+        for b in range(a, n):
+            H[:, a, :3, b] = np.cross(J[:, 3:, a], J[:, :3, b])
+            H[:, a, 3:, b] = np.cross(J[:, 3:, a], J[:, 3:, b])
+            if b != a:
+                H[:, b, :3, a] = H[:, a, :3, b]
+    return H
+
+
+def test_hessian_every_joint_count_grid_stride_and_alignment():
+    """k_hessian (b2k_extra.cu): every instantiated joint count, both dtypes, more rows than one wave of warps (each warp
+    walks several rows with its per-thread index table), a ragged last block, and an output pointer that is only
+    element-aligned (scalar-store path) -- against the vectorised restatement, itself checked against oracle.hessian."""
+    from importlib import import_module
+    B = import_module("b2kin")._buffers
+    lib = rtb._lib.lib()
+    rng = np.random.default_rng(77)
+    Jc = rng.normal(size=(3, 6, 5))
+    for k in range(3):
+        np.testing.assert_allclose(_hessian_batch(Jc)[k], orc.hessian(Jc[k]), rtol=0, atol=1e-15)
+    for n in range(1, 11):
+        N = 9001 if n not in (6, 7) else 150_003
+        J = rng.normal(size=(N, 6, n))
+        ref = _hessian_batch(J)
+        for dt, tol in ((np.float64, dict(rtol=0, atol=1e-14)), (np.float32, dict(rtol=0, atol=2e-6))):
+            Jd = dev(J, dt)
+            H = torch.full((N * 6 * n * n + 1,), float("nan"), dtype=Jd.dtype, device="cuda")
+            for off in (0, 1):  # off = 1: rows start one element past a 16-byte boundary
+                out = H[off:off + N * 6 * n * n]
+                out.fill_(float("nan"))
+                rtb._lib.check(lib.b2k_hessian(B.code(np.dtype(dt)), n, B.ptr(Jd), N, B.ptr(out), B.stream_ptr(Jd)))
+                np.testing.assert_allclose(host(out).reshape(N, n, 6, n), ref.astype(dt) if dt == np.float32 else ref, **tol,
+                                           err_msg=f"n={n} {dt.__name__} offset={off}")
