@@ -78,6 +78,117 @@ __global__ void __launch_bounds__(256) k_hessian(const real *__restrict__ J, lon
     }
 }
 
+// The same Hessian for output arrays that are 16-byte aligned (every torch allocation): a LANE per row, the row's J in
+// registers, every output a compile-time choice of four registers -- no shared-memory operand reads at all (the kernel
+// above spends 8 LDS.64 per output pair, 3.2 bank cycles each: shared-memory bandwidth, not HBM, bounds it at 0.61 ms).
+// A block of 4 warps owns a tile of 32 rows; warp w produces the 16-byte units w, w + 4, ... of every row and stores
+// them into a shared-memory image of the tile's output block, which leaves through the TMA engine
+// (cp.async.bulk shared -> global: no LDS / STG instructions).  The row pitch of the image is an odd number of units,
+// so the lane-per-row vector stores are bank-conflict free: where the row itself is an odd number of units the image is
+// exact and ONE bulk copy moves the tile; otherwise a 16-byte pad follows each row and the lane that owns a row issues
+// its copy.  One-shot grid (a tile per block), 3 resident blocks per SM at n = 7 fp64 (75 KB of image each): while one
+// block's image drains the others compute.
+template <typename real, int N> struct HessTile {
+    static constexpr int E = 6 * N;
+    static constexpr int U = (sizeof(real) == 8 || N % 2 == 0) ? 16 : 8; // bytes per unit
+    static constexpr int EPU = U / (int)sizeof(real);                    // elements per unit
+    static constexpr int ROWB = 6 * N * N * (int)sizeof(real);
+    static constexpr int RU = ROWB / U;  // units per row
+    static constexpr int PU = RU | 1;    // pitch in units (odd)
+    static constexpr bool EXACT = PU == RU;
+    static constexpr int SMEM = 32 * PU * U;
+    static_assert(ROWB % U == 0, "row is a whole number of units");
+    static_assert(32 * E * (int)sizeof(real) <= SMEM, "the J tile fits in front of the image");
+};
+
+template <typename real, int N>
+__device__ __forceinline__ real hess_elem(const real (&j)[6 * N], int e)
+{
+    const int a = e / (6 * N), r = (e / N) % 6, b = e % N;
+    if (!(b >= a || r < 3)) return (real)0;
+    const int lo = b >= a ? a : b, hi = b >= a ? b : a;
+    const int c = r % 3, c1 = (c + 1) % 3, c2 = (c + 2) % 3, wrow = r < 3 ? 0 : 3;
+    return j[(3 + c1) * N + lo] * j[(wrow + c2) * N + hi] - j[(3 + c2) * N + lo] * j[(wrow + c1) * N + hi];
+}
+
+template <typename real, int N, int W>
+__device__ __forceinline__ void hess_units(const real (&j)[6 * N], unsigned char *rowimg)
+{
+    typedef HessTile<real, N> HT;
+#pragma unroll
+    for (int u = W; u < HT::RU; u += 4) {
+        real v[HT::EPU];
+#pragma unroll
+        for (int k = 0; k < HT::EPU; k++) v[k] = hess_elem<real, N>(j, u * HT::EPU + k);
+        if constexpr (HT::U == 16 && sizeof(real) == 8) {
+            *reinterpret_cast<double2 *>(rowimg + u * 16) = make_double2(v[0], v[1]);
+        } else if constexpr (HT::U == 16) {
+            *reinterpret_cast<float4 *>(rowimg + u * 16) = make_float4(v[0], v[1], v[2], v[3]);
+        } else {
+            *reinterpret_cast<float2 *>(rowimg + u * 8) = make_float2(v[0], v[1]);
+        }
+    }
+}
+
+template <typename real, int N>
+__global__ void __launch_bounds__(128) k_hessian_tile(const real *__restrict__ J, long long nrows, real *__restrict__ H)
+{
+    typedef HessTile<real, N> HT;
+    extern __shared__ __align__(16) unsigned char hess_img[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long row0 = (long long)blockIdx.x * 32;
+    const int rows = (int)(nrows - row0 < 32 ? nrows - row0 : 32);
+
+    // the tile's J block (contiguous) -> front of the image, coalesced; then a lane takes its row into registers
+    {
+        real *sj = reinterpret_cast<real *>(hess_img);
+        const real *g = J + row0 * HT::E;
+        for (int e = threadIdx.x; e < rows * HT::E; e += 128) sj[e] = g[e];
+    }
+    __syncthreads();
+    real j[HT::E];
+    {
+        const real *sj = reinterpret_cast<const real *>(hess_img) + lane * HT::E;
+#pragma unroll
+        for (int e = 0; e < HT::E; e++) j[e] = sj[e];
+    }
+    __syncthreads(); // the image overwrites the J tile
+
+    unsigned char *rowimg = hess_img + (size_t)lane * (HT::PU * HT::U);
+    switch (warp) {
+    case 0: hess_units<real, N, 0>(j, rowimg); break;
+    case 1: hess_units<real, N, 1>(j, rowimg); break;
+    case 2: hess_units<real, N, 2>(j, rowimg); break;
+    default: hess_units<real, N, 3>(j, rowimg); break;
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+
+    real *gout = H + row0 * (6 * N * N);
+    if constexpr (HT::EXACT) {
+        const unsigned bytes = (unsigned)rows * HT::ROWB;
+        if ((bytes & 15u) == 0) {
+            if (threadIdx.x == 0) {
+                const unsigned sa = (unsigned)__cvta_generic_to_shared(hess_img);
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gout), "r"(sa), "r"(bytes) : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            }
+        } else { // ragged last tile of an fp32 / odd-n array whose byte count is 8 mod 16
+            const real *img = reinterpret_cast<const real *>(hess_img);
+            for (int e = threadIdx.x; e < rows * 6 * N * N; e += 128) gout[e] = img[e];
+        }
+    } else {
+        if (threadIdx.x < rows) {
+            const unsigned sa = (unsigned)__cvta_generic_to_shared(rowimg);
+            const unsigned bytes = HT::ROWB;
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gout + (size_t)lane * (6 * N * N)), "r"(sa), "r"(bytes) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        }
+    }
+}
+
 // ---- lane-per-row kernels over Jacobian rows: 64-thread blocks, each warp stages its tile of 32 rows (6N reals each)
 // through shared memory so that the global loads / stores are coalesced, and a lane then owns one row in registers.
 // (Reading the rows straight from global memory -- 32 lanes x a 6N-real stride per load instruction -- measured
@@ -448,6 +559,13 @@ __global__ void __launch_bounds__(128) k_singular(const real *__restrict__ J, lo
     m[row] = kind == 0 ? smin : (smax > 0 ? smin / smax : (real)0);
 }
 
+// B2K_HESSIAN_LUT=1 keeps every call on the warp-per-row kernel (measurement / tests of that path)
+static bool hessian_lut_only()
+{
+    static const bool v = [] { const char *e = getenv("B2K_HESSIAN_LUT"); return e && atoi(e) != 0; }();
+    return v;
+}
+
 template <typename real>
 static int extra_launch(int what, int n, const void *J, long long N, unsigned axes_mask, void *out, cudaStream_t st,
                         const void *aux = nullptr)
@@ -460,7 +578,10 @@ static int extra_launch(int what, int n, const void *J, long long N, unsigned ax
             /* index table is set up once per ~200 rows                                                             */ \
             const long long cap = (long long)b2k_num_sms() * (what == 0 ? 4 : 16);                                    \
             if (blocks > cap) blocks = cap;                                                                           \
-            if (what == 0) k_hessian<real, NN><<<(unsigned)blocks, 256, 0, st>>>((const real *)J, N, (real *)out, (int)(((uintptr_t)out & (2 * sizeof(real) - 1)) == 0)); \
+            if (what == 0 && NN >= 3 && ((uintptr_t)out & 15) == 0 && !hessian_lut_only() &&                          \
+                b2k_blocks_per_sm((const void *)k_hessian_tile<real, NN>, 128, HessTile<real, NN>::SMEM) >= 1)         \
+                k_hessian_tile<real, NN><<<(unsigned)((N + 31) / 32), 128, HessTile<real, NN>::SMEM, st>>>((const real *)J, N, (real *)out); \
+            else if (what == 0) k_hessian<real, NN><<<(unsigned)blocks, 256, 0, st>>>((const real *)J, N, (real *)out, (int)(((uintptr_t)out & (2 * sizeof(real) - 1)) == 0)); \
             else k_jacob_dot_lane<real, NN><<<(unsigned)((N + B2K_XT - 1) / B2K_XT), B2K_XT, 0, st>>>((const real *)J, (const real *)aux, N, (real *)out); \
         } else if (what == 3) {                                                                                       \
             if (axes_mask == 63u && NN >= 6) k_jacobm_all<real, NN><<<(unsigned)((N + 127) / 128), 128, 0, st>>>((const real *)J, N, (real *)out); \
