@@ -220,3 +220,35 @@ void b2k_fill_chain(const b2k_chain_s *c, const double *base, const double *tool
     P.all_rz = c->all_rz;
     b2k_fill_trig<real>(P.trig);
 }
+
+#ifdef __CUDACC__
+// The three used rows of a row-major 4x4 pose (12 reals) as 16-byte vector loads / the whole pose as 16-byte vector
+// stores; the caller has checked that the array is 16-byte aligned (any torch allocation is).
+template <typename real> __device__ __forceinline__ void load12(const real *p, real *o);
+template <> __device__ __forceinline__ void load12<double>(const double *p, double *o)
+{
+    const double2 *v = reinterpret_cast<const double2 *>(p);
+#pragma unroll
+    for (int k = 0; k < 6; k++) { const double2 x = __ldg(v + k); o[2 * k] = x.x; o[2 * k + 1] = x.y; }
+}
+template <> __device__ __forceinline__ void load12<float>(const float *p, float *o)
+{
+    const float4 *v = reinterpret_cast<const float4 *>(p);
+#pragma unroll
+    for (int k = 0; k < 3; k++) { const float4 x = __ldg(v + k); o[4 * k] = x.x; o[4 * k + 1] = x.y; o[4 * k + 2] = x.z; o[4 * k + 3] = x.w; }
+}
+
+template <typename real> __device__ __forceinline__ void store16(real *p, const real *v);
+template <> __device__ __forceinline__ void store16<double>(double *p, const double *v)
+{
+    double2 *o = reinterpret_cast<double2 *>(p);
+#pragma unroll
+    for (int k = 0; k < 8; k++) o[k] = make_double2(v[2 * k], v[2 * k + 1]);
+}
+template <> __device__ __forceinline__ void store16<float>(float *p, const float *v)
+{
+    float4 *o = reinterpret_cast<float4 *>(p);
+#pragma unroll
+    for (int k = 0; k < 4; k++) o[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+}
+#endif // __CUDACC__

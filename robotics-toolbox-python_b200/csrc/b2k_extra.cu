@@ -737,20 +737,6 @@ extern "C" int b2k_jtraj(int dtype, int n, const double *q0, const double *qf, c
 // Batched fknm.Angle_Axis (fknm.cpp:112-162 -> _angle_axis ik.cpp:241-286) and tools/p_servo.py:46-106 with
 // method="angle-axis": e = angle_axis(Te, Tep), v = gain .* e, arrived = sum|e| < threshold.
 // Lane per row; tep_stride = 0 broadcasts one target to every row.
-template <typename real> __device__ __forceinline__ void load12(const real *p, real *o);
-template <> __device__ __forceinline__ void load12<double>(const double *p, double *o)
-{
-    const double2 *v = reinterpret_cast<const double2 *>(p);
-#pragma unroll
-    for (int k = 0; k < 6; k++) { const double2 x = __ldg(v + k); o[2 * k] = x.x; o[2 * k + 1] = x.y; }
-}
-template <> __device__ __forceinline__ void load12<float>(const float *p, float *o)
-{
-    const float4 *v = reinterpret_cast<const float4 *>(p);
-#pragma unroll
-    for (int k = 0; k < 3; k++) { const float4 x = __ldg(v + k); o[4 * k] = x.x; o[4 * k + 1] = x.y; o[4 * k + 2] = x.z; o[4 * k + 3] = x.w; }
-}
-
 template <typename real, bool VEC>
 __global__ void __launch_bounds__(256) k_pose_error(const real *__restrict__ Te, const real *__restrict__ Tep,
                                                     long long tep_stride, long long nrows, real g0, real g1, real g2,

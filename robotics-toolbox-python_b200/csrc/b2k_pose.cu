@@ -163,23 +163,34 @@ __global__ void __launch_bounds__(64) k_janalytical(const real *__restrict__ T, 
 }
 
 // e = [Re^T (tp - te); rpy_zyx(Re^T Rep)], v = gain .* e, arrived = sum |e| < threshold
-template <typename real>
+template <typename real, bool VEC>
 __global__ void __launch_bounds__(256) k_servo_rpy(const real *__restrict__ Te, const real *__restrict__ Tep, long long tep_stride,
                                                    long long nrows, real g0, real g1, real g2, real g3, real g4, real g5,
                                                    real threshold, real *__restrict__ out, int *__restrict__ arrived)
 {
     const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= nrows) return;
-    const real *a = Te + row * 16, *b = Tep + row * tep_stride;
+    // the three used rows of both poses: 16-byte vector loads where the arrays allow (the launcher looks)
+    real a[12], b[12];
+    if (VEC) {
+        load12<real>(Te + row * 16, a);
+        load12<real>(Tep + row * tep_stride, b);
+    } else {
+#pragma unroll
+        for (int k = 0; k < 12; k++) { a[k] = Te[row * 16 + k]; b[k] = Tep[row * tep_stride + k]; }
+    }
     real R[3][3], e[6];
     const real d[3] = {b[3] - a[3], b[7] - a[7], b[11] - a[11]};
+#pragma unroll
     for (int i = 0; i < 3; i++) {
         e[i] = a[0 * 4 + i] * d[0] + a[1 * 4 + i] * d[1] + a[2 * 4 + i] * d[2];
+#pragma unroll
         for (int j = 0; j < 3; j++) R[i][j] = a[0 * 4 + i] * b[0 * 4 + j] + a[1 * 4 + i] * b[1 * 4 + j] + a[2 * 4 + i] * b[2 * 4 + j];
     }
     rot_to_rpy_zyx<real>(R, e + 3);
     const real g[6] = {g0, g1, g2, g3, g4, g5};
     real sum = 0;
+#pragma unroll
     for (int k = 0; k < 6; k++) {
         sum += fabs(e[k]);
         out[row * 6 + k] = g[k] * e[k];
@@ -194,7 +205,7 @@ struct CtrajP {
     int lerp_only; // the two orientations coincide
 };
 
-template <typename real>
+template <typename real, bool VEC>
 __global__ void __launch_bounds__(256) k_ctraj(const __grid_constant__ CtrajP P, const real *__restrict__ s, long long nrows,
                                                real *__restrict__ T)
 {
@@ -211,7 +222,7 @@ __global__ void __launch_bounds__(256) k_ctraj(const __grid_constant__ CtrajP P,
         for (int k = 0; k < 4; k++) q[k] = (real)P.q0[k] * s0 + (real)P.q1[k] * s1;
     }
     const real w = q[0], x = q[1], y = q[2], z = q[3];
-    real *o = T + row * 16;
+    real o[16];
     o[0] = 1 - 2 * (y * y + z * z); o[1] = 2 * (x * y - w * z);     o[2] = 2 * (x * z + w * y);
     o[4] = 2 * (x * y + w * z);     o[5] = 1 - 2 * (x * x + z * z); o[6] = 2 * (y * z - w * x);
     o[8] = 2 * (x * z - w * y);     o[9] = 2 * (y * z + w * x);     o[10] = 1 - 2 * (x * x + y * y);
@@ -219,6 +230,12 @@ __global__ void __launch_bounds__(256) k_ctraj(const __grid_constant__ CtrajP P,
     o[7] = (real)P.p0[1] * (1 - u) + u * (real)P.p1[1];
     o[11] = (real)P.p0[2] * (1 - u) + u * (real)P.p1[2];
     o[12] = 0; o[13] = 0; o[14] = 0; o[15] = 1;
+    if (VEC) {
+        store16<real>(T + row * 16, o); // 16-byte vector stores (the launcher has looked at the alignment)
+    } else {
+#pragma unroll
+        for (int k = 0; k < 16; k++) T[row * 16 + k] = o[k];
+    }
 }
 
 // rotation matrix (row-major 4x4) -> unit quaternion with s >= 0 (spatialmath r2q's convention)
@@ -314,12 +331,13 @@ extern "C" int b2k_p_servo_rpy(int dtype, const void *Te, const void *Tep, int64
     for (int k = 0; k < 6; k++) g[k] = gain ? gain[k] : 1.0;
     cudaStream_t st = (cudaStream_t)stream;
     const unsigned blocks = (unsigned)((N + 255) / 256);
-    if (dtype == B2K_F64)
-        k_servo_rpy<double><<<blocks, 256, 0, st>>>((const double *)Te, (const double *)Tep, tep_stride, N, g[0], g[1], g[2], g[3], g[4],
-                                                    g[5], threshold, (double *)v, arrived);
-    else
-        k_servo_rpy<float><<<blocks, 256, 0, st>>>((const float *)Te, (const float *)Tep, tep_stride, N, (float)g[0], (float)g[1],
-                                                   (float)g[2], (float)g[3], (float)g[4], (float)g[5], (float)threshold, (float *)v, arrived);
+    const bool vec = (((uintptr_t)Te | (uintptr_t)Tep) & 15) == 0;
+#define B2K_SR(REAL, V)                                                                                                        \
+    k_servo_rpy<REAL, V><<<blocks, 256, 0, st>>>((const REAL *)Te, (const REAL *)Tep, tep_stride, N, (REAL)g[0], (REAL)g[1],  \
+                                                 (REAL)g[2], (REAL)g[3], (REAL)g[4], (REAL)g[5], (REAL)threshold, (REAL *)v, arrived)
+    if (dtype == B2K_F64) { if (vec) B2K_SR(double, true); else B2K_SR(double, false); }
+    else { if (vec) B2K_SR(float, true); else B2K_SR(float, false); }
+#undef B2K_SR
     b2k_count_launch();
     B2K_CUDA(cudaGetLastError());
     return B2K_OK;
@@ -349,8 +367,14 @@ extern "C" int b2k_ctraj(int dtype, const double *T0, const double *T1, const vo
     for (int k = 0; k < 3; k++) { P.p0[k] = T0[4 * k + 3]; P.p1[k] = T1[4 * k + 3]; }
     cudaStream_t st = (cudaStream_t)stream;
     const unsigned blocks = (unsigned)((N + 255) / 256);
-    if (dtype == B2K_F64) k_ctraj<double><<<blocks, 256, 0, st>>>(P, (const double *)s, N, (double *)T);
-    else k_ctraj<float><<<blocks, 256, 0, st>>>(P, (const float *)s, N, (float *)T);
+    const bool vec = ((uintptr_t)T & 15) == 0;
+    if (dtype == B2K_F64) {
+        if (vec) k_ctraj<double, true><<<blocks, 256, 0, st>>>(P, (const double *)s, N, (double *)T);
+        else k_ctraj<double, false><<<blocks, 256, 0, st>>>(P, (const double *)s, N, (double *)T);
+    } else {
+        if (vec) k_ctraj<float, true><<<blocks, 256, 0, st>>>(P, (const float *)s, N, (float *)T);
+        else k_ctraj<float, false><<<blocks, 256, 0, st>>>(P, (const float *)s, N, (float *)T);
+    }
     b2k_count_launch();
     B2K_CUDA(cudaGetLastError());
     return B2K_OK;

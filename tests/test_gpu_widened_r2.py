@@ -333,3 +333,50 @@ def test_hessian_every_joint_count_grid_stride_and_alignment():
                 rtb._lib.check(lib.b2k_hessian(B.code(np.dtype(dt)), n, B.ptr(Jd), N, B.ptr(out), B.stream_ptr(Jd)))
                 np.testing.assert_allclose(host(out).reshape(N, n, 6, n), ref.astype(dt) if dt == np.float32 else ref, **tol,
                                            err_msg=f"n={n} {dt.__name__} offset={off}")
+
+
+def test_pose_kernels_on_element_aligned_arrays():
+    """The pose consumers / producers take 16-byte vector loads and stores when the arrays allow it; a C-ABI caller may
+    hand over arrays that are only element-aligned.  Both code paths against the same restatements: p_servo("rpy"),
+    p_servo("angle-axis") on pose batches that start one element past a 16-byte boundary, ctraj into such an array."""
+    B = rtb._buffers
+    lib = rtb._lib.lib()
+    rng = np.random.default_rng(91)
+    Ch = orc.Chain(ch.panda_ets())
+    N = 3001
+    Te, Tep = Ch.fkine(rng.uniform(-2, 2, (N, 7))), Ch.fkine(rng.uniform(-2, 2, (N, 7)))
+    gain = np.array([1, 2, 3, 0.5, 0.25, 4.0])
+    T0, T1 = Te[0], Tep[0]
+    A0, A1 = np.ascontiguousarray(T0), np.ascontiguousarray(T1)
+    s = rng.uniform(-0.1, 1.1, N)
+    for dt, tol in ((np.float64, dict(rtol=1e-9, atol=1e-11)), (np.float32, dict(rtol=2e-3, atol=2e-3))):
+        code = B.code(np.dtype(dt))
+        bufE = torch.zeros(N * 16 + 1, dtype=B.tdtype(np.dtype(dt)), device="cuda")
+        bufP = torch.zeros(N * 16 + 1, dtype=bufE.dtype, device="cuda")
+        res = {}
+        for off in (0, 1):
+            e_, p_ = bufE[off:off + N * 16], bufP[off:off + N * 16]
+            e_.copy_(dev(Te, dt).reshape(-1)); p_.copy_(dev(Tep, dt).reshape(-1))
+            for name, fn in (("rpy", lib.b2k_p_servo_rpy), ("aa", lib.b2k_p_servo)):
+                v = torch.empty(N * 6, dtype=bufE.dtype, device="cuda")
+                arrived = torch.empty(N, dtype=torch.int32, device="cuda")
+                rtb._lib.check(fn(code, B.ptr(e_), B.ptr(p_), N, 16, rtb._lib.dptr(gain), 2.5, B.ptr(v),
+                                  B.ptr(arrived), B.stream_ptr(v)))
+                res[name, off] = (host(v).reshape(N, 6), host(arrived))
+            out = torch.full((N * 16 + 1,), float("nan"), dtype=bufE.dtype, device="cuda")
+            sd = dev(s, dt)
+            rtb._lib.check(lib.b2k_ctraj(code, rtb._lib.dptr(A0), rtb._lib.dptr(A1), B.ptr(sd), N,
+                                         B.ptr(out[off:]), B.stream_ptr(sd)))
+            res["ctraj", off] = host(out[off:off + N * 16]).reshape(N, 4, 4)
+        for name in ("rpy", "aa"):  # the two load paths do the same arithmetic
+            np.testing.assert_array_equal(res[name, 0][0], res[name, 1][0])
+            np.testing.assert_array_equal(res[name, 0][1], res[name, 1][1])
+        np.testing.assert_array_equal(res["ctraj", 0], res["ctraj", 1])
+        wv, wa = orc.p_servo_rpy(Te, Tep, gain, 2.5)
+        far = np.abs(np.abs(wv[:, 3:] / gain[3:]) - np.pi).min(axis=1) > 0.05  # away from the +-pi wrap (fp32)
+        np.testing.assert_allclose(res["rpy", 1][0][far], wv[far], **tol)
+        if dt == np.float64:
+            np.testing.assert_array_equal(res["rpy", 1][1], wa)
+            np.testing.assert_allclose(res["ctraj", 1], orc.ctraj_poses(T0, T1, s), rtol=1e-10, atol=1e-12)
+        else:
+            np.testing.assert_allclose(res["ctraj", 1], orc.ctraj_poses(T0, T1, s), rtol=1e-4, atol=1e-5)
