@@ -251,4 +251,18 @@ template <> __device__ __forceinline__ void store16<float>(float *p, const float
 #pragma unroll
     for (int k = 0; k < 4; k++) o[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
 }
+// element index of an (N, n) array -> (row, axis).  n is a run-time value: the 64-bit division the plain expression
+// compiles to is a ~100-instruction software routine per element (it, not the 168 B / row of stores, bounded k_jtraj and
+// k_mtraj at 60 us per 1M x 7 samples); arrays below 2^32 elements take the 32-bit division.
+__device__ __forceinline__ void split_elem(long long e, int n, long long total, long long &row, int &j)
+{
+    if (total <= 0xffffffffLL) {
+        const unsigned r = (unsigned)e / (unsigned)n;
+        row = r;
+        j = (int)((unsigned)e - r * (unsigned)n);
+    } else {
+        row = e / n;
+        j = (int)(e - row * n);
+    }
+}
 #endif // __CUDACC__

@@ -682,8 +682,8 @@ __global__ void __launch_bounds__(256) k_jtraj(const __grid_constant__ JtrajP P,
 {
     const long long total = nrows * P.n;
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-        const long long row = e / P.n;
-        const int j = (int)(e - row * P.n);
+        long long row; int j;
+        split_elem(e, P.n, total, row, j);
         // normalised time: the caller's samples, or np.linspace(0, 1, N)[row] (last sample exactly 1)
         const real s = ts ? ts[row] * (real)P.inv_tscal
                           : (row == nrows - 1 ? (real)1 : (real)((double)row * P.inv_nm1));
@@ -820,8 +820,8 @@ __global__ void __launch_bounds__(256) k_mtraj(const __grid_constant__ MtrajP P,
 {
     const long long total = nrows * P.n;
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-        const long long row = e / P.n;
-        const int j = (int)(e - row * P.n);
+        long long row; int j;
+        split_elem(e, P.n, total, row, j);
         const real tk = t ? t[row] : (real)row; // `t: int` means t = arange(0, t) (trajectory.py:330, 489)
         real p, pd, pdd;
         if (P.kind == 0) { // np.polyval of coeffs, coeffs_d, coeffs_dd (trajectory.py:405-415)

@@ -127,20 +127,28 @@ __device__ __forceinline__ void rotvel_inverse(int rep, const real g[3], real A[
 
 // One lane per row; the warp stages its 32 Jacobian rows through shared memory (coalesced both ways) and converts them
 // in place: the translational rows pass through, the rotational ones are multiplied by A^-1(Gamma(R)).
-template <typename real>
+// Shared memory is sized for the robot at hand (2 warps x 32 rows x 6n reals: 21.5 KB at n = 7 fp64, 10 resident blocks
+// per SM; a tile sized for B2K_MAX_JOINTS held the kernel to 7).
+template <typename real, bool VEC>
 __global__ void __launch_bounds__(64) k_janalytical(const real *__restrict__ T, const real *__restrict__ J, long long nrows, int n,
                                                     int rep, real *__restrict__ Ja)
 {
-    __shared__ real tile[2][32 * 6 * B2K_MAX_JOINTS];
+    extern __shared__ __align__(16) unsigned char jan_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long row0 = ((long long)blockIdx.x * 2 + warp) * 32;
     if (row0 >= nrows) return;
     const int rows = (int)(nrows - row0 < 32 ? nrows - row0 : 32), w = 6 * n;
-    real *tl = tile[warp];
+    real *tl = reinterpret_cast<real *>(jan_smem) + warp * 32 * w;
     for (int e = lane; e < rows * w; e += 32) tl[e] = J[row0 * w + e];
     __syncwarp();
     if (lane < rows) {
-        const real *t = T + (row0 + lane) * 16;
+        real t[12];
+        if (VEC) {
+            load12<real>(T + (row0 + lane) * 16, t);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 12; k++) t[k] = T[(row0 + lane) * 16 + k];
+        }
         real R[3][3], g[3], A[3][3];
 #pragma unroll
         for (int i = 0; i < 3; i++)
@@ -275,8 +283,8 @@ __global__ void __launch_bounds__(256) k_mstraj(const MsPiece *__restrict__ piec
 {
     const long long total = nrows * n;
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-        const long long row = e / n;
-        const int j = (int)(e - row * n);
+        long long row; int j;
+        split_elem(e, n, total, row, j);
         int lo = 0, hi = npieces - 1; // the piece that holds this row
         while (lo < hi) {
             const int mid = (lo + hi + 1) >> 1;
@@ -311,8 +319,15 @@ extern "C" int b2k_jacob0_analytical(int dtype, int n, const void *T, const void
     B2K_ON_DEVICE_OF(J);
     cudaStream_t st = (cudaStream_t)stream;
     const unsigned blocks = (unsigned)((N + 63) / 64);
-    if (dtype == B2K_F64) k_janalytical<double><<<blocks, 64, 0, st>>>((const double *)T, (const double *)J, N, n, representation, (double *)Ja);
-    else k_janalytical<float><<<blocks, 64, 0, st>>>((const float *)T, (const float *)J, N, n, representation, (float *)Ja);
+    const bool vec = ((uintptr_t)T & 15) == 0;
+    const size_t smem = (size_t)2 * 32 * 6 * n * (dtype == B2K_F64 ? 8 : 4);
+    if (dtype == B2K_F64) {
+        if (vec) k_janalytical<double, true><<<blocks, 64, smem, st>>>((const double *)T, (const double *)J, N, n, representation, (double *)Ja);
+        else k_janalytical<double, false><<<blocks, 64, smem, st>>>((const double *)T, (const double *)J, N, n, representation, (double *)Ja);
+    } else {
+        if (vec) k_janalytical<float, true><<<blocks, 64, smem, st>>>((const float *)T, (const float *)J, N, n, representation, (float *)Ja);
+        else k_janalytical<float, false><<<blocks, 64, smem, st>>>((const float *)T, (const float *)J, N, n, representation, (float *)Ja);
+    }
     b2k_count_launch();
     B2K_CUDA(cudaGetLastError());
     return B2K_OK;
