@@ -107,6 +107,18 @@ int b2k_chain_info(b2k_chain_t chain, int *n, int *m, int *q_width);
 int b2k_fkine(b2k_chain_t chain, int dtype, const void *q, int64_t N, int64_t ldq,
               const double *base, const double *tool, void *T, void *stream);
 
+/* The poses of several frames along one chain from a single walk: the device side of fkine_all (reference
+ * Robot.fkine_all, Robot.py:638-700, and DHRobot.fkine_all, DHRobot.py:1018-1064: Python loops over the links).
+ * Frame k is  base * A_0 J_0(q) ... J_after[k](q) * tails[k]  -- the pose right after joint after[k] (0-based position
+ * of the joint along the chain) times a constant 4x4 (row-major, host) -- or, for after[k] = -1, the constant tails[k]
+ * itself (the base frame, links that depend on no joint; the caller multiplies the base in).  after[] ascending.
+ * out is (N, nslots, 4, 4) row-major, 32-byte aligned; frame k goes to slot[k] of every row; slots not named are left
+ * untouched (a branched robot takes one call per branch into the same array).  The chain's tool constant and the
+ * transforms behind its last joint do not enter. */
+int b2k_fkine_frames(b2k_chain_t chain, int dtype, const void *q, int64_t N, int64_t ldq, const double *base,
+                     int nframes, const int32_t *after, const int32_t *slot, const double *tails, void *out,
+                     int64_t nslots, void *stream);
+
 /* Replaces fknm.ETS_jacob0 (fknm.cpp:785-850 -> _ETS_jacob0 methods.cpp:112-216), batched:
  * J[i] = geometric Jacobian in the chain's start frame, (6,n) row-major per row; no base
  * (reference RobotKinematics.py:158), tool included. */

@@ -19,6 +19,7 @@ slow Python (ETS.py:1075-1078) is deliberately not reproduced.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import List, Optional, Union
 
 import numpy as np
@@ -286,9 +287,11 @@ class ETS:
     def eval_frames(chains, q, base=None, dtype=None):
         """Poses of several frames of one robot for the same q batch: ``chains[k]`` is the ETS from the robot's base to
         frame k + 1, frame 0 is the base itself.  Returns (K+1,4,4) for one configuration, (N,K+1,4,4) for a batch (a
-        device tensor for device input -- a view of frame-major memory, every kernel writes its frame contiguously --,
-        numpy for host input).  One FK launch per frame over the full q rows (each chain reads the joints it needs):
-        the building block of ``fkine_all`` (reference Robot.fkine_all, Robot.py:638-700; DHRobot.fkine_all 1018-1064)."""
+        device tensor for device input, numpy for host input).  The chains are sorted into walks: a chain that is a
+        prefix of a longer one is "the pose after its last joint times its constant tail" on the longer chain's walk,
+        so a serial robot takes ONE launch for all of its frames and a branched one a launch per branch
+        (``b2k_fkine_frames``); frames that depend on no joint are constants carried by the first launch.  The building
+        block of ``fkine_all`` (reference Robot.fkine_all, Robot.py:638-700; DHRobot.fkine_all 1018-1064)."""
         if not chains:
             raise ValueError("no frames requested")
         jointed = [e for e in chains if e.n > 0]
@@ -301,24 +304,101 @@ class ETS:
         qd = B.to_device(q2, dt).contiguous()
         N = qd.shape[0]
         base = _mat44(base, "base")
-        frames = B.empty((len(chains) + 1, N, 4, 4), dt, like=qd)
-        t = B.require_cuda()
         b0 = np.eye(4) if base is None else base
-        frames[0] = t.as_tensor(b0, dtype=frames.dtype, device=frames.device)
+        if not ETS.frames_single_walk:
+            # one pose launch per frame over the prefix chains into frame-major memory (each launch re-reads q and
+            # re-walks its prefix); kept selectable for measurement, see DESIGN 3.6
+            frames = B.empty((len(chains) + 1, N, 4, 4), dt, like=qd)
+            t = B.require_cuda()
+            b0 = np.eye(4) if base is None else base
+            frames[0] = t.as_tensor(b0, dtype=frames.dtype, device=frames.device)
+            L = _lib.lib()
+            for k, e in enumerate(chains):
+                if e.n == 0:  # a static frame (a link before the first joint): base times the constant transforms
+                    Tc = b0.copy()
+                    for et in e:
+                        Tc = Tc @ et.A()
+                    frames[k + 1] = t.as_tensor(Tc, dtype=frames.dtype, device=frames.device)
+                    continue
+                _lib.check(L.b2k_fkine(e._chain, B.code(dt), B.ptr(qd), N, qd.shape[1], _lib.dptr(base), None, B.ptr(frames[k + 1]),
+                                       B.stream_ptr(qd)))
+            out = frames.permute(1, 0, 2, 3)
+            if host:
+                out = np.ascontiguousarray(B.to_host(out.contiguous()))
+            return out[0] if single else out
+        K = len(chains)
+        out = B.empty((N, K + 1, 4, 4), dt, like=qd)
         L = _lib.lib()
-        for k, e in enumerate(chains):
-            if e.n == 0:  # a static frame (a link before the first joint): base times the constant transforms
-                Tc = b0.copy()
-                for et in e:
-                    Tc = Tc @ et.A()
-                frames[k + 1] = t.as_tensor(Tc, dtype=frames.dtype, device=frames.device)
-                continue
-            _lib.check(L.b2k_fkine(e._chain, B.code(dt), B.ptr(qd), N, qd.shape[1], _lib.dptr(base), None, B.ptr(frames[k + 1]),
-                                   B.stream_ptr(qd)))
-        out = frames.permute(1, 0, 2, 3)
+        for walk, after, slot, tails, nconst in ETS._frame_plan(chains):
+            if nconst:  # the constants (base frame, links ahead of every joint) are expressed in the base frame
+                tails = tails.copy()
+                tails[:nconst] = b0 @ tails[:nconst]
+            _lib.check(L.b2k_fkine_frames(walk._chain, B.code(dt), B.ptr(qd), N, qd.shape[1], _lib.dptr(base), len(after),
+                                          after.ctypes.data_as(_lib.ip), slot.ctypes.data_as(_lib.ip), _lib.dptr(tails),
+                                          B.ptr(out), K + 1, B.stream_ptr(qd)))
         if host:
-            out = np.ascontiguousarray(B.to_host(out.contiguous()))
+            out = B.to_host(out)
         return out[0] if single else out
+
+    frames_single_walk = os.environ.get("B2K_FRAMES_SINGLE_WALK", "1") != "0"
+    _frame_plans: dict = {}  # tuple(id(chain)) -> (the chains (kept alive: their ids stay theirs), launches)
+
+    @staticmethod
+    def _frame_plan(chains):
+        """The launches of ``eval_frames`` for this list of chains, [(walk, after, slot, tails, nconst)], planned once
+        per list of chain objects (a robot keeps its prefix chains; planning costs more host time than the launch)."""
+        key = tuple(id(e) for e in chains)
+        hit = ETS._frame_plans.get(key)
+        if hit is not None:
+            return hit[1]
+        launches = []
+        for walk, frames in ETS._frame_walks(chains):
+            const = []
+            if not launches:  # the constants ride on the first launch: the base frame and the links ahead of every joint
+                const.append((0, -1, np.eye(4)))
+                for k, e in enumerate(chains):
+                    if e.n == 0:
+                        Tc = np.eye(4)
+                        for et in e:
+                            Tc = Tc @ et.A()
+                        const.append((k + 1, -1, Tc))
+            frames = const + sorted(frames, key=lambda f: f[1])
+            launches.append((walk, np.ascontiguousarray([f[1] for f in frames], dtype=np.int32),
+                             np.ascontiguousarray([f[0] for f in frames], dtype=np.int32),
+                             np.ascontiguousarray(np.stack([f[2] for f in frames]), dtype=np.float64), len(const)))
+        if len(ETS._frame_plans) >= 32:
+            ETS._frame_plans.pop(next(iter(ETS._frame_plans)))
+        ETS._frame_plans[key] = (tuple(chains), launches)
+        return launches
+
+    @staticmethod
+    def _frame_walks(chains):
+        """Sort the jointed chains of ``eval_frames`` into walks: [(walk ETS, [(slot, after, tail 4x4), ...]), ...].  A
+        chain belongs to the first longer chain it is a prefix of (same elementary transforms, joint indices and
+        constants); ``after`` is the 0-based position of its last joint along the walk, ``tail`` the product of the
+        constant transforms behind that joint."""
+        descs = [e.describe() for e in chains]
+
+        def is_prefix(k, w):
+            m = chains[k].m
+            if m > chains[w].m:
+                return False
+            dk, dw = descs[k], descs[w]
+            return all(np.array_equal(dk[key][:m], dw[key][:m]) for key in ("isjoint", "axis", "flip", "jindex", "T"))
+
+        walks = []  # [walk index, frames]
+        for k in sorted((k for k, e in enumerate(chains) if e.n > 0), key=lambda k: -chains[k].m):
+            owner = next((w for w in walks if is_prefix(k, w[0])), None)
+            if owner is None:
+                owner = [k, []]
+                walks.append(owner)
+            ets = list(chains[k])
+            last = max(i for i, et in enumerate(ets) if et.isjoint)
+            tail = np.eye(4)
+            for et in ets[last + 1:]:
+                tail = tail @ et.A()
+            owner[1].append((k + 1, chains[k].n - 1, tail))
+        return [(chains[w], fr) for w, fr in walks]
 
     def fkine(self, q, base=None, tool=None, include_base: bool = True, dtype=None) -> SE3:
         """Forward kinematics as an SE3 container (reference ETS.fkine, ETS.py:951-1019); one

@@ -36,6 +36,7 @@ _PROTOS = {
     "b2k_chain_destroy": (C.c_int, [vp]),
     "b2k_chain_info": (C.c_int, [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "b2k_fkine": (C.c_int, [vp, C.c_int, vp, i64, i64, dp, dp, vp, vp]),
+    "b2k_fkine_frames": (C.c_int, [vp, C.c_int, vp, i64, i64, dp, C.c_int, ip, ip, dp, vp, i64, vp]),
     "b2k_jacob0": (C.c_int, [vp, C.c_int, vp, i64, i64, dp, vp, vp]),
     "b2k_jacobe": (C.c_int, [vp, C.c_int, vp, i64, i64, dp, vp, vp]),
     "b2k_fkine_jacob0": (C.c_int, [vp, C.c_int, vp, i64, i64, dp, dp, vp, vp, vp]),

@@ -239,8 +239,17 @@ if want("extra_"):
         ("extra_mtraj_trapezoidal_f64", lambda i: rtb.mtraj(rtb.trapezoidal, np.zeros(7), np.ones(7), NX, device=True), 21 * 8),
         ("extra_ctraj_f64", lambda i: rtb.ctraj(Tx[0].cpu().numpy(), Tx[1].cpu().numpy(), NX, device=True), 16 * 8),
         ("extra_fkine_all_panda_f64", lambda i: PD.fkine_all(Qx), (7 + 8 * 16) * 8),
+        ("extra_fkine_all_panda_f64_per_frame_launches", lambda i: fkine_all_per_frame(PD, Qx), (7 + 8 * 16) * 8),
     ]
     PD = rtb.models.DH.Panda()
+
+    def fkine_all_per_frame(robot, Q):  # the earlier route: one pose launch per frame over the prefix chains
+        rtb.ETS.frames_single_walk = False
+        try:
+            return robot.fkine_all(Q)
+        finally:
+            rtb.ETS.frames_single_walk = True
+
     for name, fn, bpr in cases:
         if not want(name):
             continue

@@ -108,6 +108,25 @@ def test_widened_entry_points_validate_before_launching():
     assert lib.b2k_jtraj(7, 6, q0.ctypes.data_as(dp), q0.ctypes.data_as(dp), None, None, 8, None, 1.0, p, p, p, None) == -1
     assert lib.b2k_jtraj(1, 6, q0.ctypes.data_as(dp), q0.ctypes.data_as(dp), None, None, 0, None, 1.0, None, None, None, None) == 0
     assert lib.b2k_hessian(1, 7, None, 4, None, None) == -1
+    # fkine_all's single-walk entry point: frame table validation happens before anything touches the device
+    ip = rtb._lib.ip
+    panda_ets = rtb.models.Panda().ets()  # owns the handle: keep it alive
+    hc = panda_ets._chain
+    aft, slt, tl = np.array([0, 3, 2], np.int32), np.array([1, 2, 3], np.int32), np.tile(np.eye(4), (3, 1, 1))
+    a_ = lambda x: x.ctypes.data_as(ip)  # noqa: E731
+    p32 = (p + 31) & ~31
+    assert lib.b2k_fkine_frames(None, 1, p, 4, 7, None, 3, a_(aft), a_(slt), tl.ctypes.data_as(dp), p32, 4, None) == -1
+    assert lib.b2k_fkine_frames(hc, 1, p, 4, 7, None, 3, a_(aft), a_(slt), tl.ctypes.data_as(dp), p32, 4, None) == -1
+    assert b"ascending" in lib.b2k_last_error()
+    aft[:] = [0, 2, 7]
+    assert lib.b2k_fkine_frames(hc, 1, p, 4, 7, None, 3, a_(aft), a_(slt), tl.ctypes.data_as(dp), p32, 4, None) == -1
+    aft[:] = [-1, 2, 6]; slt[2] = 4
+    assert lib.b2k_fkine_frames(hc, 1, p, 4, 7, None, 3, a_(aft), a_(slt), tl.ctypes.data_as(dp), p32, 4, None) == -1
+    assert b"slot" in lib.b2k_last_error()
+    slt[2] = 3
+    assert lib.b2k_fkine_frames(hc, 1, p, 4, 7, None, 3, a_(aft), a_(slt), tl.ctypes.data_as(dp), p32 + 8, 4, None) == -1
+    assert b"32-byte" in lib.b2k_last_error()
+    assert lib.b2k_fkine_frames(hc, 1, p, 0, 7, None, 3, a_(aft), a_(slt), tl.ctypes.data_as(dp), p32, 4, None) == 0
     assert lib.b2k_manipulability(1, 7, p, 4, 0, p, None) == -1 and b"axis" in lib.b2k_last_error()
     assert lib.b2k_jacobm(1, 7, p, 4, 0, p, None) == -1
     assert lib.b2k_jacob_dot(3, 7, p, p, 4, p, None) == -1

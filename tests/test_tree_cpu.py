@@ -206,3 +206,36 @@ def test_changed_link_parameters_rebuild_the_tree_program():
     assert h2 is not h1
     assert rob.rne_kernel_info() != info0  # an off-axis centre of mass adds terms to the generated recursion
     assert isinstance(h2, C.c_void_p)
+
+
+def test_frame_walks_of_fkine_all():
+    """ETS._frame_walks (the plan behind fkine_all / b2k_fkine_frames): every link frame is 'the pose after joint
+    `after` of its walk, times a constant tail'.  Checked with the oracle: FK of the walk cut behind that joint, times
+    the tail, equals FK of the link's own chain -- for a serial DH robot (one walk), a DH robot with joint offsets and
+    a prismatic joint, and a branched tree (a walk per branch, static links on constants)."""
+    rng = np.random.default_rng(5)
+
+    def check(chains, qwidth, nwalks):
+        walks = ETS._frame_walks(chains)
+        assert len(walks) == nwalks
+        Q = rng.uniform(-2, 2, (7, qwidth))
+        seen = set()
+        for walk, frames in walks:
+            ets = list(walk)
+            joints = [i for i, et in enumerate(ets) if et.isjoint]
+            for slot, after, tail in frames:
+                assert 0 <= after < walk.n and slot not in seen
+                seen.add(slot)
+                cut = ETS(ets[:joints[after] + 1])
+                want = fk(chains[slot - 1], Q)
+                np.testing.assert_allclose(fk(cut, Q) @ tail, want, rtol=1e-12, atol=1e-13)
+        assert seen == {k + 1 for k, e in enumerate(chains) if e.n > 0}
+
+    puma = rtb.models.Puma560()
+    check([ETS.from_links([l.ets for l in puma.links[:k + 1]]) for k in range(puma.n)], 6, 1)
+    mixed = rtb.DHRobot([rtb.RevoluteDH(d=0.3, a=0.1, alpha=0.5, offset=0.2), rtb.PrismaticDH(theta=0.4, a=0.2, alpha=-0.3),
+                         rtb.RevoluteDH(d=0.1, a=0.3, alpha=0.7, flip=True)])
+    check([ETS.from_links([l.ets for l in mixed.links[:k + 1]]) for k in range(mixed.n)], 3, 1)
+    r = make_tree()
+    chains = [r.ets(end=l) for l in r.links]
+    check(chains, r.n, 2)  # two branches; their common trunk rides on the longer branch's walk
