@@ -195,6 +195,7 @@ class ETS:
     def _update_internals(self):
         """Drop the compiled chain (call after mutating an ET's jindex / qlim); reference ETS.py:62-69."""
         self._release()
+        ETS._frame_plans.clear()  # a cached fkine_all plan may have been derived from the old contents
 
     def _release(self):
         if getattr(self, "_handle", None):

@@ -22,6 +22,7 @@ ncu) echo "== ncu captures"
   cap rne32 k_rne rne_puma_f32 2
   cap coriolis k_rne_fan dyn_coriolis 1;;
 ncu_rne) cap rne64s k_rne_spec rne_puma_f64 2; cap rne32s k_rne_spec rne_puma_f32 2;; ncu_rne_old) cap rne64 "${NCU_RNE_K:-k_rne}" rne_puma_f64 2; cap rne32 "${NCU_RNE_K:-k_rne}" rne_puma_f32 2;;
+ncu_late) cap hesstile k_hessian_tile extra_hessian 1; cap frames k_fk_frames extra_fkine_all_panda_f64 1;;
 launches) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv --log-file gpurun_out/launches.csv python bench.py --steps 4 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_list.log 2>&1; echo "launch list rc=$?";;
 esac; done
 ls -la gpurun_out | head -40
